@@ -1,0 +1,587 @@
+/*
+ * oracle/oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, single-threaded CPU restatement of the librir (v6.1.2) algorithms on the
+ * per-frame hot path.  It exists so that the CUDA path can be
+ * checked against something that runs on the GPU box, where /root/reference is absent.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load it; librir_b200 itself never does (no CPU fallback exists in the product).
+ *
+ * Pinning: every function here is compared, on seeded inputs, against the reference's own
+ * sources compiled by oracle/build_ref.sh (oracle/_ref/libs/libsignal_processing.so) in
+ * tests/test_oracle_vs_ref.py, and against the golden vectors that build produced
+ * (tests/golden/, generator tests/golden/make_golden.py).  The byte-plane split/merge
+ * (video_io) cannot be compiled here (needs ffmpeg/x264); it is pinned by the reference
+ * code it restates (h264.cpp:1066-1103, 3016-3051) and by the round-trip identity the
+ * reference's tests assert (tests/python/test_IRMovie.py:46-49).  The temporal delta stage
+ * has no counterpart in the reference: PARITY UNPINNED, defined by this repo.
+ *
+ * Compile: gcc -O2 -ffp-contract=off -fPIC -shared oracle.c -lm   (no -march, no
+ * -ffast-math: the reference's stock build has no FMA contraction).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+typedef unsigned short u16;
+
+/* ------------------------------------------------------------------------------------ */
+/* helpers                                                                              */
+/* ------------------------------------------------------------------------------------ */
+
+static int cmp_u16(const void *a, const void *b)
+{
+    u16 x = *(const u16 *)a, y = *(const u16 *)b;
+    return (x > y) - (x < y);
+}
+
+/* k-th smallest (0-based) of n<=25 values; any exact selection equals std::nth_element /
+ * std::sort element k. */
+static u16 kth_smallest(u16 *v, int n, int k)
+{
+    for (int i = 1; i < n; ++i) {
+        u16 key = v[i];
+        int j = i - 1;
+        while (j >= 0 && v[j] > key) {
+            v[j + 1] = v[j];
+            --j;
+        }
+        v[j + 1] = key;
+    }
+    return v[k];
+}
+
+/* Frame median (upper median, sorted[N/2]) and the spread around it as the reference
+ * computes them: Filters.h:145-156 and BadPixels.cpp:19-30.  The squared difference is an
+ * int product there; it is exact here as long as |p - median| < 46341 (the reference
+ * overflows beyond that). */
+static void frame_median_std(const u16 *img, size_t n, int *median, double *std_out)
+{
+    u16 *tmp = (u16 *)malloc(n * sizeof(u16));
+    memcpy(tmp, img, n * sizeof(u16));
+    qsort(tmp, n, sizeof(u16), cmp_u16);
+    int m = tmp[n / 2];
+    double sum = 0;
+    for (size_t i = 0; i < n; ++i) {
+        int d = (int)tmp[i] - m;
+        sum += (double)(d * d);
+    }
+    free(tmp);
+    sum /= (double)(int)n;
+    *median = m;
+    *std_out = sqrt(sum);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a-1  bad-pixel detection    Filters.h:135-193, BadPixels.cpp:13-32                    */
+/* ------------------------------------------------------------------------------------ */
+
+/* Writes up to cap (x,y) pairs in raster order into xy[2*i], xy[2*i+1]; returns the number
+ * of bad pixels found (may exceed cap: call again with a larger buffer).  *global_thr gets
+ * the "p < median - 5*std" threshold (Filters.h:157-160). */
+ORC_API int orc_bad_pixels_detect(const u16 *img, int w, int h, double std_factor,
+                                  int *xy, int cap, int *global_thr)
+{
+    size_t n = (size_t)w * (size_t)h;
+    int median;
+    double gstd;
+    frame_median_std(img, n, &median, &gstd);
+    u16 cut = (u16)(gstd * std_factor); /* (T)(double): truncation, Filters.h:157 */
+    u16 gthr = ((u16)median > cut) ? (u16)(median - cut) : 0;
+    if (global_thr)
+        *global_thr = gthr;
+
+    int count = 0;
+    u16 win[25];
+    for (long y = 0; y < h; ++y)
+        for (long x = 0; x < w; ++x) {
+            int m = 0;
+            for (long yy = y - 2; yy <= y + 2; ++yy)
+                for (long xx = x - 2; xx <= x + 2; ++xx)
+                    if (xx >= 0 && yy >= 0 && xx < w && yy < h)
+                        win[m++] = img[xx + yy * w];
+            kth_smallest(win, m, 0); /* full insertion sort */
+            long med = win[m / 2];
+            double sum2 = 0;
+            long c = 0;
+            for (long i = m / 5; i < m * 4 / 5; ++i, ++c) {
+                long d = (long)win[i] - med;
+                sum2 += (double)(d * d);
+            }
+            sum2 /= (double)c;
+            double sd = sqrt(sum2);
+            double lower = (double)med - std_factor * sd;
+            double upper = (double)med + std_factor * sd;
+            u16 p = img[x + y * w];
+            if ((double)p < lower || (double)p > upper || p < gthr) {
+                if (count < cap && xy) {
+                    xy[2 * count] = (int)x;
+                    xy[2 * count + 1] = (int)y;
+                }
+                ++count;
+            }
+        }
+    return count;
+}
+
+/* Clamp level "median - (int)(2*std)" kept by BadPixels::init (BadPixels.cpp:19-31). */
+ORC_API int orc_bad_pixels_clamp_value(const u16 *img, int w, int h)
+{
+    int median;
+    double gstd;
+    frame_median_std(img, (size_t)w * (size_t)h, &median, &gstd);
+    return median - (int)(gstd * 2);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a-2  bad-pixel correction   BadPixels.cpp:34-66, Filters.cpp:43-49                    */
+/* ------------------------------------------------------------------------------------ */
+
+ORC_API void orc_bad_pixels_correct(const u16 *in, u16 *out, int w, int h, const int *xy,
+                                    int count, int clamp_value)
+{
+    size_t n = (size_t)w * (size_t)h;
+    if (in != out)
+        memcpy(out, in, n * sizeof(u16));
+    for (int i = 0; i < count; ++i) {
+        int x = xy[2 * i], y = xy[2 * i + 1];
+        u16 v[9];
+        int c = 0;
+        for (int xx = x - 1; xx <= x + 1; ++xx)     /* column-major gather, from `in` */
+            for (int yy = y - 1; yy <= y + 1; ++yy)
+                if (xx >= 0 && yy >= 0 && xx < w && yy < h)
+                    v[c++] = in[xx + yy * w];
+        out[x + y * w] = kth_smallest(v, c, c / 2);
+    }
+    if (clamp_value > 0) {
+        u16 lo = (u16)clamp_value;
+        for (size_t i = 0; i < n; ++i)
+            if (out[i] < lo)
+                out[i] = lo;
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a-3  loader variant         IRFileLoader.cpp:722-802                                  */
+/* ------------------------------------------------------------------------------------ */
+
+/* In place on rows [0,h) (callers pass height-3).  3x3 window shifted inside the image,
+ * cells flagged bad are skipped, no clamp.  When every cell of the window is bad the
+ * reference reads a stale stack slot (undefined); this restatement leaves the pixel as is. */
+ORC_API void orc_loader_remove_bad_pixels(u16 *img, int w, int h, const int *xy, int count)
+{
+    if (w < 3 || h < 3) {
+        for (int i = 0; i < count; ++i) { /* sequential, in place: IRFileLoader.cpp:735-752 */
+            int x = xy[2 * i], y = xy[2 * i + 1];
+            u16 v[9];
+            int c = 0;
+            for (int xx = x - 1; xx <= x + 1; ++xx)
+                for (int yy = y - 1; yy <= y + 1; ++yy)
+                    if (xx >= 0 && yy >= 0 && xx < w && yy < h)
+                        v[c++] = img[xx + yy * w];
+            if (c)
+                img[x + y * w] = kth_smallest(v, c, c / 2);
+        }
+        return;
+    }
+    unsigned char *bad = (unsigned char *)calloc((size_t)w * (size_t)h, 1);
+    for (int i = 0; i < count; ++i)
+        bad[xy[2 * i] + xy[2 * i + 1] * w] = 1;
+    for (int i = 0; i < count; ++i) {
+        int x = xy[2 * i], y = xy[2 * i + 1];
+        int x0 = x - 1, y0 = y - 1;
+        if (x == 0) x0 = 0; else if (x == w - 1) x0 = w - 3;
+        if (y == 0) y0 = 0; else if (y == h - 1) y0 = h - 3;
+        u16 v[9];
+        int c = 0;
+        for (int xx = x0; xx <= x0 + 2; ++xx)
+            for (int yy = y0; yy <= y0 + 2; ++yy)
+                if (!bad[xx + yy * w])
+                    v[c++] = img[xx + yy * w];
+        if (c)
+            img[x + y * w] = kth_smallest(v, c, c / 2);
+    }
+    free(bad);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a-4  gaussian filter        signal_processing.cpp:79-148                              */
+/* ------------------------------------------------------------------------------------ */
+
+ORC_API int orc_gaussian_radius(float sigma)
+{
+    int r = (int)(sigma * 2);
+    return r < 1 ? 1 : r;
+}
+
+/* (2r+1)^2 float taps, index [dx+r + (dy+r)*kw]; signal_processing.cpp:79-99 */
+ORC_API void orc_gaussian_kernel(float sigma, int r, float *k)
+{
+    float s = 2.0f * sigma * sigma;
+    float sum = 0.0f;
+    int kw = 2 * r + 1;
+    for (int x = -r; x <= r; ++x)
+        for (int y = -r; y <= r; ++y) {
+            float rho = (float)sqrt((double)(x * x + y * y));
+            float e = expf(-(rho * rho) / s);             /* std::exp(float) */
+            float t = (float)((double)e / (3.14159265358979323846 * (double)s));
+            k[x + r + (y + r) * kw] = t;
+            sum += t;
+        }
+    for (int i = 0; i < kw * kw; ++i)
+        k[i] /= sum;
+}
+
+ORC_API int orc_gaussian_filter(const float *src, float *dst, int w, int h, float sigma)
+{
+    int r = orc_gaussian_radius(sigma);
+    int kw = 2 * r + 1;
+    float *k = (float *)malloc(sizeof(float) * (size_t)kw * (size_t)kw);
+    orc_gaussian_kernel(sigma, r, k);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int interior = x >= r && x < w - r && y >= r && y < h - r;
+            float acc = 0, ksum = 0;
+            for (int dx = -r; dx <= r; ++dx)
+                for (int dy = -r; dy <= r; ++dy) {
+                    int xx = x + dx, yy = y + dy;
+                    if (interior || (xx >= 0 && xx < w && yy >= 0 && yy < h)) {
+                        float t = k[dx + r + (dy + r) * kw];
+                        ksum += t;
+                        acc += t * src[xx + yy * w];
+                    }
+                }
+            dst[x + y * w] = interior ? acc : acc / ksum;
+        }
+    free(k);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a-5  translate              Filters.h:249-326, signal_processing.cpp:14-73            */
+/* ------------------------------------------------------------------------------------ */
+
+enum { ORC_NOBORDER = 0, ORC_BACKGROUND = 1, ORC_WRAP = 2, ORC_NEAREST = 3 };
+
+/* (size_t)float as x86-64 evaluates it for the value range seen here: truncate toward zero
+ * as a signed 64-bit integer, then reinterpret. */
+static inline uint64_t f2size(float v) { return (uint64_t)(int64_t)v; }
+static inline uint64_t wrap_idx(uint64_t v, uint64_t n) { return (v + n) % n; }
+
+/* One generic body; T = storage type, U = destination type, TODBL converts a pixel to the
+ * double it is promoted to in the blend, CAST is detail::cast<U> (Filters.h:232-235). */
+#define ORC_DEFINE_TRANSLATE(NAME, T, U, CAST)                                                 \
+    static void NAME(const T *src, U *dst, U background, size_t w, size_t h, float dx,        \
+                     float dy, int strategy)                                                   \
+    {                                                                                          \
+        for (size_t y = 0; y < h; ++y)                                                         \
+            for (size_t x = 0; x < w; ++x) {                                                   \
+                float px = (float)x - dx;                                                      \
+                float py = (float)y - dy;                                                      \
+                size_t l, rt, t, b;                                                            \
+                double u, v;                                                                   \
+                if (px < 0 || px >= (float)w || py < 0 || py >= (float)h) {                    \
+                    if (strategy == ORC_NOBORDER)                                              \
+                        continue;                                                              \
+                    if (strategy == ORC_BACKGROUND) {                                          \
+                        dst[x + y * w] = background;                                           \
+                        continue;                                                              \
+                    }                                                                          \
+                    if (strategy == ORC_NEAREST) {                                             \
+                        size_t sx = px < 0 ? 0 : (px >= (float)w ? w - 1 : (size_t)px);        \
+                        size_t sy = py < 0 ? 0 : (py >= (float)h ? h - 1 : (size_t)py);        \
+                        dst[x + y * w] = (U)src[sx + sy * w];                                  \
+                        continue;                                                              \
+                    }                                                                          \
+                    l = wrap_idx(f2size(px), w);                                               \
+                    rt = wrap_idx(f2size(px + 1), w);                                          \
+                    t = wrap_idx(f2size(py), h);                                               \
+                    b = wrap_idx(f2size(py + 1), h);                                           \
+                    u = (double)fabsf(px - (float)(int)px);                                    \
+                    v = (double)fabsf(py - (float)(int)py);                                    \
+                } else {                                                                       \
+                    l = (size_t)px;                                                            \
+                    rt = (size_t)(px + 1);                                                     \
+                    if (rt == w) rt = l;                                                       \
+                    t = (size_t)py;                                                            \
+                    b = (size_t)(py + 1);                                                      \
+                    if (b == h) b = t;                                                         \
+                    u = (double)(px - (float)l);                                               \
+                    v = (double)((float)b - py);                                               \
+                }                                                                              \
+                double p1 = (double)src[b * w + l], p2 = (double)src[t * w + l];               \
+                double p3 = (double)src[b * w + rt], p4 = (double)src[t * w + rt];             \
+                double val = (p1 * (1 - v) + p2 * v) * (1 - u) + (p3 * (1 - v) + p4 * v) * u;  \
+                dst[x + y * w] = CAST(val);                                                    \
+            }                                                                                  \
+    }
+
+#define CAST_BOOL(v) ((unsigned char)((v) != 0))
+ORC_DEFINE_TRANSLATE(tr_bool, unsigned char, unsigned char, CAST_BOOL)
+ORC_DEFINE_TRANSLATE(tr_i8, signed char, signed char, (signed char))
+ORC_DEFINE_TRANSLATE(tr_u8, unsigned char, unsigned char, (unsigned char))
+ORC_DEFINE_TRANSLATE(tr_i16, short, short, (short))
+ORC_DEFINE_TRANSLATE(tr_u16, u16, u16, (u16))
+ORC_DEFINE_TRANSLATE(tr_i32, int, int, (int))
+ORC_DEFINE_TRANSLATE(tr_u32, unsigned int, unsigned int, (unsigned int))
+ORC_DEFINE_TRANSLATE(tr_i64, long long, long long, (long long))
+ORC_DEFINE_TRANSLATE(tr_u64, unsigned long long, unsigned long long, (unsigned long long))
+ORC_DEFINE_TRANSLATE(tr_f32, float, float, (float))
+ORC_DEFINE_TRANSLATE(tr_f64, double, double, (double))
+ORC_DEFINE_TRANSLATE(tr_u16_f32, u16, float, (float))
+
+static int strategy_code(const char *s)
+{
+    if (!s || !*s || strcmp(s, "noborder") == 0) return ORC_NOBORDER;
+    if (strcmp(s, "background") == 0) return ORC_BACKGROUND;
+    if (strcmp(s, "wrap") == 0) return ORC_WRAP;
+    if (strcmp(s, "nearest") == 0) return ORC_NEAREST;
+    return -1;
+}
+
+/* Same signature and return codes as the C facade (signal_processing.cpp:44-73). */
+ORC_API int orc_translate(int type, const void *src, void *dst, int w, int h, float dx, float dy,
+                          const void *background, const char *strategy)
+{
+    int st = strategy_code(strategy);
+    size_t W = (size_t)w, H = (size_t)h;
+#define ORC_CASE(CH, FN, T)                                                                    \
+    case CH:                                                                                   \
+        if (st < 0) return -1;                                                                 \
+        FN((const T *)src, (T *)dst, *(const T *)background, W, H, dx, dy, st);                \
+        return 0;
+    switch (type) {
+        ORC_CASE('?', tr_bool, unsigned char)
+        ORC_CASE('b', tr_i8, signed char)
+        ORC_CASE('B', tr_u8, unsigned char)
+        ORC_CASE('h', tr_i16, short)
+        ORC_CASE('H', tr_u16, u16)
+        ORC_CASE('i', tr_i32, int)
+        ORC_CASE('I', tr_u32, unsigned int)
+        ORC_CASE('l', tr_i64, long long)
+        ORC_CASE('L', tr_u64, unsigned long long)
+        ORC_CASE('f', tr_f32, float)
+        ORC_CASE('d', tr_f64, double)
+    default:
+        return -1;
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a-6  motion-correction variant   IRFileLoader.cpp:617-627                             */
+/* ------------------------------------------------------------------------------------ */
+
+/* In place on rows [0,h) (callers pass height-3): u16 -> float translate by
+ * (-shift_x, -shift_y), nearest border, then float -> u16 truncation. */
+ORC_API void orc_loader_remove_motion(u16 *img, int w, int h, double shift_x, double shift_y)
+{
+    size_t n = (size_t)w * (size_t)h;
+    float *tmp = (float *)malloc(n * sizeof(float));
+    tr_u16_f32(img, tmp, 0.f, (size_t)w, (size_t)h, (float)(-shift_x), (float)(-shift_y), ORC_NEAREST);
+    for (size_t i = 0; i < n; ++i)
+        img[i] = (u16)tmp[i];
+    free(tmp);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a-7  lossless-writer pre-coder   h264.cpp:1050-1103 (split), 3016-3051 (merge)        */
+/* ------------------------------------------------------------------------------------ */
+
+/* YUV444P layout: Y = 0 (or the 8-bit integration-time image), U = low bytes, V = high
+ * bytes, each plane [h][linesize]; padding bytes of a row are left untouched. */
+ORC_API void orc_split_444(const u16 *img, const unsigned char *it, int w, int h,
+                           unsigned char *y_plane, unsigned char *u_plane, unsigned char *v_plane,
+                           int ls_y, int ls_u, int ls_v)
+{
+    for (int r = 0; r < h; ++r)
+        for (int i = 0; i < w; ++i) {
+            u16 p = img[i + r * w];
+            u_plane[i + (size_t)r * ls_u] = (unsigned char)(p & 0xFF);
+            v_plane[i + (size_t)r * ls_v] = (unsigned char)(p >> 8);
+            y_plane[i + (size_t)r * ls_y] = it ? it[i + r * w] : 0;
+        }
+}
+
+ORC_API void orc_merge_444(const unsigned char *y_plane, const unsigned char *u_plane,
+                           const unsigned char *v_plane, int ls_y, int ls_u, int ls_v, int w,
+                           int h, u16 *img, unsigned char *it)
+{
+    for (int r = 0; r < h; ++r)
+        for (int i = 0; i < w; ++i) {
+            img[i + r * w] = (u16)(u_plane[i + (size_t)r * ls_u] | (v_plane[i + (size_t)r * ls_v] << 8));
+            if (it)
+                it[i + r * w] = y_plane[i + (size_t)r * ls_y];
+        }
+}
+
+/* YUV420P layout (kvazaar/vp8 path): luma plane of 2h rows, rows [0,h) = low bytes, rows
+ * [h,2h) = high bytes: a type-size-2 byte shuffle of the frame (h264.cpp:1089-1102). */
+ORC_API void orc_split_420(const u16 *img, int w, int h, unsigned char *y_plane, int ls_y)
+{
+    for (int r = 0; r < h; ++r)
+        for (int i = 0; i < w; ++i) {
+            u16 p = img[i + r * w];
+            y_plane[i + (size_t)r * ls_y] = (unsigned char)(p & 0xFF);
+            y_plane[i + (size_t)(h + r) * ls_y] = (unsigned char)(p >> 8);
+        }
+}
+
+ORC_API void orc_merge_420(const unsigned char *y_plane, int ls_y, int w, int h, u16 *img)
+{
+    for (int r = 0; r < h; ++r)
+        for (int i = 0; i < w; ++i)
+            img[i + r * w] = (u16)(y_plane[i + (size_t)r * ls_y] | (y_plane[i + (size_t)(h + r) * ls_y] << 8));
+}
+
+/* Key-frame rule of AddFrame (h264.cpp:1050-1061): frame n is a key frame iff n == 0 or
+ * n - last_key >= gop.  Fills key[0..nframes) with 0/1 for a writer that starts at n = 0. */
+ORC_API void orc_key_frames(int nframes, int gop, unsigned char *key)
+{
+    int last = 0;
+    for (int n = 0; n < nframes; ++n) {
+        int k = (n == 0) || (n - last >= gop);
+        if (k)
+            last = n;
+        key[n] = (unsigned char)k;
+    }
+}
+
+/* Movie-level pre-coder, dense planes: lo[t][h][w], hi[t][h][w].  delta == 0 is exactly the
+ * reference's split.  delta != 0 (THIS REPO'S DEFINITION, parity unpinned): a non-key frame
+ * is replaced by (frame[t] - frame[t-1]) mod 2^16 before the split; key frames (rule above)
+ * are stored raw. */
+ORC_API void orc_precode_movie(const u16 *mov, int nframes, int w, int h, int gop, int delta,
+                               unsigned char *lo, unsigned char *hi)
+{
+    size_t n = (size_t)w * (size_t)h;
+    unsigned char *key = (unsigned char *)malloc((size_t)nframes + 1);
+    orc_key_frames(nframes, gop, key);
+    for (int t = 0; t < nframes; ++t) {
+        const u16 *cur = mov + (size_t)t * n;
+        const u16 *prev = cur - n;
+        int use_delta = delta && !key[t];
+        for (size_t i = 0; i < n; ++i) {
+            u16 p = use_delta ? (u16)(cur[i] - prev[i]) : cur[i];
+            lo[(size_t)t * n + i] = (unsigned char)(p & 0xFF);
+            hi[(size_t)t * n + i] = (unsigned char)(p >> 8);
+        }
+    }
+    free(key);
+}
+
+ORC_API void orc_decode_movie(const unsigned char *lo, const unsigned char *hi, int nframes, int w,
+                              int h, int gop, int delta, u16 *mov)
+{
+    size_t n = (size_t)w * (size_t)h;
+    unsigned char *key = (unsigned char *)malloc((size_t)nframes + 1);
+    orc_key_frames(nframes, gop, key);
+    for (int t = 0; t < nframes; ++t) {
+        u16 *cur = mov + (size_t)t * n;
+        const u16 *prev = cur - n;
+        int use_delta = delta && !key[t];
+        for (size_t i = 0; i < n; ++i) {
+            u16 p = (u16)(lo[(size_t)t * n + i] | (hi[(size_t)t * n + i] << 8));
+            cur[i] = use_delta ? (u16)(p + prev[i]) : p;
+        }
+    }
+    free(key);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a-8  statistics    Filters.cpp:56-101, h264.cpp:1955-1991, 2093-2097                  */
+/* ------------------------------------------------------------------------------------ */
+
+/* 65,535 bins in the reference (value 65535 is out of bounds there); inputs must stay
+ * below 65535.  s = round(size*percent) is evaluated in float (size_t * float). */
+ORC_API int orc_find_median_pixel(const u16 *p, int size, float percent)
+{
+    size_t *hist = (size_t *)calloc(65536, sizeof(size_t));
+    size_t n = (size_t)size;
+    for (size_t i = 0; i < n; ++i)
+        hist[p[i]]++;
+    size_t s = (size_t)roundf((float)n * percent);
+    size_t c = 0;
+    int res = 0;
+    for (int i = 0; i < 65535; ++i) {
+        c += hist[i];
+        if (c >= s) {
+            res = i;
+            break;
+        }
+    }
+    free(hist);
+    return res;
+}
+
+ORC_API int orc_find_median_pixel_mask(const u16 *p, const unsigned char *mask, int size, float percent)
+{
+    size_t *hist = (size_t *)calloc(65536, sizeof(size_t));
+    size_t n = (size_t)size, cnt = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (mask[i]) {
+            hist[p[i]]++;
+            ++cnt;
+        }
+    size_t s = (size_t)(int)roundf((float)cnt * percent);
+    size_t c = 0;
+    int res = 0;
+    for (int i = 0; i < 65535; ++i) {
+        c += hist[i];
+        if (c >= s) {
+            res = i;
+            break;
+        }
+    }
+    free(hist);
+    return res;
+}
+
+/* Mode of the 16,384-bin histogram of p>>2, first maximum wins -> (bin<<2)+1. */
+ORC_API unsigned orc_get_background(const u16 *p, int size)
+{
+    unsigned *hist = (unsigned *)calloc(16384, sizeof(unsigned));
+    for (int i = 0; i < size; ++i)
+        hist[p[i] >> 2]++;
+    unsigned best = hist[0], idx = 0;
+    for (unsigned i = 1; i < 16384; ++i)
+        if (hist[i] > best) {
+            best = hist[i];
+            idx = i;
+        }
+    free(hist);
+    return (idx << 2) + 1;
+}
+
+/* Movie statistics that the multi-GPU path all-reduces: min, max, 65,536-bin histogram. */
+ORC_API void orc_movie_stats(const u16 *p, size_t n, unsigned *minv, unsigned *maxv,
+                             unsigned long long *hist65536)
+{
+    unsigned lo = 65535, hi = 0;
+    if (hist65536)
+        memset(hist65536, 0, 65536 * sizeof(unsigned long long));
+    for (size_t i = 0; i < n; ++i) {
+        unsigned v = p[i];
+        if (v < lo) lo = v;
+        if (v > hi) hi = v;
+        if (hist65536)
+            hist65536[v]++;
+    }
+    *minv = lo;
+    *maxv = hi;
+}
+
+/* Quantile from an (all-reduced) histogram, same rule as orc_find_median_pixel. */
+ORC_API int orc_quantile_from_hist(const unsigned long long *hist65536, unsigned long long total, float percent)
+{
+    size_t s = (size_t)roundf((float)(size_t)total * percent);
+    size_t c = 0;
+    for (int i = 0; i < 65535; ++i) {
+        c += (size_t)hist65536[i];
+        if (c >= s)
+            return i;
+    }
+    return 0;
+}
