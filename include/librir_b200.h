@@ -1,0 +1,149 @@
+/*
+ * include/librir_b200.h -- C ABI of libsignal_processing_b200.so
+ *
+ * A B200-native (sm_100a CUDA) implementation of librir's per-frame hot path, behind the
+ * reference's own C interface.  Part 1 re-declares, with identical names, argument order and
+ * status codes, the entry points of the reference's signal_processing library that the path
+ * touches -- the library can therefore be dropped into librir/libs/ in place of
+ * libsignal_processing.so and is picked up by librir/low_level/misc.py:98-136 unchanged.
+ * Part 2 holds additive entry points (prefix rirb_) that make the speed reachable: batches of
+ * frames in one launch, device-resident buffers, the writer's pre-coder, movie statistics.
+ *
+ * Conventions (same as the reference):
+ *   - images are dense row-major [h][w]; WIDTH IS PASSED BEFORE HEIGHT;
+ *   - the caller owns every buffer; nothing is retained after a call returns
+ *     (bad_pixels_create copies what it needs);
+ *   - status: 0 success, -1 failure (rirb_last_error() / the reference's get_last_log_error
+ *     convention), create-functions return a handle > 0 or 0 on failure;
+ *   - no exception crosses the boundary; every entry is re-entrant.
+ * Pointers may be HOST pointers (pageable or pinned: the call stages them through the GPU and
+ * returns when the result is in the caller's buffer) or DEVICE pointers (detected with
+ * cudaPointerGetAttributes: zero copies, the work is enqueued on the calling thread's stream
+ * set with rirb_set_stream and the call returns without synchronising).
+ * There is NO CPU implementation behind any compute entry: without a CUDA device they fail (-1).
+ */
+#ifndef LIBRIR_B200_H
+#define LIBRIR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIRB_API __attribute__((visibility("default")))
+
+/* ===================== Part 1: the reference's interface (signal_processing.h) ============ */
+
+/* replaces translate, signal_processing.h:29 / signal_processing.cpp:44-73
+ * (rir::translate<T,T>, Filters.h:249-326).  type = numpy char code '?bBhHiIlLfd';
+ * strategy = NULL / "" / "noborder" / "background" / "wrap" / "nearest";
+ * -1 for an unknown type or strategy. */
+RIRB_API int translate(int type, void* src, void* dst, int w, int h, float dx, float dy, void* background,
+                       const char* strategy);
+
+/* replaces gaussian_filter, signal_processing.h:33 / signal_processing.cpp:101-148. */
+RIRB_API int gaussian_filter(float* src, float* dst, int w, int h, float sigma);
+
+/* replace find_median_pixel(_mask), signal_processing.h:39,44 / Filters.cpp:56-101. */
+RIRB_API int find_median_pixel(unsigned short* pixels, int size, float percent);
+RIRB_API int find_median_pixel_mask(unsigned short* pixels, unsigned char* mask, int size, float percent);
+
+/* replace bad_pixels_create / _correct / _destroy, signal_processing.h:77,81,85 /
+ * signal_processing.cpp:199-222 (BadPixels.cpp:13-66, Filters.h:135-193). */
+RIRB_API int bad_pixels_create(unsigned short* first_image, int width, int height);
+RIRB_API int bad_pixels_correct(int handle, unsigned short* in, unsigned short* out);
+RIRB_API void bad_pixels_destroy(int handle);
+
+/* Out of the hot path (1-D time series, connected components, hashing): forwarded verbatim to
+ * the reference build named by $LIBRIR_B200_FORWARD_LIB (a libsignal_processing.so of the
+ * reference), -1 when it is not set.  signal_processing.h:55,71,90,92,94. */
+RIRB_API int extract_times(double* time_vector, int vector_count, int* vector_sizes, int s, double* output,
+                           int* output_size);
+RIRB_API int resample_time_serie(double* sample_x, double* sample_y, int size, double* times, int times_size, int s,
+                                 double padds, double* output, int* output_size);
+RIRB_API int label_image(int type, void* src, int* dst, int w, int h, void* background, double* out_xy, int* out_area);
+RIRB_API int keep_largest_area(int type, void* src, int* dst, int w, int h, void* background, int foreground);
+RIRB_API size_t hash_bytes(void* ptr, size_t len);
+
+/* ===================== Part 2: additive entry points ====================================== */
+
+/* ---- runtime ---- */
+RIRB_API int rirb_device_count(void);                 /* 0 when no CUDA device is usable */
+RIRB_API int rirb_set_device(int device);             /* cudaSetDevice for the calling thread */
+RIRB_API int rirb_set_stream(void* cuda_stream);      /* stream for the calling thread (NULL = default) */
+RIRB_API int rirb_synchronize(void);                  /* wait for the calling thread's stream */
+RIRB_API const char* rirb_last_error(void);           /* calling thread's last error text */
+RIRB_API long long rirb_kernel_launch_count(void);    /* kernels launched by this library so far */
+RIRB_API const char* rirb_version(void);
+
+/* ---- batches of frames (nframes dense frames back to back) ---- */
+
+/* translate on nframes frames; n_shifts == 1: one (dx[0],dy[0]) for all frames, n_shifts ==
+ * nframes: per-frame shifts (registration).  dx/dy: host or device arrays of float. */
+RIRB_API int rirb_translate_batch(int type, const void* src, void* dst, int w, int h, long long nframes, const float* dx,
+                                  const float* dy, long long n_shifts, const void* background, const char* strategy);
+
+RIRB_API int rirb_gaussian_filter_batch(const float* src, float* dst, int w, int h, long long nframes, float sigma);
+/* fused uint16 -> float32 variant (what rir_signal_processing.py:100 does on the host first) */
+RIRB_API int rirb_gaussian_filter_u16_batch(const unsigned short* src, float* dst, int w, int h, long long nframes,
+                                            float sigma);
+
+RIRB_API int rirb_bad_pixels_correct_batch(int handle, const unsigned short* in, unsigned short* out, long long nframes);
+/* introspection of a handle: number of flagged pixels; raster-ordered (x,y) list; clamp level */
+RIRB_API int rirb_bad_pixels_count(int handle);
+RIRB_API int rirb_bad_pixels_get(int handle, int* xy, int capacity, int* clamp_value);
+
+/* ---- in-library variants used by the reference's file loader ---- */
+
+/* IRFileLoader::removeBadPixels, IRFileLoader.cpp:722-802: in place, on the handle's w x h
+ * region of each frame (create the handle on the first frame cropped to height-3, as
+ * setBadPixelsEnabled :693-716 does); frames are frame_stride pixels apart. */
+RIRB_API int rirb_loader_remove_bad_pixels(int handle, unsigned short* frames, long long nframes, size_t frame_stride);
+/* removeMotionGeneric, IRFileLoader.cpp:617-627: rows [0,h) of each frame are translated by
+ * (-shift_x[t], -shift_y[t]) (uint16 -> float, nearest border, float -> uint16 truncation);
+ * the remaining rows up to frame_stride are copied.  in == out allowed. */
+RIRB_API int rirb_loader_remove_motion(const unsigned short* in, unsigned short* out, int w, int h, long long nframes,
+                                       size_t frame_stride, const double* shift_x, const double* shift_y);
+
+/* ---- lossless-writer pre-coder (H264Capture::AddFrame, h264.cpp:1066-1103; inverse
+ *      VideoGrabber::toArray, h264.cpp:3016-3051) ---- */
+
+/* YUV444P: Y = it[] or 0, U = low bytes, V = high bytes; planes [h][linesize]. it may be NULL. */
+RIRB_API int rirb_split_yuv444(const unsigned short* img, const unsigned char* it, int w, int h, unsigned char* y_plane,
+                               unsigned char* u_plane, unsigned char* v_plane, int ls_y, int ls_u, int ls_v);
+RIRB_API int rirb_merge_yuv444(const unsigned char* y_plane, const unsigned char* u_plane, const unsigned char* v_plane,
+                               int ls_y, int ls_u, int ls_v, int w, int h, unsigned short* img, unsigned char* it);
+/* YUV420P: luma plane of 2h rows (rows [0,h) low bytes, [h,2h) high bytes); u_plane (h rows)
+ * receives it[] when both are non-NULL. */
+RIRB_API int rirb_split_yuv420(const unsigned short* img, const unsigned char* it, int w, int h, unsigned char* y_plane,
+                               int ls_y, unsigned char* u_plane, int ls_u);
+RIRB_API int rirb_merge_yuv420(const unsigned char* y_plane, int ls_y, const unsigned char* u_plane, int ls_u, int w, int h,
+                               unsigned short* img, unsigned char* it);
+/* Whole movie, dense planes lo[t][h][w], hi[t][h][w].  delta = 0: the reference's split.
+ * delta = 1: non-key frames hold (frame[t]-frame[t-1]) mod 2^16; key frames follow the AddFrame
+ * rule for a writer whose frame counter is first_frame + t (key iff counter % gop == 0);
+ * first_frame must be a multiple of gop (shards start on key frames). */
+RIRB_API int rirb_precode_movie(const unsigned short* movie, long long nframes, int w, int h, int gop, int delta,
+                                long long first_frame, unsigned char* lo, unsigned char* hi);
+RIRB_API int rirb_decode_movie(const unsigned char* lo, const unsigned char* hi, long long nframes, int w, int h, int gop,
+                               int delta, long long first_frame, unsigned short* movie);
+/* key[t] = 1 iff frame t of a writer starting at frame 0 is a key frame (h264.cpp:1050-1061) */
+RIRB_API int rirb_key_frames(long long nframes, int gop, unsigned char* key);
+
+/* ---- statistics (the quantities the multi-GPU path all-reduces) ---- */
+
+/* minmax[2] = {min, max}; hist = 65,536 x uint64 or NULL.  accumulate != 0: fold into the
+ * existing contents (several chunks / later NCCL all-reduce); else outputs are initialised. */
+RIRB_API int rirb_movie_stats(const unsigned short* pixels, size_t n, unsigned int* minmax, unsigned long long* hist,
+                              int accumulate);
+/* find_median_pixel's rule on an (all-reduced) histogram holding `count` pixels */
+RIRB_API int rirb_hist_quantile(const unsigned long long* hist, long long count, float percent);
+/* get_background (h264.cpp:1955-1991) of one image */
+RIRB_API int rirb_get_background(const unsigned short* pixels, int size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIBRIR_B200_H */

@@ -1,0 +1,923 @@
+// librir_b200/csrc/capi.cu -- the C ABI (include/librir_b200.h): argument checking, host<->device
+// staging for host-pointer callers, the bad-pixel handle table, forwarding of the out-of-scope
+// entries.  All compute happens in the kernels of this directory; there is no CPU path.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "../../include/librir_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rirb {
+
+// ------------------------------------------------------------------------------------------------
+// per-thread state: last error, stream, scratch buffers
+// ------------------------------------------------------------------------------------------------
+std::atomic<long long> g_launches{0};
+
+struct ThreadState {
+    char err[512] = {0};
+    cudaStream_t stream = 0;
+    // grow-only device scratch slots for host-pointer callers (never shared between threads)
+    void* dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[6] = {0, 0, 0, 0, 0, 0};
+    int dev_of[6] = {-1, -1, -1, -1, -1, -1};
+};
+static thread_local ThreadState tls;
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tls.err, sizeof(tls.err), fmt, ap);
+    va_end(ap);
+    if (getenv("LIBRIR_B200_VERBOSE")) fprintf(stderr, "[librir_b200] %s\n", tls.err);
+}
+
+cudaStream_t current_stream() { return tls.stream; }
+
+int sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// No device -> every compute entry fails loudly: this library has no CPU fallback.
+static int require_device()
+{
+    static std::atomic<int> state{0};  // 0 unknown, 1 ok, -1 none
+    int s = state.load();
+    if (s == 0) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        s = (e == cudaSuccess && n > 0) ? 1 : -1;
+        if (s < 0) cudaGetLastError();
+        state.store(s);
+    }
+    if (s < 0) {
+        set_error("no usable CUDA device: librir_b200 computes on the GPU only and has no CPU fallback");
+        return -1;
+    }
+    return 0;
+}
+
+static bool is_device_ptr(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static void* scratch(int slot, size_t bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (tls.cap[slot] < bytes || tls.dev_of[slot] != dev) {
+        if (tls.dev[slot] && tls.dev_of[slot] == dev) cudaFree(tls.dev[slot]);
+        tls.dev[slot] = nullptr;
+        tls.cap[slot] = 0;
+        size_t want = bytes < (1u << 20) ? (1u << 20) : bytes + bytes / 4;
+        if (cudaMalloc(&tls.dev[slot], want) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("out of device memory for a %zu-byte staging buffer", want);
+            return nullptr;
+        }
+        tls.cap[slot] = want;
+        tls.dev_of[slot] = dev;
+    }
+    return tls.dev[slot];
+}
+
+// Input operand: device pointer as is, host pointer uploaded into scratch slot `slot`.
+static const void* stage_in(const void* p, size_t bytes, int slot, cudaStream_t st)
+{
+    if (is_device_ptr(p)) return p;
+    void* d = scratch(slot, bytes);
+    if (!d) return nullptr;
+    if (cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        set_error("host->device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return d;
+}
+
+// Output operand: `preload` uploads the caller's current contents first (outputs that are only
+// partially overwritten, e.g. translate's "noborder" strategy or padded planes).
+struct StagedOut {
+    void* dev = nullptr;
+    void* host = nullptr;
+    size_t bytes = 0;
+};
+static bool stage_out(StagedOut& o, void* p, size_t bytes, int slot, bool preload, cudaStream_t st)
+{
+    o.bytes = bytes;
+    if (is_device_ptr(p)) {
+        o.dev = p;
+        o.host = nullptr;
+        return true;
+    }
+    o.host = p;
+    o.dev = scratch(slot, bytes);
+    if (!o.dev) return false;
+    if (preload && cudaMemcpyAsync(o.dev, p, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        set_error("host->device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return false;
+    }
+    return true;
+}
+// Copies staged outputs back and waits; device-pointer outputs return without synchronising.
+static int finish_out(StagedOut* outs, int n, cudaStream_t st)
+{
+    bool any = false;
+    for (int i = 0; i < n; ++i)
+        if (outs[i].host && outs[i].bytes) {
+            RIRB_CUDA_OK(cudaMemcpyAsync(outs[i].host, outs[i].dev, outs[i].bytes, cudaMemcpyDeviceToHost, st));
+            any = true;
+        }
+    if (any) RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int strategy_code(const char* s)
+{
+    if (!s || !*s || strcmp(s, "noborder") == 0) return STRAT_NOBORDER;
+    if (strcmp(s, "background") == 0) return STRAT_BACKGROUND;
+    if (strcmp(s, "wrap") == 0) return STRAT_WRAP;
+    if (strcmp(s, "nearest") == 0) return STRAT_NEAREST;
+    return -1;
+}
+
+static size_t dtype_size(int type)
+{
+    switch (type) {
+    case '?': case 'b': case 'B': return 1;
+    case 'h': case 'H': return 2;
+    case 'i': case 'I': case 'f': return 4;
+    case 'l': case 'L': case 'd': return 8;
+    default: return 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bad-pixel handle table (the reference's set_void_ptr / get_void_ptr / rm_void_ptr, tools.cpp:40-85:
+// process-global, mutex-guarded, lowest free positive slot)
+// ------------------------------------------------------------------------------------------------
+struct BadPixelState {
+    int w = 0, h = 0, device = 0;
+    int clamp_value = -1;         // m_median_value, BadPixels.cpp:22-31
+    unsigned global_thr = 0;      // Filters.h:157-160
+    u8* mask_dev = nullptr;       // bitmap, row stride (w+7)/8
+    int* xy_dev = nullptr;        // raster-ordered list (x,y), device copy
+    std::vector<int> xy;          // host copy
+    ~BadPixelState()
+    {
+        if (mask_dev) cudaFree(mask_dev);
+        if (xy_dev) cudaFree(xy_dev);
+    }
+};
+static std::mutex g_handles_mutex;
+static std::map<int, std::shared_ptr<BadPixelState>> g_handles;
+
+static int register_handle(std::shared_ptr<BadPixelState> s)
+{
+    std::lock_guard<std::mutex> lock(g_handles_mutex);
+    int id = 1;
+    for (auto& kv : g_handles) {
+        if (kv.first != id) break;
+        ++id;
+    }
+    g_handles[id] = s;
+    return id;
+}
+static std::shared_ptr<BadPixelState> find_handle(int id)
+{
+    std::lock_guard<std::mutex> lock(g_handles_mutex);
+    auto it = g_handles.find(id);
+    return it == g_handles.end() ? nullptr : it->second;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forwarding of out-of-scope entries to a reference build
+// ------------------------------------------------------------------------------------------------
+static void* forward_symbol(const char* name)
+{
+    static std::mutex m;
+    static void* lib = nullptr;
+    static bool tried = false;
+    std::lock_guard<std::mutex> lock(m);
+    if (!tried) {
+        tried = true;
+        const char* path = getenv("LIBRIR_B200_FORWARD_LIB");
+        if (path && *path) lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    }
+    if (!lib) {
+        set_error("%s is outside the GPU hot path; set LIBRIR_B200_FORWARD_LIB to a reference libsignal_processing.so", name);
+        return nullptr;
+    }
+    void* f = dlsym(lib, name);
+    if (!f) set_error("%s not found in LIBRIR_B200_FORWARD_LIB", name);
+    return f;
+}
+
+}  // namespace rirb
+
+using namespace rirb;
+
+#define RIRB_REQUIRE_DEVICE()            \
+    do {                                 \
+        if (require_device() != 0) return -1; \
+    } while (0)
+
+// =================================================================================================
+// runtime
+// =================================================================================================
+extern "C" {
+
+int rirb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int rirb_set_device(int device)
+{
+    RIRB_REQUIRE_DEVICE();
+    RIRB_CUDA_OK(cudaSetDevice(device));
+    return 0;
+}
+int rirb_set_stream(void* s)
+{
+    tls.stream = (cudaStream_t)s;
+    return 0;
+}
+int rirb_synchronize(void)
+{
+    RIRB_REQUIRE_DEVICE();
+    RIRB_CUDA_OK(cudaStreamSynchronize(tls.stream));
+    return 0;
+}
+const char* rirb_last_error(void) { return tls.err; }
+long long rirb_kernel_launch_count(void) { return g_launches.load(); }
+const char* rirb_version(void) { return "librir_b200 0.1 (sm_100a)"; }
+
+// =================================================================================================
+// translate
+// =================================================================================================
+int rirb_translate_batch(int type, const void* src, void* dst, int w, int h, long long nframes, const float* dx, const float* dy,
+                         long long n_shifts, const void* background, const char* strategy)
+{
+    const size_t esize = dtype_size(type);
+    const int strat = strategy_code(strategy);
+    if (esize == 0 || strat < 0) {
+        set_error("translate: unknown %s", esize == 0 ? "dtype code" : "strategy");
+        return -1;
+    }
+    if (!src || !dst || !dx || !dy || !background || w <= 0 || h <= 0 || nframes < 0 || (n_shifts != 1 && n_shifts != nframes)) {
+        set_error("translate: bad arguments");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    RIRB_REQUIRE_DEVICE();
+    if (src == dst) {
+        set_error("translate: src and dst must not alias");
+        return -1;
+    }
+    cudaStream_t st = tls.stream;
+    const size_t bytes = (size_t)w * h * esize * (size_t)nframes;
+    const void* d_src = stage_in(src, bytes, 0, st);
+    if (!d_src) return -1;
+    StagedOut out;
+    if (!stage_out(out, dst, bytes, 1, strat == STRAT_NOBORDER, st)) return -1;
+    // background: one element, host or device
+    unsigned long long bg = 0;
+    if (is_device_ptr(background)) {
+        RIRB_CUDA_OK(cudaMemcpyAsync(&bg, background, esize, cudaMemcpyDeviceToHost, st));
+        RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    } else {
+        memcpy(&bg, background, esize);
+    }
+    const float *d_dx = nullptr, *d_dy = nullptr;
+    float dx0 = 0.f, dy0 = 0.f;
+    if (n_shifts == 1 && !is_device_ptr(dx) && !is_device_ptr(dy)) {
+        dx0 = dx[0];
+        dy0 = dy[0];
+    } else {
+        d_dx = (const float*)stage_in(dx, sizeof(float) * (size_t)n_shifts, 2, st);
+        d_dy = (const float*)stage_in(dy, sizeof(float) * (size_t)n_shifts, 3, st);
+        if (!d_dx || !d_dy) return -1;
+        if (n_shifts == 1 && nframes > 1) {  // broadcast a device-resident scalar shift
+            float tmp[2];
+            RIRB_CUDA_OK(cudaMemcpyAsync(&tmp[0], d_dx, sizeof(float), cudaMemcpyDeviceToHost, st));
+            RIRB_CUDA_OK(cudaMemcpyAsync(&tmp[1], d_dy, sizeof(float), cudaMemcpyDeviceToHost, st));
+            RIRB_CUDA_OK(cudaStreamSynchronize(st));
+            dx0 = tmp[0];
+            dy0 = tmp[1];
+            d_dx = d_dy = nullptr;
+        }
+    }
+    if (launch_translate(type, d_src, out.dev, w, h, nframes, d_dx, d_dy, dx0, dy0, strat, &bg, st) != 0) return -1;
+    return finish_out(&out, 1, st);
+}
+
+int translate(int type, void* src, void* dst, int w, int h, float dx, float dy, void* background, const char* strategy)
+{
+    return rirb_translate_batch(type, src, dst, w, h, 1, &dx, &dy, 1, background, strategy);
+}
+
+// =================================================================================================
+// gaussian
+// =================================================================================================
+static int gaussian_any(const void* src, bool src_u16, float* dst, int w, int h, long long nframes, float sigma)
+{
+    if (!src || !dst || w <= 0 || h <= 0 || nframes < 0) {
+        set_error("gaussian_filter: bad arguments");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    GaussTaps taps;
+    if (gaussian_taps_host(sigma, &taps) != 0) return -1;
+    RIRB_REQUIRE_DEVICE();
+    if ((const void*)src == (const void*)dst) {
+        set_error("gaussian_filter: src and dst must not alias");
+        return -1;
+    }
+    cudaStream_t st = tls.stream;
+    const size_t npx = (size_t)w * h * (size_t)nframes;
+    const void* d_src = stage_in(src, npx * (src_u16 ? 2 : 4), 0, st);
+    if (!d_src) return -1;
+    StagedOut out;
+    if (!stage_out(out, dst, npx * 4, 1, false, st)) return -1;
+    int rc = src_u16 ? launch_gaussian_u16((const u16*)d_src, (float*)out.dev, w, h, nframes, taps, st)
+                     : launch_gaussian_f32((const float*)d_src, (float*)out.dev, w, h, nframes, taps, st);
+    if (rc != 0) return -1;
+    return finish_out(&out, 1, st);
+}
+
+int rirb_gaussian_filter_batch(const float* src, float* dst, int w, int h, long long nframes, float sigma)
+{
+    return gaussian_any(src, false, dst, w, h, nframes, sigma);
+}
+int rirb_gaussian_filter_u16_batch(const unsigned short* src, float* dst, int w, int h, long long nframes, float sigma)
+{
+    return gaussian_any(src, true, dst, w, h, nframes, sigma);
+}
+int gaussian_filter(float* src, float* dst, int w, int h, float sigma)
+{
+    // the reference has no failure path here and Python ignores the result
+    // (rir_signal_processing.py:103-111); we still report ours.
+    return gaussian_any(src, false, dst, w, h, 1, sigma);
+}
+
+// =================================================================================================
+// bad pixels
+// =================================================================================================
+int bad_pixels_create(unsigned short* first_image, int width, int height)
+{
+    if (!first_image || width <= 0 || height <= 0) {
+        set_error("bad_pixels_create: bad arguments");
+        return 0;
+    }
+    if (require_device() != 0) return 0;
+    cudaStream_t st = tls.stream;
+    const size_t n = (size_t)width * height;
+    auto fail = [](const char* what) {
+        set_error("bad_pixels_create: %s: %s", what, cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    };
+    const u16* d_img = (const u16*)stage_in(first_image, n * 2, 0, st);
+    if (!d_img) return 0;
+    // (i) frame histogram -> median (sorted[N/2]) and spread, as Filters.h:145-160 / BadPixels.cpp:19-31
+    unsigned* d_hist = (unsigned*)scratch(1, 65536 * sizeof(unsigned));
+    if (!d_hist) return 0;
+    if (launch_hist_frame(d_img, n, d_hist, st) != 0) return 0;
+    std::vector<unsigned> hist(65536);
+    if (cudaMemcpyAsync(hist.data(), d_hist, 65536 * sizeof(unsigned), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail("D2H");
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail("sync");
+    int median = 0;
+    {
+        size_t cum = 0;
+        const size_t rank = n / 2;  // 0-based index into the sorted frame
+        for (int v = 0; v < 65536; ++v) {
+            cum += hist[v];
+            if (cum > rank) {
+                median = v;
+                break;
+            }
+        }
+    }
+    // sum of int squares, exact (the reference adds int products into a double, which stays
+    // exact below 2^53); beyond |d| >= 46341 the reference's int product overflows (UB)
+    unsigned long long ssum = 0;
+    for (int v = 0; v < 65536; ++v) {
+        long long d = (long long)v - median;
+        ssum += (unsigned long long)(d * d) * hist[v];
+    }
+    double gstd = sqrt((double)ssum / (double)(int)n);
+    const double std_factor = 5.0;
+    double cutd = gstd * std_factor;
+    unsigned cut = cutd >= 65535.0 ? 65535u : (unsigned)cutd;  // (T)(double) truncation
+    unsigned gthr = ((unsigned)median > cut) ? (unsigned)median - cut : 0u;
+    int clamp_value = median - (int)(gstd * 2);
+
+    auto state = std::make_shared<BadPixelState>();
+    state->w = width;
+    state->h = height;
+    cudaGetDevice(&state->device);
+    state->clamp_value = clamp_value;
+    state->global_thr = gthr;
+    const int mstride = (width + 7) / 8;
+    const size_t mbytes = (size_t)mstride * height;
+    if (cudaMalloc(&state->mask_dev, mbytes) != cudaSuccess) return fail("cudaMalloc(mask)");
+    // (ii) per-pixel 5x5 test -> bitmap
+    if (launch_bp_detect(d_img, width, height, std_factor, gthr, state->mask_dev, st) != 0) return 0;
+    std::vector<u8> mask(mbytes);
+    if (cudaMemcpyAsync(mask.data(), state->mask_dev, mbytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail("D2H(mask)");
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail("sync");
+    // raster-ordered list, the order the reference's Polygon has
+    for (int y = 0; y < height; ++y)
+        for (int xb = 0; xb < mstride; ++xb) {
+            unsigned m = mask[(size_t)y * mstride + xb];
+            while (m) {
+                int b = __builtin_ctz(m);
+                m &= m - 1;
+                state->xy.push_back(xb * 8 + b);
+                state->xy.push_back(y);
+            }
+        }
+    if (!state->xy.empty()) {
+        if (cudaMalloc(&state->xy_dev, state->xy.size() * sizeof(int)) != cudaSuccess) return fail("cudaMalloc(list)");
+        if (cudaMemcpyAsync(state->xy_dev, state->xy.data(), state->xy.size() * sizeof(int), cudaMemcpyHostToDevice, st) !=
+            cudaSuccess)
+            return fail("H2D(list)");
+        if (cudaStreamSynchronize(st) != cudaSuccess) return fail("sync");
+    }
+    return register_handle(state);
+}
+
+int rirb_bad_pixels_correct_batch(int handle, const unsigned short* in, unsigned short* out, long long nframes)
+{
+    auto s = find_handle(handle);
+    if (!s) {
+        set_error("bad_pixels_correct: unknown handle %d", handle);
+        return -1;
+    }
+    if (!in || !out || nframes < 0) {
+        set_error("bad_pixels_correct: bad arguments");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const size_t fpx = (size_t)s->w * s->h;
+    const size_t bytes = fpx * 2 * (size_t)nframes;
+    if (in == out) {  // sequential in-place meaning of the reference (BadPixels.cpp:41-59)
+        StagedOut io;
+        if (!stage_out(io, out, bytes, 0, true, st)) return -1;
+        if (launch_bp_correct_inplace((u16*)io.dev, s->xy_dev, (int)(s->xy.size() / 2), s->w, s->h, s->clamp_value, nframes, fpx,
+                                      st) != 0)
+            return -1;
+        return finish_out(&io, 1, st);
+    }
+    const u16* d_in = (const u16*)stage_in(in, bytes, 0, st);
+    if (!d_in) return -1;
+    StagedOut o;
+    if (!stage_out(o, out, bytes, 1, false, st)) return -1;
+    if (launch_bp_correct(d_in, (u16*)o.dev, s->mask_dev, s->w, s->h, s->clamp_value, nframes, fpx, st) != 0) return -1;
+    return finish_out(&o, 1, st);
+}
+
+int bad_pixels_correct(int handle, unsigned short* in, unsigned short* out)
+{
+    return rirb_bad_pixels_correct_batch(handle, in, out, 1);
+}
+
+void bad_pixels_destroy(int handle)
+{
+    std::lock_guard<std::mutex> lock(g_handles_mutex);
+    g_handles.erase(handle);
+}
+
+int rirb_bad_pixels_count(int handle)
+{
+    auto s = find_handle(handle);
+    if (!s) {
+        set_error("bad_pixels: unknown handle %d", handle);
+        return -1;
+    }
+    return (int)(s->xy.size() / 2);
+}
+
+int rirb_bad_pixels_get(int handle, int* xy, int capacity, int* clamp_value)
+{
+    auto s = find_handle(handle);
+    if (!s) {
+        set_error("bad_pixels: unknown handle %d", handle);
+        return -1;
+    }
+    const int k = (int)(s->xy.size() / 2);
+    if (clamp_value) *clamp_value = s->clamp_value;
+    if (xy) {
+        if (capacity < k) return -2;  // "output too small" convention, signal_processing.h:52
+        memcpy(xy, s->xy.data(), s->xy.size() * sizeof(int));
+    }
+    return k;
+}
+
+int rirb_loader_remove_bad_pixels(int handle, unsigned short* frames, long long nframes, size_t frame_stride)
+{
+    auto s = find_handle(handle);
+    if (!s) {
+        set_error("remove_bad_pixels: unknown handle %d", handle);
+        return -1;
+    }
+    if (!frames || nframes < 0 || frame_stride < (size_t)s->w * s->h) {
+        set_error("remove_bad_pixels: bad arguments");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    StagedOut io;
+    if (!stage_out(io, frames, frame_stride * 2 * (size_t)nframes, 0, true, st)) return -1;
+    if (launch_loader_bp((u16*)io.dev, s->xy_dev, s->mask_dev, (int)(s->xy.size() / 2), s->w, s->h, nframes, frame_stride, st) != 0)
+        return -1;
+    return finish_out(&io, 1, st);
+}
+
+// =================================================================================================
+// motion-correction variant
+// =================================================================================================
+int rirb_loader_remove_motion(const unsigned short* in, unsigned short* out, int w, int h, long long nframes, size_t frame_stride,
+                              const double* shift_x, const double* shift_y)
+{
+    if (!in || !out || !shift_x || !shift_y || w <= 0 || h <= 0 || nframes < 0 || frame_stride < (size_t)w * h) {
+        set_error("remove_motion: bad arguments");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    // shifts: doubles on the host (PointF), negated and narrowed to float as the reference's call does
+    std::vector<double> sx((size_t)nframes), sy((size_t)nframes);
+    if (is_device_ptr(shift_x) || is_device_ptr(shift_y)) {
+        RIRB_CUDA_OK(cudaMemcpyAsync(sx.data(), shift_x, sizeof(double) * nframes, cudaMemcpyDefault, st));
+        RIRB_CUDA_OK(cudaMemcpyAsync(sy.data(), shift_y, sizeof(double) * nframes, cudaMemcpyDefault, st));
+        RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    } else {
+        memcpy(sx.data(), shift_x, sizeof(double) * nframes);
+        memcpy(sy.data(), shift_y, sizeof(double) * nframes);
+    }
+    std::vector<float> fx((size_t)nframes), fy((size_t)nframes);
+    for (long long i = 0; i < nframes; ++i) {
+        fx[i] = (float)(-sx[i]);
+        fy[i] = (float)(-sy[i]);
+    }
+    const float* d_dx = (const float*)stage_in(fx.data(), sizeof(float) * nframes, 2, st);
+    const float* d_dy = (const float*)stage_in(fy.data(), sizeof(float) * nframes, 3, st);
+    if (!d_dx || !d_dy) return -1;
+    const size_t bytes = frame_stride * 2 * (size_t)nframes;
+    const bool inplace = (in == out);
+    const u16* d_in;
+    StagedOut o;
+    if (inplace) {
+        // the reference translates into a temporary and copies back; keep a private copy of the input
+        if (!stage_out(o, out, bytes, 1, true, st)) return -1;
+        void* copy = scratch(0, bytes);
+        if (!copy) return -1;
+        RIRB_CUDA_OK(cudaMemcpyAsync(copy, o.dev, bytes, cudaMemcpyDeviceToDevice, st));
+        d_in = (const u16*)copy;
+    } else {
+        d_in = (const u16*)stage_in(in, bytes, 0, st);
+        if (!d_in) return -1;
+        if (!stage_out(o, out, bytes, 1, false, st)) return -1;
+        if (frame_stride > (size_t)w * h)  // pass the untouched tail rows through
+            RIRB_CUDA_OK(cudaMemcpy2DAsync((u16*)o.dev + (size_t)w * h, frame_stride * 2, d_in + (size_t)w * h, frame_stride * 2,
+                                           (frame_stride - (size_t)w * h) * 2, (size_t)nframes, cudaMemcpyDeviceToDevice, st));
+    }
+    if (launch_translate_u16(d_in, (u16*)o.dev, w, h, nframes, frame_stride, frame_stride, d_dx, d_dy, 0.f, 0.f, STRAT_NEAREST, 0u,
+                             true, st) != 0)
+        return -1;
+    if (o.host) {
+        RIRB_CUDA_OK(cudaMemcpyAsync(o.host, o.dev, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    // fx/fy are stack-owned host vectors read by an async copy: always wait before returning
+    RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// =================================================================================================
+// pre-coder
+// =================================================================================================
+int rirb_split_yuv444(const unsigned short* img, const unsigned char* it, int w, int h, unsigned char* y_plane,
+                      unsigned char* u_plane, unsigned char* v_plane, int ls_y, int ls_u, int ls_v)
+{
+    if (!img || !u_plane || !v_plane || w <= 0 || h <= 0 || ls_u < w || ls_v < w || (y_plane && ls_y < w)) {
+        set_error("split_yuv444: bad arguments");
+        return -1;
+    }
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const u16* d_img = (const u16*)stage_in(img, (size_t)w * h * 2, 0, st);
+    if (!d_img) return -1;
+    const u8* d_it = nullptr;
+    if (it) {
+        d_it = (const u8*)stage_in(it, (size_t)w * h, 1, st);
+        if (!d_it) return -1;
+    }
+    StagedOut o[3];
+    // row padding must survive untouched: preload padded planes
+    if (!stage_out(o[1], u_plane, (size_t)ls_u * h, 3, ls_u != w, st)) return -1;
+    if (!stage_out(o[2], v_plane, (size_t)ls_v * h, 4, ls_v != w, st)) return -1;
+    if (y_plane && !stage_out(o[0], y_plane, (size_t)ls_y * h, 2, ls_y != w, st)) return -1;
+    if (launch_split_planes(d_img, d_it, w, h, (u8*)o[0].dev, (u8*)o[1].dev, (u8*)o[2].dev, ls_y, ls_u, ls_v, st) != 0) return -1;
+    return finish_out(o, 3, st);
+}
+
+int rirb_merge_yuv444(const unsigned char* y_plane, const unsigned char* u_plane, const unsigned char* v_plane, int ls_y, int ls_u,
+                      int ls_v, int w, int h, unsigned short* img, unsigned char* it)
+{
+    if (!img || !u_plane || !v_plane || w <= 0 || h <= 0 || ls_u < w || ls_v < w) {
+        set_error("merge_yuv444: bad arguments");
+        return -1;
+    }
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const u8* d_u = (const u8*)stage_in(u_plane, (size_t)ls_u * h, 0, st);
+    const u8* d_v = (const u8*)stage_in(v_plane, (size_t)ls_v * h, 1, st);
+    if (!d_u || !d_v) return -1;
+    const u8* d_y = nullptr;
+    if (y_plane && it) {
+        d_y = (const u8*)stage_in(y_plane, (size_t)ls_y * h, 2, st);
+        if (!d_y) return -1;
+    }
+    StagedOut o[2];
+    if (!stage_out(o[0], img, (size_t)w * h * 2, 3, false, st)) return -1;
+    if (it && d_y && !stage_out(o[1], it, (size_t)w * h, 4, false, st)) return -1;
+    if (launch_merge_planes(d_y, d_u, d_v, ls_y, ls_u, ls_v, w, h, (u16*)o[0].dev, (u8*)o[1].dev, st) != 0) return -1;
+    return finish_out(o, 2, st);
+}
+
+int rirb_split_yuv420(const unsigned short* img, const unsigned char* it, int w, int h, unsigned char* y_plane, int ls_y,
+                      unsigned char* u_plane, int ls_u)
+{
+    if (!img || !y_plane || w <= 0 || h <= 0 || ls_y < w) {
+        set_error("split_yuv420: bad arguments");
+        return -1;
+    }
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const u16* d_img = (const u16*)stage_in(img, (size_t)w * h * 2, 0, st);
+    if (!d_img) return -1;
+    const bool with_it = it && u_plane;
+    const u8* d_it = nullptr;
+    if (with_it) {
+        d_it = (const u8*)stage_in(it, (size_t)w * h, 1, st);
+        if (!d_it) return -1;
+    }
+    StagedOut o[2];
+    if (!stage_out(o[0], y_plane, (size_t)ls_y * 2 * h, 2, ls_y != w, st)) return -1;
+    if (with_it && !stage_out(o[1], u_plane, (size_t)ls_u * h, 3, ls_u != w, st)) return -1;
+    u8* d_y = (u8*)o[0].dev;
+    if (launch_split_planes(d_img, d_it, w, h, with_it ? (u8*)o[1].dev : nullptr, d_y, d_y + (size_t)h * ls_y, ls_u, ls_y, ls_y,
+                            st) != 0)
+        return -1;
+    return finish_out(o, 2, st);
+}
+
+int rirb_merge_yuv420(const unsigned char* y_plane, int ls_y, const unsigned char* u_plane, int ls_u, int w, int h,
+                      unsigned short* img, unsigned char* it)
+{
+    if (!img || !y_plane || w <= 0 || h <= 0 || ls_y < w) {
+        set_error("merge_yuv420: bad arguments");
+        return -1;
+    }
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const u8* d_yp = (const u8*)stage_in(y_plane, (size_t)ls_y * 2 * h, 0, st);
+    if (!d_yp) return -1;
+    const bool with_it = it && u_plane;
+    const u8* d_up = nullptr;
+    if (with_it) {
+        d_up = (const u8*)stage_in(u_plane, (size_t)ls_u * h, 1, st);
+        if (!d_up) return -1;
+    }
+    StagedOut o[2];
+    if (!stage_out(o[0], img, (size_t)w * h * 2, 2, false, st)) return -1;
+    if (with_it && !stage_out(o[1], it, (size_t)w * h, 3, false, st)) return -1;
+    if (launch_merge_planes(d_up, d_yp, d_yp + (size_t)h * ls_y, ls_u, ls_y, ls_y, w, h, (u16*)o[0].dev, (u8*)o[1].dev, st) != 0)
+        return -1;
+    return finish_out(o, 2, st);
+}
+
+int rirb_precode_movie(const unsigned short* movie, long long nframes, int w, int h, int gop, int delta, long long first_frame,
+                       unsigned char* lo, unsigned char* hi)
+{
+    if (!movie || !lo || !hi || w <= 0 || h <= 0 || nframes < 0 || gop < 1) {
+        set_error("precode_movie: bad arguments");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const size_t n = (size_t)w * h * (size_t)nframes;
+    const u16* d_mov = (const u16*)stage_in(movie, n * 2, 0, st);
+    if (!d_mov) return -1;
+    StagedOut o[2];
+    if (!stage_out(o[0], lo, n, 1, false, st) || !stage_out(o[1], hi, n, 2, false, st)) return -1;
+    if (launch_precode_movie(d_mov, nframes, w, h, gop, delta, first_frame, (u8*)o[0].dev, (u8*)o[1].dev, st) != 0) return -1;
+    return finish_out(o, 2, st);
+}
+
+int rirb_decode_movie(const unsigned char* lo, const unsigned char* hi, long long nframes, int w, int h, int gop, int delta,
+                      long long first_frame, unsigned short* movie)
+{
+    if (!movie || !lo || !hi || w <= 0 || h <= 0 || nframes < 0 || gop < 1) {
+        set_error("decode_movie: bad arguments");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const size_t n = (size_t)w * h * (size_t)nframes;
+    const u8* d_lo = (const u8*)stage_in(lo, n, 0, st);
+    const u8* d_hi = (const u8*)stage_in(hi, n, 1, st);
+    if (!d_lo || !d_hi) return -1;
+    StagedOut o;
+    if (!stage_out(o, movie, n * 2, 2, false, st)) return -1;
+    if (launch_decode_movie(d_lo, d_hi, nframes, w, h, gop, delta, first_frame, (u16*)o.dev, st) != 0) return -1;
+    return finish_out(&o, 1, st);
+}
+
+// host-side writer logic, no device involved: AddFrame's key-frame decision (h264.cpp:1050-1061)
+int rirb_key_frames(long long nframes, int gop, unsigned char* key)
+{
+    if (!key || nframes < 0) {
+        set_error("key_frames: bad arguments");
+        return -1;
+    }
+    long long last = 0;
+    for (long long n = 0; n < nframes; ++n) {
+        const bool k = (n == 0) || (n - last >= gop);
+        if (k) last = n;
+        key[n] = k ? 1 : 0;
+    }
+    return 0;
+}
+
+// =================================================================================================
+// statistics
+// =================================================================================================
+int rirb_movie_stats(const unsigned short* pixels, size_t n, unsigned int* minmax, unsigned long long* hist, int accumulate)
+{
+    if (!pixels || !minmax) {
+        set_error("movie_stats: bad arguments");
+        return -1;
+    }
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const u16* d_p = (const u16*)stage_in(pixels, n * 2, 0, st);
+    if (!d_p) return -1;
+    StagedOut o[2];
+    if (!stage_out(o[0], minmax, 2 * sizeof(unsigned), 1, accumulate != 0, st)) return -1;
+    if (hist && !stage_out(o[1], hist, 65536 * sizeof(unsigned long long), 2, accumulate != 0, st)) return -1;
+    if (!accumulate && launch_stats_init((unsigned*)o[0].dev, (unsigned long long*)o[1].dev, st) != 0) return -1;
+    if (launch_movie_stats(d_p, n, nullptr, (unsigned*)o[0].dev, (unsigned long long*)o[1].dev, st) != 0) return -1;
+    return finish_out(o, 2, st);
+}
+
+int rirb_hist_quantile(const unsigned long long* hist, long long count, float percent)
+{
+    if (!hist) {
+        set_error("hist_quantile: bad arguments");
+        return -1;
+    }
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const unsigned long long* d_h = (const unsigned long long*)stage_in(hist, 65536 * sizeof(unsigned long long), 0, st);
+    int* d_out = (int*)scratch(5, sizeof(int));
+    if (!d_h || !d_out) return -1;
+    if (launch_hist_quantile(d_h, count, percent, 0, d_out, st) != 0) return -1;
+    int r = 0;
+    RIRB_CUDA_OK(cudaMemcpyAsync(&r, d_out, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    return r;
+}
+
+static int median_pixel_any(const unsigned short* pixels, const unsigned char* mask, int size, float percent)
+{
+    if (!pixels || size < 0) {
+        set_error("find_median_pixel: bad arguments");
+        return -1;
+    }
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const u16* d_p = (const u16*)stage_in(pixels, (size_t)size * 2, 0, st);
+    if (!d_p && size) return -1;
+    const u8* d_m = nullptr;
+    if (mask) {
+        d_m = (const u8*)stage_in(mask, (size_t)size, 1, st);
+        if (!d_m && size) return -1;
+    }
+    unsigned long long* d_hist = (unsigned long long*)scratch(2, 65536 * sizeof(unsigned long long));
+    unsigned* d_mm = (unsigned*)scratch(3, 2 * sizeof(unsigned));
+    int* d_out = (int*)scratch(5, sizeof(int));
+    if (!d_hist || !d_mm || !d_out) return -1;
+    if (launch_stats_init(d_mm, d_hist, st) != 0) return -1;
+    if (launch_movie_stats(d_p, (size_t)size, d_m, d_mm, d_hist, st) != 0) return -1;
+    if (launch_hist_quantile(d_hist, mask ? -1 : (long long)size, percent, mask ? 1 : 0, d_out, st) != 0) return -1;
+    int r = 0;
+    RIRB_CUDA_OK(cudaMemcpyAsync(&r, d_out, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    return r;
+}
+
+int find_median_pixel(unsigned short* pixels, int size, float percent) { return median_pixel_any(pixels, nullptr, size, percent); }
+int find_median_pixel_mask(unsigned short* pixels, unsigned char* mask, int size, float percent)
+{
+    if (!mask) {
+        set_error("find_median_pixel_mask: NULL mask");
+        return -1;
+    }
+    return median_pixel_any(pixels, mask, size, percent);
+}
+
+int rirb_get_background(const unsigned short* pixels, int size)
+{
+    if (!pixels || size <= 0) {
+        set_error("get_background: bad arguments");
+        return -1;
+    }
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const u16* d_p = (const u16*)stage_in(pixels, (size_t)size * 2, 0, st);
+    unsigned long long* d_hist = (unsigned long long*)scratch(2, 65536 * sizeof(unsigned long long));
+    unsigned* d_mm = (unsigned*)scratch(3, 2 * sizeof(unsigned));
+    unsigned* d_out = (unsigned*)scratch(5, sizeof(unsigned));
+    if (!d_p || !d_hist || !d_mm || !d_out) return -1;
+    if (launch_stats_init(d_mm, d_hist, st) != 0) return -1;
+    if (launch_movie_stats(d_p, (size_t)size, nullptr, d_mm, d_hist, st) != 0) return -1;
+    if (launch_hist_mode4(d_hist, d_out, st) != 0) return -1;
+    unsigned r = 0;
+    RIRB_CUDA_OK(cudaMemcpyAsync(&r, d_out, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    return (int)r;
+}
+
+// =================================================================================================
+// forwarded entries (outside the hot path)
+// =================================================================================================
+int extract_times(double* time_vector, int vector_count, int* vector_sizes, int s, double* output, int* output_size)
+{
+    typedef int (*fn)(double*, int, int*, int, double*, int*);
+    fn f = (fn)forward_symbol("extract_times");
+    return f ? f(time_vector, vector_count, vector_sizes, s, output, output_size) : -1;
+}
+int resample_time_serie(double* sample_x, double* sample_y, int size, double* times, int times_size, int s, double padds,
+                        double* output, int* output_size)
+{
+    typedef int (*fn)(double*, double*, int, double*, int, int, double, double*, int*);
+    fn f = (fn)forward_symbol("resample_time_serie");
+    return f ? f(sample_x, sample_y, size, times, times_size, s, padds, output, output_size) : -1;
+}
+int label_image(int type, void* src, int* dst, int w, int h, void* background, double* out_xy, int* out_area)
+{
+    typedef int (*fn)(int, void*, int*, int, int, void*, double*, int*);
+    fn f = (fn)forward_symbol("label_image");
+    return f ? f(type, src, dst, w, h, background, out_xy, out_area) : -1;
+}
+int keep_largest_area(int type, void* src, int* dst, int w, int h, void* background, int foreground)
+{
+    typedef int (*fn)(int, void*, int*, int, int, void*, int);
+    fn f = (fn)forward_symbol("keep_largest_area");
+    return f ? f(type, src, dst, w, h, background, foreground) : -1;
+}
+size_t hash_bytes(void* ptr, size_t len)
+{
+    typedef size_t (*fn)(void*, size_t);
+    fn f = (fn)forward_symbol("hash_bytes");
+    return f ? f(ptr, len) : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,295 @@
+// librir_b200/csrc/gaussian.cu -- Gaussian filter, separable, streaming.
+//
+// Reference semantics: gaussian_filter / generate_kernel, signal_processing.cpp:79-148 (dense
+// (2r+1)^2 float convolution, r = max(1,(int)(2*sigma)), partial-kernel renormalisation at the
+// borders).  The reference's 2-D kernel is a product of 1-D kernels, and so is its border
+// normaliser (the in-bounds tap set is a rectangle), so a separable evaluation agrees with it to
+// float rounding (tolerance 1e-5 relative, BASELINE.json).
+//
+// Kernel design (r <= 4, w % 4 == 0 -- sigma < 2.5, every shape in BASELINE.json):
+//   one WARP owns a 128-pixel-wide column strip of one frame and walks down its rows.  A lane
+//   loads 4 pixels of the row (128-bit for f32, 64-bit for u16), takes the r pixels it needs from
+//   each neighbour lane with warp shuffles (lanes 0/31 fetch the strip's halo vector, an L2 hit),
+//   does the horizontal pass in registers, and pushes the result into a (2r+1)-row register ring
+//   from which the vertical pass produces one output row per input row.  Every input byte is
+//   read from HBM once and every output byte written once: 8 B/px (f32 -> f32), 6 B/px (u16 -> f32).
+//   No shared memory, no __syncthreads; rows are loaded in batches of 4 for memory parallelism.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rirb {
+
+int gaussian_taps_host(float sigma, GaussTaps* taps)
+{
+    int r = (int)(sigma * 2);
+    if (r < 1) r = 1;
+    if (r > GAUSS_MAX_RADIUS) {
+        set_error("gaussian_filter: radius %d (sigma %g) exceeds the supported maximum %d", r, (double)sigma, GAUSS_MAX_RADIUS);
+        return -1;
+    }
+    const int kw = 2 * r + 1;
+    // the reference's 2-D taps, in float, same expression and accumulation order
+    float* k2 = new float[(size_t)kw * kw];
+    const float s = 2.0f * sigma * sigma;
+    float sum = 0.0f;
+    for (int x = -r; x <= r; ++x)
+        for (int y = -r; y <= r; ++y) {
+            float rho = (float)sqrt((double)(x * x + y * y));
+            float e = expf(-(rho * rho) / s);
+            float t = (float)((double)e / (3.14159265358979323846 * (double)s));
+            k2[x + r + (y + r) * kw] = t;
+            sum += t;
+        }
+    for (int i = 0; i < kw * kw; ++i) k2[i] /= sum;
+    // 1-D taps = row sums (K[dx,dy] = k1[dx] * k1[dy])
+    taps->radius = r;
+    for (int d = 0; d < kw; ++d) {
+        double acc = 0;
+        for (int y = 0; y < kw; ++y) acc += (double)k2[d + y * kw];
+        taps->k[d] = (float)acc;
+    }
+    delete[] k2;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path
+// ------------------------------------------------------------------------------------------------
+template <typename TIN> struct RowVec;
+template <> struct RowVec<float> {
+    __device__ static __forceinline__ void load(const float* p, float (&a)[4])
+    {
+        float4 v = ld_stream(reinterpret_cast<const float4*>(p));
+        a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+    }
+};
+template <> struct RowVec<u16> {
+    __device__ static __forceinline__ void load(const u16* p, float (&a)[4])
+    {
+        uint2 v = ld_stream(reinterpret_cast<const uint2*>(p));
+        a[0] = (float)(v.x & 0xFFFFu); a[1] = (float)(v.x >> 16);
+        a[2] = (float)(v.y & 0xFFFFu); a[3] = (float)(v.y >> 16);
+    }
+};
+
+constexpr int GS_ROWS = 4;     // rows loaded per batch
+constexpr int GS_WARPS = 4;    // warps (independent work items) per CTA
+constexpr int GS_STRIP = 128;  // pixels per warp-row
+
+template <int R, typename TIN>
+__global__ void __launch_bounds__(GS_WARPS * 32)
+gauss_sep_kernel(const TIN* __restrict__ src, float* __restrict__ dst, int w, int h, long long nframes, int xstrips, int ystrips,
+                 int rows_per_strip, GaussTaps taps)
+{
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * GS_WARPS + (threadIdx.x >> 5);
+    const long long items = nframes * ystrips * xstrips;
+    if (item >= items) return;  // warp-uniform
+    const int xstrip = (int)(item % xstrips);
+    const int ystrip = (int)((item / xstrips) % ystrips);
+    const long long f = item / ((long long)xstrips * ystrips);
+
+    const int xs = xstrip * GS_STRIP;
+    const int x = xs + 4 * lane;
+    const bool xin = x < w;  // w % 4 == 0: a lane is entirely inside or outside
+    const int ys = ystrip * rows_per_strip;
+    const int ye = min(h, ys + rows_per_strip);
+    const TIN* frame = src + (size_t)f * w * h;
+    float* oframe = dst + (size_t)f * w * h;
+
+    float k[2 * R + 1];
+#pragma unroll
+    for (int d = 0; d <= 2 * R; ++d) k[d] = taps.k[d];
+
+    float kfull = 0.f;
+#pragma unroll
+    for (int d = 0; d <= 2 * R; ++d) kfull += k[d];
+
+    // horizontal normaliser per owned pixel (sum of taps that fall inside the row)
+    float nx[4];
+    bool xborder[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d <= 2 * R; ++d) {
+            int xx = x + j + d - R;
+            if (xx >= 0 && xx < w) s += k[d];
+        }
+        nx[j] = s;
+        xborder[j] = (x + j < R) || (x + j >= w - R);
+    }
+
+    const bool halo_l = (lane == 0) && (xs > 0);
+    const bool halo_r = (lane == 31) && (xs + GS_STRIP < w);
+    const int halo_x = halo_l ? x - 4 : x + 4;
+
+    float ring[2 * R + 1][4];
+#pragma unroll
+    for (int i = 0; i <= 2 * R; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ring[i][j] = 0.f;
+
+    for (int y0 = ys - R; y0 < ye + R; y0 += GS_ROWS) {
+        float a[GS_ROWS][4], hv[GS_ROWS][4];
+#pragma unroll
+        for (int g = 0; g < GS_ROWS; ++g) {
+            const int yy = y0 + g;
+            const bool rowok = (yy >= 0) && (yy < h) && (yy < ye + R);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a[g][j] = 0.f;
+                hv[g][j] = 0.f;
+            }
+            if (rowok && xin) RowVec<TIN>::load(frame + (size_t)yy * w + x, a[g]);
+            if (rowok && (halo_l || halo_r)) RowVec<TIN>::load(frame + (size_t)yy * w + halo_x, hv[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < GS_ROWS; ++g) {
+            const int yy = y0 + g;
+            if (yy >= ye + R) break;  // warp-uniform
+            // neighbours' pixels: left lane's last R, right lane's first R
+            float win[4 + 2 * R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                float fromL = __shfl_up_sync(0xFFFFFFFFu, a[g][4 - R + i], 1);
+                float fromR = __shfl_down_sync(0xFFFFFFFFu, a[g][i], 1);
+                win[i] = (lane == 0) ? hv[g][4 - R + i] : fromL;
+                win[R + 4 + i] = (lane == 31) ? hv[g][i] : fromR;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) win[R + j] = a[g][j];
+            // shift the ring, insert the horizontal pass of this row
+#pragma unroll
+            for (int i = 0; i < 2 * R; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ring[i][j] = ring[i + 1][j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float s = 0.f;
+#pragma unroll
+                for (int d = 0; d <= 2 * R; ++d) s = fmaf(k[d], win[j + d], s);
+                ring[2 * R][j] = s;
+            }
+            // vertical pass -> output row yo
+            const int yo = yy - R;
+            if (yo >= ys && yo < ye) {
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int d = 0; d <= 2 * R; ++d) s = fmaf(k[d], ring[d][j], s);
+                    o[j] = s;
+                }
+                const bool yborder = (yo < R) || (yo >= h - R);
+                float ny = 0.f;
+                if (yborder) {
+#pragma unroll
+                    for (int d = 0; d <= 2 * R; ++d) {
+                        int yyy = yo + d - R;
+                        if (yyy >= 0 && yyy < h) ny += k[d];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (yborder || xborder[j]) o[j] = o[j] / ((yborder ? ny : kfull) * (xborder[j] ? nx[j] : kfull));
+                }
+                if (xin) st_stream(reinterpret_cast<float4*>(oframe + (size_t)yo * w + x), make_float4(o[0], o[1], o[2], o[3]));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic path: any width, any radius up to GAUSS_MAX_RADIUS -- one thread per output pixel
+// ------------------------------------------------------------------------------------------------
+template <typename TIN>
+__global__ void __launch_bounds__(256)
+gauss_generic_kernel(const TIN* __restrict__ src, float* __restrict__ dst, int w, int h, long long nframes, GaussTaps taps)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int r = taps.radius;
+    const bool border = (x < r) || (x >= w - r) || (y < r) || (y >= h - r);
+    for (long long f = blockIdx.z; f < nframes; f += gridDim.z) {
+        const TIN* frame = src + (size_t)f * w * h;
+        float acc = 0.f, nxs = 0.f, nys = 0.f;
+        for (int dy = -r; dy <= r; ++dy) {  // rows outside the image contribute nothing
+            int yy = y + dy;
+            if (yy < 0 || yy >= h) continue;
+            float ky = taps.k[dy + r];
+            nys += ky;
+            float rowacc = 0.f;
+            for (int dx = -r; dx <= r; ++dx) {
+                int xx = x + dx;
+                if (xx < 0 || xx >= w) continue;
+                rowacc = fmaf(taps.k[dx + r], (float)frame[(size_t)yy * w + xx], rowacc);
+            }
+            acc = fmaf(ky, rowacc, acc);
+        }
+        if (border) {
+            for (int dx = -r; dx <= r; ++dx) {
+                int xx = x + dx;
+                if (xx >= 0 && xx < w) nxs += taps.k[dx + r];
+            }
+            acc = acc / (nxs * nys);
+        }
+        dst[(size_t)f * w * h + (size_t)y * w + x] = acc;
+    }
+}
+
+template <typename TIN>
+static int launch_gaussian(const TIN* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st)
+{
+    if (nframes <= 0 || w <= 0 || h <= 0) return 0;
+    const int r = taps.radius;
+    const bool fast = (r <= 4) && (w % 4 == 0) && aligned16(dst) && aligned16(src);
+    if (!fast) {
+        dim3 block(32, 8);
+        dim3 grid((unsigned)ceil_div(w, 32), (unsigned)ceil_div(h, 8), (unsigned)min(nframes, 32768LL));
+        RIRB_LAUNCH(gauss_generic_kernel<TIN>, grid, block, 0, st, src, dst, w, h, nframes, taps);
+        return 0;
+    }
+    const int xstrips = (int)ceil_div(w, GS_STRIP);
+    // full-height strips when there are enough frames; otherwise cut rows to fill the GPU
+    const long long target = (long long)sm_count() * 16;
+    long long ystrips = ceil_div(target, nframes * xstrips);
+    const long long max_ystrips = ceil_div(h, 16);
+    if (ystrips > max_ystrips) ystrips = max_ystrips;
+    if (ystrips < 1) ystrips = 1;
+    int rows = (int)ceil_div(h, ystrips);
+    rows = (int)ceil_div(rows, GS_ROWS) * GS_ROWS;
+    ystrips = ceil_div(h, rows);
+    const long long items = nframes * ystrips * xstrips;
+    const long long grid = ceil_div(items, GS_WARPS);
+    if (grid > 0x7FFFFFFFLL) {
+        set_error("gaussian_filter: too many frames in one call (%lld)", nframes);
+        return -1;
+    }
+#define RIRB_GS(RR)                                                                                                         \
+    RIRB_LAUNCH((gauss_sep_kernel<RR, TIN>), (unsigned)grid, GS_WARPS * 32, 0, st, src, dst, w, h, nframes, xstrips, (int)ystrips, \
+                rows, taps)
+    switch (r) {
+    case 1: RIRB_GS(1); break;
+    case 2: RIRB_GS(2); break;
+    case 3: RIRB_GS(3); break;
+    default: RIRB_GS(4); break;
+    }
+#undef RIRB_GS
+    return 0;
+}
+
+int launch_gaussian_f32(const float* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st)
+{
+    return launch_gaussian<float>(src, dst, w, h, nframes, taps, st);
+}
+int launch_gaussian_u16(const u16* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st)
+{
+    return launch_gaussian<u16>(src, dst, w, h, nframes, taps, st);
+}
+
+}  // namespace rirb

@@ -1,0 +1,65 @@
+// librir_b200/csrc/kernels.h -- internal launch API between the kernel files and capi.cu.
+// Every function enqueues on `st`, returns 0 on success or -1 after set_error(); pointers are
+// DEVICE pointers unless named *_host.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace rirb {
+
+typedef unsigned short u16;
+typedef unsigned char u8;
+
+enum { STRAT_NOBORDER = 0, STRAT_BACKGROUND = 1, STRAT_WRAP = 2, STRAT_NEAREST = 3 };
+
+// bad_pixels.cu
+int launch_hist_frame(const u16* img, size_t n, unsigned* hist65536, cudaStream_t st);
+int launch_bp_detect(const u16* img, int w, int h, double std_factor, unsigned gthr, u8* mask, cudaStream_t st);
+int launch_bp_correct(const u16* in, u16* out, const u8* mask, int w, int h, int clamp_value, long long nframes,
+                      size_t frame_stride, cudaStream_t st);
+int launch_bp_correct_inplace(u16* img, const int* xy_dev, int count, int w, int h, int clamp_value, long long nframes,
+                              size_t frame_stride, cudaStream_t st);
+int launch_loader_bp(u16* img, const int* xy_dev, const u8* mask, int count, int w, int h, long long nframes,
+                     size_t frame_stride, cudaStream_t st);
+
+// translate.cu
+int launch_translate(int type, const void* src, void* dst, int w, int h, long long nframes, const float* dxs, const float* dys,
+                     float dx0, float dy0, int strategy, const void* background_host, cudaStream_t st);
+int launch_translate_u16(const u16* src, u16* dst, int w, int h, long long nframes, size_t src_stride, size_t dst_stride,
+                         const float* dxs, const float* dys, float dx0, float dy0, int strategy, unsigned background, bool motion,
+                         cudaStream_t st);
+
+// gaussian.cu
+constexpr int GAUSS_MAX_RADIUS = 64;
+struct GaussTaps {
+    int radius;
+    float k[2 * GAUSS_MAX_RADIUS + 1];  // 1-D taps, k[d + radius]
+};
+// Host: taps the way the reference builds its 2-D kernel (signal_processing.cpp:79-99), reduced
+// to 1-D by row sums.  Returns -1 if the radius exceeds GAUSS_MAX_RADIUS.
+int gaussian_taps_host(float sigma, GaussTaps* taps);
+int launch_gaussian_f32(const float* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st);
+int launch_gaussian_u16(const u16* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st);
+
+// precode.cu
+int launch_split_planes(const u16* img, const u8* it, int w, int h, u8* y_plane, u8* u_plane, u8* v_plane, int ls_y, int ls_u,
+                        int ls_v, cudaStream_t st);
+int launch_merge_planes(const u8* y_plane, const u8* u_plane, const u8* v_plane, int ls_y, int ls_u, int ls_v, int w, int h,
+                        u16* img, u8* it, cudaStream_t st);
+int launch_precode_movie(const u16* mov, long long nframes, int w, int h, int gop, int delta, long long first_frame, u8* lo,
+                         u8* hi, cudaStream_t st);
+int launch_decode_movie(const u8* lo, const u8* hi, long long nframes, int w, int h, int gop, int delta, long long first_frame,
+                        u16* mov, cudaStream_t st);
+
+// stats.cu
+// minmax[0] = min, minmax[1] = max (unsigned, device); hist = 65536 x u64 (device) or nullptr.
+// Accumulates INTO the outputs: callers zero hist / seed minmax with {65535, 0} first
+// (launch_stats_init) so that several chunks of one movie can be reduced in place.
+int launch_stats_init(unsigned* minmax, unsigned long long* hist, cudaStream_t st);
+int launch_movie_stats(const u16* mov, size_t n, const u8* mask, unsigned* minmax, unsigned long long* hist, cudaStream_t st);
+
+int launch_hist_quantile(const unsigned long long* hist, long long count, float percent, int masked_rule, int* out,
+                         cudaStream_t st);
+int launch_hist_mode4(const unsigned long long* hist, unsigned* out, cudaStream_t st);
+
+}  // namespace rirb

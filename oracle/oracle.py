@@ -178,6 +178,16 @@ class Port(_Base):
         f(_p(img), _p(out), w, h, _p(xy), len(xy), int(clamp))
         return out
 
+    def bad_pixels_correct_inplace(self, xy, clamp, image):
+        """BadPixels::correct with in == out (sequential: later pixels see earlier corrections)."""
+        img = np.array(image, dtype=np.uint16, order="C")
+        h, w = img.shape
+        xy = _c(xy, np.int32)
+        f = self.lib.orc_bad_pixels_correct
+        f.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p, ct.c_int, ct.c_int]
+        f(_p(img), _p(img), w, h, _p(xy), len(xy), int(clamp))
+        return img
+
     def bad_pixels_create(self, first):
         xy, _thr, clamp = self.bad_pixels_detect(first)
         return (xy, clamp)

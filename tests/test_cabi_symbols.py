@@ -1,0 +1,98 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every symbol that
+include/librir_b200.h declares (and every reference symbol of signal_processing.h), and --
+with no GPU -- every compute entry FAILS LOUDLY instead of falling back to the CPU."""
+import ctypes as ct
+import os
+import re
+
+import numpy as np
+import pytest
+
+from librir_b200 import _lib, signal_processing as sp, video_io as vio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+REFERENCE_EXPORTS = [  # signal_processing.h:29-94 of the reference
+    "translate", "gaussian_filter", "find_median_pixel", "find_median_pixel_mask", "extract_times",
+    "resample_time_serie", "bad_pixels_create", "bad_pixels_correct", "bad_pixels_destroy", "label_image",
+    "keep_largest_area", "hash_bytes",
+]
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "librir_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return re.findall(r"RIRB_API\s+[\w\s\*]+?\b(\w+)\s*\(", text)
+
+
+def test_header_declares_reference_interface():
+    names = declared_symbols()
+    assert len(names) == len(set(names)) and len(names) >= 35
+    for n in REFERENCE_EXPORTS:
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ct.CDLL(_lib.lib_path())
+    for n in declared_symbols():
+        assert hasattr(lib, n), f"{n} declared in include/librir_b200.h but not exported"
+    assert set(declared_symbols()) == set(_lib.SIGNATURES), "ctypes table and header disagree"
+
+
+def test_library_matches_reference_glob():
+    # librir/low_level/misc.py:115 globs "*signal_processing*.so"
+    assert "signal_processing" in os.path.basename(_lib.lib_path())
+
+
+def test_version_and_host_only_entries():
+    lib = _lib.load()
+    assert b"sm_100a" in lib.rirb_version()
+    key = vio.key_frames(130, 50)
+    assert list(np.flatnonzero(key)) == [0, 50, 100]
+    assert lib.rirb_key_frames(3, 50, None) == -1 and "bad arguments" in _lib.last_error()
+
+
+@pytest.mark.skipif(_lib.device_available(), reason="checks behaviour WITHOUT a CUDA device")
+def test_no_gpu_means_failure_not_fallback():
+    img = np.arange(20 * 24, dtype=np.uint16).reshape(20, 24)
+    for call in (
+        lambda: sp.translate(img, 1.5, 0.5, "nearest"),
+        lambda: sp.gaussian_filter(img, 1.0),
+        lambda: sp.find_median_pixel(img),
+        lambda: sp.bad_pixels_create(img),
+        lambda: vio.split_yuv444(img),
+        lambda: vio.precode_movie(img[None]),
+    ):
+        with pytest.raises(RuntimeError) as e:
+            call()
+        assert "no CPU fallback" in str(e.value) or "no usable CUDA device" in str(e.value)
+
+
+def test_argument_errors_match_reference_conventions():
+    img = np.zeros((4, 5), dtype=np.uint16)
+    with pytest.raises(RuntimeError):  # test_rir.py:202-211 of the reference
+        sp.translate(np.zeros((2, 3, 4), dtype=np.uint16), 1, 1)
+    with pytest.raises(RuntimeError):
+        sp.translate(img, 1, 1, "background", None)
+    with pytest.raises(RuntimeError):
+        sp.translate(img.astype(np.float16), 1, 1)
+    with pytest.raises(RuntimeError):
+        sp.translate(img, 1, 1, "no-such-strategy", 0)
+    with pytest.raises(RuntimeError):
+        sp.gaussian_filter(np.zeros((2, 3, 4)), 1.0)
+    with pytest.raises(RuntimeError):
+        sp.find_median_pixel(np.zeros((2, 3, 4)))
+    with pytest.raises(RuntimeError):  # test_rir.py:275-277: unknown handle
+        sp.bad_pixels_correct(0, img)
+    lib = _lib.load()
+    assert lib.rirb_bad_pixels_count(12345) == -1
+
+
+def test_forwarded_entries_fail_cleanly_without_forward_lib():
+    if os.environ.get("LIBRIR_B200_FORWARD_LIB"):
+        pytest.skip("forward lib configured")
+    lib = _lib.load()
+    out = np.zeros(4)
+    n = ct.c_int(4)
+    assert lib.extract_times(None, 0, None, 0, out.ctypes.data_as(ct.c_void_p), ct.byref(n)) == -1
+    assert "LIBRIR_B200_FORWARD_LIB" in _lib.last_error()

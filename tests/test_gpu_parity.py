@@ -1,0 +1,457 @@
+"""Parity of the CUDA path with the oracle, THROUGH THE C ABI (numpy in -> ctypes -> CUDA ->
+numpy out for the per-frame entries; torch CUDA tensors for the batched ones).
+
+Bars (BASELINE.json north_star): bit-exact for bad pixels, pre-coder, statistics -- and, since
+the blend is evaluated in the reference's fp64 order, for integer translate as well (the
+allowed +-1 LSB is not used); 1e-5 relative (+1e-6*max floor) for float32 Gaussian output.
+"""
+import numpy as np
+import pytest
+
+from tests.conftest import ir_frame, ir_movie
+from tests.golden.make_golden import DTYPES, STRATEGIES, typed_image
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from librir_b200 import _lib, signal_processing as sp, video_io as vio  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def best():
+    return O.best()
+
+
+def to_dev(a):
+    """numpy (u)int/float array -> torch CUDA tensor of the same dtype."""
+    if a.dtype == np.uint16:
+        return torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
+    return torch.from_numpy(a).cuda()
+
+
+def rand_u16(shape, seed, high=16384):
+    """Random uint16 CUDA tensor (values < 2**15, built through int16: same bits)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randint(0, high, shape, generator=g, device="cuda", dtype=torch.int32).to(torch.int16).view(torch.uint16)
+
+
+def as_int(t):
+    """uint16 CUDA tensor (values < 2**15) -> int32, via the int16 view."""
+    return t.view(torch.int16).to(torch.int32)
+
+
+def to_host(t):
+    if t.dtype == torch.uint16:
+        return t.cpu().view(torch.int16).numpy().view(np.uint16)
+    return t.cpu().numpy()
+
+
+def assert_gauss_close(got, want):
+    tol = 1e-5 * np.abs(want) + 1e-6 * float(np.abs(want).max())
+    bad = np.abs(got.astype(np.float64) - want.astype(np.float64)) > tol
+    assert not bad.any(), f"{bad.sum()} pixels out of tolerance, max abs err {np.abs(got - want).max()}"
+
+
+# ---------------------------------------------------------------------------------------------
+# the library really is the thing that runs
+# ---------------------------------------------------------------------------------------------
+def test_device_present_and_kernels_launch():
+    assert _lib.device_available()
+    before = _lib.launch_count()
+    sp.gaussian_filter(np.ones((8, 8), np.float32), 1.0)
+    assert _lib.launch_count() > before
+
+
+# ---------------------------------------------------------------------------------------------
+# translate
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", DTYPES)
+def test_translate_golden_all_dtypes(golden, dt):
+    img = golden[f"tr_{dt}_in"]
+    for si, st in enumerate(STRATEGIES):
+        for k, (dx, dy) in enumerate(golden["tr_shifts"]):
+            got = sp.translate(img, dx, dy, st, background=1)
+            want = golden[f"tr_{dt}_{si}_{k}"]
+            assert got.dtype == want.dtype
+            np.testing.assert_array_equal(got, want, err_msg=f"{dt} {st!r} dx={dx} dy={dy}")
+
+
+def test_translate_golden_ir_frame(golden):
+    f = golden["tr_ir_in"]
+    for si, st in enumerate(STRATEGIES):
+        np.testing.assert_array_equal(sp.translate(f, 1.3, -2.7, st, background=7), golden[f"tr_ir_{si}"])
+    np.testing.assert_array_equal(sp.translate(f, 1.3, -2.7, "constant", background=7), golden["tr_ir_1"])
+
+
+@pytest.mark.parametrize("strategy", ["", "background", "wrap", "nearest"])
+def test_translate_u16_full_frame_many_shifts(best, strategy):
+    f = ir_frame(512, 640, 21)
+    shifts = [(1.3, -2.7), (0.0, 0.0), (3.0, -2.0), (-0.5, 0.5), (0.3, 0.7), (-0.3, -0.7), (2.9999998, 511.5),
+              (639.25, 0.0), (-640.0, 3.0), (1e-30, -1e-30), (0.99999994, 0.99999994), (100.125, -200.0625), (700.0, 3.0)]
+    for dx, dy in shifts:
+        got = sp.translate(f, dx, dy, strategy, background=123)
+        want = best.translate(f, dx, dy, strategy, background=123)
+        np.testing.assert_array_equal(got, want, err_msg=f"{strategy!r} dx={dx} dy={dy}")
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (5, 7), (1, 1), (2, 9), (64, 66)])
+def test_translate_u16_odd_shapes(best, shape):
+    rng = np.random.default_rng(3)
+    f = rng.integers(0, 65536, shape, dtype=np.uint16)
+    for st in ["", "background", "wrap", "nearest"]:
+        for dx, dy in [(1.3, -2.7), (0.5, 0.5), (-0.25, 0.75), (0, 0)]:
+            np.testing.assert_array_equal(sp.translate(f, dx, dy, st, 9), best.translate(f, dx, dy, st, 9))
+
+
+def test_translate_batch_per_frame_shifts_device(best):
+    mov = ir_movie(9, 96, 128)
+    rng = np.random.default_rng(777)
+    dx = rng.uniform(-3, 3, len(mov)).astype(np.float32)
+    dy = rng.uniform(-3, 3, len(mov)).astype(np.float32)
+    d = to_dev(mov)
+    got = to_host(sp.translate_batch(d, to_dev(dx), to_dev(dy), "nearest", 0))
+    for t in range(len(mov)):
+        np.testing.assert_array_equal(got[t], best.translate(mov[t], dx[t], dy[t], "nearest", 0), err_msg=f"frame {t}")
+    # host arrays of shifts, host movie, uniform shift
+    got2 = sp.translate_batch(mov, dx, dy, "nearest", 0)
+    np.testing.assert_array_equal(got2, got)
+    got3 = sp.translate_batch(mov, 1.3, -2.7, "wrap", 0)
+    for t in range(len(mov)):
+        np.testing.assert_array_equal(got3[t], best.translate(mov[t], 1.3, -2.7, "wrap", 0))
+
+
+def test_translate_float_dtypes_live(best):
+    rng = np.random.default_rng(5)
+    for dt in ["float32", "float64", "int32", "uint8", "int64"]:
+        img = typed_image(dt, 61, 83, rng)
+        for st in STRATEGIES:
+            np.testing.assert_array_equal(sp.translate(img, 2.37, -1.61, st, 1), best.translate(img, 2.37, -1.61, st, 1))
+
+
+def test_translate_identity_and_integer_shift_properties():
+    f = ir_frame(512, 640, 33)
+    np.testing.assert_array_equal(sp.translate(f, 0, 0, "nearest"), f)
+    got = sp.translate(f, 5, -3, "background", background=0)
+    want = np.zeros_like(f)
+    want[:-3, 5:] = f[3:, :-5]
+    np.testing.assert_array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------
+# gaussian
+# ---------------------------------------------------------------------------------------------
+def test_gaussian_golden(golden):
+    g = golden["ga_in"]
+    for k, s in enumerate(golden["ga_sigmas"]):
+        assert_gauss_close(sp.gaussian_filter(g, float(s)), golden[f"ga_{k}"])
+
+
+@pytest.mark.parametrize("sigma", [0.5, 1.0, 2.0])
+def test_gaussian_full_frame(best, sigma):
+    f = ir_frame(512, 640, 41)
+    want = best.gaussian_filter(f, sigma)
+    assert_gauss_close(sp.gaussian_filter(f, sigma), want)
+    d = to_dev(np.stack([f, f[::-1].copy()]))
+    got = sp.gaussian_filter_batch(d, sigma).cpu().numpy()  # fused uint16 -> float32 path
+    assert_gauss_close(got[0], want)
+    assert_gauss_close(got[1], best.gaussian_filter(f[::-1].copy(), sigma))
+    gotf = sp.gaussian_filter_batch(d.view(torch.int16).to(torch.float32), sigma).cpu().numpy()
+    np.testing.assert_array_equal(gotf, got)
+
+
+@pytest.mark.parametrize("shape,sigma", [((37, 53), 1.0), ((5, 7), 1.0), ((3, 3), 2.0), ((40, 56), 4.2), ((64, 128), 3.0),
+                                         ((33, 132), 0.5), ((16, 260), 1.5)])
+def test_gaussian_odd_shapes_and_large_sigma(best, shape, sigma):
+    rng = np.random.default_rng(6)
+    img = (rng.random(shape) * 4000).astype(np.float32)
+    assert_gauss_close(sp.gaussian_filter(img, sigma), best.gaussian_filter(img, sigma))
+
+
+def test_gaussian_constant_image_stays_constant():
+    img = np.full((512, 640), 1234.0, dtype=np.float32)
+    out = sp.gaussian_filter(img, 1.0)
+    np.testing.assert_allclose(out, 1234.0, rtol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# bad pixels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", range(5))
+def test_bad_pixels_golden(golden, k):
+    first, other = golden[f"bp_{k}_first"], golden[f"bp_{k}_other"]
+    bp = sp.BadPixels(first)
+    xy, _clamp = sp.bad_pixels_list(bp.handle)
+    np.testing.assert_array_equal(xy, golden[f"bp_{k}_xy"])
+    np.testing.assert_array_equal(bp.correct(first), golden[f"bp_{k}_first_out"])
+    np.testing.assert_array_equal(bp.correct(other), golden[f"bp_{k}_other_out"])
+
+
+@pytest.mark.parametrize("shape", [(512, 640), (256, 320), (100, 101), (1, 1), (2, 2), (7, 40)])
+def test_bad_pixels_live(port, shape):
+    h, w = shape
+    first = ir_frame(h, w, 51)
+    oxy, _thr, oclamp = port.bad_pixels_detect(first)
+    handle = sp.bad_pixels_create(first)
+    assert handle > 0
+    xy, clamp = sp.bad_pixels_list(handle)
+    np.testing.assert_array_equal(xy, oxy)
+    assert clamp == oclamp
+    mov = np.stack([ir_frame(h, w, 60 + i) for i in range(4)])
+    want = np.stack([port.bad_pixels_correct_with(oxy, oclamp, f) for f in mov])
+    for t in range(len(mov)):
+        np.testing.assert_array_equal(sp.bad_pixels_correct(handle, mov[t]), want[t])
+    np.testing.assert_array_equal(to_host(sp.bad_pixels_correct_batch(handle, to_dev(mov))), want)
+    np.testing.assert_array_equal(sp.bad_pixels_correct_batch(handle, mov), want)
+    sp.bad_pixels_destroy(handle)
+    with pytest.raises(RuntimeError):
+        sp.bad_pixels_correct(handle, first)
+
+
+def test_bad_pixels_handles_are_lowest_free_slot():
+    f = ir_frame(16, 16, 1)
+    a, b, c = (sp.bad_pixels_create(f) for _ in range(3))
+    assert len({a, b, c}) == 3 and min(a, b, c) > 0
+    sp.bad_pixels_destroy(b)
+    assert sp.bad_pixels_create(f) == b
+    for h in (a, b, c):
+        sp.bad_pixels_destroy(h)
+
+
+def test_bad_pixels_in_place_is_sequential_like_the_reference(port):
+    first = ir_frame(48, 64, 71, n_bad_frac=0.15)  # dense enough that bad pixels touch each other
+    oxy, _thr, oclamp = port.bad_pixels_detect(first)
+    handle = sp.bad_pixels_create(first)
+    lib = _lib.load()
+    img = ir_frame(48, 64, 72, n_bad_frac=0.15)
+    want = port.bad_pixels_correct_inplace(oxy, oclamp, img)
+    assert not np.array_equal(want, port.bad_pixels_correct_with(oxy, oclamp, img)), "case too sparse to tell the two apart"
+    got = img.copy()
+    assert lib.bad_pixels_correct(handle, sp._ptr(got), sp._ptr(got)) == 0
+    np.testing.assert_array_equal(got, want)
+    sp.bad_pixels_destroy(handle)
+
+
+def test_loader_bad_pixels_variant(port):
+    mov = np.stack([ir_frame(67, 80, 80 + i) for i in range(3)])
+    lb = vio.LoaderBadPixels(mov[0])
+    oxy, _, _ = port.bad_pixels_detect(mov[0][:64])
+    want = mov.copy()
+    for t in range(3):
+        want[t, :64] = port.loader_remove_bad_pixels(mov[t, :64], oxy)
+    got = lb.remove(mov.copy())
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(to_host(lb.remove(to_dev(mov))), want)
+
+
+# ---------------------------------------------------------------------------------------------
+# motion-correction variant
+# ---------------------------------------------------------------------------------------------
+def test_remove_motion_golden_and_live(golden, best, port):
+    for k in range(5):
+        first = golden[f"bp_{k}_first"]
+        h, w = first.shape
+        got = vio.remove_motion(first, 1.3, -2.7, meta_rows=0)
+        np.testing.assert_array_equal(got, golden[f"bp_{k}_motion"])
+    mov = np.stack([ir_frame(67, 80, 90 + i) for i in range(4)])
+    sx = np.array([1.3, -0.5, 0.0, 7.25])
+    sy = np.array([-2.7, 0.5, 0.0, -3.125])
+    want = mov.copy()
+    for t in range(4):
+        want[t, :64] = best.loader_remove_motion(mov[t, :64], sx[t], sy[t])
+    np.testing.assert_array_equal(vio.remove_motion(mov, sx, sy), want)
+    d = to_dev(mov)
+    np.testing.assert_array_equal(to_host(vio.remove_motion(d, sx, sy, out=d)), want)  # in place
+
+
+# ---------------------------------------------------------------------------------------------
+# statistics
+# ---------------------------------------------------------------------------------------------
+def test_find_median_pixel_golden(golden):
+    f, m = golden["mp_in"], golden["mp_mask"]
+    for p, want, want_m in zip(golden["mp_percents"], golden["mp_out"], golden["mp_out_mask"]):
+        assert sp.find_median_pixel(f, float(p)) == want
+        assert sp.find_median_pixel(f, float(p), m) == want_m
+
+
+def test_stats_live(port):
+    import ctypes as ct
+
+    lib = _lib.load()
+    mov = ir_movie(6, 96, 128)
+    mov[2, 5, 5] = 60000  # exercises the global-atomic range above the shared-memory bins
+    d = to_dev(mov)
+    mm = torch.zeros(2, dtype=torch.int32, device="cuda")
+    hist = torch.zeros(65536, dtype=torch.int64, device="cuda")
+    _lib.use_torch_stream()
+    assert lib.rirb_movie_stats(sp._ptr(d[:3]), d[:3].numel(), ct.c_void_p(mm.data_ptr()), ct.c_void_p(hist.data_ptr()), 0) == 0
+    assert lib.rirb_movie_stats(sp._ptr(d[3:]), d[3:].numel(), ct.c_void_p(mm.data_ptr()), ct.c_void_p(hist.data_ptr()), 1) == 0
+    lo, hi, ohist = port.movie_stats(mov)
+    assert (int(mm[0]), int(mm[1])) == (lo, hi)
+    np.testing.assert_array_equal(hist.cpu().numpy().astype(np.uint64), ohist)
+    for pc in [0.0, 0.1, 0.5, 0.9, 1.0]:
+        assert lib.rirb_hist_quantile(ct.c_void_p(hist.data_ptr()), mov.size, pc) == port.quantile_from_hist(ohist, pc)
+    for t in range(3):
+        assert lib.rirb_get_background(sp._ptr(mov[t]), mov[t].size) == port.get_background(mov[t])
+    # host-pointer variant
+    mmh = np.zeros(2, np.uint32)
+    hh = np.zeros(65536, np.uint64)
+    assert lib.rirb_movie_stats(sp._ptr(mov), mov.size, sp._ptr(mmh), sp._ptr(hh), 0) == 0
+    assert tuple(mmh) == (lo, hi)
+    np.testing.assert_array_equal(hh, ohist)
+
+
+# ---------------------------------------------------------------------------------------------
+# pre-coder
+# ---------------------------------------------------------------------------------------------
+def test_split_merge_layouts(port):
+    rng = np.random.default_rng(5)
+    for shape in [(13, 37), (64, 96), (512, 640)]:
+        img = rng.integers(0, 65536, shape, dtype=np.uint16)
+        it = rng.integers(0, 256, shape, dtype=np.uint8)
+        h, w = shape
+        for got, want in zip(vio.split_yuv444(img, it), port.split_444(img, it)):
+            w_ = want.copy()
+            w_[:, w:] = 0  # the oracle marks untouched padding with 0xAA, ours starts from zeros
+            np.testing.assert_array_equal(got, w_)
+        y, u, v = vio.split_yuv444(img)
+        assert not y.any()
+        back, _ = vio.merge_yuv444(y, u, v, w)
+        np.testing.assert_array_equal(back, img)
+        p = vio.split_yuv420(img)
+        np.testing.assert_array_equal(p[:h, :w], img & 0xFF)
+        np.testing.assert_array_equal(p[h:, :w], img >> 8)
+        np.testing.assert_array_equal(vio.merge_yuv420(p, w), img)
+        p2, u2 = vio.split_yuv420(img, it)
+        np.testing.assert_array_equal(p2, p)
+        np.testing.assert_array_equal(u2[:, :w], it)
+        back, it_back = vio.merge_yuv420(p2, w, u2)
+        np.testing.assert_array_equal(back, img)
+        np.testing.assert_array_equal(it_back, it)
+
+
+def test_split_preserves_row_padding():
+    import ctypes as ct
+
+    lib = _lib.load()
+    img = np.arange(5 * 7, dtype=np.uint16).reshape(5, 7) * 300
+    planes = [np.full((5, 32), 0xAA, np.uint8) for _ in range(3)]
+    assert lib.rirb_split_yuv444(sp._ptr(img), None, 7, 5, *(sp._ptr(p) for p in planes), 32, 32, 32) == 0
+    for p in planes:
+        assert (p[:, 7:] == 0xAA).all()
+    np.testing.assert_array_equal(planes[1][:, :7], img & 0xFF)
+    np.testing.assert_array_equal(planes[2][:, :7], img >> 8)
+
+
+@pytest.mark.parametrize("shape", [(23, 20, 28), (12, 64, 96), (7, 5, 3), (120, 32, 48)])
+@pytest.mark.parametrize("delta", [False, True])
+def test_precode_movie_vs_oracle(port, shape, delta):
+    mov = ir_movie(*shape) if shape[1] >= 16 else np.random.default_rng(1).integers(0, 65536, shape, dtype=np.uint16)
+    for gop in (5, 50):
+        lo, hi = vio.precode_movie(mov, gop, delta)
+        olo, ohi = port.precode_movie(mov, gop, delta)
+        np.testing.assert_array_equal(lo, olo)
+        np.testing.assert_array_equal(hi, ohi)
+        np.testing.assert_array_equal(vio.decode_movie(lo, hi, gop, delta), mov)
+        d = to_dev(mov)
+        dlo, dhi = vio.precode_movie(d, gop, delta)
+        np.testing.assert_array_equal(dlo.cpu().numpy(), olo)
+        np.testing.assert_array_equal(dhi.cpu().numpy(), ohi)
+        assert torch.equal(vio.decode_movie(dlo, dhi, gop, delta).view(torch.int16), d.view(torch.int16))
+
+
+def test_precode_delta_needs_key_frame_aligned_shards():
+    mov = ir_movie(10, 16, 16)
+    with pytest.raises(RuntimeError):
+        vio.precode_movie(mov, gop=5, delta=True, first_frame=3)
+    lo, hi = vio.precode_movie(mov, gop=5, delta=True, first_frame=10)
+    lo0, hi0 = vio.precode_movie(mov, gop=5, delta=True, first_frame=0)
+    np.testing.assert_array_equal(lo, lo0)
+    np.testing.assert_array_equal(hi, hi0)
+
+
+def test_lossless_precoder_frame_by_frame(port):
+    mov = ir_movie(7, 32, 40)
+    pre = vio.LosslessPrecoder(40, 32, gop=3)
+    keys = []
+    for f in mov:
+        key, y, u, v = pre.add_image(f)
+        keys.append(key)
+        img, _ = vio.merge_yuv444(y, u, v, 40)  # what the reader gets back: the writer's identity guarantee
+        np.testing.assert_array_equal(img, f)
+    assert keys == [bool(k) for k in port.key_frames(7, 3)]
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties
+# ---------------------------------------------------------------------------------------------
+def test_full_size_c2_round_trip_and_checksums():
+    """640x512x1000 (configs[1]): decode(precode(x)) == x with and without delta, and the byte
+    planes carry exactly the movie's bytes (checksum of checksums)."""
+    mov = rand_u16((1000, 512, 640), 1234)
+    for delta in (False, True):
+        lo, hi = vio.precode_movie(mov, 50, delta)
+        back = vio.decode_movie(lo, hi, 50, delta)
+        assert torch.equal(back.view(torch.int16), mov.view(torch.int16))
+        if not delta:
+            total = lo.to(torch.int64).sum() + 256 * hi.to(torch.int64).sum()
+            assert int(total) == int(as_int(mov).to(torch.int64).sum())
+        else:  # key frames are raw, the rest are differences
+            raw = (lo[::50].to(torch.int32) | (hi[::50].to(torch.int32) << 8))
+            assert torch.equal(raw, as_int(mov[::50]))
+
+
+def test_full_size_c4_translate_properties():
+    """1024x1024 with per-frame shifts (configs[3]): zero shift is the identity, integer shifts
+    move pixels exactly, and min/max of a nearest-border translate stay inside the source's."""
+    mov = rand_u16((64, 1024, 1024), 777)
+    n = mov.shape[0]
+    zero = torch.zeros(n, device="cuda")
+    assert torch.equal(sp.translate_batch(mov, zero, zero, "nearest", 0).view(torch.int16), mov.view(torch.int16))
+    dx = torch.arange(n, device="cuda", dtype=torch.float32) - 32
+    out = sp.translate_batch(mov, dx, zero, "background", 0)
+    for t in (0, 17, 32, 63):
+        s = int(dx[t])
+        src = as_int(mov[t])
+        want = torch.zeros_like(src)
+        if s > 0:
+            want[:, s:] = src[:, :-s]
+        elif s < 0:
+            want[:, :s] = src[:, -s:]
+        else:
+            want = src
+        assert torch.equal(as_int(out[t]), want), f"frame {t} shift {s}"
+    fr = torch.rand(n, device="cuda") * 6 - 3
+    o2 = as_int(sp.translate_batch(mov, fr, -fr, "nearest", 0))
+    assert int(o2.min()) >= int(as_int(mov).min()) and int(o2.max()) <= int(as_int(mov).max())
+
+
+def test_full_size_pipeline_matches_oracle_on_sampled_frames(port):
+    """configs[0]/[2] shape (640x512): the four stages chained on the device, a few frames of the
+    chunk checked end to end against the oracle."""
+    from librir_b200 import movie
+
+    mov = ir_movie(60, 512, 640)
+    cfg = movie.PipelineConfig(chunk_frames=60, gop=50, delta=True, sigma=1.0)
+    pipe = movie.FramePipeline(cfg)
+    d = to_dev(mov)
+    pipe.set_first_frame(d[0])
+    rng = np.random.default_rng(777)
+    dx = rng.uniform(-3, 3, 60).astype(np.float32)
+    dy = rng.uniform(-3, 3, 60).astype(np.float32)
+    c, s, r, lo, hi = pipe.process_chunk(d, to_dev(dx), to_dev(dy), first_frame=0)
+    oxy, _thr, oclamp = port.bad_pixels_detect(mov[0])
+    for t in (0, 1, 49, 50, 59):
+        oc = port.bad_pixels_correct_with(oxy, oclamp, mov[t])
+        np.testing.assert_array_equal(to_host(c[t]), oc)
+        assert_gauss_close(s[t].cpu().numpy(), port.gaussian_filter(oc.astype(np.float32), 1.0))
+        np.testing.assert_array_equal(to_host(r[t]), port.translate(oc, dx[t], dy[t], "nearest", 0))
+    reg = to_host(r)
+    olo, ohi = port.precode_movie(reg, 50, True)
+    np.testing.assert_array_equal(lo.cpu().numpy(), olo)
+    np.testing.assert_array_equal(hi.cpu().numpy(), ohi)
+    glo, ghi, ghist = port.movie_stats(reg)
+    assert (pipe.stats.min(), pipe.stats.max()) == (glo, ghi)
+    np.testing.assert_array_equal(pipe.stats.histogram(), ghist)
+    assert pipe.stats.quantile(0.5) == port.quantile_from_hist(ghist, 0.5)
