@@ -7,9 +7,9 @@
 //
 // Layout in HBM: the bad-pixel set of a movie is a BITMAP, one bit per pixel, row-padded to
 // bytes (bit x&7 of mask[y*mstride + x/8]); at 640x512 that is 40 KB, shared by every frame and
-// L2-resident.  Correction is one streaming pass (4 B/px algorithmic): a CTA stages a band of
-// rows in shared memory, each thread re-reads its 8 pixels, patches the (rare) flagged ones with
-// the 3x3 median taken from the staged INPUT band (halo rows from global), clamps, and stores.
+// L2-resident, plus the raster-ordered (x,y) list the reference keeps.  Correction is one
+// streaming pass (4 B/px algorithmic): copy + clamp at full width, then one thread per flagged
+// pixel takes the 3x3 median from the INPUT frame and overwrites the pixel.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -50,148 +50,112 @@ __device__ __forceinline__ unsigned pick_mid(const unsigned (&v)[9], int c)
 }
 
 // ------------------------------------------------------------------------------------------------
-// a-2  correction, banded streaming kernel
+// a-2  correction: streaming copy+clamp, then list-driven fix-ups
 // ------------------------------------------------------------------------------------------------
-// 3x3 median around (x,y) as BadPixels::correct takes it: in-bounds neighbours incl. centre, all
-// read from the INPUT frame; band rows come from shared memory, the two halo rows from global.
-__device__ __forceinline__ unsigned median3x3_input(const u16* __restrict__ frame, const u16* tile, int w, int h, int y0,
-                                                    int y1, int x, int y)
+// A CTA owns a flat span of BP_SPAN pixels of one frame.
+//   pass 1 (every byte of the movie, once): 256-bit streaming load -> per-halfword max with the
+//           clamp -> 256-bit streaming store.  ~1 instruction per 16 bytes moved.
+//   pass 2 (K flagged pixels per frame, K/N ~ 1 %): the raster-ordered list of flagged pixels is
+//           cut per span at create time (span_off); ONE THREAD PER FLAGGED PIXEL gathers the
+//           in-bounds 3x3 neighbourhood from the INPUT frame (L2 hits: the CTA has just streamed
+//           those rows), sorts 9 registers, and overwrites the pixel.  No divergence tax on the
+//           clean pixels, which is what made the band-in-shared-memory version ALU-bound
+//           (profiles/r1_v1_ncu_summary.md: 64 % ALU at 29 % of HBM peak).
+// The two passes touch the same output address from different threads: __syncthreads orders them.
+__device__ __forceinline__ unsigned median3x3_global(const u16* __restrict__ frame, int w, int h, int x, int y)
 {
     unsigned v[9];
+    if (x > 0 && y > 0 && x < w - 1 && y < h - 1) {  // interior: 9 unconditional loads
+        const u16* p = frame + (size_t)(y - 1) * w + (x - 1);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[r * 3 + c] = p[(size_t)r * w + c];
+        sort9(v);
+        return v[4];
+    }
     int c = 0;
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-        int yy = y + dy;
-        bool rowok = (yy >= 0) && (yy < h);
-        bool in_tile = (yy >= y0) && (yy < y1);
+    for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
         for (int dx = -1; dx <= 1; ++dx) {
-            int xx = x + dx;
-            bool ok = rowok && (xx >= 0) && (xx < w);
-            unsigned val = 0xFFFFFFFFu;
-            if (ok) {
-                val = in_tile ? (unsigned)tile[(yy - y0) * w + xx] : (unsigned)frame[(size_t)yy * w + xx];
-                ++c;
-            }
-            v[(dy + 1) * 3 + (dx + 1)] = val;
+            const int xx = x + dx, yy = y + dy;
+            const bool ok = xx >= 0 && yy >= 0 && xx < w && yy < h;
+            v[(dy + 1) * 3 + dx + 1] = ok ? (unsigned)frame[(size_t)yy * w + xx] : 0xFFFFFFFFu;
+            c += ok;
         }
-    }
     sort9(v);
     return pick_mid(v, c);
 }
 
 constexpr int BP_THREADS = 256;
+constexpr int BP_UNROLL = BP_SPAN / (BP_THREADS * 16);  // 256-bit vectors per thread
+static_assert(BP_UNROLL * BP_THREADS * 16 == BP_SPAN, "BP_SPAN must be a multiple of one CTA-wide row of vectors");
 
-// VEC == 8: w % 8 == 0 and 16-byte aligned frames (128-bit path).  VEC == 1: anything else.
-template <int VEC>
+// VEC: frames 32-byte aligned (base and stride), so span starts are too.
+template <bool VEC>
 __global__ void __launch_bounds__(BP_THREADS)
-bp_correct_kernel(const u16* __restrict__ in, u16* __restrict__ out, const u8* __restrict__ mask, int w, int h, int mstride,
-                  int band_rows, int bands, unsigned clamp, size_t frame_stride)
+bp_correct_kernel(const u16* __restrict__ in, u16* __restrict__ out, const int* __restrict__ xy, const int* __restrict__ span_off,
+                  int w, int h, int npx, int spans, unsigned clamp, size_t frame_stride)
 {
-    extern __shared__ __align__(16) u16 tile[];
-    const int band = blockIdx.x % bands;
-    const size_t f = blockIdx.x / bands;
-    const int y0 = band * band_rows;
-    const int y1 = min(h, y0 + band_rows);
+    const int span = blockIdx.x % spans;
+    const size_t f = blockIdx.x / spans;
+    const int s0 = span * BP_SPAN;
+    const int s1 = min(npx, s0 + BP_SPAN);
     const u16* frame = in + f * frame_stride;
     u16* oframe = out + f * frame_stride;
-    const int npx = (y1 - y0) * w;
-
-    if (VEC == 8) {
-        const uint4* g = reinterpret_cast<const uint4*>(frame + (size_t)y0 * w);
-        uint4* s = reinterpret_cast<uint4*>(tile);
-        const int nvec = npx >> 3;
-        // phase 1: band -> shared memory, loads issued in independent batches of 4
-        for (int i = threadIdx.x; i < nvec; i += 4 * BP_THREADS) {
-            uint4 r[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int j = i + k * BP_THREADS;
-                if (j < nvec) r[k] = ld_stream(g + j);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int j = i + k * BP_THREADS;
-                if (j < nvec) s[j] = r[k];
-            }
-        }
-        __syncthreads();
-        // phase 2: patch flagged pixels, clamp, store
+    int done = s0;
+    if (VEC) {
         const unsigned c2 = clamp | (clamp << 16);
-        uint4* o = reinterpret_cast<uint4*>(oframe + (size_t)y0 * w);
-        const int vec_per_row = w >> 3;
-        for (int j = threadIdx.x; j < nvec; j += BP_THREADS) {
-            uint4 v = s[j];
-            int ry = j / vec_per_row;
-            int xv = j - ry * vec_per_row;
-            int y = y0 + ry;
-            unsigned m = mask[(size_t)y * mstride + xv];
-            if (m) {
-                unsigned px[8] = {v.x & 0xFFFF, v.x >> 16, v.y & 0xFFFF, v.y >> 16, v.z & 0xFFFF, v.z >> 16, v.w & 0xFFFF, v.w >> 16};
+        const int nvec = (s1 - s0) >> 4;
+        const U32x8* g = reinterpret_cast<const U32x8*>(frame + s0);
+        U32x8* o = reinterpret_cast<U32x8*>(oframe + s0);
+        U32x8 r[BP_UNROLL];
 #pragma unroll
-                for (int b = 0; b < 8; ++b)
-                    if (m & (1u << b)) px[b] = median3x3_input(frame, tile, w, h, y0, y1, xv * 8 + b, y);
-                v.x = px[0] | (px[1] << 16);
-                v.y = px[2] | (px[3] << 16);
-                v.z = px[4] | (px[5] << 16);
-                v.w = px[6] | (px[7] << 16);
+        for (int k = 0; k < BP_UNROLL; ++k) {
+            const int j = threadIdx.x + k * BP_THREADS;
+            if (j < nvec) r[k] = ld_stream256(g + j);
+        }
+#pragma unroll
+        for (int k = 0; k < BP_UNROLL; ++k) {
+            const int j = threadIdx.x + k * BP_THREADS;
+            if (j < nvec) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) r[k].v[q] = vmaxu2(r[k].v[q], c2);
+                st_stream256(o + j, r[k]);
             }
-            v.x = vmaxu2(v.x, c2);
-            v.y = vmaxu2(v.y, c2);
-            v.z = vmaxu2(v.z, c2);
-            v.w = vmaxu2(v.w, c2);
-            st_stream(o + j, v);
         }
-    } else {
-        const u16* g = frame + (size_t)y0 * w;
-        for (int i = threadIdx.x; i < npx; i += BP_THREADS) tile[i] = g[i];
-        __syncthreads();
-        u16* o = oframe + (size_t)y0 * w;
-        for (int i = threadIdx.x; i < npx; i += BP_THREADS) {
-            int ry = i / w;
-            int x = i - ry * w;
-            int y = y0 + ry;
-            unsigned v = tile[i];
-            if (mask[(size_t)y * mstride + (x >> 3)] & (1u << (x & 7))) v = median3x3_input(frame, tile, w, h, y0, y1, x, y);
-            o[i] = (u16)max(v, clamp);
-        }
+        done = s0 + (nvec << 4);
+    }
+    for (int i = done + threadIdx.x; i < s1; i += BP_THREADS) oframe[i] = (u16)max((unsigned)frame[i], clamp);
+    const int a = span_off[span], b = span_off[span + 1];
+    if (a == b) return;  // CTA-uniform
+    __syncthreads();
+    for (int i = a + threadIdx.x; i < b; i += BP_THREADS) {
+        const int2 p = reinterpret_cast<const int2*>(xy)[i];
+        oframe[(size_t)p.y * w + p.x] = (u16)max(median3x3_global(frame, w, h, p.x, p.y), clamp);
     }
 }
 
-int launch_bp_correct(const u16* in, u16* out, const u8* mask, int w, int h, int clamp_value, long long nframes,
-                      size_t frame_stride, cudaStream_t st)
+int launch_bp_correct(const u16* in, u16* out, const int* xy_dev, const int* span_off_dev, int w, int h, int clamp_value,
+                      long long nframes, size_t frame_stride, cudaStream_t st)
 {
     if (nframes <= 0 || w <= 0 || h <= 0) return 0;
-    const int mstride = (w + 7) / 8;
     const unsigned clamp = clamp_value > 0 ? (unsigned)clamp_value & 0xFFFFu : 0u;
-    // band: <= 24 KB of shared memory and <= 2048 vectors, so >= 8 CTAs fit on an SM
-    int band_rows = (int)(12288 / w);
-    if (band_rows < 1) band_rows = 1;
-    if (band_rows > 32) band_rows = 32;
-    if (band_rows > h) band_rows = h;
-    const int bands = (int)ceil_div(h, band_rows);
-    const size_t smem = (size_t)band_rows * w * sizeof(u16);
-    if (smem > 200 * 1024) {
-        set_error("bad_pixels_correct: image width %d too large", w);
+    const long long npx = (long long)w * h;
+    const long long spans = ceil_div(npx, BP_SPAN);
+    const long long grid = nframes * spans;
+    if (npx > 0x7FFFFFFFLL || grid > 0x7FFFFFFFLL) {
+        set_error("bad_pixels_correct: too many pixels or frames in one call (%lld frames)", nframes);
         return -1;
     }
-    const long long grid = nframes * bands;
-    if (grid > 0x7FFFFFFFLL) {
-        set_error("bad_pixels_correct: too many frames in one call (%lld)", nframes);
-        return -1;
-    }
-    const bool vec = (w % 8 == 0) && aligned16(in) && aligned16(out) && (frame_stride % 8 == 0);
-    if (vec) {
-        if (smem > 48 * 1024)
-            RIRB_CUDA_OK(cudaFuncSetAttribute(bp_correct_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RIRB_LAUNCH(bp_correct_kernel<8>, (unsigned)grid, BP_THREADS, smem, st, in, out, mask, w, h, mstride, band_rows, bands,
-                    clamp, frame_stride);
-    } else {
-        if (smem > 48 * 1024)
-            RIRB_CUDA_OK(cudaFuncSetAttribute(bp_correct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RIRB_LAUNCH(bp_correct_kernel<1>, (unsigned)grid, BP_THREADS, smem, st, in, out, mask, w, h, mstride, band_rows, bands,
-                    clamp, frame_stride);
-    }
+    const bool vec = aligned32(in) && aligned32(out) && (frame_stride % 16 == 0);
+    if (vec)
+        RIRB_LAUNCH(bp_correct_kernel<true>, (unsigned)grid, BP_THREADS, 0, st, in, out, xy_dev, span_off_dev, w, h, (int)npx,
+                    (int)spans, clamp, frame_stride);
+    else
+        RIRB_LAUNCH(bp_correct_kernel<false>, (unsigned)grid, BP_THREADS, 0, st, in, out, xy_dev, span_off_dev, w, h, (int)npx,
+                    (int)spans, clamp, frame_stride);
     return 0;
 }
 

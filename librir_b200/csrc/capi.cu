@@ -187,11 +187,13 @@ struct BadPixelState {
     unsigned global_thr = 0;      // Filters.h:157-160
     u8* mask_dev = nullptr;       // bitmap, row stride (w+7)/8
     int* xy_dev = nullptr;        // raster-ordered list (x,y), device copy
+    int* span_off_dev = nullptr;  // list offsets per BP_SPAN-pixel span (correction kernel)
     std::vector<int> xy;          // host copy
     ~BadPixelState()
     {
         if (mask_dev) cudaFree(mask_dev);
         if (xy_dev) cudaFree(xy_dev);
+        if (span_off_dev) cudaFree(span_off_dev);
     }
 };
 static std::mutex g_handles_mutex;
@@ -466,13 +468,28 @@ int bad_pixels_create(unsigned short* first_image, int width, int height)
                 state->xy.push_back(y);
             }
         }
+    // where each BP_SPAN-pixel span of the frame starts in the (raster-ordered, hence sorted) list
+    const size_t nspans = (n + BP_SPAN - 1) / BP_SPAN;
+    std::vector<int> span_off(nspans + 1, 0);
+    {
+        const size_t k = state->xy.size() / 2;
+        size_t i = 0;
+        for (size_t s = 0; s <= nspans; ++s) {
+            const size_t first_px = s * (size_t)BP_SPAN;
+            while (i < k && (size_t)state->xy[2 * i + 1] * width + state->xy[2 * i] < first_px) ++i;
+            span_off[s] = (int)i;
+        }
+    }
+    if (cudaMalloc(&state->span_off_dev, span_off.size() * sizeof(int)) != cudaSuccess) return fail("cudaMalloc(span offsets)");
+    if (cudaMemcpyAsync(state->span_off_dev, span_off.data(), span_off.size() * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return fail("H2D(span offsets)");
     if (!state->xy.empty()) {
         if (cudaMalloc(&state->xy_dev, state->xy.size() * sizeof(int)) != cudaSuccess) return fail("cudaMalloc(list)");
         if (cudaMemcpyAsync(state->xy_dev, state->xy.data(), state->xy.size() * sizeof(int), cudaMemcpyHostToDevice, st) !=
             cudaSuccess)
             return fail("H2D(list)");
-        if (cudaStreamSynchronize(st) != cudaSuccess) return fail("sync");
     }
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail("sync");
     return register_handle(state);
 }
 
@@ -504,7 +521,7 @@ int rirb_bad_pixels_correct_batch(int handle, const unsigned short* in, unsigned
     if (!d_in) return -1;
     StagedOut o;
     if (!stage_out(o, out, bytes, 1, false, st)) return -1;
-    if (launch_bp_correct(d_in, (u16*)o.dev, s->mask_dev, s->w, s->h, s->clamp_value, nframes, fpx, st) != 0) return -1;
+    if (launch_bp_correct(d_in, (u16*)o.dev, s->xy_dev, s->span_off_dev, s->w, s->h, s->clamp_value, nframes, fpx, st) != 0) return -1;
     return finish_out(&o, 1, st);
 }
 

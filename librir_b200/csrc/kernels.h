@@ -15,8 +15,11 @@ enum { STRAT_NOBORDER = 0, STRAT_BACKGROUND = 1, STRAT_WRAP = 2, STRAT_NEAREST =
 // bad_pixels.cu
 int launch_hist_frame(const u16* img, size_t n, unsigned* hist65536, cudaStream_t st);
 int launch_bp_detect(const u16* img, int w, int h, double std_factor, unsigned gthr, u8* mask, cudaStream_t st);
-int launch_bp_correct(const u16* in, u16* out, const u8* mask, int w, int h, int clamp_value, long long nframes,
-                      size_t frame_stride, cudaStream_t st);
+// Correction CTAs own flat spans of BP_SPAN pixels; span_off[s] .. span_off[s+1] is the slice of the
+// raster-ordered (x,y) list that falls into span s (ceil(w*h / BP_SPAN) + 1 entries, built at create).
+constexpr int BP_SPAN = 16384;
+int launch_bp_correct(const u16* in, u16* out, const int* xy_dev, const int* span_off_dev, int w, int h, int clamp_value,
+                      long long nframes, size_t frame_stride, cudaStream_t st);
 int launch_bp_correct_inplace(u16* img, const int* xy_dev, int count, int w, int h, int clamp_value, long long nframes,
                               size_t frame_stride, cudaStream_t st);
 int launch_loader_bp(u16* img, const int* xy_dev, const u8* mask, int count, int w, int h, long long nframes,
