@@ -6,7 +6,15 @@
 // normaliser (the in-bounds tap set is a rectangle), so a separable evaluation agrees with it to
 // float rounding (tolerance 1e-5 relative, BASELINE.json).
 //
-// Kernel design (r <= 4, w % 4 == 0 -- sigma < 2.5, every shape in BASELINE.json):
+// Kernel design (r <= 4 -- sigma < 2.5, every shape in BASELINE.json):
+//  gauss_tile_kernel (TMA-compatible layouts: 16-byte aligned rows): a CTA owns a 128 x 64 output
+//   tile; ONE TMA box load brings the (128 + 2 halo vectors) x (64+2r) source window into shared memory, with
+//   the out-of-image halo zero-filled by the hardware -- which is exactly the reference's
+//   "taps outside the image do not count" once the sum is renormalised.  Each of the 4 warps walks
+//   16 output rows: a lane reads its 4+2r source pixels of a row with two vector LDS, runs the
+//   horizontal pass in registers and keeps a (2r+1)-row register ring for the vertical pass, which
+//   is issued as packed FFMA2 (two columns per instruction, sm_100's fma.rn.f32x2).
+//  gauss_sep_kernel (fallback, w % 4 == 0, no shared memory):
 //   one WARP owns a 128-pixel-wide column strip of one frame and walks down its rows.  A lane
 //   loads 4 pixels of the row (128-bit for f32, 64-bit for u16), takes the r pixels it needs from
 //   each neighbour lane with warp shuffles (lanes 0/31 fetch the strip's halo vector, an L2 hit),
@@ -16,8 +24,11 @@
 //   No shared memory, no __syncthreads; rows are loaded in batches of 4 for memory parallelism.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
+#include "tma.cuh"
 
 namespace rirb {
 
@@ -204,6 +215,153 @@ gauss_sep_kernel(const TIN* __restrict__ src, float* __restrict__ dst, int w, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA-tiled path
+// ------------------------------------------------------------------------------------------------
+constexpr int GT_W = 128;          // output columns per CTA (4 per lane)
+constexpr int GT_WARPS = 4;        // warps per CTA
+constexpr int GT_RG = 16;          // output rows per warp
+constexpr int GT_H = GT_WARPS * GT_RG;
+// TMA boxes start on 16-byte boundaries in x (tma.cuh), so the left halo is a whole vector: GT_HALO
+// source pixels (16 bytes) on each side, of which the r nearest are used.
+template <typename TIN> struct GtBox {
+    static constexpr int HALO = 16 / (int)sizeof(TIN);  // 8 (u16) or 4 (f32)
+    static constexpr int BW = GT_W + 2 * HALO;
+};
+
+// 4 consecutive tile elements starting at p (8-byte aligned for u16, 16-byte aligned for f32) -> float
+__device__ __forceinline__ void load4(const u16* p, float (&a)[4])
+{
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    a[0] = (float)(v.x & 0xFFFFu); a[1] = (float)(v.x >> 16);
+    a[2] = (float)(v.y & 0xFFFFu); a[3] = (float)(v.y >> 16);
+}
+__device__ __forceinline__ void load4(const float* p, float (&a)[4])
+{
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+}
+
+template <int R, typename TIN>
+__global__ void __launch_bounds__(GT_WARPS * 32)
+gauss_tile_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ dst, int w, int h, int tiles_x, int tiles_y,
+                  GaussTaps taps)
+{
+    constexpr int BH = GT_H + 2 * R;
+    constexpr int HALO = GtBox<TIN>::HALO;
+    static_assert(R <= 4, "the window below is 4 pixels either side of the lane's own 4");
+    __shared__ __align__(128) TIN tile[BH][GtBox<TIN>::BW];
+    __shared__ __align__(8) unsigned long long bar;
+    const int tiles = tiles_x * tiles_y;
+    const long long f = blockIdx.x / tiles;
+    const int tile_id = (int)(blockIdx.x - f * tiles);
+    const int ty = tile_id / tiles_x, tx = tile_id - ty * tiles_x;
+    const int x0t = tx * GT_W, y0t = ty * GT_H;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (unsigned)sizeof(tile));
+        tma_load_box(&tile[0][0], &tmap, &bar, x0t - HALO, y0t - R, (int)f);
+    }
+
+    // ---- per-thread constants (while the box is in flight) ---------------------------------------
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int x = x0t + 4 * lane;
+    float k[2 * R + 1];
+#pragma unroll
+    for (int d = 0; d <= 2 * R; ++d) k[d] = taps.k[d];
+    float kfull = 0.f;
+#pragma unroll
+    for (int d = 0; d <= 2 * R; ++d) kfull += k[d];
+    float nx[4];
+    bool xborder = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d <= 2 * R; ++d) {
+            const int xx = x + j + d - R;
+            if (xx >= 0 && xx < w) s += k[d];
+        }
+        const bool xb = (x + j < R) || (x + j >= w - R);
+        nx[j] = xb ? s : kfull;
+        xborder = xborder || xb;
+    }
+    float* oframe = dst + (size_t)f * w * h;
+    float2 ring[2 * R + 1][2];
+#pragma unroll
+    for (int i = 0; i <= 2 * R; ++i) ring[i][0] = ring[i][1] = make_float2(0.f, 0.f);
+
+    mbar_wait(&bar, 0);
+
+#pragma unroll
+    for (int rr = 0; rr < GT_RG + 2 * R; ++rr) {
+        // aligned vectors left / own / right of the lane's 4 pixels; win[j] = source column x - R + j
+        const TIN* srow = &tile[wi * GT_RG + rr][HALO + 4 * lane];
+        float vl[4], vc[4], vr[4], win[4 + 2 * R];
+        load4(srow - 4, vl);
+        load4(srow, vc);
+        load4(srow + 4, vr);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            win[j] = vl[4 - R + j];
+            win[R + 4 + j] = vr[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) win[R + j] = vc[j];
+        // horizontal pass of this source row -> newest ring slot
+#pragma unroll
+        for (int i = 0; i < 2 * R; ++i) {
+            ring[i][0] = ring[i + 1][0];
+            ring[i][1] = ring[i + 1][1];
+        }
+        float hsum[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float s = k[0] * win[j];
+#pragma unroll
+            for (int d = 1; d <= 2 * R; ++d) s = fmaf(k[d], win[j + d], s);
+            hsum[j] = s;
+        }
+        ring[2 * R][0] = make_float2(hsum[0], hsum[1]);
+        ring[2 * R][1] = make_float2(hsum[2], hsum[3]);
+        if (rr >= 2 * R) {
+            const int yo = y0t + wi * GT_RG + rr - 2 * R;
+            // vertical pass, two columns per FFMA2
+            float2 o0 = make_float2(k[0] * ring[0][0].x, k[0] * ring[0][0].y);
+            float2 o1 = make_float2(k[0] * ring[0][1].x, k[0] * ring[0][1].y);
+#pragma unroll
+            for (int d = 1; d <= 2 * R; ++d) {
+                const float2 kk = make_float2(k[d], k[d]);
+                o0 = __ffma2_rn(kk, ring[d][0], o0);
+                o1 = __ffma2_rn(kk, ring[d][1], o1);
+            }
+            float o[4] = {o0.x, o0.y, o1.x, o1.y};
+            const bool yborder = (yo < R) || (yo >= h - R);
+            if (yborder || xborder) {  // partial-kernel renormalisation (signal_processing.cpp:130-144)
+                float ny = kfull;
+                if (yborder) {
+                    ny = 0.f;
+#pragma unroll
+                    for (int d = 0; d <= 2 * R; ++d) {
+                        const int yyy = yo + d - R;
+                        if (yyy >= 0 && yyy < h) ny += k[d];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool xb = (x + j < R) || (x + j >= w - R);
+                    if (yborder || xb) o[j] = o[j] / (ny * nx[j]);
+                }
+            }
+            if (x < w && yo < h) st_stream(reinterpret_cast<float4*>(oframe + (size_t)yo * w + x), make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic path: any width, any radius up to GAUSS_MAX_RADIUS -- one thread per output pixel
 // ------------------------------------------------------------------------------------------------
 template <typename TIN>
@@ -252,6 +410,31 @@ static int launch_gaussian(const TIN* src, float* dst, int w, int h, long long n
         dim3 block(32, 8);
         dim3 grid((unsigned)ceil_div(w, 32), (unsigned)ceil_div(h, 8), (unsigned)min(nframes, 32768LL));
         RIRB_LAUNCH(gauss_generic_kernel<TIN>, grid, block, 0, st, src, dst, w, h, nframes, taps);
+        return 0;
+    }
+    static const bool tma_enabled = []() {  // RIRB_GAUSS_TMA=0 selects the warp-strip kernel (A/B measurements)
+        const char* e = getenv("RIRB_GAUSS_TMA");
+        return !(e && e[0] == '0');
+    }();
+    const size_t esz = sizeof(TIN);
+    const int tiles_x = (int)ceil_div(w, GT_W), tiles_y = (int)ceil_div(h, GT_H);
+    const long long tgrid = nframes * tiles_x * tiles_y;
+    if (tma_enabled && tma_compatible(src, (size_t)w * esz, (size_t)w * h * esz) && nframes <= 0x7FFFFFFFLL && tgrid <= 0x7FFFFFFFLL) {
+        CUtensorMap tmap;
+#define RIRB_GT(RR)                                                                                                          \
+    do {                                                                                                                     \
+        if (make_movie_tensor_map(&tmap, src, (int)esz, w, h, nframes, (size_t)w * esz, (size_t)w * h * esz, GtBox<TIN>::BW, \
+                                  GT_H + 2 * RR) != 0)                                                                       \
+            return -1;                                                                                                       \
+        RIRB_LAUNCH((gauss_tile_kernel<RR, TIN>), (unsigned)tgrid, GT_WARPS * 32, 0, st, tmap, dst, w, h, tiles_x, tiles_y, taps); \
+    } while (0)
+        switch (r) {
+        case 1: RIRB_GT(1); break;
+        case 2: RIRB_GT(2); break;
+        case 3: RIRB_GT(3); break;
+        default: RIRB_GT(4); break;
+        }
+#undef RIRB_GT
         return 0;
     }
     const int xstrips = (int)ceil_div(w, GS_STRIP);

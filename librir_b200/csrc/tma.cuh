@@ -1,13 +1,17 @@
 // librir_b200/csrc/tma.cuh -- Tensor Memory Accelerator plumbing for the tiled kernels (sm_100a).
 //
 // A movie is described to the TMA unit as a 3-D tensor (x, y, frame) of 2- or 4-byte elements.
-// One elected thread asks for a box at ARBITRARY element coordinates (negative / past-the-edge
+// One elected thread asks for a box at signed element coordinates (negative / past-the-edge
 // parts are zero-filled by the hardware) and the box lands densely in shared memory; completion
 // is signalled on an mbarrier.  Two things on this path are exactly that access pattern:
 //   * translate: the source window of a destination tile starts at (x0 + floor(-dx), y0 + floor(-dy)),
-//     an unaligned position that differs per frame -- TMA re-aligns it for free;
+//     a position that differs per frame and can hang over any image edge;
 //   * gaussian: tiles need a halo of `radius` pixels whose out-of-image taps count as zero, which
 //     is the hardware's out-of-bounds fill.
+// Measured constraint (scripts/probes/tma_probe.cu on B200): the box's INNERMOST start coordinate
+// must fall on a 16-byte boundary (x % 8 == 0 for uint16, x % 4 == 0 for float32), otherwise the
+// load traps ("illegal instruction"); negative and past-the-edge coordinates are fine in every
+// dimension.  The kernels therefore round the box origin down and keep the residual in registers.
 // SASS: UTMALDG (cp.async.bulk.tensor), SYNCS (mbarrier).
 #pragma once
 
@@ -63,7 +67,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     while (!mbar_try_wait(bar, parity)) {
     }
 }
-// box at element coordinates (x, y, frame) -> dense [box_h][box_w] at `dst` (128-byte aligned)
+// box at element coordinates (x, y, frame), x on a 16-byte boundary -> dense [box_h][box_w] at `dst` (128-byte aligned)
 __device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, unsigned long long* bar, int x, int y, int frame)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(

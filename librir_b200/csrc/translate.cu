@@ -8,14 +8,21 @@
 // order and NO fused multiply-add (__dmul_rn/__dadd_rn), truncating store -- so integer outputs
 // are bit-identical to the reference, not merely within +-1 LSB.
 //
-// Two kernels:
+// Three kernels:
 //   translate_generic_kernel<T,U>  every dtype / strategy, one thread per destination pixel.
-//   translate_u16_kernel           the uint16 hot path: 4 pixels per thread, the two source rows
-//                                  staged once per thread as 5 columns, the vertical blend done
-//                                  in exact 64-bit integer arithmetic (see the comment there) so
-//                                  that the FP64 pipe carries 5.25 instead of 13 ops per pixel.
+//   translate_u16_tma_kernel       the uint16 hot path: the source window of a 128x32 destination
+//                                  tile is fetched by ONE TMA box load at the per-frame position
+//                                  (x0 + floor(-dx), y0 + floor(-dy)); a thread turns 8
+//                                  pixels of a row with two 128-bit shared-memory reads, the
+//                                  vertical blend in exact 64-bit integer arithmetic and 4 fp64
+//                                  operations per pixel, no type conversions (see the comments there).
+//   translate_u16_kernel           same arithmetic without shared memory, 4 pixels per thread:
+//                                  widths that are not a multiple of 8 / unaligned buffers.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
+#include "tma.cuh"
 
 namespace rirb {
 
@@ -238,11 +245,235 @@ translate_u16_kernel(const u16* __restrict__ src, u16* __restrict__ dst, int w, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// uint16 hot path, TMA-tiled
+// ------------------------------------------------------------------------------------------------
+// Destination tile TT_W x TT_H; its source window is [x0+sx, x0+sx+TT_W+2) x [y0+sy, y0+sy+TT_H+2)
+// with sx = floor(-dx), sy = floor(-dy): the real source coordinate x-dx lies in [x+sx, x+sx+1), its
+// float32 rounding px in [x+sx, x+sx+1], so l = trunc(px) is x+sx (or x+sx+1 when px rounds up to
+// the integer -- those rare groups take the per-pixel routine) and rt <= l+1.
+// TMA wants the box's innermost start coordinate on a 16-byte boundary (measured: any other x
+// traps, scripts/probes/tma_probe.cu), so the box starts at (x0+sx) rounded down to 8 pixels and
+// every thread of the CTA applies the same residual offset XOFF = 0..7 when it unpacks its two
+// 128-bit shared-memory reads: the row routine is instantiated for the 8 offsets and picked by a
+// CTA-uniform switch.
+//
+// Per thread: 8 consecutive destination pixels of one row, validated through a few probe pixels:
+//   * px_i = RN32(x_i - dx) sits on a grid g_i = ulp(px_i) that only gets coarser with i, and the
+//     fraction it carries is u_i = RN_{g_i}(frac(-dx)).  If u is equal at both ends of a run of
+//     pixels it is representable on both grids, hence on every grid in between: uniform on the run.
+//   * the grid changes where px crosses a power of two P >= 8, i.e. at source column l = P, a
+//     multiple of 8; a group starts at source column 8m + XOFF, so inside a group the change can
+//     only sit between pixel 7-XOFF and pixel 8-XOFF -- a COMPILE-TIME position in the XOFF
+//     instance.  A thread therefore carries two sets of horizontal weights, (a) from pixel 0 for
+//     pixels < 8-XOFF and (b) from pixel 7 for the rest, checked at the two pixels next to the split.
+//     (Groups that still fail -- source columns below 8, where grids change at 1, 2, 4 -- are slow.)
+//   * a round-up of px_i (or of px_i + 1.0f, which decides rt) to the next integer needs
+//     frac >= 1 - g/2; if it happens at some i it also happens at the coarser pixel 7 (ties go to
+//     the even neighbour, which is the integer, on every grid < 1), so l_7 == l_0 + 7 and
+//     trunc(px + 1) == l + 1 at pixel 7 and at the last pixel of run (a) exclude it for the group.
+// With u uniform on a run, (1-u) and u are thread constants, and with M_j = 2^29 + c_j (c_j the exact
+// column blend, see int_to_double_scaled23) the reference's RN(c_l*(1-u)) is one DFMA:
+//   RN(M_l*(1-u) - 2^29*(1-u)) = RN((M_l - 2^29)*(1-u))      (the FMA product is exact, 2^29*(1-u) is exact)
+// so a pixel costs 2 DFMA + 1 DADD + one DADD.RM with 2^52 that leaves trunc(val) in the low word
+// (val >= 0): 4 fp64 instructions and no F2I/I2F/F2F (those issue at 16/clk/SM and were the limiter of
+// the 4-pixel kernel: profiles/r1_v1_ncu_summary.md).
+//
+// Warp shape: 2 column groups x 16 rows, so that the slow groups (image edges, source columns < 8)
+// are confined to the warps that own the edge columns instead of costing every warp of an edge tile
+// a divergent detour.  Row pitch 288 B keeps the 128-bit reads of 4 rows x 2 groups conflict-free.
+constexpr int TT_W = 128, TT_H = 32;
+constexpr int TT_BW = TT_W + 16, TT_BH = TT_H + 2;  // box: thread c reads columns [8c, 8c+16); +2 rows
+constexpr int TT_THREADS = 256;
+
+struct HWeights {  // horizontal weights of a run of pixels with the same fraction u
+    double u, omu, k_l, k_r;
+};
+__device__ __forceinline__ HWeights make_hweights(float uf)
+{
+    HWeights c;
+    c.u = (double)uf;
+    c.omu = __dsub_rn(1.0, c.u);
+    c.k_l = __dmul_rn(-536870912.0, c.omu);
+    c.k_r = __dmul_rn(-536870912.0, c.u);
+    return c;
+}
+
+// columns D .. D+8 of the 16 pixels held in two 128-bit words (little-endian pairs)
+template <int D>
+__device__ __forceinline__ void unpack9(const uint4& a, const uint4& b, unsigned (&p)[9])
+{
+    const unsigned wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const int c = D + j;
+        p[j] = (c & 1) ? (wv[c >> 1] >> 16) : (wv[c >> 1] & 0xFFFFu);
+    }
+}
+
+// One fast group: 8 destination pixels from the two staged source rows.
+template <int XOFF, bool MOTION>
+__device__ __forceinline__ void blend_group(const uint4* rowb, const uint4* rowt, unsigned A, unsigned B, bool clamp_rt,
+                                            const HWeights& ca, const HWeights& cb, u16* orow)
+{
+    unsigned pb[9], pt[9];
+    unpack9<XOFF>(rowb[0], rowb[1], pb);
+    unpack9<XOFF>(rowt[0], rowt[1], pt);
+    if (clamp_rt) {  // rt of the last pixel clamps to its l (Filters.h:309)
+        pb[8] = pb[7];
+        pt[8] = pt[7];
+    }
+    double m[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {  // bits(2^29) + N: the double 2^29 + N * 2^-23, N = p_b*A + p_t*B < 2^40 (two IMAD.WIDE.U32)
+        unsigned long long n = (unsigned long long)pb[j] * A + 0x41C0000000000000ULL;
+        n += (unsigned long long)pt[j] * B;
+        m[j] = __longlong_as_double((long long)n);
+    }
+    unsigned o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const HWeights& c = (XOFF != 0 && j >= 8 - XOFF) ? cb : ca;  // static choice
+        const double val = __dadd_rn(__fma_rn(m[j], c.omu, c.k_l), __fma_rn(m[j + 1], c.u, c.k_r));
+        if (MOTION)
+            o[j] = (unsigned)(u16)(float)val;  // double -> float (nearest) -> uint16 (truncation), IRFileLoader.cpp:624
+        else
+            o[j] = (unsigned)__double2loint(__dadd_rd(val, 4503599627370496.0));  // trunc(val), 0 <= val < 2^16
+    }
+    uint4 ov;
+    ov.x = __byte_perm(o[0], o[1], 0x5410);
+    ov.y = __byte_perm(o[2], o[3], 0x5410);
+    ov.z = __byte_perm(o[4], o[5], 0x5410);
+    ov.w = __byte_perm(o[6], o[7], 0x5410);
+    st_stream(reinterpret_cast<uint4*>(orow), ov);
+}
+
+template <bool MOTION>
+__global__ void __launch_bounds__(TT_THREADS)
+translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __restrict__ src, u16* __restrict__ dst, int w, int h,
+                         size_t src_stride, size_t dst_stride, const float* __restrict__ dxs, const float* __restrict__ dys,
+                         float dx0, float dy0, int strategy, unsigned background, int tiles_x, int tiles_y)
+{
+    __shared__ __align__(128) u16 tile[TT_BH][TT_BW];
+    __shared__ __align__(8) unsigned long long bar;
+    const int tiles = tiles_x * tiles_y;
+    const long long f = blockIdx.x / tiles;
+    const int tile_id = (int)(blockIdx.x - f * tiles);
+    const int ty = tile_id / tiles_x, tx = tile_id - ty * tiles_x;
+    const int x0t = tx * TT_W, y0t = ty * TT_H;
+    const float dx = dxs ? dxs[f] : dx0;
+    const float dy = dys ? dys[f] : dy0;
+    const float fw = (float)w, fh = (float)h;
+    // integer part of the shift, kept in a range where the int arithmetic below cannot overflow
+    // (a clamped value simply never matches l0, and the group takes the per-pixel routine)
+    const int sx = (int)fminf(fmaxf(floorf(-dx), -fw - 16.f), fw + 16.f);
+    const int sy = (int)fminf(fmaxf(floorf(-dy), -fh - 16.f), fh + 16.f);
+    const int xs = (x0t + sx) & ~7, ys = y0t + sy;  // box origin: 16-byte aligned column
+    const int xoff = (x0t + sx) - xs;               // 0..7, the same for every fast group of the CTA
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (unsigned)sizeof(tile));
+        tma_load_box(&tile[0][0], &tmap, &bar, xs, ys, (int)f);
+    }
+
+    // ---- per-thread column constants (while the box is in flight) --------------------------------
+    const int lane = threadIdx.x & 31;
+    const int cx = 2 * (threadIdx.x >> 5) + (lane & 1), ry = lane >> 1;
+    const int x0 = x0t + 8 * cx;
+    const int isplit = (8 - xoff) & 7;  // first pixel of run (b); 0: a single run
+    const float pxf = (float)x0 - dx, pxl = (float)(x0 + 7) - dx;
+    const int l0 = (int)pxf, l7 = (int)pxl;
+    const float u0 = pxf - (float)l0, u7 = pxl - (float)l7;
+    bool xfast = (x0 + 8 <= w) && !(pxf < 0) && (pxl < fw) && (l0 == x0 + sx) && (l7 == l0 + 7) && ((int)(pxl + 1.0f) == l7 + 1);
+    if (isplit == 0) {
+        xfast = xfast && (u0 == u7);
+    } else {  // the two pixels either side of the only place where the grid of px may change
+        const float pxa = (float)(x0 + isplit - 1) - dx, pxb = (float)(x0 + isplit) - dx;
+        const int la = l0 + isplit - 1;
+        xfast = xfast && (pxa - (float)la == u0) && (pxb - (float)(la + 1) == u7) && ((int)(pxa + 1.0f) == la + 1);
+    }
+    const bool clamp_rt = (l0 + 8 == w);
+    const HWeights ca = make_hweights(u0), cb = make_hweights(u7);
+    const u16* frame = src + f * src_stride;
+    u16* oframe = dst + f * dst_stride;
+
+    mbar_wait(&bar, 0);
+
+#pragma unroll 1
+    for (int k = 0; k < TT_H / 16; ++k) {
+        const int y = y0t + ry + 16 * k;
+        if (y >= h || x0 >= w) continue;
+        u16* orow = oframe + (size_t)y * w + x0;
+        const float py = (float)y - dy;
+        const int t = (int)py;
+        int b = (int)(py + 1.0f);
+        if (b == h) b = t;
+        const float vf = (float)b - py;
+        const float vs = vf * 8388608.0f;
+        const int tr = t - ys, br = b - ys;
+        const bool fast = xfast && !(py < 0) && (py < fh) && (vs == truncf(vs)) && (fabsf(vf) <= 1.0f) && (tr >= 0) && (br >= tr) &&
+                          (br < TT_BH);
+        if (fast) {
+            // b == t (bottom row clamped, v = -frac): both rows are the same pixel, N = p * 2^23
+            const unsigned B = (br == tr) ? 0u : (unsigned)(int)vs;
+            const unsigned A = 8388608u - B;
+            const uint4* rowb = reinterpret_cast<const uint4*>(&tile[br][8 * cx]);
+            const uint4* rowt = reinterpret_cast<const uint4*>(&tile[tr][8 * cx]);
+            switch (xoff) {  // CTA-uniform
+            case 0: blend_group<0, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
+            case 1: blend_group<1, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
+            case 2: blend_group<2, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
+            case 3: blend_group<3, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
+            case 4: blend_group<4, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
+            case 5: blend_group<5, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
+            case 6: blend_group<6, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
+            default: blend_group<7, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+                if (x0 + i < w) {
+                    if (MOTION) {
+                        float r;
+                        if (translate_pixel<u16, float>(frame, w, h, x0 + i, y, dx, dy, strategy, (float)background, r))
+                            orow[i] = (u16)r;
+                    } else {
+                        u16 r;
+                        if (translate_pixel<u16, u16>(frame, w, h, x0 + i, y, dx, dy, strategy, (u16)background, r)) orow[i] = r;
+                    }
+                }
+            }
+        }
+    }
+}
+
 int launch_translate_u16(const u16* src, u16* dst, int w, int h, long long nframes, size_t src_stride, size_t dst_stride,
                          const float* dxs, const float* dys, float dx0, float dy0, int strategy, unsigned background, bool motion,
                          cudaStream_t st)
 {
     if (nframes <= 0 || w <= 0 || h <= 0) return 0;
+    static const bool tma_enabled = []() {  // RIRB_TRANSLATE_TMA=0 selects the plain kernel (A/B measurements)
+        const char* e = getenv("RIRB_TRANSLATE_TMA");
+        return !(e && e[0] == '0');
+    }();
+    const int tiles_x = (int)ceil_div(w, TT_W), tiles_y = (int)ceil_div(h, TT_H);
+    const long long tgrid = nframes * tiles_x * tiles_y;
+    if (tma_enabled && (w % 8 == 0) && aligned16(dst) && (dst_stride % 8 == 0) &&
+        tma_compatible(src, (size_t)w * 2, src_stride * 2) && nframes <= 0x7FFFFFFFLL && tgrid <= 0x7FFFFFFFLL) {
+        CUtensorMap tmap;
+        if (make_movie_tensor_map(&tmap, src, 2, w, h, nframes, (size_t)w * 2, src_stride * 2, TT_BW, TT_BH) != 0) return -1;
+        if (motion)
+            RIRB_LAUNCH(translate_u16_tma_kernel<true>, (unsigned)tgrid, TT_THREADS, 0, st, tmap, src, dst, w, h, src_stride,
+                        dst_stride, dxs, dys, dx0, dy0, strategy, background, tiles_x, tiles_y);
+        else
+            RIRB_LAUNCH(translate_u16_tma_kernel<false>, (unsigned)tgrid, TT_THREADS, 0, st, tmap, src, dst, w, h, src_stride,
+                        dst_stride, dxs, dys, dx0, dy0, strategy, background, tiles_x, tiles_y);
+        return 0;
+    }
     dim3 block(32, 8);
     dim3 grid((unsigned)ceil_div(ceil_div(w, TR_PX), 32), (unsigned)ceil_div(h, 8), (unsigned)min(nframes, 32768LL));
     if (motion)
