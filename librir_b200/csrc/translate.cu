@@ -10,7 +10,7 @@
 //
 // Three kernels:
 //   translate_generic_kernel<T,U>  every dtype / strategy, one thread per destination pixel.
-//   translate_u16_tma_kernel       the uint16 hot path: the source window of a 128x32 destination
+//   translate_u16_tma_kernel       the uint16 hot path: the source window of a 128x128 destination
 //                                  tile is fetched by ONE TMA box load at the per-frame position
 //                                  (x0 + floor(-dx), y0 + floor(-dy)); a thread turns 8
 //                                  pixels of a row with two 128-bit shared-memory reads, the
@@ -54,10 +54,17 @@ __device__ __forceinline__ double blend4(double p1, double p2, double p3, double
     return __dadd_rn(__dmul_rn(left, omu), __dmul_rn(right, u));
 }
 
+// Source accessors: where translate_pixel reads src[row][col] from.
+template <typename T> struct GlobalSrc {
+    const T* __restrict__ p;
+    int w;
+    __device__ __forceinline__ T operator()(long long row, long long col) const { return p[row * w + col]; }
+};
+
 // One destination pixel, any strategy.  Returns false when dst must be left untouched.
-template <typename T, typename U>
-__device__ __forceinline__ bool translate_pixel(const T* __restrict__ src, int w, int h, int x, int y, float dx, float dy,
-                                                int strategy, U background, U& result)
+template <typename T, typename U, typename SRC>
+__device__ __forceinline__ bool translate_pixel(const SRC& src, int w, int h, int x, int y, float dx, float dy, int strategy,
+                                                U background, U& result)
 {
     const float px = (float)x - dx;
     const float py = (float)y - dy;
@@ -74,7 +81,7 @@ __device__ __forceinline__ bool translate_pixel(const T* __restrict__ src, int w
             long long sx = px < 0 ? 0 : (px >= fw ? w - 1 : (long long)px);
             long long sy = py < 0 ? 0 : (py >= fh ? h - 1 : (long long)py);
             // plain conversion T -> U (identity for the facade; u16 -> float in the motion variant)
-            result = Pix<U>::from_double(Pix<T>::to_double(src[sy * w + sx]));
+            result = Pix<U>::from_double(Pix<T>::to_double(src(sy, sx)));
             return true;
         }
         l = (long long)wrap_idx(f2size(px), (unsigned long long)w);
@@ -93,12 +100,18 @@ __device__ __forceinline__ bool translate_pixel(const T* __restrict__ src, int w
         u = (double)(px - (float)l);
         v = (double)((float)b - py);
     }
-    const double p1 = Pix<T>::to_double(src[b * w + l]);
-    const double p2 = Pix<T>::to_double(src[t * w + l]);
-    const double p3 = Pix<T>::to_double(src[b * w + rt]);
-    const double p4 = Pix<T>::to_double(src[t * w + rt]);
+    const double p1 = Pix<T>::to_double(src(b, l));
+    const double p2 = Pix<T>::to_double(src(t, l));
+    const double p3 = Pix<T>::to_double(src(b, rt));
+    const double p4 = Pix<T>::to_double(src(t, rt));
     result = Pix<U>::from_double(blend4(p1, p2, p3, p4, u, v));
     return true;
+}
+template <typename T, typename U>
+__device__ __forceinline__ bool translate_pixel(const T* __restrict__ src, int w, int h, int x, int y, float dx, float dy,
+                                                int strategy, U background, U& result)
+{
+    return translate_pixel<T, U>(GlobalSrc<T>{src, w}, w, h, x, y, dx, dy, strategy, background, result);
 }
 
 template <typename T>
@@ -282,7 +295,7 @@ translate_u16_kernel(const u16* __restrict__ src, u16* __restrict__ dst, int w, 
 // Warp shape: 2 column groups x 16 rows, so that the slow groups (image edges, source columns < 8)
 // are confined to the warps that own the edge columns instead of costing every warp of an edge tile
 // a divergent detour.  Row pitch 288 B keeps the 128-bit reads of 4 rows x 2 groups conflict-free.
-constexpr int TT_W = 128, TT_H = 32;
+constexpr int TT_W = 128, TT_H = 128;
 constexpr int TT_BW = TT_W + 16, TT_BH = TT_H + 2;  // box: thread c reads columns [8c, 8c+16); +2 rows
 constexpr int TT_THREADS = 256;
 
@@ -348,19 +361,74 @@ __device__ __forceinline__ void blend_group(const uint4* rowb, const uint4* rowt
     st_stream(reinterpret_cast<uint4*>(orow), ov);
 }
 
+// Staged box first, global memory for the few source pixels outside it (clamped / wrapped borders).
+struct TileSrc {
+    const u16* tile;  // [TT_BH][TT_BW], box origin (xs, ys)
+    const u16* __restrict__ frame;
+    int xs, ys, w;
+    __device__ __forceinline__ u16 operator()(long long row, long long col) const
+    {
+        const long long r = row - ys, c = col - xs;
+        if (r >= 0 && r < TT_BH && c >= 0 && c < TT_BW) return tile[r * TT_BW + c];
+        return frame[row * w + col];
+    }
+};
+
+// Per-row parameters, computed once per CTA (one thread per destination row, while the box is in
+// flight) instead of by each of the 16 threads that share the row.
+struct RowInfo {
+    int B;       // v * 2^23 (0 when the bottom row is clamped onto the top row); < 0: the row is slow
+    int rows;    // tr | br << 16, box rows of the top / bottom source row
+};
+__device__ __forceinline__ RowInfo make_row_info(int y, int h, float dy, int ys)
+{
+    RowInfo ri;
+    ri.B = -1;
+    ri.rows = 0;
+    const float fh = (float)h;
+    const float py = (float)y - dy;
+    const int t = (int)py;
+    int b = (int)(py + 1.0f);
+    if (b == h) b = t;
+    const float vf = (float)b - py;
+    const float vs = vf * 8388608.0f;  // v on the 2^-23 grid -> the vertical blend is exact in 64-bit integers
+    const int tr = t - ys, br = b - ys;
+    if (y < h && !(py < 0) && (py < fh) && (vs == truncf(vs)) && (fabsf(vf) <= 1.0f) && (tr >= 0) && (br >= tr) && (br < TT_BH)) {
+        ri.B = (br == tr) ? 0 : (int)vs;  // b == t (v = -frac): both rows are the same pixel, N = p * 2^23
+        ri.rows = tr | (br << 16);
+    }
+    return ri;
+}
+
+template <int XOFF, bool MOTION>
+__device__ __forceinline__ void fast_rows(const u16 (*tile)[TT_BW], const RowInfo* rowinfo, int cx, int ry, bool xfast, bool clamp_rt,
+                                          const HWeights& ca, const HWeights& cb, u16* ocol, int w, unsigned& slow_rows)
+{
+#pragma unroll 1
+    for (int k = 0; k < TT_H / 16; ++k) {
+        const RowInfo ri = rowinfo[ry + 16 * k];
+        if (xfast && ri.B >= 0) {
+            const unsigned B = (unsigned)ri.B, A = 8388608u - B;
+            const uint4* rowt = reinterpret_cast<const uint4*>(&tile[ri.rows & 0xFFFF][8 * cx]);
+            const uint4* rowb = reinterpret_cast<const uint4*>(&tile[ri.rows >> 16][8 * cx]);
+            blend_group<XOFF, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, ocol + (size_t)(16 * k) * w);
+        } else {
+            slow_rows |= 1u << k;
+        }
+    }
+}
+
 template <bool MOTION>
 __global__ void __launch_bounds__(TT_THREADS)
 translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __restrict__ src, u16* __restrict__ dst, int w, int h,
                          size_t src_stride, size_t dst_stride, const float* __restrict__ dxs, const float* __restrict__ dys,
-                         float dx0, float dy0, int strategy, unsigned background, int tiles_x, int tiles_y)
+                         float dx0, float dy0, int strategy, unsigned background)
 {
     __shared__ __align__(128) u16 tile[TT_BH][TT_BW];
     __shared__ __align__(8) unsigned long long bar;
-    const int tiles = tiles_x * tiles_y;
-    const long long f = blockIdx.x / tiles;
-    const int tile_id = (int)(blockIdx.x - f * tiles);
-    const int ty = tile_id / tiles_x, tx = tile_id - ty * tiles_x;
-    const int x0t = tx * TT_W, y0t = ty * TT_H;
+    __shared__ RowInfo rowinfo[TT_H];
+    const int f = blockIdx.z;
+    const int x0t = blockIdx.x * TT_W, y0t = blockIdx.y * TT_H;
     const float dx = dxs ? dxs[f] : dx0;
     const float dy = dys ? dys[f] : dy0;
     const float fw = (float)w, fh = (float)h;
@@ -374,15 +442,16 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
         mbar_init(&bar, 1);
         mbar_fence_init();
     }
+    if (threadIdx.x < TT_H) rowinfo[threadIdx.x] = make_row_info(y0t + threadIdx.x, h, dy, ys);
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bar, (unsigned)sizeof(tile));
-        tma_load_box(&tile[0][0], &tmap, &bar, xs, ys, (int)f);
+        tma_load_box(&tile[0][0], &tmap, &bar, xs, ys, f);
     }
 
     // ---- per-thread column constants (while the box is in flight) --------------------------------
-    const int lane = threadIdx.x & 31;
-    const int cx = 2 * (threadIdx.x >> 5) + (lane & 1), ry = lane >> 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cx = 2 * warp + (lane & 1), ry = lane >> 1;
     const int x0 = x0t + 8 * cx;
     const int isplit = (8 - xoff) & 7;  // first pixel of run (b); 0: a single run
     const float pxf = (float)x0 - dx, pxl = (float)(x0 + 7) - dx;
@@ -398,55 +467,52 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
     }
     const bool clamp_rt = (l0 + 8 == w);
     const HWeights ca = make_hweights(u0), cb = make_hweights(u7);
-    const u16* frame = src + f * src_stride;
-    u16* oframe = dst + f * dst_stride;
+    const u16* frame = src + (size_t)f * src_stride;
+    u16* oframe = dst + (size_t)f * dst_stride;
+    u16* ocol = oframe + (size_t)(y0t + ry) * w + x0;
 
     mbar_wait(&bar, 0);
 
+    unsigned slow_rows = 0;  // bit k: this thread's group of row ry + 16k is not done yet
+    switch (xoff) {          // CTA-uniform
+    case 0: fast_rows<0, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
+    case 1: fast_rows<1, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
+    case 2: fast_rows<2, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
+    case 3: fast_rows<3, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
+    case 4: fast_rows<4, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
+    case 5: fast_rows<5, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
+    case 6: fast_rows<6, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
+    default: fast_rows<7, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
+    }
+
+    // ---- slow groups (image edges, source columns < 8, rows with 0 <= py < 1): the warp does them
+    // together, one PIXEL per lane, 4 groups at a time, reading the staged box where it can --
+    // instead of 1-2 lanes walking 8 pixels each through dependent global loads.
+    if (x0 >= w) slow_rows = 0;
 #pragma unroll 1
     for (int k = 0; k < TT_H / 16; ++k) {
-        const int y = y0t + ry + 16 * k;
-        if (y >= h || x0 >= w) continue;
-        u16* orow = oframe + (size_t)y * w + x0;
-        const float py = (float)y - dy;
-        const int t = (int)py;
-        int b = (int)(py + 1.0f);
-        if (b == h) b = t;
-        const float vf = (float)b - py;
-        const float vs = vf * 8388608.0f;
-        const int tr = t - ys, br = b - ys;
-        const bool fast = xfast && !(py < 0) && (py < fh) && (vs == truncf(vs)) && (fabsf(vf) <= 1.0f) && (tr >= 0) && (br >= tr) &&
-                          (br < TT_BH);
-        if (fast) {
-            // b == t (bottom row clamped, v = -frac): both rows are the same pixel, N = p * 2^23
-            const unsigned B = (br == tr) ? 0u : (unsigned)(int)vs;
-            const unsigned A = 8388608u - B;
-            const uint4* rowb = reinterpret_cast<const uint4*>(&tile[br][8 * cx]);
-            const uint4* rowt = reinterpret_cast<const uint4*>(&tile[tr][8 * cx]);
-            switch (xoff) {  // CTA-uniform
-            case 0: blend_group<0, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
-            case 1: blend_group<1, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
-            case 2: blend_group<2, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
-            case 3: blend_group<3, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
-            case 4: blend_group<4, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
-            case 5: blend_group<5, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
-            case 6: blend_group<6, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
-            default: blend_group<7, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, orow); break;
-            }
-        } else {
-#pragma unroll 1
-            for (int i = 0; i < 8; ++i) {
-                if (x0 + i < w) {
+        unsigned pending = __ballot_sync(0xFFFFFFFFu, ((slow_rows >> k) & 1u) && (y0t + ry + 16 * k < h));
+        while (pending) {  // warp-uniform
+            unsigned m = pending;
+            for (int q = 0; q < (lane >> 3); ++q) m &= m - 1;  // drop the groups taken by lanes below
+            if (m) {
+                const int sl = __ffs(m) - 1;  // lane that owns the group
+                const int gx = x0t + 8 * (2 * warp + (sl & 1)) + (lane & 7);
+                const int gy = y0t + (sl >> 1) + 16 * k;
+                if (gx < w) {
+                    const TileSrc ts{&tile[0][0], frame, xs, ys, w};
+                    u16* o = oframe + (size_t)gy * w + gx;
                     if (MOTION) {
                         float r;
-                        if (translate_pixel<u16, float>(frame, w, h, x0 + i, y, dx, dy, strategy, (float)background, r))
-                            orow[i] = (u16)r;
+                        if (translate_pixel<u16, float>(ts, w, h, gx, gy, dx, dy, strategy, (float)background, r)) *o = (u16)r;
                     } else {
                         u16 r;
-                        if (translate_pixel<u16, u16>(frame, w, h, x0 + i, y, dx, dy, strategy, (u16)background, r)) orow[i] = r;
+                        if (translate_pixel<u16, u16>(ts, w, h, gx, gy, dx, dy, strategy, (u16)background, r)) *o = r;
                     }
                 }
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pending &= pending - 1;
         }
     }
 }
@@ -461,17 +527,25 @@ int launch_translate_u16(const u16* src, u16* dst, int w, int h, long long nfram
         return !(e && e[0] == '0');
     }();
     const int tiles_x = (int)ceil_div(w, TT_W), tiles_y = (int)ceil_div(h, TT_H);
-    const long long tgrid = nframes * tiles_x * tiles_y;
-    if (tma_enabled && (w % 8 == 0) && aligned16(dst) && (dst_stride % 8 == 0) &&
-        tma_compatible(src, (size_t)w * 2, src_stride * 2) && nframes <= 0x7FFFFFFFLL && tgrid <= 0x7FFFFFFFLL) {
-        CUtensorMap tmap;
-        if (make_movie_tensor_map(&tmap, src, 2, w, h, nframes, (size_t)w * 2, src_stride * 2, TT_BW, TT_BH) != 0) return -1;
-        if (motion)
-            RIRB_LAUNCH(translate_u16_tma_kernel<true>, (unsigned)tgrid, TT_THREADS, 0, st, tmap, src, dst, w, h, src_stride,
-                        dst_stride, dxs, dys, dx0, dy0, strategy, background, tiles_x, tiles_y);
-        else
-            RIRB_LAUNCH(translate_u16_tma_kernel<false>, (unsigned)tgrid, TT_THREADS, 0, st, tmap, src, dst, w, h, src_stride,
-                        dst_stride, dxs, dys, dx0, dy0, strategy, background, tiles_x, tiles_y);
+    if (tma_enabled && (w % 8 == 0) && aligned16(dst) && (dst_stride % 8 == 0) && tma_compatible(src, (size_t)w * 2, src_stride * 2) &&
+        tiles_y <= 65535) {
+        // grid = (tile column, tile row, frame); gridDim.z <= 65535, so long movies go in several launches
+        for (long long f0 = 0; f0 < nframes; f0 += 65535) {
+            const long long n = min(nframes - f0, 65535LL);
+            const u16* s0 = src + f0 * src_stride;
+            u16* d0 = dst + f0 * dst_stride;
+            const float* dx_p = dxs ? dxs + f0 : nullptr;
+            const float* dy_p = dys ? dys + f0 : nullptr;
+            CUtensorMap tmap;
+            if (make_movie_tensor_map(&tmap, s0, 2, w, h, n, (size_t)w * 2, src_stride * 2, TT_BW, TT_BH) != 0) return -1;
+            const dim3 tgrid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)n);
+            if (motion)
+                RIRB_LAUNCH(translate_u16_tma_kernel<true>, tgrid, TT_THREADS, 0, st, tmap, s0, d0, w, h, src_stride, dst_stride,
+                            dx_p, dy_p, dx0, dy0, strategy, background);
+            else
+                RIRB_LAUNCH(translate_u16_tma_kernel<false>, tgrid, TT_THREADS, 0, st, tmap, s0, d0, w, h, src_stride, dst_stride,
+                            dx_p, dy_p, dx0, dy0, strategy, background);
+        }
         return 0;
     }
     dim3 block(32, 8);
