@@ -309,6 +309,8 @@ __device__ __forceinline__ HWeights make_hweights(float uf)
     c.omu = __dsub_rn(1.0, c.u);
     c.k_l = __dmul_rn(-536870912.0, c.omu);
     c.k_r = __dmul_rn(-536870912.0, c.u);
+    // keep them in registers: ptxas otherwise re-derives them with two DMULs per row
+    asm volatile("" : "+d"(c.k_l), "+d"(c.k_r));
     return c;
 }
 
@@ -325,13 +327,21 @@ __device__ __forceinline__ void unpack9(const uint4& a, const uint4& b, unsigned
 }
 
 // One fast group: 8 destination pixels from the two staged source rows.
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+// rowb / rowt: shared-memory byte addresses of the thread's 16 staged pixels in the bottom / top row
 template <int XOFF, bool MOTION>
-__device__ __forceinline__ void blend_group(const uint4* rowb, const uint4* rowt, unsigned A, unsigned B, bool clamp_rt,
-                                            const HWeights& ca, const HWeights& cb, u16* orow)
+__device__ __forceinline__ void blend_group(uint32_t rowb, uint32_t rowt, unsigned A, unsigned B, bool clamp_rt,
+                                            const HWeights& ca, const HWeights& cb, unsigned long long magic, u16* orow)
 {
     unsigned pb[9], pt[9];
-    unpack9<XOFF>(rowb[0], rowb[1], pb);
-    unpack9<XOFF>(rowt[0], rowt[1], pt);
+    unpack9<XOFF>(lds128(rowb), lds128(rowb + 16), pb);
+    unpack9<XOFF>(lds128(rowt), lds128(rowt + 16), pt);
     if (clamp_rt) {  // rt of the last pixel clamps to its l (Filters.h:309)
         pb[8] = pb[7];
         pt[8] = pt[7];
@@ -339,7 +349,7 @@ __device__ __forceinline__ void blend_group(const uint4* rowb, const uint4* rowt
     double m[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) {  // bits(2^29) + N: the double 2^29 + N * 2^-23, N = p_b*A + p_t*B < 2^40 (two IMAD.WIDE.U32)
-        unsigned long long n = (unsigned long long)pb[j] * A + 0x41C0000000000000ULL;
+        unsigned long long n = (unsigned long long)pb[j] * A + magic;  // magic = bits(2^29), a register pair: one IMAD.WIDE
         n += (unsigned long long)pt[j] * B;
         m[j] = __longlong_as_double((long long)n);
     }
@@ -378,7 +388,7 @@ struct TileSrc {
 // flight) instead of by each of the 16 threads that share the row.
 struct RowInfo {
     int B;       // v * 2^23 (0 when the bottom row is clamped onto the top row); < 0: the row is slow
-    int rows;    // tr | br << 16, box rows of the top / bottom source row
+    unsigned rows;  // byte offsets in the staged box of the top (low half) / bottom (high half) source row
 };
 __device__ __forceinline__ RowInfo make_row_info(int y, int h, float dy, int ys)
 {
@@ -395,40 +405,57 @@ __device__ __forceinline__ RowInfo make_row_info(int y, int h, float dy, int ys)
     const int tr = t - ys, br = b - ys;
     if (y < h && !(py < 0) && (py < fh) && (vs == truncf(vs)) && (fabsf(vf) <= 1.0f) && (tr >= 0) && (br >= tr) && (br < TT_BH)) {
         ri.B = (br == tr) ? 0 : (int)vs;  // b == t (v = -frac): both rows are the same pixel, N = p * 2^23
-        ri.rows = tr | (br << 16);
+        ri.rows = (unsigned)(tr * (TT_BW * 2)) | ((unsigned)(br * (TT_BW * 2)) << 16);
     }
     return ri;
 }
 
+static_assert(TT_BH * TT_BW * 2 <= 65536, "row byte offsets are packed in 16 bits");
+
+// tbase: shared address of the thread's column slot in box row 0; rinfo: shared address of rowinfo[ry].
+// Groups that cannot take the fast path are appended to the CTA's queue as cx | row << 4.
 template <int XOFF, bool MOTION>
-__device__ __forceinline__ void fast_rows(const u16 (*tile)[TT_BW], const RowInfo* rowinfo, int cx, int ry, bool xfast, bool clamp_rt,
-                                          const HWeights& ca, const HWeights& cb, u16* ocol, int w, unsigned& slow_rows)
+__device__ __forceinline__ void fast_rows(uint32_t tbase, uint32_t rinfo, bool xfast, bool clamp_rt, const HWeights& ca,
+                                          const HWeights& cb, u16* ocol, size_t row_step, int cx, int ry, int rows_left,
+                                          unsigned short* slowq, unsigned* slow_count)
 {
+    unsigned long long magic = 0x41C0000000000000ULL;
+    asm volatile("" : "+l"(magic));  // opaque: otherwise ptxas ORs the constant into every column's high word
 #pragma unroll 1
     for (int k = 0; k < TT_H / 16; ++k) {
-        const RowInfo ri = rowinfo[ry + 16 * k];
-        if (xfast && ri.B >= 0) {
-            const unsigned B = (unsigned)ri.B, A = 8388608u - B;
-            const uint4* rowt = reinterpret_cast<const uint4*>(&tile[ri.rows & 0xFFFF][8 * cx]);
-            const uint4* rowb = reinterpret_cast<const uint4*>(&tile[ri.rows >> 16][8 * cx]);
-            blend_group<XOFF, MOTION>(rowb, rowt, A, B, clamp_rt, ca, cb, ocol + (size_t)(16 * k) * w);
-        } else {
-            slow_rows |= 1u << k;
-        }
+        int B;
+        unsigned rows;
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(B), "=r"(rows) : "r"(rinfo + k * (16 * (int)sizeof(RowInfo))));
+        if (xfast && B >= 0)
+            blend_group<XOFF, MOTION>(tbase + (rows >> 16), tbase + (rows & 0xFFFFu), 8388608u - (unsigned)B, (unsigned)B, clamp_rt, ca,
+                                      cb, magic, ocol);
+        else if (ry + 16 * k < rows_left)
+            slowq[atomicAdd(slow_count, 1u)] = (unsigned short)(cx | ((ry + 16 * k) << 4));
+        ocol += row_step;
     }
 }
 
+// A CTA owns one 128-pixel column of tiles of one frame and walks down it: the horizontal weights
+// depend on (dx, x) only and are computed once; the box of tile ty+1 is in flight (second shared
+// memory stage, its own mbarrier) while tile ty is being blended.
+constexpr int TT_STAGES = 2;
+constexpr unsigned TT_STAGE_BYTES = (TT_BH * TT_BW * 2 + 127u) & ~127u;
+
 template <bool MOTION>
-__global__ void __launch_bounds__(TT_THREADS)
+__global__ void __launch_bounds__(TT_THREADS, 3)
 translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __restrict__ src, u16* __restrict__ dst, int w, int h,
                          size_t src_stride, size_t dst_stride, const float* __restrict__ dxs, const float* __restrict__ dys,
-                         float dx0, float dy0, int strategy, unsigned background)
+                         float dx0, float dy0, int strategy, unsigned background, int tiles_y)
 {
-    __shared__ __align__(128) u16 tile[TT_BH][TT_BW];
-    __shared__ __align__(8) unsigned long long bar;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar[TT_STAGES];
     __shared__ RowInfo rowinfo[TT_H];
-    const int f = blockIdx.z;
-    const int x0t = blockIdx.x * TT_W, y0t = blockIdx.y * TT_H;
+    __shared__ unsigned short slowq[(TT_W / 8) * TT_H];
+    __shared__ unsigned slow_count;
+    constexpr unsigned TILE_BYTES = TT_BH * TT_BW * 2;
+    constexpr unsigned STAGE_BYTES = TT_STAGE_BYTES;  // TMA destinations are 128-byte aligned
+    const int f = blockIdx.y;
+    const int x0t = blockIdx.x * TT_W;
     const float dx = dxs ? dxs[f] : dx0;
     const float dy = dys ? dys[f] : dy0;
     const float fw = (float)w, fh = (float)h;
@@ -436,20 +463,24 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
     // (a clamped value simply never matches l0, and the group takes the per-pixel routine)
     const int sx = (int)fminf(fmaxf(floorf(-dx), -fw - 16.f), fw + 16.f);
     const int sy = (int)fminf(fmaxf(floorf(-dy), -fh - 16.f), fh + 16.f);
-    const int xs = (x0t + sx) & ~7, ys = y0t + sy;  // box origin: 16-byte aligned column
-    const int xoff = (x0t + sx) - xs;               // 0..7, the same for every fast group of the CTA
+    const int xs = (x0t + sx) & ~7;      // box origin: 16-byte aligned column
+    const int xoff = (x0t + sx) - xs;    // 0..7, the same for every fast group of the CTA
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+#pragma unroll
+        for (int s = 0; s < TT_STAGES; ++s) mbar_init(&bar[s], 1);
         mbar_fence_init();
     }
-    if (threadIdx.x < TT_H) rowinfo[threadIdx.x] = make_row_info(y0t + threadIdx.x, h, dy, ys);
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar, (unsigned)sizeof(tile));
-        tma_load_box(&tile[0][0], &tmap, &bar, xs, ys, f);
+#pragma unroll
+        for (int s = 0; s < TT_STAGES; ++s)
+            if (s < tiles_y) {
+                mbar_expect_tx(&bar[s], TILE_BYTES);
+                tma_load_box(smem_raw + s * STAGE_BYTES, &tmap, &bar[s], xs, s * TT_H + sy, f);
+            }
     }
 
-    // ---- per-thread column constants (while the box is in flight) --------------------------------
+    // ---- per-thread column constants (while the first boxes are in flight) -----------------------
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cx = 2 * warp + (lane & 1), ry = lane >> 1;
     const int x0 = x0t + 8 * cx;
@@ -469,50 +500,60 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
     const HWeights ca = make_hweights(u0), cb = make_hweights(u7);
     const u16* frame = src + (size_t)f * src_stride;
     u16* oframe = dst + (size_t)f * dst_stride;
-    u16* ocol = oframe + (size_t)(y0t + ry) * w + x0;
+    const uint32_t rinfo = smem_addr(&rowinfo[ry]);
+    const size_t row_step = (size_t)16 * w;
 
-    mbar_wait(&bar, 0);
-
-    unsigned slow_rows = 0;  // bit k: this thread's group of row ry + 16k is not done yet
-    switch (xoff) {          // CTA-uniform
-    case 0: fast_rows<0, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
-    case 1: fast_rows<1, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
-    case 2: fast_rows<2, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
-    case 3: fast_rows<3, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
-    case 4: fast_rows<4, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
-    case 5: fast_rows<5, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
-    case 6: fast_rows<6, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
-    default: fast_rows<7, MOTION>(tile, rowinfo, cx, ry, xfast, clamp_rt, ca, cb, ocol, w, slow_rows); break;
-    }
-
-    // ---- slow groups (image edges, source columns < 8, rows with 0 <= py < 1): the warp does them
-    // together, one PIXEL per lane, 4 groups at a time, reading the staged box where it can --
-    // instead of 1-2 lanes walking 8 pixels each through dependent global loads.
-    if (x0 >= w) slow_rows = 0;
 #pragma unroll 1
-    for (int k = 0; k < TT_H / 16; ++k) {
-        unsigned pending = __ballot_sync(0xFFFFFFFFu, ((slow_rows >> k) & 1u) && (y0t + ry + 16 * k < h));
-        while (pending) {  // warp-uniform
-            unsigned m = pending;
-            for (int q = 0; q < (lane >> 3); ++q) m &= m - 1;  // drop the groups taken by lanes below
-            if (m) {
-                const int sl = __ffs(m) - 1;  // lane that owns the group
-                const int gx = x0t + 8 * (2 * warp + (sl & 1)) + (lane & 7);
-                const int gy = y0t + (sl >> 1) + 16 * k;
-                if (gx < w) {
-                    const TileSrc ts{&tile[0][0], frame, xs, ys, w};
-                    u16* o = oframe + (size_t)gy * w + gx;
-                    if (MOTION) {
-                        float r;
-                        if (translate_pixel<u16, float>(ts, w, h, gx, gy, dx, dy, strategy, (float)background, r)) *o = (u16)r;
-                    } else {
-                        u16 r;
-                        if (translate_pixel<u16, u16>(ts, w, h, gx, gy, dx, dy, strategy, (u16)background, r)) *o = r;
-                    }
+    for (int ty = 0; ty < tiles_y; ++ty) {
+        const int stage = ty % TT_STAGES;
+        const unsigned parity = (unsigned)(ty / TT_STAGES) & 1u;
+        const int y0t = ty * TT_H, ys = y0t + sy;
+        if (threadIdx.x < TT_H) rowinfo[threadIdx.x] = make_row_info(y0t + threadIdx.x, h, dy, ys);
+        if (threadIdx.x == 0) slow_count = 0;
+        __syncthreads();  // row parameters visible, queue empty
+        mbar_wait(&bar[stage], parity);
+        const u16* tile = reinterpret_cast<const u16*>(smem_raw + stage * STAGE_BYTES);
+        u16* ocol = oframe + (size_t)(y0t + ry) * w + x0;
+        const int rows_left = (x0 < w) ? h - y0t : 0;  // destination rows of this tile that exist (none for columns past the edge)
+
+        const uint32_t tbase = smem_addr(tile + 8 * cx);
+        switch (xoff) {  // CTA-uniform
+        case 0: fast_rows<0, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
+        case 1: fast_rows<1, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
+        case 2: fast_rows<2, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
+        case 3: fast_rows<3, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
+        case 4: fast_rows<4, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
+        case 5: fast_rows<5, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
+        case 6: fast_rows<6, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
+        default: fast_rows<7, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
+        }
+        __syncthreads();  // queue complete
+
+        // ---- slow groups (image edges, source columns < 8, rows with 0 <= py < 1), spread over the whole
+        // CTA one PIXEL per thread, reading the staged box where they can -- instead of the few threads
+        // that own them walking 8 pixels each through dependent loads while their CTA waits.
+        const int nslow = (int)slow_count * 8;
+#pragma unroll 1
+        for (int i = threadIdx.x; i < nslow; i += TT_THREADS) {
+            const unsigned g = slowq[i >> 3];
+            const int gx = x0t + 8 * (int)(g & 15u) + (i & 7);
+            const int gy = y0t + (int)(g >> 4);
+            if (gx < w) {
+                const TileSrc ts{tile, frame, xs, ys, w};
+                u16* o = oframe + (size_t)gy * w + gx;
+                if (MOTION) {
+                    float r;
+                    if (translate_pixel<u16, float>(ts, w, h, gx, gy, dx, dy, strategy, (float)background, r)) *o = (u16)r;
+                } else {
+                    u16 r;
+                    if (translate_pixel<u16, u16>(ts, w, h, gx, gy, dx, dy, strategy, (u16)background, r)) *o = r;
                 }
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) pending &= pending - 1;
+        }
+        __syncthreads();  // every warp is done with this stage (and with rowinfo)
+        if (threadIdx.x == 0 && ty + TT_STAGES < tiles_y) {
+            mbar_expect_tx(&bar[stage], TILE_BYTES);
+            tma_load_box(smem_raw + stage * STAGE_BYTES, &tmap, &bar[stage], xs, (ty + TT_STAGES) * TT_H + sy, f);
         }
     }
 }
@@ -527,9 +568,15 @@ int launch_translate_u16(const u16* src, u16* dst, int w, int h, long long nfram
         return !(e && e[0] == '0');
     }();
     const int tiles_x = (int)ceil_div(w, TT_W), tiles_y = (int)ceil_div(h, TT_H);
-    if (tma_enabled && (w % 8 == 0) && aligned16(dst) && (dst_stride % 8 == 0) && tma_compatible(src, (size_t)w * 2, src_stride * 2) &&
-        tiles_y <= 65535) {
-        // grid = (tile column, tile row, frame); gridDim.z <= 65535, so long movies go in several launches
+    if (tma_enabled && (w % 8 == 0) && aligned16(dst) && (dst_stride % 8 == 0) && tma_compatible(src, (size_t)w * 2, src_stride * 2)) {
+        const size_t smem = (size_t)TT_STAGES * TT_STAGE_BYTES;
+        static bool attr_set = false;
+        if (!attr_set) {
+            RIRB_CUDA_OK(cudaFuncSetAttribute(translate_u16_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RIRB_CUDA_OK(cudaFuncSetAttribute(translate_u16_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        // grid = (tile column, frame); gridDim.y <= 65535, so long movies go in several launches
         for (long long f0 = 0; f0 < nframes; f0 += 65535) {
             const long long n = min(nframes - f0, 65535LL);
             const u16* s0 = src + f0 * src_stride;
@@ -538,13 +585,13 @@ int launch_translate_u16(const u16* src, u16* dst, int w, int h, long long nfram
             const float* dy_p = dys ? dys + f0 : nullptr;
             CUtensorMap tmap;
             if (make_movie_tensor_map(&tmap, s0, 2, w, h, n, (size_t)w * 2, src_stride * 2, TT_BW, TT_BH) != 0) return -1;
-            const dim3 tgrid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)n);
+            const dim3 tgrid((unsigned)tiles_x, (unsigned)n);
             if (motion)
-                RIRB_LAUNCH(translate_u16_tma_kernel<true>, tgrid, TT_THREADS, 0, st, tmap, s0, d0, w, h, src_stride, dst_stride,
-                            dx_p, dy_p, dx0, dy0, strategy, background);
+                RIRB_LAUNCH(translate_u16_tma_kernel<true>, tgrid, TT_THREADS, smem, st, tmap, s0, d0, w, h, src_stride, dst_stride,
+                            dx_p, dy_p, dx0, dy0, strategy, background, tiles_y);
             else
-                RIRB_LAUNCH(translate_u16_tma_kernel<false>, tgrid, TT_THREADS, 0, st, tmap, s0, d0, w, h, src_stride, dst_stride,
-                            dx_p, dy_p, dx0, dy0, strategy, background);
+                RIRB_LAUNCH(translate_u16_tma_kernel<false>, tgrid, TT_THREADS, smem, st, tmap, s0, d0, w, h, src_stride, dst_stride,
+                            dx_p, dy_p, dx0, dy0, strategy, background, tiles_y);
         }
         return 0;
     }
