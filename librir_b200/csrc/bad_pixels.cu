@@ -105,17 +105,29 @@ bp_correct_kernel(const u16* __restrict__ in, u16* __restrict__ out, const int* 
     const u16* frame = in + f * frame_stride;
     u16* oframe = out + f * frame_stride;
     int done = s0;
+    const int a = span_off[span], b = span_off[span + 1];
+    U32x8 r[BP_UNROLL];
+    const int nvec = VEC ? (s1 - s0) >> 4 : 0;
     if (VEC) {
-        const unsigned c2 = clamp | (clamp << 16);
-        const int nvec = (s1 - s0) >> 4;
         const U32x8* g = reinterpret_cast<const U32x8*>(frame + s0);
-        U32x8* o = reinterpret_cast<U32x8*>(oframe + s0);
-        U32x8 r[BP_UNROLL];
 #pragma unroll
         for (int k = 0; k < BP_UNROLL; ++k) {
             const int j = threadIdx.x + k * BP_THREADS;
-            if (j < nvec) r[k] = ld_stream256(g + j);
+            if (j < nvec) r[k] = ld_stream256_keep(g + j);
         }
+    }
+    // first fix-up of this thread: its gather is issued while the stream loads are still in flight,
+    // so the neighbour rows are found in L2 (behind the same misses) instead of being re-read from HBM
+    const int i0 = a + (int)threadIdx.x;
+    int2 p0 = make_int2(0, 0);
+    unsigned med0 = 0;
+    if (i0 < b) {
+        p0 = reinterpret_cast<const int2*>(xy)[i0];
+        med0 = median3x3_global(frame, w, h, p0.x, p0.y);
+    }
+    if (VEC) {
+        const unsigned c2 = clamp | (clamp << 16);
+        U32x8* o = reinterpret_cast<U32x8*>(oframe + s0);
 #pragma unroll
         for (int k = 0; k < BP_UNROLL; ++k) {
             const int j = threadIdx.x + k * BP_THREADS;
@@ -128,10 +140,10 @@ bp_correct_kernel(const u16* __restrict__ in, u16* __restrict__ out, const int* 
         done = s0 + (nvec << 4);
     }
     for (int i = done + threadIdx.x; i < s1; i += BP_THREADS) oframe[i] = (u16)max((unsigned)frame[i], clamp);
-    const int a = span_off[span], b = span_off[span + 1];
     if (a == b) return;  // CTA-uniform
     __syncthreads();
-    for (int i = a + threadIdx.x; i < b; i += BP_THREADS) {
+    if (i0 < b) oframe[(size_t)p0.y * w + p0.x] = (u16)max(med0, clamp);
+    for (int i = i0 + BP_THREADS; i < b; i += BP_THREADS) {
         const int2 p = reinterpret_cast<const int2*>(xy)[i];
         oframe[(size_t)p.y * w + p.x] = (u16)max(median3x3_global(frame, w, h, p.x, p.y), clamp);
     }

@@ -92,8 +92,8 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v)
                  : "memory");
 }
 
-// sm_100 has 256-bit per-thread global accesses (LDG.E.256 / STG.E.256); ptxas only accepts
-// the .L2::evict_first hint on this width.  32-byte alignment required.
+// sm_100 has 256-bit per-thread global accesses (LDG.E.256 / STG.E.256).  32-byte alignment
+// required.  evict_first: the line is not needed again (pure streams).
 struct __align__(32) U32x8 {
     unsigned v[8];
 };
@@ -111,6 +111,17 @@ __device__ __forceinline__ void st_stream256(void* p, const U32x8& r)
     asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]),
                  "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
                  : "memory");
+}
+// same width, normal L2 eviction priority: for streams whose lines are touched again shortly after
+// (bad-pixel fix-ups gather the neighbours of flagged pixels from the rows their CTA just streamed)
+__device__ __forceinline__ U32x8 ld_stream256_keep(const void* p)
+{
+    U32x8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                   "=r"(r.v[7])
+                 : "l"(p));
+    return r;
 }
 static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 

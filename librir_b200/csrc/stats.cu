@@ -59,23 +59,32 @@ movie_stats_kernel(const u16* __restrict__ p, size_t n, const u8* __restrict__ m
     if (mask == nullptr && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
         const size_t nvec = n >> 3;
         const uint4* pv = reinterpret_cast<const uint4*>(p);
-        for (size_t i = tid; i < nvec; i += 2 * nthreads) {
-            uint4 a = ld_stream(pv + i);
-            const bool second = (i + nthreads) < nvec;
-            uint4 b = second ? ld_stream(pv + i + nthreads) : a;
-            unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        unsigned lo2 = 0xFFFFFFFFu, hi2 = 0u;  // packed per-halfword min / max
+        constexpr int U = 4;                   // 128-bit loads in flight per thread
+        for (size_t i = tid; i < nvec; i += U * nthreads) {
+            uint4 a[U];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (k >= 4 && !second) break;
-                const unsigned v0 = w[k] & 0xFFFFu, v1 = w[k] >> 16;
-                lo = min(lo, min(v0, v1));
-                hi = max(hi, max(v0, v1));
-                if (HIST) {
-                    count_px(v0, sh, hist);
-                    count_px(v1, sh, hist);
+            for (int q = 0; q < U; ++q) {
+                const size_t j = i + q * nthreads;
+                a[q] = (j < nvec) ? ld_stream(pv + j) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                if (i + q * nthreads >= nvec) break;
+                const unsigned w[4] = {a[q].x, a[q].y, a[q].z, a[q].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    lo2 = __vminu2(lo2, w[k]);
+                    hi2 = __vmaxu2(hi2, w[k]);
+                    if (HIST) {
+                        count_px(w[k] & 0xFFFFu, sh, hist);
+                        count_px(w[k] >> 16, sh, hist);
+                    }
                 }
             }
         }
+        lo = min(lo2 & 0xFFFFu, lo2 >> 16);
+        hi = max(hi2 & 0xFFFFu, hi2 >> 16);
         for (size_t i = (nvec << 3) + tid; i < n; i += nthreads) {  // tail
             const unsigned v = p[i];
             lo = min(lo, v);
