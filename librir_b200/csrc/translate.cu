@@ -295,7 +295,7 @@ translate_u16_kernel(const u16* __restrict__ src, u16* __restrict__ dst, int w, 
 // Warp shape: 2 column groups x 16 rows, so that the slow groups (image edges, source columns < 8)
 // are confined to the warps that own the edge columns instead of costing every warp of an edge tile
 // a divergent detour.  Row pitch 288 B keeps the 128-bit reads of 4 rows x 2 groups conflict-free.
-constexpr int TT_W = 128, TT_H = 128;
+constexpr int TT_W = 128, TT_H = 64;
 constexpr int TT_BW = TT_W + 16, TT_BH = TT_H + 2;  // box: thread c reads columns [8c, 8c+16); +2 rows
 constexpr int TT_THREADS = 256;
 
@@ -442,16 +442,16 @@ constexpr int TT_STAGES = 2;
 constexpr unsigned TT_STAGE_BYTES = (TT_BH * TT_BW * 2 + 127u) & ~127u;
 
 template <bool MOTION>
-__global__ void __launch_bounds__(TT_THREADS, 3)
+__global__ void __launch_bounds__(TT_THREADS, 4)
 translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __restrict__ src, u16* __restrict__ dst, int w, int h,
                          size_t src_stride, size_t dst_stride, const float* __restrict__ dxs, const float* __restrict__ dys,
                          float dx0, float dy0, int strategy, unsigned background, int tiles_y)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar[TT_STAGES];
-    __shared__ RowInfo rowinfo[TT_H];
+    __shared__ RowInfo rowinfo[2][TT_H];  // double-buffered with the queue counter: tile ty+1's are prepared
+    __shared__ unsigned slow_count[2];    // between the two barriers of tile ty
     __shared__ unsigned short slowq[(TT_W / 8) * TT_H];
-    __shared__ unsigned slow_count;
     constexpr unsigned TILE_BYTES = TT_BH * TT_BW * 2;
     constexpr unsigned STAGE_BYTES = TT_STAGE_BYTES;  // TMA destinations are 128-byte aligned
     const int f = blockIdx.y;
@@ -469,7 +469,9 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
 #pragma unroll
         for (int s = 0; s < TT_STAGES; ++s) mbar_init(&bar[s], 1);
         mbar_fence_init();
+        slow_count[0] = 0;
     }
+    if (threadIdx.x < TT_H) rowinfo[0][threadIdx.x] = make_row_info(threadIdx.x, h, dy, sy);
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -500,7 +502,7 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
     const HWeights ca = make_hweights(u0), cb = make_hweights(u7);
     const u16* frame = src + (size_t)f * src_stride;
     u16* oframe = dst + (size_t)f * dst_stride;
-    const uint32_t rinfo = smem_addr(&rowinfo[ry]);
+    const uint32_t rinfo = smem_addr(&rowinfo[0][ry]);
     const size_t row_step = (size_t)16 * w;
 
 #pragma unroll 1
@@ -508,9 +510,7 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
         const int stage = ty % TT_STAGES;
         const unsigned parity = (unsigned)(ty / TT_STAGES) & 1u;
         const int y0t = ty * TT_H, ys = y0t + sy;
-        if (threadIdx.x < TT_H) rowinfo[threadIdx.x] = make_row_info(y0t + threadIdx.x, h, dy, ys);
-        if (threadIdx.x == 0) slow_count = 0;
-        __syncthreads();  // row parameters visible, queue empty
+        const int pp = ty & 1;  // which rowinfo / queue counter this tile uses
         mbar_wait(&bar[stage], parity);
         const u16* tile = reinterpret_cast<const u16*>(smem_raw + stage * STAGE_BYTES);
         u16* ocol = oframe + (size_t)(y0t + ry) * w + x0;
@@ -518,21 +518,24 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
 
         const uint32_t tbase = smem_addr(tile + 8 * cx);
         switch (xoff) {  // CTA-uniform
-        case 0: fast_rows<0, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
-        case 1: fast_rows<1, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
-        case 2: fast_rows<2, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
-        case 3: fast_rows<3, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
-        case 4: fast_rows<4, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
-        case 5: fast_rows<5, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
-        case 6: fast_rows<6, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
-        default: fast_rows<7, MOTION>(tbase, rinfo, xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count); break;
+        case 0: fast_rows<0, MOTION>(tbase, rinfo + pp * (int)sizeof(rowinfo[0]), xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count[pp]); break;
+        case 1: fast_rows<1, MOTION>(tbase, rinfo + pp * (int)sizeof(rowinfo[0]), xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count[pp]); break;
+        case 2: fast_rows<2, MOTION>(tbase, rinfo + pp * (int)sizeof(rowinfo[0]), xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count[pp]); break;
+        case 3: fast_rows<3, MOTION>(tbase, rinfo + pp * (int)sizeof(rowinfo[0]), xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count[pp]); break;
+        case 4: fast_rows<4, MOTION>(tbase, rinfo + pp * (int)sizeof(rowinfo[0]), xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count[pp]); break;
+        case 5: fast_rows<5, MOTION>(tbase, rinfo + pp * (int)sizeof(rowinfo[0]), xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count[pp]); break;
+        case 6: fast_rows<6, MOTION>(tbase, rinfo + pp * (int)sizeof(rowinfo[0]), xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count[pp]); break;
+        default: fast_rows<7, MOTION>(tbase, rinfo + pp * (int)sizeof(rowinfo[0]), xfast, clamp_rt, ca, cb, ocol, row_step, cx, ry, rows_left, slowq, &slow_count[pp]); break;
         }
         __syncthreads();  // queue complete
+        // row parameters and an empty queue for the next tile (nobody reads that half before the barrier below)
+        if (threadIdx.x < TT_H) rowinfo[pp ^ 1][threadIdx.x] = make_row_info(y0t + TT_H + threadIdx.x, h, dy, ys + TT_H);
+        if (threadIdx.x == 0) slow_count[pp ^ 1] = 0;
 
         // ---- slow groups (image edges, source columns < 8, rows with 0 <= py < 1), spread over the whole
         // CTA one PIXEL per thread, reading the staged box where they can -- instead of the few threads
         // that own them walking 8 pixels each through dependent loads while their CTA waits.
-        const int nslow = (int)slow_count * 8;
+        const int nslow = (int)slow_count[pp] * 8;
 #pragma unroll 1
         for (int i = threadIdx.x; i < nslow; i += TT_THREADS) {
             const unsigned g = slowq[i >> 3];
@@ -550,7 +553,7 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
                 }
             }
         }
-        __syncthreads();  // every warp is done with this stage (and with rowinfo)
+        __syncthreads();  // every warp is done with this stage and the queue; next tile's row parameters are visible
         if (threadIdx.x == 0 && ty + TT_STAGES < tiles_y) {
             mbar_expect_tx(&bar[stage], TILE_BYTES);
             tma_load_box(smem_raw + stage * STAGE_BYTES, &tmap, &bar[stage], xs, (ty + TT_STAGES) * TT_H + sy, f);
