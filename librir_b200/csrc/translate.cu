@@ -421,7 +421,7 @@ __device__ __forceinline__ void fast_rows(uint32_t tbase, uint32_t rinfo, bool x
 {
     unsigned long long magic = 0x41C0000000000000ULL;
     asm volatile("" : "+l"(magic));  // opaque: otherwise ptxas ORs the constant into every column's high word
-#pragma unroll 1
+#pragma unroll 2
     for (int k = 0; k < TT_H / 16; ++k) {
         int B;
         unsigned rows;
@@ -442,7 +442,7 @@ constexpr int TT_STAGES = 2;
 constexpr unsigned TT_STAGE_BYTES = (TT_BH * TT_BW * 2 + 127u) & ~127u;
 
 template <bool MOTION>
-__global__ void __launch_bounds__(TT_THREADS, 4)
+__global__ void __launch_bounds__(TT_THREADS, 3)
 translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __restrict__ src, u16* __restrict__ dst, int w, int h,
                          size_t src_stride, size_t dst_stride, const float* __restrict__ dxs, const float* __restrict__ dys,
                          float dx0, float dy0, int strategy, unsigned background, int tiles_y)

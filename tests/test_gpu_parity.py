@@ -105,6 +105,33 @@ def test_translate_u16_odd_shapes(best, shape):
             np.testing.assert_array_equal(sp.translate(f, dx, dy, st, 9), best.translate(f, dx, dy, st, 9))
 
 
+@pytest.mark.parametrize("shape", [(8, 8), (1, 8), (3, 16), (64, 128), (65, 136), (129, 256), (130, 264), (200, 320), (70, 1032)])
+def test_translate_u16_tiled_shapes(best, shape):
+    """Widths that are multiples of 8 take the TMA-tiled kernel: tile / stage boundaries (128 columns,
+    64 rows), images smaller than one box, every residual column offset 0..7 and both signs of shift."""
+    rng = np.random.default_rng(31)
+    f = rng.integers(0, 65536, shape, dtype=np.uint16)
+    shifts = [(0.0, 0.0), (1.3, -2.7), (-2.6, 1.4), (7.5, 0.25), (-8.0, -8.0), (3.999999, 63.5), (-65.25, 64.0), (130.5, -129.75),
+              (0.5, 1e-7), (5.0000005, -0.99999994)]
+    shifts += [tuple(rng.uniform(-9, 9, 2).astype(np.float32)) for _ in range(6)]
+    for st in ["nearest", "background", "wrap", ""]:
+        for dx, dy in shifts:
+            np.testing.assert_array_equal(sp.translate(f, dx, dy, st, 77), best.translate(f, dx, dy, st, 77),
+                                          err_msg=f"{shape} {st!r} dx={dx} dy={dy}")
+
+
+def test_translate_u16_random_shifts_full_size(best):
+    """Many random sub-pixel shifts on the shapes of configs 3 and 4 (per-frame shifts, one launch)."""
+    rng = np.random.default_rng(32)
+    for h, w, n in [(512, 640, 12), (1024, 1024, 4)]:
+        mov = np.stack([ir_frame(h, w, 100 + t) for t in range(n)])
+        dx = rng.uniform(-3, 3, n).astype(np.float32)
+        dy = rng.uniform(-3, 3, n).astype(np.float32)
+        got = to_host(sp.translate_batch(to_dev(mov), to_dev(dx), to_dev(dy), "nearest", 0))
+        for t in range(n):
+            np.testing.assert_array_equal(got[t], best.translate(mov[t], dx[t], dy[t], "nearest", 0), err_msg=f"{h}x{w} frame {t}")
+
+
 def test_translate_batch_per_frame_shifts_device(best):
     mov = ir_movie(9, 96, 128)
     rng = np.random.default_rng(777)
@@ -167,6 +194,19 @@ def test_gaussian_odd_shapes_and_large_sigma(best, shape, sigma):
     rng = np.random.default_rng(6)
     img = (rng.random(shape) * 4000).astype(np.float32)
     assert_gauss_close(sp.gaussian_filter(img, sigma), best.gaussian_filter(img, sigma))
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (1, 8), (64, 128), (65, 136), (130, 264), (63, 120), (200, 320)])
+@pytest.mark.parametrize("sigma", [0.5, 1.0, 1.7, 2.4])
+def test_gaussian_tiled_shapes_u16_and_f32(best, shape, sigma):
+    """TMA-tiled kernel (16-byte aligned rows), radius 1..4, uint16 and float32 input, tile edges."""
+    rng = np.random.default_rng(61)
+    f = rng.integers(0, 16384, shape, dtype=np.uint16)
+    want = best.gaussian_filter(f.astype(np.float32), sigma)
+    assert_gauss_close(sp.gaussian_filter(f, sigma), want)
+    got = sp.gaussian_filter_batch(to_dev(np.stack([f, f])), sigma).cpu().numpy()
+    assert_gauss_close(got[0], want)
+    assert_gauss_close(got[1], want)
 
 
 def test_gaussian_constant_image_stays_constant():
