@@ -202,7 +202,7 @@ def time_cpu(frames, dx, dy, threads):
     return len(frames) / el, kind, el
 
 
-def run_reference(args):
+def run_reference(args, out):
     """--impl reference: the reference's own CPU implementation of the path on this box's host
     cores, every step a bounded sample of the same workload."""
     import numpy as np
@@ -211,7 +211,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = max(32, 2 * cores)
+    sample = max(64, 8 * cores)
     mov = synth_movie_numpy(sample)
     rng = np.random.default_rng(777)
     dx = rng.uniform(-3, 3, sample).astype(np.float32)
@@ -235,7 +235,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    out.emit(line)
 
 
 def workload_config(chunk, n_gpus):
@@ -252,7 +252,7 @@ def workload_config(chunk, n_gpus):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def run_ours(args, out):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -383,9 +383,30 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": 1, "kind": kind,
                                     "sample": f"first {ncpu} frames of the step's chunk, {el:.1f} s, stock single-threaded "
                                               f"build (what librir ships: its OpenMP pragmas are never enabled)"}
-        print(json.dumps(line), flush=True)
+        out.emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+class JsonOnlyStdout:
+    """The driver reads ONE JSON line from stdout.  Native libraries (NCCL prints its version
+    banner there) write to file descriptor 1 behind Python's back, so fd 1 is pointed at stderr
+    for the duration of the run and the JSON line goes to the saved descriptor."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, obj):
+        os.write(self.saved, (json.dumps(obj) + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
@@ -400,10 +421,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with JsonOnlyStdout() as out:
+        if args.impl == "reference":
+            run_reference(args, out)
+        else:
+            run_ours(args, out)
 
 
 if __name__ == "__main__":
