@@ -319,7 +319,7 @@ def run_ours(args, out):
 
     # ---- e2e: same pipeline through the public API with pinned host buffers ---------------------
     e2e_n = min(args.e2e_frames, chunk)
-    sub = 256
+    sub = args.e2e_sub
     host_in = torch.empty((e2e_n, H, W), dtype=torch.uint16).pin_memory()
     host_in.copy_(frames[:e2e_n])
     host_dx, host_dy = dx[:e2e_n].cpu().pin_memory(), dy[:e2e_n].cpu().pin_memory()
@@ -373,7 +373,7 @@ def run_ours(args, out):
                     "frames_per_step_per_gpu": e2e_n, "steps": e2e_steps, "matches_device_path": ok,
                     "wall_ms_rank0": e2e_wall_ms,
                     "what": "pinned host u16 frames + shifts -> GPU pipeline -> pinned host byte planes (lo, hi), "
-                            "sub-chunks of 256 frames double-buffered on two streams"},
+                            f"sub-chunks of {sub} frames double-buffered on two streams"},
             "gpu_launches": int(cnt[0]), "clocks": clocks, "stats_allreduce_ms": allreduce_ms,
         }
         if world == 1 and not args.no_cpu:
@@ -417,6 +417,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=4000, help="frames per step per GPU (multiple of the GOP)")
     ap.add_argument("--e2e-frames", type=int, default=1000)
+    ap.add_argument("--e2e-sub", type=int, default=100, help="frames per sub-chunk of the host path (rounded to whole GOPs)")
     ap.add_argument("--cpu-frames", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -187,9 +187,10 @@ class FramePipeline:
         mark(5)
         return c, s, r, lo, hi
 
-    def process_host(self, frames_host, dx_host, dy_host, first_frame: int, lo_host, hi_host, sub_frames: int = 256):
+    def process_host(self, frames_host, dx_host, dy_host, first_frame: int, lo_host, hi_host, sub_frames: int = 256,
+                     slots: int = 3):
         """End-to-end call on HOST buffers (pinned torch CPU tensors): the chunk is cut into
-        sub-chunks that alternate between two streams, so that the upload of one, the kernels of
+        sub-chunks that rotate over `slots` streams, so that the upload of one, the kernels of
         another and the download of a third overlap (PCIe is full duplex).  ``lo_host``/``hi_host``
         receive the pre-coded byte planes -- what the host codec / zstd stage consumes.  Returns
         after everything has landed in the host buffers."""
@@ -205,7 +206,7 @@ class FramePipeline:
             self._e2e = [dict(stream=torch.cuda.Stream(device=self.device),
                               inp=torch.empty((sub, h, w), dtype=torch.uint16, device=self.device),
                               dx=torch.empty(sub, dtype=torch.float32, device=self.device),
-                              dy=torch.empty(sub, dtype=torch.float32, device=self.device)) for _ in range(2)]
+                              dy=torch.empty(sub, dtype=torch.float32, device=self.device)) for _ in range(slots)]
             self._e2e_sub = sub
         if self._e2e_sub != sub:
             raise RuntimeError("process_host: sub_frames changed between calls")
@@ -214,7 +215,8 @@ class FramePipeline:
         for a in range(0, n, sub):
             b = min(n, a + sub)
             m = b - a
-            slot = self._e2e[k % 2]
+            ns = len(self._e2e)
+            slot = self._e2e[k % ns]
             st = slot["stream"]
             st.wait_stream(main)
             with torch.cuda.stream(st):
@@ -222,7 +224,7 @@ class FramePipeline:
                 slot["dx"][:m].copy_(dx_host[a:b], non_blocking=True)
                 slot["dy"][:m].copy_(dy_host[a:b], non_blocking=True)
                 # the chunk buffers are shared: give each stream its own window of them
-                off = (k % 2) * sub
+                off = (k % ns) * sub
                 c = self.corrected[off:off + m]
                 s = self.smoothed[off:off + m]
                 r = self.registered[off:off + m]
