@@ -231,9 +231,12 @@ template <typename TIN> struct GtBox {
 // 4 consecutive tile elements starting at p (8-byte aligned for u16, 16-byte aligned for f32) -> float
 __device__ __forceinline__ void load4(const u16* p, float (&a)[4])
 {
+    // uint16 -> float without I2F (16 lanes/clk/SM): PRMT builds the bits of 2^23 + p, FADD removes 2^23
     const uint2 v = *reinterpret_cast<const uint2*>(p);
-    a[0] = (float)(v.x & 0xFFFFu); a[1] = (float)(v.x >> 16);
-    a[2] = (float)(v.y & 0xFFFFu); a[3] = (float)(v.y >> 16);
+    a[0] = __uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7610)) - 8388608.0f;
+    a[1] = __uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7632)) - 8388608.0f;
+    a[2] = __uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7610)) - 8388608.0f;
+    a[3] = __uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7632)) - 8388608.0f;
 }
 __device__ __forceinline__ void load4(const float* p, float (&a)[4])
 {
@@ -275,8 +278,13 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ 
     float kfull = 0.f;
 #pragma unroll
     for (int d = 0; d <= 2 * R; ++d) kfull += k[d];
-    float nx[4];
-    bool xborder = false;
+    // Horizontal normaliser of each owned column: the partial tap sum at the image's left / right
+    // edge, the full sum elsewhere.  rx[j] is what an output of a row that is NOT a top/bottom
+    // border row is multiplied by: 1 for interior columns (the reference does not normalise interior
+    // pixels, and x * 1.0f is exact), 1 / (kfull * partial) for edge columns.  Multiplying instead of
+    // branching keeps the warps that own the image's edge columns from taking a divergent division
+    // on every row (that cost 40 % of the tiles of a 640-wide frame their speed).
+    float nx[4], rx[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float s = 0.f;
@@ -287,7 +295,7 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ 
         }
         const bool xb = (x + j < R) || (x + j >= w - R);
         nx[j] = xb ? s : kfull;
-        xborder = xborder || xb;
+        rx[j] = xb ? 1.0f / (kfull * s) : 1.0f;
     }
     float* oframe = dst + (size_t)f * w * h;
     float2 ring[2 * R + 1][2];
@@ -340,21 +348,18 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ 
             }
             float o[4] = {o0.x, o0.y, o1.x, o1.y};
             const bool yborder = (yo < R) || (yo >= h - R);
-            if (yborder || xborder) {  // partial-kernel renormalisation (signal_processing.cpp:130-144)
-                float ny = kfull;
-                if (yborder) {
-                    ny = 0.f;
+            if (yborder) {  // warp-uniform; partial-kernel renormalisation (signal_processing.cpp:130-144)
+                float ny = 0.f;
 #pragma unroll
-                    for (int d = 0; d <= 2 * R; ++d) {
-                        const int yyy = yo + d - R;
-                        if (yyy >= 0 && yyy < h) ny += k[d];
-                    }
+                for (int d = 0; d <= 2 * R; ++d) {
+                    const int yyy = yo + d - R;
+                    if (yyy >= 0 && yyy < h) ny += k[d];
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool xb = (x + j < R) || (x + j >= w - R);
-                    if (yborder || xb) o[j] = o[j] / (ny * nx[j]);
-                }
+                for (int j = 0; j < 4; ++j) o[j] = o[j] / (ny * nx[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] *= rx[j];
             }
             if (x < w && yo < h) st_stream(reinterpret_cast<float4*>(oframe + (size_t)yo * w + x), make_float4(o[0], o[1], o[2], o[3]));
         }
