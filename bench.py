@@ -39,6 +39,17 @@ METRIC = "frames/s at 640x512 u16 (full per-frame pipeline: bad-pixel correct + 
 BYTES_PER_PX = {"bp_correct": 4, "gaussian_u16_f32": 6, "translate_u16": 4, "precode_delta_split": 4, "stats_minmax_hist": 2}
 
 
+def ncu_traffic(kernel, frames):
+    """DRAM bytes (read + write) of one launch of `kernel` over `frames` frames, from the committed
+    ncu capture (profiles/ncu_traffic.json, one `ncu --set full` launch, scaled per frame)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)["kernels"][kernel]
+        return t["dram_bytes_per_frame"] * frames
+    except Exception:
+        return None
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -357,6 +368,7 @@ def run_ours(args, out):
         for name, t_ms in zip(pipe.STAGES, per_stage):
             gbs = BYTES_PER_PX[name] * npx * chunk / (t_ms * 1e-3) / 1e9
             kernels[name] = {"ms_per_launch": t_ms, "algorithmic_bytes_per_launch": BYTES_PER_PX[name] * npx * chunk,
+                             "ncu_dram_bytes_per_launch": ncu_traffic(name, chunk),
                              "achieved_gbs": gbs, "frac_of_peak": gbs / peak, "share_of_step": t_ms / sum(per_stage)}
         dom = max(kernels, key=lambda k: kernels[k]["ms_per_launch"])
         value = chunk * world * args.steps / (ms * 1e-3)
@@ -365,7 +377,9 @@ def run_ours(args, out):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
             "data": "synthetic", "config": workload_config(chunk, world),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kernels[dom]["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                         "frac": kernels[dom]["frac_of_peak"], "traffic": ncu_traffic(dom, chunk),
+                         "traffic_source": "profiles/ncu_traffic.json (ncu --set full, one launch, scaled per frame)",
+                         "algorithmic_bytes": kernels[dom]["algorithmic_bytes_per_launch"], "peak_source": peak_src,
                          "pipeline_achieved": sum(BYTES_PER_PX.values()) * npx * chunk / (sum(per_stage) * 1e-3) / 1e9},
             "kernels": kernels,
             "e2e": {"value": e2e_n * world * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s",

@@ -40,13 +40,51 @@ WANT = [
 ]
 
 
+SHORT = [("bp_correct_kernel", "bp_correct"), ("gauss_tile_kernel", "gaussian_u16_f32"), ("translate_u16_tma_kernel", "translate_u16"),
+         ("delta_split_kernel", "precode_delta_split"), ("movie_stats_kernel", "stats_minmax_hist")]
+
+
+def to_bytes(value, unit):
+    v = float(value.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
+
+
+def launch_shares(path):
+    """`ncu --metrics gpu__time_duration.sum --csv` launch list -> per-kernel totals and shares."""
+    lines = [ln for ln in open(path) if ln.startswith('"')]
+    rows = list(csv.reader(lines))
+    hdr, data = rows[0], rows[1:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    tot = {}
+    for d in data:
+        if d[idx["Metric Name"]] != "gpu__time_duration.sum":
+            continue
+        name = d[idx["Kernel Name"]].split("(")[0].replace("void ", "")
+        v = float(d[idx["Metric Value"]].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(d[idx["Metric Unit"]], 1.0)
+        n, t = tot.get(name, (0, 0.0))
+        tot[name] = (n + 1, t + v)
+    total = sum(t for _, t in tot.values())
+    print("| kernel | launches | total us | us/launch | share |\n|---|---|---|---|---|")
+    for name, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{name[:90]}` | {n} | {t:.1f} | {t / n:.1f} | {t / total:.3f} |")
+
+
 def main():
+    if sys.argv[1] == "--launches":
+        return launch_shares(sys.argv[2])
     rows = list(csv.reader(open(sys.argv[1])))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
     out = []
+    traffic = {}
     for d in data:
         name = d[idx["Kernel Name"]]
+        for pat, short in SHORT:
+            if pat in name and short not in traffic and "dram__bytes_read.sum" in idx:
+                rd = to_bytes(d[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
+                wr = to_bytes(d[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+                traffic[short] = {"dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
+                                  "duration_us_under_ncu": d[idx["gpu__time_duration.sum"]]}
         out.append(f"\n### {name[:110]}\n")
         out.append("| metric | value | unit |\n|---|---|---|")
         for key, label in WANT:
@@ -55,6 +93,15 @@ def main():
     text = "\n".join(out)
     if len(sys.argv) > 2:
         open(sys.argv[2], "w").write(text + "\n")
+    if len(sys.argv) > 4:  # ncu_summary.py raw.csv out.md traffic.json <frames per launch of the profiled command>
+        import json
+
+        frames = int(sys.argv[4])
+        for v in traffic.values():
+            v["frames_per_launch"] = frames
+            v["dram_bytes_per_frame"] = v["dram_bytes_per_launch"] / frames
+        json.dump({"source": sys.argv[1], "how": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch",
+                   "kernels": traffic}, open(sys.argv[3], "w"), indent=1)
     print(text)
 
 
