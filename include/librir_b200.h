@@ -107,6 +107,19 @@ RIRB_API int rirb_loader_remove_bad_pixels(int handle, unsigned short* frames, l
 RIRB_API int rirb_loader_remove_motion(const unsigned short* in, unsigned short* out, int w, int h, long long nframes,
                                        size_t frame_stride, const double* shift_x, const double* shift_y);
 
+/* IRFileLoader::readImage's post-decode chain for a run of frames (IRFileLoader.cpp:1168-1247, the
+ * calibration == 0 branch), from the decoder's byte planes to corrected, registered uint16 frames:
+ *   v = lo | hi << 8                          VideoGrabber::toArray, h264.cpp:3016-3051
+ *   v += min_T on rows [0, min_T_height)      IRFileLoader.cpp:1174-1179 (min_T == 0: skipped)
+ *   removeBadPixels on rows [0, h-meta_rows)  IRFileLoader.cpp:722-802 (handle == 0: skipped; else a handle
+ *                                             created on the first frame cropped to h-meta_rows rows)
+ *   removeMotion on rows [0, h-meta_rows)     IRFileLoader.cpp:617-627 (shift_x/shift_y NULL: skipped)
+ * lo, hi: dense planes [nframes][h][w]; out: [nframes][h][w].  Merge, min_T and the bad-pixel medians are
+ * one streaming pass (2 B/px read, 2 B/px written), the motion step a second one. */
+RIRB_API int rirb_loader_read_movie(int handle, const unsigned char* lo, const unsigned char* hi, long long nframes, int w, int h,
+                                    int min_T, int min_T_height, const double* shift_x, const double* shift_y, int meta_rows,
+                                    unsigned short* out);
+
 /* ---- lossless-writer pre-coder (H264Capture::AddFrame, h264.cpp:1066-1103; inverse
  *      VideoGrabber::toArray, h264.cpp:3016-3051) ---- */
 

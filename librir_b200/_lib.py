@@ -60,6 +60,7 @@ SIGNATURES = {
     "rirb_bad_pixels_get": (_i, [_i, _vp, _i, _vp]),
     "rirb_loader_remove_bad_pixels": (_i, [_i, _vp, _ll, _sz]),
     "rirb_loader_remove_motion": (_i, [_vp, _vp, _i, _i, _ll, _sz, _vp, _vp]),
+    "rirb_loader_read_movie": (_i, [_i, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "rirb_split_yuv444": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i]),
     "rirb_merge_yuv444": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rirb_split_yuv420": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i]),

@@ -645,6 +645,82 @@ int rirb_loader_remove_motion(const unsigned short* in, unsigned short* out, int
 }
 
 // =================================================================================================
+// reader's post-decode chain
+// =================================================================================================
+int rirb_loader_read_movie(int handle, const unsigned char* lo, const unsigned char* hi, long long nframes, int w, int h, int min_T,
+                           int min_T_height, const double* shift_x, const double* shift_y, int meta_rows, unsigned short* out)
+{
+    if (!lo || !hi || !out || w <= 0 || h <= 0 || nframes < 0 || meta_rows < 0 || meta_rows >= h || (!shift_x) != (!shift_y)) {
+        set_error("loader_read_movie: bad arguments");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    const int hb = h - meta_rows;
+    std::shared_ptr<BadPixelState> s;
+    if (handle != 0) {
+        s = find_handle(handle);
+        if (!s) {
+            set_error("loader_read_movie: unknown handle %d", handle);
+            return -1;
+        }
+        if (s->w != w || s->h != hb) {
+            set_error("loader_read_movie: the handle was created on a %dx%d image, expected %dx%d", s->w, s->h, w, hb);
+            return -1;
+        }
+    }
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const size_t fpx = (size_t)w * h;
+    const size_t pbytes = fpx * (size_t)nframes;
+    const u8* d_lo = (const u8*)stage_in(lo, pbytes, 0, st);
+    const u8* d_hi = (const u8*)stage_in(hi, pbytes, 1, st);
+    if (!d_lo || !d_hi) return -1;
+    StagedOut o;
+    if (!stage_out(o, out, pbytes * 2, 2, false, st)) return -1;
+    const bool motion = shift_x != nullptr;
+    u16* merged = (u16*)o.dev;
+    if (motion) {  // the translate reads one buffer and writes another
+        merged = (u16*)scratch(3, pbytes * 2);
+        if (!merged) return -1;
+    }
+    const int k = s ? (int)(s->xy.size() / 2) : 0;
+    const bool fused_bp = s && k > 0 && w >= 3 && hb >= 3;
+    if (launch_loader_merge(d_lo, d_hi, merged, w, h, hb, nframes, fpx, min_T, min_T_height, fused_bp ? s->xy_dev : nullptr,
+                            fused_bp ? s->span_off_dev : nullptr, fused_bp ? s->mask_dev : nullptr, st) != 0)
+        return -1;
+    if (s && k > 0 && !fused_bp)  // degenerate sizes keep the reference's sequential loop (IRFileLoader.cpp:735-752)
+        if (launch_loader_bp(merged, s->xy_dev, s->mask_dev, k, w, hb, nframes, fpx, st) != 0) return -1;
+    if (motion) {
+        std::vector<double> sx((size_t)nframes), sy((size_t)nframes);
+        if (is_device_ptr(shift_x) || is_device_ptr(shift_y)) {
+            RIRB_CUDA_OK(cudaMemcpyAsync(sx.data(), shift_x, sizeof(double) * nframes, cudaMemcpyDefault, st));
+            RIRB_CUDA_OK(cudaMemcpyAsync(sy.data(), shift_y, sizeof(double) * nframes, cudaMemcpyDefault, st));
+            RIRB_CUDA_OK(cudaStreamSynchronize(st));
+        } else {
+            memcpy(sx.data(), shift_x, sizeof(double) * nframes);
+            memcpy(sy.data(), shift_y, sizeof(double) * nframes);
+        }
+        std::vector<float> fx((size_t)nframes), fy((size_t)nframes);
+        for (long long i = 0; i < nframes; ++i) {  // translate(..., -x[pos], -y[pos], ...) with float arguments (:621)
+            fx[i] = (float)(-sx[i]);
+            fy[i] = (float)(-sy[i]);
+        }
+        const float* d_dx = (const float*)stage_in(fx.data(), sizeof(float) * nframes, 4, st);
+        const float* d_dy = (const float*)stage_in(fy.data(), sizeof(float) * nframes, 5, st);
+        if (!d_dx || !d_dy) return -1;
+        if (meta_rows > 0)  // the metadata rows are not translated
+            RIRB_CUDA_OK(cudaMemcpy2DAsync((u16*)o.dev + (size_t)w * hb, fpx * 2, merged + (size_t)w * hb, fpx * 2,
+                                           (size_t)w * meta_rows * 2, (size_t)nframes, cudaMemcpyDeviceToDevice, st));
+        if (launch_translate_u16(merged, (u16*)o.dev, w, hb, nframes, fpx, fpx, d_dx, d_dy, 0.f, 0.f, STRAT_NEAREST, 0u, true, st) != 0)
+            return -1;
+        if (o.host) RIRB_CUDA_OK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st));
+        RIRB_CUDA_OK(cudaStreamSynchronize(st));  // fx / fy are host vectors read by an async copy
+        return 0;
+    }
+    return finish_out(&o, 1, st);
+}
+
+// =================================================================================================
 // pre-coder
 // =================================================================================================
 int rirb_split_yuv444(const unsigned short* img, const unsigned char* it, int w, int h, unsigned char* y_plane,

@@ -25,6 +25,11 @@ int launch_bp_correct_inplace(u16* img, const int* xy_dev, int count, int w, int
 int launch_loader_bp(u16* img, const int* xy_dev, const u8* mask, int count, int w, int h, long long nframes,
                      size_t frame_stride, cudaStream_t st);
 
+// loader.cu
+int launch_loader_merge(const u8* lo, const u8* hi, u16* out, int w, int h, int hb, long long nframes, size_t frame_stride,
+                        int min_t, int min_t_height, const int* xy_dev, const int* span_off_dev, const u8* mask_dev,
+                        cudaStream_t st);
+
 // translate.cu
 int launch_translate(int type, const void* src, void* dst, int w, int h, long long nframes, const float* dxs, const float* dys,
                      float dx0, float dy0, int strategy, const void* background_host, cudaStream_t st);

@@ -1,0 +1,162 @@
+// librir_b200/csrc/loader.cu -- the reader's post-decode chain on a run of frames.
+//
+// Reference: IRFileLoader::readImage, IRFileLoader.cpp:1148-1247 (calibration == 0 branch):
+//   bin_read_image -> H264_Loader -> VideoGrabber::toArray   byte-plane merge      h264.cpp:3016-3051
+//   pixels[i] += min_T on the first min_T_height rows                              IRFileLoader.cpp:1174-1179
+//   removeBadPixels(pixels, w, h - 3)                                              IRFileLoader.cpp:722-802
+//   removeMotion(pixels, w, h - 3, pos) -> removeMotionGeneric                     IRFileLoader.cpp:617-627
+//
+// The reference walks the frame four times (merge, add, fix, translate + copy back).  Here:
+//   loader_merge_kernel   ONE streaming pass: 16 low bytes + 16 high bytes (two 128-bit loads) are
+//                         interleaved with PRMT, min_T is added per halfword where the row asks for
+//                         it, 256-bit store; then one thread per flagged pixel of the span takes the
+//                         median of the un-flagged cells of its shifted 3x3 window straight from the
+//                         two byte planes (rows the CTA is streaming anyway: L2 hits) and overwrites
+//                         the pixel.  4 B/px: 2 read + 2 written.
+//   translate_u16_tma_kernel<MOTION>  (translate.cu) for the motion step, 4 B/px.
+#include "common.cuh"
+#include "kernels.h"
+#include "sort9.cuh"
+
+namespace rirb {
+
+constexpr int LD_THREADS = 256;
+constexpr int LD_UNROLL = BP_SPAN / (LD_THREADS * 16);
+static_assert(LD_UNROLL * LD_THREADS * 16 == BP_SPAN, "a span is a whole number of CTA-wide rows of 16-pixel vectors");
+
+__device__ __forceinline__ unsigned merged_px(const u8* __restrict__ lo, const u8* __restrict__ hi, size_t i, unsigned add)
+{
+    return (((unsigned)lo[i] | ((unsigned)hi[i] << 8)) + add) & 0xFFFFu;
+}
+
+// VEC: planes 16-byte aligned, output 32-byte aligned, plane/frame strides multiples of 16 pixels
+// and w % 16 == 0 (so a 16-pixel vector never straddles the min_T row limit).
+template <bool VEC>
+__global__ void __launch_bounds__(LD_THREADS)
+loader_merge_kernel(const u8* __restrict__ lo, const u8* __restrict__ hi, u16* __restrict__ out, const int* __restrict__ xy,
+                    const int* __restrict__ span_off, const u8* __restrict__ mask, int handle_spans, int w, int h, int hb, int npx,
+                    int spans, unsigned min_t, int t_limit_px, size_t frame_stride)
+{
+    const int span = blockIdx.x % spans;
+    const size_t f = blockIdx.x / spans;
+    const int s0 = span * BP_SPAN;
+    const int s1 = min(npx, s0 + BP_SPAN);
+    const u8* flo = lo + f * frame_stride;
+    const u8* fhi = hi + f * frame_stride;
+    u16* oframe = out + f * frame_stride;
+    const int mstride = (w + 7) >> 3;
+    int a = 0, b = 0;
+    if (xy != nullptr && span < handle_spans) {
+        a = span_off[span];
+        b = span_off[span + 1];
+    }
+    uint4 rl[LD_UNROLL], rh[LD_UNROLL];
+    const int nvec = VEC ? (s1 - s0) >> 4 : 0;
+    if (VEC) {
+        const uint4* gl = reinterpret_cast<const uint4*>(flo + s0);
+        const uint4* gh = reinterpret_cast<const uint4*>(fhi + s0);
+#pragma unroll
+        for (int k = 0; k < LD_UNROLL; ++k) {
+            const int j = threadIdx.x + k * LD_THREADS;
+            if (j < nvec) {
+                rl[k] = ld_stream(gl + j);
+                rh[k] = ld_stream(gh + j);
+            }
+        }
+    }
+    // first fix-up of this thread, gathered while the stream loads are in flight (as in bp_correct_kernel)
+    const int i0 = a + (int)threadIdx.x;
+    int2 p0 = make_int2(0, 0);
+    unsigned med0 = 0;
+    bool have0 = false;
+    auto fix = [&](int2 p, unsigned& med) -> bool {
+        // IRFileLoader.cpp:754-795: 3x3 window shifted inside the hb-row image, flagged cells skipped
+        int x0 = p.x - 1, y0 = p.y - 1;
+        if (p.x == 0) x0 = 0; else if (p.x == w - 1) x0 = w - 3;
+        if (p.y == 0) y0 = 0; else if (p.y == hb - 1) y0 = hb - 3;
+        // all 27 loads are independent of one another (the cell values do not wait for the bitmap)
+        unsigned v[9], flagged[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int xx = x0 + k / 3, yy = y0 + k % 3;
+            const size_t i = (size_t)yy * w + xx;
+            flagged[k] = mask[(size_t)yy * mstride + (xx >> 3)] & (1u << (xx & 7));
+            v[k] = merged_px(flo, fhi, i, (int)i < t_limit_px ? min_t : 0u);
+        }
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            if (flagged[k]) v[k] = 0xFFFFFFFFu;
+            else ++c;
+        }
+        if (c == 0) return false;  // the reference reads a stale stack slot here (undefined): leave the pixel
+        sort9(v);
+        med = pick_mid(v, c);
+        return true;
+    };
+    if (i0 < b) {
+        p0 = reinterpret_cast<const int2*>(xy)[i0];
+        have0 = fix(p0, med0);
+    }
+    int done = s0;
+    if (VEC) {
+        const unsigned t2 = min_t | (min_t << 16);
+        U32x8* o = reinterpret_cast<U32x8*>(oframe + s0);
+#pragma unroll
+        for (int k = 0; k < LD_UNROLL; ++k) {
+            const int j = threadIdx.x + k * LD_THREADS;
+            if (j < nvec) {
+                const unsigned add = (s0 + 16 * j < t_limit_px) ? t2 : 0u;
+                const unsigned l[4] = {rl[k].x, rl[k].y, rl[k].z, rl[k].w};
+                const unsigned hh[4] = {rh[k].x, rh[k].y, rh[k].z, rh[k].w};
+                U32x8 r;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // bytes (l0 h0 l1 h1) and (l2 h2 l3 h3): v = lo | hi << 8 (h264.cpp:3030,3044)
+                    r.v[2 * q] = __vadd2(__byte_perm(l[q], hh[q], 0x5140), add);
+                    r.v[2 * q + 1] = __vadd2(__byte_perm(l[q], hh[q], 0x7362), add);
+                }
+                st_stream256(o + j, r);
+            }
+        }
+        done = s0 + (nvec << 4);
+    }
+    for (int i = done + threadIdx.x; i < s1; i += LD_THREADS) oframe[i] = (u16)merged_px(flo, fhi, i, i < t_limit_px ? min_t : 0u);
+    if (a == b) return;  // CTA-uniform
+    __syncthreads();
+    if (have0) oframe[(size_t)p0.y * w + p0.x] = (u16)med0;
+    for (int i = i0 + LD_THREADS; i < b; i += LD_THREADS) {
+        const int2 p = reinterpret_cast<const int2*>(xy)[i];
+        unsigned med;
+        if (fix(p, med)) oframe[(size_t)p.y * w + p.x] = (u16)med;
+    }
+}
+
+// xy_dev / span_off_dev / mask_dev: the handle's list, span offsets and bitmap for a w x hb image
+// (nullptr: no bad-pixel correction in this pass).  frame_stride in pixels for all three buffers.
+int launch_loader_merge(const u8* lo, const u8* hi, u16* out, int w, int h, int hb, long long nframes, size_t frame_stride,
+                        int min_t, int min_t_height, const int* xy_dev, const int* span_off_dev, const u8* mask_dev,
+                        cudaStream_t st)
+{
+    if (nframes <= 0 || w <= 0 || h <= 0) return 0;
+    const long long npx = (long long)w * h;
+    const long long spans = ceil_div(npx, BP_SPAN);
+    const long long grid = nframes * spans;
+    if (npx > 0x7FFFFFFFLL || grid > 0x7FFFFFFFLL) {
+        set_error("loader_read: too many pixels or frames in one call (%lld frames)", nframes);
+        return -1;
+    }
+    const int handle_spans = (int)ceil_div((long long)w * hb, BP_SPAN);
+    const int rows_t = min_t_height < 0 ? 0 : (min_t_height > h ? h : min_t_height);
+    const int t_limit_px = min_t != 0 ? rows_t * w : 0;
+    const unsigned mt = (unsigned)min_t & 0xFFFFu;
+    const bool vec = (w % 16 == 0) && aligned16(lo) && aligned16(hi) && aligned32(out) && (frame_stride % 16 == 0);
+    if (vec)
+        RIRB_LAUNCH(loader_merge_kernel<true>, (unsigned)grid, LD_THREADS, 0, st, lo, hi, out, xy_dev, span_off_dev, mask_dev,
+                    handle_spans, w, h, hb, (int)npx, (int)spans, mt, t_limit_px, frame_stride);
+    else
+        RIRB_LAUNCH(loader_merge_kernel<false>, (unsigned)grid, LD_THREADS, 0, st, lo, hi, out, xy_dev, span_off_dev, mask_dev,
+                    handle_spans, w, h, hb, (int)npx, (int)spans, mt, t_limit_px, frame_stride);
+    return 0;
+}
+
+}  // namespace rirb

@@ -411,13 +411,45 @@ __device__ __forceinline__ RowInfo make_row_info(int y, int h, float dy, int ys)
 }
 
 static_assert(TT_BH * TT_BW * 2 <= 65536, "row byte offsets are packed in 16 bits");
+static_assert(TT_H <= 64 && TT_W / 8 <= 16, "queue entries pack cx in 4 bits and the row in 6");
+
+// ---- edge groups --------------------------------------------------------------------------------
+// The first and the last 8-pixel group of an image row are where the regular structure breaks:
+// some of their pixels have no source (px < 0 or px >= w: border strategy), and source columns
+// below 8 change binade at 1, 2 and 4, so the fraction differs from pixel to pixel.  Their
+// horizontal weights depend on (dx, x) only -- not on the row -- so the CTA that owns such a group
+// tabulates them once per pixel in shared memory (EdgeTable) together with a mask of the pixels
+// the table is valid for.  The groups still go through the CTA's queue (so that the work is
+// spread over all threads instead of stalling the warp that owns the image edge), but a valid
+// pixel of a regular row then costs the fast path's arithmetic instead of the literal routine.
+struct EdgeTable {
+    HWeights wt[8];
+    unsigned valid;     // bit i: pixel i is in range, its source column is l0 + i and rt is l + 1 (or clamped)
+    unsigned clamped;   // bit i: rt of pixel i clamps onto l (l == w - 1)
+};
+
+// One pixel of an edge group in a regular row: the fast path's arithmetic with the pixel's own
+// weights.  col: the pixel's source column l in the staged box.
+template <bool MOTION>
+__device__ __forceinline__ u16 blend_edge_pixel(const u16* tile, unsigned rows, unsigned A, unsigned B, int col, bool clamped,
+                                                const HWeights& c)
+{
+    const u16* rt_ = tile + (rows & 0xFFFFu) / 2 + col;
+    const u16* rb = tile + (rows >> 16) / 2 + col;
+    const int r = clamped ? 0 : 1;
+    const unsigned long long nl = (unsigned long long)rb[0] * A + (unsigned long long)rt_[0] * B + 0x41C0000000000000ULL;
+    const unsigned long long nr = (unsigned long long)rb[r] * A + (unsigned long long)rt_[r] * B + 0x41C0000000000000ULL;
+    const double val = __dadd_rn(__fma_rn(__longlong_as_double((long long)nl), c.omu, c.k_l),
+                                 __fma_rn(__longlong_as_double((long long)nr), c.u, c.k_r));
+    return MOTION ? (u16)(float)val : (u16)__double2loint(__dadd_rd(val, 4503599627370496.0));
+}
 
 // tbase: shared address of the thread's column slot in box row 0; rinfo: shared address of rowinfo[ry].
-// Groups that cannot take the fast path are appended to the CTA's queue as cx | row << 4.
+// Groups that cannot be done here are appended to the CTA's queue as cx | row << 4.
 template <int XOFF, bool MOTION>
 __device__ __forceinline__ void fast_rows(uint32_t tbase, uint32_t rinfo, bool xfast, bool clamp_rt, const HWeights& ca,
                                           const HWeights& cb, u16* ocol, size_t row_step, int cx, int ry, int rows_left,
-                                          unsigned short* slowq, unsigned* slow_count)
+                                          unsigned* slowq, unsigned* slow_count)
 {
     unsigned long long magic = 0x41C0000000000000ULL;
     asm volatile("" : "+l"(magic));  // opaque: otherwise ptxas ORs the constant into every column's high word
@@ -426,11 +458,12 @@ __device__ __forceinline__ void fast_rows(uint32_t tbase, uint32_t rinfo, bool x
         int B;
         unsigned rows;
         asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(B), "=r"(rows) : "r"(rinfo + k * (16 * (int)sizeof(RowInfo))));
-        if (xfast && B >= 0)
+        if (xfast && B >= 0) {
             blend_group<XOFF, MOTION>(tbase + (rows >> 16), tbase + (rows & 0xFFFFu), 8388608u - (unsigned)B, (unsigned)B, clamp_rt, ca,
                                       cb, magic, ocol);
-        else if (ry + 16 * k < rows_left)
-            slowq[atomicAdd(slow_count, 1u)] = (unsigned short)(cx | ((ry + 16 * k) << 4));
+        } else if (ry + 16 * k < rows_left) {
+            slowq[atomicAdd(slow_count, 1u)] = (unsigned)cx | ((unsigned)(ry + 16 * k) << 4);
+        }
         ocol += row_step;
     }
 }
@@ -451,7 +484,8 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
     __shared__ __align__(8) unsigned long long bar[TT_STAGES];
     __shared__ RowInfo rowinfo[2][TT_H];  // double-buffered with the queue counter: tile ty+1's are prepared
     __shared__ unsigned slow_count[2];    // between the two barriers of tile ty
-    __shared__ unsigned short slowq[(TT_W / 8) * TT_H];
+    __shared__ unsigned slowq[(TT_W / 8) * TT_H];
+    __shared__ EdgeTable edge_tab[2];  // [0]: the image's first group of a row, [1]: its last
     constexpr unsigned TILE_BYTES = TT_BH * TT_BW * 2;
     constexpr unsigned STAGE_BYTES = TT_STAGE_BYTES;  // TMA destinations are 128-byte aligned
     const int f = blockIdx.y;
@@ -472,6 +506,23 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
         slow_count[0] = 0;
     }
     if (threadIdx.x < TT_H) rowinfo[0][threadIdx.x] = make_row_info(threadIdx.x, h, dy, sy);
+    if (threadIdx.x >= TT_THREADS - 32 && threadIdx.x < TT_THREADS - 16) {  // 16 lanes of the last warp: 2 tables x 8 pixels
+        const int e = (threadIdx.x >> 3) & 1, i = threadIdx.x & 7;
+        const int xe0 = e ? w - 8 : 0;
+        const int x = xe0 + i;
+        const float px = (float)x - dx;
+        bool ok = (xe0 >= x0t) && (xe0 < x0t + TT_W) && !(px < 0) && (px < fw);
+        const int l = (int)px;
+        const int rt = (int)(px + 1.0f);
+        const bool cl = ok && (rt == w) && (l == w - 1);
+        ok = ok && (l == x + sx) && (cl || rt == l + 1);
+        edge_tab[e].wt[i] = make_hweights(ok ? px - (float)l : 0.f);
+        const unsigned vb = __ballot_sync(0x0000FFFFu, ok), cb2 = __ballot_sync(0x0000FFFFu, cl);
+        if (i == 0) {
+            edge_tab[e].valid = (vb >> (8 * e)) & 0xFFu;
+            edge_tab[e].clamped = (cb2 >> (8 * e)) & 0xFFu;
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -539,18 +590,26 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
 #pragma unroll 1
         for (int i = threadIdx.x; i < nslow; i += TT_THREADS) {
             const unsigned g = slowq[i >> 3];
-            const int gx = x0t + 8 * (int)(g & 15u) + (i & 7);
-            const int gy = y0t + (int)(g >> 4);
-            if (gx < w) {
-                const TileSrc ts{tile, frame, xs, ys, w};
-                u16* o = oframe + (size_t)gy * w + gx;
-                if (MOTION) {
-                    float r;
-                    if (translate_pixel<u16, float>(ts, w, h, gx, gy, dx, dy, strategy, (float)background, r)) *o = (u16)r;
-                } else {
-                    u16 r;
-                    if (translate_pixel<u16, u16>(ts, w, h, gx, gy, dx, dy, strategy, (u16)background, r)) *o = r;
-                }
+            const int gcx = (int)(g & 15u), grow = (int)(g >> 4), gi = i & 7;
+            const int gx = x0t + 8 * gcx + gi;
+            const int gy = y0t + grow;
+            if (gx >= w) continue;
+            u16* o = oframe + (size_t)gy * w + gx;
+            const int gx0 = x0t + 8 * gcx;
+            const int e = (gx0 == 0) ? 0 : ((gx0 == w - 8) ? 1 : -1);
+            const RowInfo ri = rowinfo[pp][grow];
+            if (e >= 0 && ri.B >= 0 && ((edge_tab[e].valid >> gi) & 1u)) {
+                *o = blend_edge_pixel<MOTION>(tile, ri.rows, 8388608u - (unsigned)ri.B, (unsigned)ri.B, 8 * gcx + xoff + gi,
+                                              (edge_tab[e].clamped >> gi) & 1u, edge_tab[e].wt[gi]);
+                continue;
+            }
+            const TileSrc ts{tile, frame, xs, ys, w};
+            if (MOTION) {
+                float r;
+                if (translate_pixel<u16, float>(ts, w, h, gx, gy, dx, dy, strategy, (float)background, r)) *o = (u16)r;
+            } else {
+                u16 r;
+                if (translate_pixel<u16, u16>(ts, w, h, gx, gy, dx, dy, strategy, (u16)background, r)) *o = r;
             }
         }
         __syncthreads();  // every warp is done with this stage and the queue; next tile's row parameters are visible

@@ -208,6 +208,39 @@ def remove_motion(frames, shifts_x, shifts_y, meta_rows=3, out=None):
     return out
 
 
+def read_movie(lo, hi, bad_pixels=None, min_T=0, min_T_height=0, shifts_x=None, shifts_y=None, meta_rows=3, out=None):
+    """``IRFileLoader::readImage``'s post-decode chain (IRFileLoader.cpp:1168-1247, calibration 0) on a
+    run of decoded frames: byte planes ``lo``/``hi`` ``[n, h, w]`` (what ``VideoGrabber::toArray`` merges,
+    h264.cpp:3016-3051) -> ``+= min_T`` on the first ``min_T_height`` rows -> ``removeBadPixels`` on rows
+    ``[0, h-meta_rows)`` (``bad_pixels``: a :class:`LoaderBadPixels` or None) -> ``removeMotion`` by the
+    per-frame shifts of the ``.regfile`` (None: off).  Returns uint16 ``[n, h, w]``."""
+    lib = _lib.load()
+    _prepare_device_call(lo)
+    single = len(lo.shape) == 2
+    n = 1 if single else lo.shape[0]
+    h, w = lo.shape[-2:]
+    if tuple(hi.shape) != tuple(lo.shape):
+        raise RuntimeError("read_movie: lo and hi planes differ in shape")
+    handle = 0
+    if bad_pixels is not None:
+        if (bad_pixels.height, bad_pixels.width) != (h, w) or bad_pixels.rows != h - meta_rows:
+            raise RuntimeError("read_movie: wrong image size for this bad-pixel state")
+        handle = bad_pixels.handle
+    sx = sy = None
+    if shifts_x is not None or shifts_y is not None:
+        sx = np.ascontiguousarray(np.atleast_1d(shifts_x), dtype=np.float64)
+        sy = np.ascontiguousarray(np.atleast_1d(shifts_y), dtype=np.float64)
+        if sx.size != n or sy.size != n:
+            raise RuntimeError("read_movie: one shift per frame expected")
+    if out is None:
+        out = _empty_like(lo, np.uint16)
+    r = lib.rirb_loader_read_movie(handle, _ptr(lo), _ptr(hi), n, w, h, int(min_T), int(min_T_height),
+                                   _ptr(sx) if sx is not None else None, _ptr(sy) if sy is not None else None, int(meta_rows),
+                                   _ptr(out))
+    _lib.check(r, "read_movie")
+    return out
+
+
 def load_translation_file(filename, nframes=None):
     """``IRFileLoader::loadTranslationFile`` (IRFileLoader.cpp:822-847): tab-separated file, one
     header line, 4 columns; shifts are columns 1 and 2.  Returns ``(x, y)`` float64 arrays."""
@@ -239,6 +272,6 @@ def save_translation_file(filename, x, y, confidence=None):
 
 __all__ = [
     "DEFAULT_GOP", "linesize", "key_frames", "split_yuv444", "merge_yuv444", "split_yuv420", "merge_yuv420",
-    "precode_movie", "decode_movie", "LosslessPrecoder", "LoaderBadPixels", "remove_motion", "load_translation_file",
+    "precode_movie", "decode_movie", "LosslessPrecoder", "LoaderBadPixels", "remove_motion", "read_movie", "load_translation_file",
     "save_translation_file",
 ]

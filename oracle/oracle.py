@@ -216,6 +216,24 @@ class Port(_Base):
         f(_p(img), w, h, float(shift_x), float(shift_y))
         return img
 
+    def loader_read_image(self, lo, hi, xy=None, min_T=0, min_T_height=0, shift=None, meta_rows=3):
+        """IRFileLoader::readImage after the decoder, calibration == 0 (IRFileLoader.cpp:1168-1247):
+        toArray's merge (h264.cpp:3016-3051) -> += min_T on the first min_T_height rows (:1174-1179)
+        -> removeBadPixels(pixels, w, h-3) (:1241) -> removeMotion(pixels, w, h-3, pos) (:1243)."""
+        lo = np.asarray(lo, dtype=np.uint8)
+        hi = np.asarray(hi, dtype=np.uint8)
+        img = (lo.astype(np.uint16) | (hi.astype(np.uint16) << 8)).astype(np.uint16)
+        h, w = img.shape
+        if min_T and min_T_height:
+            rows = min(h, int(min_T_height))
+            img[:rows] = (img[:rows].astype(np.int64) + int(min_T)).astype(np.uint16)  # unsigned short += int: wraps
+        hb = h - meta_rows
+        if xy is not None and len(xy):
+            img[:hb] = self.loader_remove_bad_pixels(img[:hb], xy)
+        if shift is not None:
+            img[:hb] = self.loader_remove_motion(img[:hb], shift[0], shift[1])
+        return img
+
     # stats -----------------------------------------------------------------------------
     def find_median_pixel(self, image, percent=0.5, mask=None):
         img = _c(image, np.uint16)

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 SIZES = [(320, 256), (640, 512), (1024, 1024), (1280, 1024), (2048, 2048)]
-BYTES_PER_PX = {"bp_correct": 4, "gaussian_u16_f32": 6, "gaussian_f32_f32": 8, "translate_u16": 4, "loader_motion_u16": 4,
+BYTES_PER_PX = {"bp_correct": 4, "gaussian_u16_f32": 6, "gaussian_f32_f32": 8, "translate_u16": 4, "loader_motion_u16": 4, "loader_merge_minT_bp": 4, "loader_read_chain": 8,
                 "precode_split": 4, "precode_delta_split": 4, "decode_delta_merge": 4, "stats_minmax_hist": 2}
 
 
@@ -73,6 +73,8 @@ def main():
         stats = movie.MovieStats(dev)
         sx = dx.double().cpu().numpy()
         sy = dy.double().cpu().numpy()
+        lbp = vio.LoaderBadPixels(frames[0].cpu().view(torch.int16).numpy().view("uint16"))
+        vio.precode_movie(frames, 50, False, 0, out=(lo, hi))  # the planes the loader kernels read
 
         def run_f32():
             nonlocal f32
@@ -86,6 +88,8 @@ def main():
             "gaussian_f32_f32": run_f32,
             "translate_u16": lambda: sp.translate_batch(frames, dx, dy, "nearest", background=0, out=out16),
             "loader_motion_u16": lambda: vio.remove_motion(frames, sx, sy, meta_rows=3, out=out16),
+            "loader_merge_minT_bp": lambda: vio.read_movie(lo, hi, lbp, 273, h - 3, None, None, out=out16),
+            "loader_read_chain": lambda: vio.read_movie(lo, hi, lbp, 273, h - 3, sx, sy, out=out16),
             "precode_split": lambda: vio.precode_movie(frames, 50, False, 0, out=(lo, hi)),
             "precode_delta_split": lambda: vio.precode_movie(frames, 50, True, 0, out=(lo, hi)),
             "decode_delta_merge": lambda: vio.decode_movie(lo, hi, 50, True, 0, out=out16),
@@ -116,7 +120,7 @@ def main():
             rows.append(row)
             if rank == 0:
                 print(json.dumps(row), flush=True)
-        del frames, out16, out32, lo, hi, f32, bp
+        del frames, out16, out32, lo, hi, f32, bp, lbp
         torch.cuda.empty_cache()
     if rank == 0:
         names = list(BYTES_PER_PX)

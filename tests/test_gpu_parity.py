@@ -308,6 +308,46 @@ def test_remove_motion_golden_and_live(golden, best, port):
 # ---------------------------------------------------------------------------------------------
 # statistics
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(12, 67, 96), (5, 131, 80), (3, 40, 37), (4, 259, 640), (2, 5, 3)])
+def test_loader_read_movie_chain(port, best, shape):
+    """The reader's post-decode chain in one call (merge -> +min_T -> removeBadPixels -> removeMotion)
+    against the restated reference chain, with each stage switched on and off."""
+    n, h, w = shape
+    rng = np.random.default_rng(91)
+    mov = ir_movie(n, h, w, seed=7)
+    mov[:, -3:] = rng.integers(0, 65536, (n, 3, w), dtype=np.uint16)  # metadata rows: arbitrary bits
+    lo, hi = (mov & 0xFF).astype(np.uint8), (mov >> 8).astype(np.uint8)
+    sx = rng.uniform(-3, 3, n)
+    sy = rng.uniform(-3, 3, n)
+    bp = vio.LoaderBadPixels(mov[0]) if h - 3 >= 1 else None
+    xy = sp.bad_pixels_list(bp.handle)[0] if bp is not None else None
+    cases = [dict(bad=False, min_T=0, rows=0, motion=False), dict(bad=True, min_T=0, rows=0, motion=False),
+             dict(bad=True, min_T=273, rows=h - 3, motion=True), dict(bad=False, min_T=60000, rows=h // 2, motion=True),
+             dict(bad=True, min_T=-5, rows=h, motion=False)]
+    for c in cases:
+        if c["bad"] and bp is None:
+            continue
+        got = vio.read_movie(lo, hi, bp if c["bad"] else None, c["min_T"], c["rows"], sx if c["motion"] else None,
+                             sy if c["motion"] else None)
+        for t in range(n):
+            want = port.loader_read_image(lo[t], hi[t], xy if c["bad"] else None, c["min_T"], c["rows"],
+                                          (sx[t], sy[t]) if c["motion"] else None)
+            np.testing.assert_array_equal(got[t], want, err_msg=f"{shape} {c} frame {t}")
+    # device-resident planes give the same frames
+    c = cases[2]
+    if bp is not None:
+        got_d = to_host(vio.read_movie(to_dev(lo), to_dev(hi), bp, c["min_T"], c["rows"], sx, sy))
+        np.testing.assert_array_equal(got_d, vio.read_movie(lo, hi, bp, c["min_T"], c["rows"], sx, sy))
+
+
+def test_loader_read_movie_is_inverse_of_the_writer_split():
+    """decode side of the lossless round trip the reference's tests pin (test_IRMovie.py:46-49): planes
+    written by the pre-coder, read back by the loader chain with every correction off = the frames."""
+    mov = ir_movie(20, 64, 96)
+    lo, hi = vio.precode_movie(mov, gop=5, delta=False)
+    np.testing.assert_array_equal(vio.read_movie(lo, hi, None), mov)
+
+
 def test_find_median_pixel_golden(golden):
     f, m = golden["mp_in"], golden["mp_mask"]
     for p, want, want_m in zip(golden["mp_percents"], golden["mp_out"], golden["mp_out_mask"]):
