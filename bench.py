@@ -337,14 +337,26 @@ def run_ours(args, out):
     host_lo = torch.empty((e2e_n, H, W), dtype=torch.uint8).pin_memory()
     host_hi = torch.empty((e2e_n, H, W), dtype=torch.uint8).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
+    if args.e2e_api == "cabi":  # ONE call of the C ABI with host pointers: rirb_process_movie_host
+        def e2e_call():
+            movie.process_movie_host(pipe.bad_pixels, host_in, host_dx, host_dy, SIGMA, "nearest", 0, GOP, True, shard.start,
+                                     host_lo, host_hi)
+        e2e_what = ("rirb_process_movie_host (one C-ABI call): pinned host u16 frames + shifts -> bad-pixel correct -> gaussian "
+                    "(kept on the device) -> translate -> delta pre-coder -> pinned host byte planes (lo, hi); sub-chunks of whole "
+                    "GOPs (~64 MB) rotating over three streams")
+    else:                       # the same chain driven from Python (torch copies + device-pointer C-ABI calls)
+        def e2e_call():
+            pipe.process_host(host_in, host_dx, host_dy, shard.start, host_lo, host_hi, sub)
+        e2e_what = ("FramePipeline.process_host: pinned host u16 frames + shifts -> GPU pipeline -> pinned host byte planes (lo, hi), "
+                    f"sub-chunks of {sub} frames rotating over three streams")
     for _ in range(2):
-        pipe.process_host(host_in, host_dx, host_dy, shard.start, host_lo, host_hi, sub)
+        e2e_call()
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(e2e_steps):
-        pipe.process_host(host_in, host_dx, host_dy, shard.start, host_lo, host_hi, sub)
+        e2e_call()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)  # device-timed; the events bracket uploads, kernels and downloads
@@ -386,8 +398,7 @@ def run_ours(args, out):
                     "h2d_bytes_per_step": e2e_n * (npx * 2 + 8), "d2h_bytes_per_step": e2e_n * npx * 2,
                     "frames_per_step_per_gpu": e2e_n, "steps": e2e_steps, "matches_device_path": ok,
                     "wall_ms_rank0": e2e_wall_ms,
-                    "what": "pinned host u16 frames + shifts -> GPU pipeline -> pinned host byte planes (lo, hi), "
-                            f"sub-chunks of {sub} frames double-buffered on two streams"},
+                    "api": args.e2e_api, "what": e2e_what},
             "gpu_launches": int(cnt[0]), "clocks": clocks, "stats_allreduce_ms": allreduce_ms,
         }
         if world == 1 and not args.no_cpu:
@@ -431,6 +442,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=4000, help="frames per step per GPU (multiple of the GOP)")
     ap.add_argument("--e2e-frames", type=int, default=1000)
+    ap.add_argument("--e2e-api", default="cabi", choices=["cabi", "torch"],
+                    help="host path: one rirb_process_movie_host call, or the Python-driven FramePipeline.process_host")
     ap.add_argument("--e2e-sub", type=int, default=100, help="frames per sub-chunk of the host path (rounded to whole GOPs)")
     ap.add_argument("--cpu-frames", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")

@@ -145,6 +145,18 @@ RIRB_API int rirb_decode_movie(const unsigned char* lo, const unsigned char* hi,
 /* key[t] = 1 iff frame t of a writer starting at frame 0 is a key frame (h264.cpp:1050-1061) */
 RIRB_API int rirb_key_frames(long long nframes, int gop, unsigned char* key);
 
+/* ---- the whole per-frame path on HOST buffers, one call (the end-to-end drop-in) ----
+ * frames[nframes][h][w] (host) -> bad_pixels_correct (handle) -> gaussian_filter (sigma; result kept on
+ * the device unless `smoothed` is non-NULL) -> translate by the per-frame shifts dx[t], dy[t] (host floats,
+ * `strategy`, `background`) -> rirb_precode_movie (gop, delta, first_frame) -> lo/hi[nframes][h][w] (host).
+ * The movie is cut into sub-chunks of whole GOPs that rotate over three CUDA streams, so the upload of
+ * one, the kernels of another and the download of a third overlap; pinned (page-locked) buffers make
+ * the copies asynchronous, pageable ones work but serialise.  Returns when lo/hi (and smoothed) are
+ * complete.  With delta != 0, first_frame must be a multiple of gop. */
+RIRB_API int rirb_process_movie_host(int handle, const unsigned short* frames, long long nframes, int w, int h, float sigma,
+                                     const float* dx, const float* dy, const char* strategy, unsigned int background, int gop,
+                                     int delta, long long first_frame, unsigned char* lo, unsigned char* hi, float* smoothed);
+
 /* ---- statistics (the quantities the multi-GPU path all-reduces) ---- */
 
 /* minmax[2] = {min, max}; hist = 65,536 x uint64 or NULL.  accumulate != 0: fold into the

@@ -880,6 +880,116 @@ int rirb_key_frames(long long nframes, int gop, unsigned char* key)
 }
 
 // =================================================================================================
+// the whole path on host buffers
+// =================================================================================================
+namespace {
+constexpr int HP_SLOTS = 3;
+struct HostPipeSlot {
+    cudaStream_t stream = nullptr;
+    void* buf = nullptr;   // in | corrected | registered | lo | hi | smoothed | dx | dy for `cap` frames
+    size_t cap_bytes = 0;
+};
+struct HostPipe {
+    HostPipeSlot slot[HP_SLOTS];
+    int device = -1;
+};
+thread_local HostPipe g_host_pipe;
+}  // namespace
+
+int rirb_process_movie_host(int handle, const unsigned short* frames, long long nframes, int w, int h, float sigma, const float* dx,
+                            const float* dy, const char* strategy, unsigned int background, int gop, int delta,
+                            long long first_frame, unsigned char* lo, unsigned char* hi, float* smoothed)
+{
+    auto s = find_handle(handle);
+    if (!s) {
+        set_error("process_movie_host: unknown handle %d", handle);
+        return -1;
+    }
+    const int strat = strategy_code(strategy);
+    if (!frames || !dx || !dy || !lo || !hi || w != s->w || h != s->h || nframes < 0 || gop < 1 || strat < 0 ||
+        (delta && first_frame % gop != 0)) {
+        set_error("process_movie_host: bad arguments");
+        return -1;
+    }
+    if (strat == STRAT_NOBORDER) {
+        // untouched pixels keep whatever the destination held (the Python wrapper pre-fills it with the
+        // image, rir_signal_processing.py:56-57); there is no caller-visible destination here
+        set_error("process_movie_host: strategy \"noborder\" needs a caller-initialised destination; use rirb_translate_batch");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    GaussTaps taps;
+    if (gaussian_taps_host(sigma, &taps) != 0) return -1;
+    RIRB_REQUIRE_DEVICE();
+    const size_t fpx = (size_t)w * h;
+    // sub-chunk: whole GOPs, about 64 MB of input
+    long long sub = (long long)((64u << 20) / (fpx * 2));
+    sub = sub / gop * gop;
+    if (sub < gop) sub = gop;
+    // per-slot layout (every section 256-byte aligned)
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_in = 0, o_cor = o_in + al(fpx * 2 * sub), o_reg = o_cor + al(fpx * 2 * sub), o_lo = o_reg + al(fpx * 2 * sub),
+                 o_hi = o_lo + al(fpx * sub), o_sm = o_hi + al(fpx * sub), o_dx = o_sm + al(fpx * 4 * sub), o_dy = o_dx + al(4 * sub),
+                 total = o_dy + al(4 * sub);
+    HostPipe& hp = g_host_pipe;
+    int dev = 0;
+    RIRB_CUDA_OK(cudaGetDevice(&dev));
+    for (int k = 0; k < HP_SLOTS; ++k) {
+        HostPipeSlot& sl = hp.slot[k];
+        if (hp.device != dev && sl.buf) {  // the thread moved to another device: drop the old buffers
+            cudaFree(sl.buf);
+            sl.buf = nullptr;
+            sl.cap_bytes = 0;
+            if (sl.stream) cudaStreamDestroy(sl.stream);
+            sl.stream = nullptr;
+        }
+        if (!sl.stream) RIRB_CUDA_OK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (sl.cap_bytes < total) {
+            if (sl.buf) cudaFree(sl.buf);
+            sl.buf = nullptr;
+            sl.cap_bytes = 0;
+            RIRB_CUDA_OK(cudaMalloc(&sl.buf, total));
+            sl.cap_bytes = total;
+        }
+    }
+    hp.device = dev;
+    // work already enqueued by this thread (e.g. bad_pixels_create) is complete before the slots start
+    RIRB_CUDA_OK(cudaStreamSynchronize(tls.stream));
+    int rc = 0;
+    long long k = 0;
+    for (long long a = 0; a < nframes && rc == 0; a += sub, ++k) {
+        const long long m = (nframes - a < sub) ? nframes - a : sub;
+        HostPipeSlot& sl = hp.slot[k % HP_SLOTS];
+        cudaStream_t st = sl.stream;
+        char* base = (char*)sl.buf;
+        u16 *d_in = (u16*)(base + o_in), *d_cor = (u16*)(base + o_cor), *d_reg = (u16*)(base + o_reg);
+        u8 *d_lo = (u8*)(base + o_lo), *d_hi = (u8*)(base + o_hi);
+        float *d_sm = (float*)(base + o_sm), *d_dx = (float*)(base + o_dx), *d_dy = (float*)(base + o_dy);
+        RIRB_CUDA_OK(cudaMemcpyAsync(d_in, frames + a * fpx, fpx * 2 * m, cudaMemcpyHostToDevice, st));
+        RIRB_CUDA_OK(cudaMemcpyAsync(d_dx, dx + a, 4 * m, cudaMemcpyHostToDevice, st));
+        RIRB_CUDA_OK(cudaMemcpyAsync(d_dy, dy + a, 4 * m, cudaMemcpyHostToDevice, st));
+        if (launch_bp_correct(d_in, d_cor, s->xy_dev, s->span_off_dev, w, h, s->clamp_value, m, fpx, st) != 0 ||
+            launch_gaussian_u16(d_cor, d_sm, w, h, m, taps, st) != 0 ||
+            launch_translate_u16(d_cor, d_reg, w, h, m, fpx, fpx, d_dx, d_dy, 0.f, 0.f, strat, background & 0xFFFFu, false, st) != 0 ||
+            launch_precode_movie(d_reg, m, w, h, gop, delta, first_frame + a, d_lo, d_hi, st) != 0) {
+            rc = -1;
+            break;
+        }
+        RIRB_CUDA_OK(cudaMemcpyAsync(lo + a * fpx, d_lo, fpx * m, cudaMemcpyDeviceToHost, st));
+        RIRB_CUDA_OK(cudaMemcpyAsync(hi + a * fpx, d_hi, fpx * m, cudaMemcpyDeviceToHost, st));
+        if (smoothed) RIRB_CUDA_OK(cudaMemcpyAsync(smoothed + a * fpx, d_sm, fpx * 4 * m, cudaMemcpyDeviceToHost, st));
+    }
+    for (int q = 0; q < HP_SLOTS; ++q) {
+        cudaError_t e = cudaStreamSynchronize(hp.slot[q].stream);
+        if (e != cudaSuccess && rc == 0) {
+            set_error("process_movie_host: %s", cudaGetErrorString(e));
+            rc = -1;
+        }
+    }
+    return rc;
+}
+
+// =================================================================================================
 // statistics
 // =================================================================================================
 int rirb_movie_stats(const unsigned short* pixels, size_t n, unsigned int* minmax, unsigned long long* hist, int accumulate)

@@ -241,6 +241,36 @@ class FramePipeline:
         main.synchronize()
 
 
+def process_movie_host(bad_pixels, frames, dx, dy, sigma=1.0, strategy="nearest", background=0, gop=vio.DEFAULT_GOP, delta=True,
+                       first_frame=0, lo=None, hi=None, smoothed=None):
+    """The whole per-frame path on HOST buffers through ONE C-ABI call (``rirb_process_movie_host``):
+    ``frames`` uint16 ``[n, h, w]`` (numpy array or CPU torch tensor, ideally pinned) -> ``(lo, hi)`` uint8
+    byte planes of the corrected, registered, pre-coded frames.  ``smoothed``: optional float32 ``[n, h, w]``
+    host buffer for the Gaussian output (otherwise it stays on the device)."""
+    lib = _lib.load()
+
+    def host_ptr(x):
+        if sp._is_torch(x):
+            if x.is_cuda or not x.is_contiguous():
+                raise RuntimeError("process_movie_host: contiguous host buffers expected")
+            return ct.c_void_p(x.data_ptr())
+        return x.ctypes.data_as(ct.c_void_p)
+
+    n, h, w = frames.shape
+    if lo is None:
+        lo = np.empty((n, h, w), np.uint8)
+    if hi is None:
+        hi = np.empty((n, h, w), np.uint8)
+    if not sp._is_torch(dx):
+        dx = np.ascontiguousarray(np.broadcast_to(np.asarray(dx, dtype=np.float32), (n,)))
+        dy = np.ascontiguousarray(np.broadcast_to(np.asarray(dy, dtype=np.float32), (n,)))
+    r = lib.rirb_process_movie_host(bad_pixels.handle, host_ptr(frames), n, w, h, float(sigma), host_ptr(dx), host_ptr(dy),
+                                    sp.toCharP(strategy), int(background), int(gop), int(bool(delta)), int(first_frame),
+                                    host_ptr(lo), host_ptr(hi), host_ptr(smoothed) if smoothed is not None else None)
+    _lib.check(r, "process_movie_host")
+    return lo, hi
+
+
 def broadcast_first_frame(frame, src: int = 0, group=None):
     """Hand frame 0 (owned by the rank holding the movie's first shard) to every rank."""
     import torch
@@ -251,4 +281,5 @@ def broadcast_first_frame(frame, src: int = 0, group=None):
     return frame
 
 
-__all__ = ["FrameShard", "shard_frames", "MovieStats", "PipelineConfig", "FramePipeline", "broadcast_first_frame"]
+__all__ = ["FrameShard", "shard_frames", "MovieStats", "PipelineConfig", "FramePipeline", "process_movie_host",
+           "broadcast_first_frame"]

@@ -466,6 +466,36 @@ def test_lossless_precoder_frame_by_frame(port):
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json full sizes: size-independent properties
 # ---------------------------------------------------------------------------------------------
+def test_process_movie_host_one_call_equals_the_staged_calls(port, best):
+    """rirb_process_movie_host (host frames in, host byte planes out, one C-ABI call, three streams)
+    against the per-stage entries and the oracle chain."""
+    from librir_b200 import movie
+
+    n, h, w = 230, 64, 96  # several sub-chunks would need a bigger movie; GOP 7 makes ragged tails
+    mov = ir_movie(n, h, w)
+    rng = np.random.default_rng(5)
+    dx = rng.uniform(-3, 3, n).astype(np.float32)
+    dy = rng.uniform(-3, 3, n).astype(np.float32)
+    bp = sp.BadPixels(mov[0])
+    smoothed = np.empty((n, h, w), np.float32)
+    for delta in (False, True):
+        lo, hi = movie.process_movie_host(bp, mov, dx, dy, 1.0, "nearest", 0, gop=7, delta=delta, first_frame=14, smoothed=smoothed)
+        corr = bp.correct_batch(mov)
+        reg = sp.translate_batch(corr, dx, dy, "nearest", 0)
+        wlo, whi = vio.precode_movie(reg, gop=7, delta=delta, first_frame=14)
+        np.testing.assert_array_equal(lo, wlo)
+        np.testing.assert_array_equal(hi, whi)
+        np.testing.assert_array_equal(smoothed, sp.gaussian_filter_batch(corr, 1.0))
+    # against the oracle, frame by frame (delta off: planes are the registered frame's bytes)
+    lo, hi = movie.process_movie_host(bp, mov[:6], dx[:6], dy[:6], 1.0, "background", 5, gop=50, delta=False)
+    xy, clamp = sp.bad_pixels_list(bp.handle)
+    for t in range(6):
+        want = best.translate(port.bad_pixels_correct_with(xy, clamp, mov[t]), dx[t], dy[t], "background", 5)
+        np.testing.assert_array_equal(lo[t].astype(np.uint16) | (hi[t].astype(np.uint16) << 8), want)
+    with pytest.raises(RuntimeError):
+        movie.process_movie_host(bp, mov[:2], dx[:2], dy[:2], strategy="noborder")
+
+
 def test_full_size_c2_round_trip_and_checksums():
     """640x512x1000 (configs[1]): decode(precode(x)) == x with and without delta, and the byte
     planes carry exactly the movie's bytes (checksum of checksums)."""
