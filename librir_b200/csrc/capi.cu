@@ -188,12 +188,14 @@ struct BadPixelState {
     u8* mask_dev = nullptr;       // bitmap, row stride (w+7)/8
     int* xy_dev = nullptr;        // raster-ordered list (x,y), device copy
     int* span_off_dev = nullptr;  // list offsets per BP_SPAN-pixel span (correction kernel)
+    int* nbr_dev = nullptr;       // per list entry: which cells of the loader variant's shifted 3x3 window are flagged
     std::vector<int> xy;          // host copy
     ~BadPixelState()
     {
         if (mask_dev) cudaFree(mask_dev);
         if (xy_dev) cudaFree(xy_dev);
         if (span_off_dev) cudaFree(span_off_dev);
+        if (nbr_dev) cudaFree(nbr_dev);
     }
 };
 static std::mutex g_handles_mutex;
@@ -483,11 +485,32 @@ int bad_pixels_create(unsigned short* first_image, int width, int height)
     if (cudaMalloc(&state->span_off_dev, span_off.size() * sizeof(int)) != cudaSuccess) return fail("cudaMalloc(span offsets)");
     if (cudaMemcpyAsync(state->span_off_dev, span_off.data(), span_off.size() * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess)
         return fail("H2D(span offsets)");
+    std::vector<int> nbr;
     if (!state->xy.empty()) {
         if (cudaMalloc(&state->xy_dev, state->xy.size() * sizeof(int)) != cudaSuccess) return fail("cudaMalloc(list)");
         if (cudaMemcpyAsync(state->xy_dev, state->xy.data(), state->xy.size() * sizeof(int), cudaMemcpyHostToDevice, st) !=
             cudaSuccess)
             return fail("H2D(list)");
+        // IRFileLoader::removeBadPixels (IRFileLoader.cpp:754-790) skips the flagged cells of its window (shifted
+        // inside the image): bit k of nbr[i] = cell (x0 + k/3, y0 + k%3) of entry i's window is flagged
+        if (width >= 3 && height >= 3) {
+            const size_t kk = state->xy.size() / 2;
+            nbr.resize(kk);
+            for (size_t i = 0; i < kk; ++i) {
+                const int x = state->xy[2 * i], y = state->xy[2 * i + 1];
+                const int x0 = x == 0 ? 0 : (x == width - 1 ? width - 3 : x - 1);
+                const int y0 = y == 0 ? 0 : (y == height - 1 ? height - 3 : y - 1);
+                int bits = 0;
+                for (int c = 0; c < 9; ++c) {
+                    const int xx = x0 + c / 3, yy = y0 + c % 3;
+                    if (mask[(size_t)yy * mstride + (xx >> 3)] & (1u << (xx & 7))) bits |= 1 << c;
+                }
+                nbr[i] = bits;
+            }
+            if (cudaMalloc(&state->nbr_dev, kk * sizeof(int)) != cudaSuccess) return fail("cudaMalloc(window flags)");
+            if (cudaMemcpyAsync(state->nbr_dev, nbr.data(), kk * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess)
+                return fail("H2D(window flags)");
+        }
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) return fail("sync");
     return register_handle(state);
@@ -686,7 +709,7 @@ int rirb_loader_read_movie(int handle, const unsigned char* lo, const unsigned c
     const int k = s ? (int)(s->xy.size() / 2) : 0;
     const bool fused_bp = s && k > 0 && w >= 3 && hb >= 3;
     if (launch_loader_merge(d_lo, d_hi, merged, w, h, hb, nframes, fpx, min_T, min_T_height, fused_bp ? s->xy_dev : nullptr,
-                            fused_bp ? s->span_off_dev : nullptr, fused_bp ? s->mask_dev : nullptr, st) != 0)
+                            fused_bp ? s->span_off_dev : nullptr, fused_bp ? s->nbr_dev : nullptr, st) != 0)
         return -1;
     if (s && k > 0 && !fused_bp)  // degenerate sizes keep the reference's sequential loop (IRFileLoader.cpp:735-752)
         if (launch_loader_bp(merged, s->xy_dev, s->mask_dev, k, w, hb, nframes, fpx, st) != 0) return -1;

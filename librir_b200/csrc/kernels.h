@@ -27,7 +27,7 @@ int launch_loader_bp(u16* img, const int* xy_dev, const u8* mask, int count, int
 
 // loader.cu
 int launch_loader_merge(const u8* lo, const u8* hi, u16* out, int w, int h, int hb, long long nframes, size_t frame_stride,
-                        int min_t, int min_t_height, const int* xy_dev, const int* span_off_dev, const u8* mask_dev,
+                        int min_t, int min_t_height, const int* xy_dev, const int* span_off_dev, const int* nbr_dev,
                         cudaStream_t st);
 
 // translate.cu

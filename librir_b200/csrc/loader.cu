@@ -34,7 +34,7 @@ __device__ __forceinline__ unsigned merged_px(const u8* __restrict__ lo, const u
 template <bool VEC>
 __global__ void __launch_bounds__(LD_THREADS)
 loader_merge_kernel(const u8* __restrict__ lo, const u8* __restrict__ hi, u16* __restrict__ out, const int* __restrict__ xy,
-                    const int* __restrict__ span_off, const u8* __restrict__ mask, int handle_spans, int w, int h, int hb, int npx,
+                    const int* __restrict__ span_off, const int* __restrict__ nbr, int handle_spans, int w, int h, int hb, int npx,
                     int spans, unsigned min_t, int t_limit_px, size_t frame_stride)
 {
     const int span = blockIdx.x % spans;
@@ -44,7 +44,6 @@ loader_merge_kernel(const u8* __restrict__ lo, const u8* __restrict__ hi, u16* _
     const u8* flo = lo + f * frame_stride;
     const u8* fhi = hi + f * frame_stride;
     u16* oframe = out + f * frame_stride;
-    const int mstride = (w + 7) >> 3;
     int a = 0, b = 0;
     if (xy != nullptr && span < handle_spans) {
         a = span_off[span];
@@ -69,25 +68,22 @@ loader_merge_kernel(const u8* __restrict__ lo, const u8* __restrict__ hi, u16* _
     int2 p0 = make_int2(0, 0);
     unsigned med0 = 0;
     bool have0 = false;
-    auto fix = [&](int2 p, unsigned& med) -> bool {
+    auto fix = [&](int2 p, int flags, unsigned& med) -> bool {
         // IRFileLoader.cpp:754-795: 3x3 window shifted inside the hb-row image, flagged cells skipped
         int x0 = p.x - 1, y0 = p.y - 1;
         if (p.x == 0) x0 = 0; else if (p.x == w - 1) x0 = w - 3;
         if (p.y == 0) y0 = 0; else if (p.y == hb - 1) y0 = hb - 3;
-        // all 27 loads are independent of one another (the cell values do not wait for the bitmap)
-        unsigned v[9], flagged[9];
+        // which of the 9 cells are flagged was worked out once, at create time (nbr): 18 independent byte loads
+        unsigned v[9];
+        int c = 0;
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
             const int xx = x0 + k / 3, yy = y0 + k % 3;
             const size_t i = (size_t)yy * w + xx;
-            flagged[k] = mask[(size_t)yy * mstride + (xx >> 3)] & (1u << (xx & 7));
-            v[k] = merged_px(flo, fhi, i, (int)i < t_limit_px ? min_t : 0u);
-        }
-        int c = 0;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            if (flagged[k]) v[k] = 0xFFFFFFFFu;
-            else ++c;
+            const unsigned val = merged_px(flo, fhi, i, (int)i < t_limit_px ? min_t : 0u);
+            const bool ok = !((flags >> k) & 1);
+            v[k] = ok ? val : 0xFFFFFFFFu;
+            c += ok;
         }
         if (c == 0) return false;  // the reference reads a stale stack slot here (undefined): leave the pixel
         sort9(v);
@@ -96,7 +92,7 @@ loader_merge_kernel(const u8* __restrict__ lo, const u8* __restrict__ hi, u16* _
     };
     if (i0 < b) {
         p0 = reinterpret_cast<const int2*>(xy)[i0];
-        have0 = fix(p0, med0);
+        have0 = fix(p0, nbr[i0], med0);
     }
     int done = s0;
     if (VEC) {
@@ -127,14 +123,14 @@ loader_merge_kernel(const u8* __restrict__ lo, const u8* __restrict__ hi, u16* _
     for (int i = i0 + LD_THREADS; i < b; i += LD_THREADS) {
         const int2 p = reinterpret_cast<const int2*>(xy)[i];
         unsigned med;
-        if (fix(p, med)) oframe[(size_t)p.y * w + p.x] = (u16)med;
+        if (fix(p, nbr[i], med)) oframe[(size_t)p.y * w + p.x] = (u16)med;
     }
 }
 
-// xy_dev / span_off_dev / mask_dev: the handle's list, span offsets and bitmap for a w x hb image
+// xy_dev / span_off_dev / nbr_dev: the handle's list, span offsets and window flags for a w x hb image
 // (nullptr: no bad-pixel correction in this pass).  frame_stride in pixels for all three buffers.
 int launch_loader_merge(const u8* lo, const u8* hi, u16* out, int w, int h, int hb, long long nframes, size_t frame_stride,
-                        int min_t, int min_t_height, const int* xy_dev, const int* span_off_dev, const u8* mask_dev,
+                        int min_t, int min_t_height, const int* xy_dev, const int* span_off_dev, const int* nbr_dev,
                         cudaStream_t st)
 {
     if (nframes <= 0 || w <= 0 || h <= 0) return 0;
@@ -151,10 +147,10 @@ int launch_loader_merge(const u8* lo, const u8* hi, u16* out, int w, int h, int 
     const unsigned mt = (unsigned)min_t & 0xFFFFu;
     const bool vec = (w % 16 == 0) && aligned16(lo) && aligned16(hi) && aligned32(out) && (frame_stride % 16 == 0);
     if (vec)
-        RIRB_LAUNCH(loader_merge_kernel<true>, (unsigned)grid, LD_THREADS, 0, st, lo, hi, out, xy_dev, span_off_dev, mask_dev,
+        RIRB_LAUNCH(loader_merge_kernel<true>, (unsigned)grid, LD_THREADS, 0, st, lo, hi, out, xy_dev, span_off_dev, nbr_dev,
                     handle_spans, w, h, hb, (int)npx, (int)spans, mt, t_limit_px, frame_stride);
     else
-        RIRB_LAUNCH(loader_merge_kernel<false>, (unsigned)grid, LD_THREADS, 0, st, lo, hi, out, xy_dev, span_off_dev, mask_dev,
+        RIRB_LAUNCH(loader_merge_kernel<false>, (unsigned)grid, LD_THREADS, 0, st, lo, hi, out, xy_dev, span_off_dev, nbr_dev,
                     handle_spans, w, h, hb, (int)npx, (int)spans, mt, t_limit_px, frame_stride);
     return 0;
 }
