@@ -77,6 +77,11 @@ RIRB_API int rirb_synchronize(void);                  /* wait for the calling th
 RIRB_API const char* rirb_last_error(void);           /* calling thread's last error text */
 RIRB_API long long rirb_kernel_launch_count(void);    /* kernels launched by this library so far */
 RIRB_API const char* rirb_version(void);
+/* string key/value switches, the reference's *_set_parameter convention (h264.cpp:1709-1781); process-wide.
+ * "translate_tma" / "gauss_tma" (default 1): TMA-tiled kernels vs the register-only ones;
+ * "loader_fused" (default 0): rirb_loader_read_movie as one fused pass instead of merge pass + motion pass.
+ * Initial values can also come from RIRB_TRANSLATE_TMA / RIRB_GAUSS_TMA / RIRB_LOADER_FUSED.  -1: unknown key. */
+RIRB_API int rirb_set_parameter(const char* key, const char* value);
 
 /* ---- batches of frames (nframes dense frames back to back) ---- */
 

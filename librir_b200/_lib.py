@@ -52,6 +52,7 @@ SIGNATURES = {
     "rirb_last_error": (ct.c_char_p, []),
     "rirb_kernel_launch_count": (_ll, []),
     "rirb_version": (ct.c_char_p, []),
+    "rirb_set_parameter": (_i, [ct.c_char_p, ct.c_char_p]),
     "rirb_translate_batch": (_i, [_i, _vp, _vp, _i, _i, _ll, _vp, _vp, _ll, _vp, ct.c_char_p]),
     "rirb_gaussian_filter_batch": (_i, [_vp, _vp, _i, _i, _ll, _f]),
     "rirb_gaussian_filter_u16_batch": (_i, [_vp, _vp, _i, _i, _ll, _f]),
@@ -88,6 +89,11 @@ def load() -> ct.CDLL:
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def set_parameter(key: str, value) -> None:
+    """``rirb_set_parameter``: process-wide kernel-variant switches ("translate_tma", "gauss_tma", "loader_fused")."""
+    check(load().rirb_set_parameter(key.encode(), str(int(value)).encode()), "set_parameter")
 
 
 def last_error() -> str:

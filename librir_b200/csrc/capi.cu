@@ -44,6 +44,25 @@ void set_error(const char* fmt, ...)
 
 cudaStream_t current_stream() { return tls.stream; }
 
+// ---- run-time switches ---------------------------------------------------------------------------
+static const char* const k_opt_names[OPT_COUNT] = {"translate_tma", "gauss_tma", "loader_fused"};
+static const char* const k_opt_env[OPT_COUNT] = {"RIRB_TRANSLATE_TMA", "RIRB_GAUSS_TMA", "RIRB_LOADER_FUSED"};
+static const int k_opt_default[OPT_COUNT] = {1, 1, 0};
+static std::atomic<int> g_opts[OPT_COUNT];
+static std::once_flag g_opts_once;
+static void init_options()
+{
+    for (int i = 0; i < OPT_COUNT; ++i) {
+        const char* e = getenv(k_opt_env[i]);
+        g_opts[i].store(e && *e ? (e[0] != '0') : k_opt_default[i]);
+    }
+}
+bool option_enabled(int which)
+{
+    std::call_once(g_opts_once, init_options);
+    return which >= 0 && which < OPT_COUNT && g_opts[which].load() != 0;
+}
+
 int sm_count()
 {
     static int cached[64] = {0};
@@ -189,6 +208,7 @@ struct BadPixelState {
     int* xy_dev = nullptr;        // raster-ordered list (x,y), device copy
     int* span_off_dev = nullptr;  // list offsets per BP_SPAN-pixel span (correction kernel)
     int* nbr_dev = nullptr;       // per list entry: which cells of the loader variant's shifted 3x3 window are flagged
+    int* row_off_dev = nullptr;   // first list entry of each image row (h + 1 entries), fused reader kernel
     std::vector<int> xy;          // host copy
     ~BadPixelState()
     {
@@ -196,6 +216,7 @@ struct BadPixelState {
         if (xy_dev) cudaFree(xy_dev);
         if (span_off_dev) cudaFree(span_off_dev);
         if (nbr_dev) cudaFree(nbr_dev);
+        if (row_off_dev) cudaFree(row_off_dev);
     }
 };
 static std::mutex g_handles_mutex;
@@ -281,6 +302,18 @@ int rirb_synchronize(void)
     RIRB_REQUIRE_DEVICE();
     RIRB_CUDA_OK(cudaStreamSynchronize(tls.stream));
     return 0;
+}
+int rirb_set_parameter(const char* key, const char* value)
+{
+    std::call_once(g_opts_once, init_options);
+    if (key && value)
+        for (int i = 0; i < OPT_COUNT; ++i)
+            if (strcmp(key, k_opt_names[i]) == 0) {
+                g_opts[i].store(value[0] != '0' && value[0] != 0);
+                return 0;
+            }
+    set_error("set_parameter: unknown key '%s'", key ? key : "(null)");
+    return -1;
 }
 const char* rirb_last_error(void) { return tls.err; }
 long long rirb_kernel_launch_count(void) { return g_launches.load(); }
@@ -485,7 +518,18 @@ int bad_pixels_create(unsigned short* first_image, int width, int height)
     if (cudaMalloc(&state->span_off_dev, span_off.size() * sizeof(int)) != cudaSuccess) return fail("cudaMalloc(span offsets)");
     if (cudaMemcpyAsync(state->span_off_dev, span_off.data(), span_off.size() * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess)
         return fail("H2D(span offsets)");
-    std::vector<int> nbr;
+    std::vector<int> nbr, row_off((size_t)height + 1, 0);
+    {
+        const size_t kk = state->xy.size() / 2;
+        size_t i = 0;
+        for (int y = 0; y <= height; ++y) {
+            while (i < kk && state->xy[2 * i + 1] < y) ++i;
+            row_off[y] = (int)i;
+        }
+        if (cudaMalloc(&state->row_off_dev, row_off.size() * sizeof(int)) != cudaSuccess) return fail("cudaMalloc(row offsets)");
+        if (cudaMemcpyAsync(state->row_off_dev, row_off.data(), row_off.size() * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess)
+            return fail("H2D(row offsets)");
+    }
     if (!state->xy.empty()) {
         if (cudaMalloc(&state->xy_dev, state->xy.size() * sizeof(int)) != cudaSuccess) return fail("cudaMalloc(list)");
         if (cudaMemcpyAsync(state->xy_dev, state->xy.data(), state->xy.size() * sizeof(int), cudaMemcpyHostToDevice, st) !=
@@ -701,46 +745,60 @@ int rirb_loader_read_movie(int handle, const unsigned char* lo, const unsigned c
     StagedOut o;
     if (!stage_out(o, out, pbytes * 2, 2, false, st)) return -1;
     const bool motion = shift_x != nullptr;
-    u16* merged = (u16*)o.dev;
-    if (motion) {  // the translate reads one buffer and writes another
-        merged = (u16*)scratch(3, pbytes * 2);
-        if (!merged) return -1;
-    }
     const int k = s ? (int)(s->xy.size() / 2) : 0;
     const bool fused_bp = s && k > 0 && w >= 3 && hb >= 3;
-    if (launch_loader_merge(d_lo, d_hi, merged, w, h, hb, nframes, fpx, min_T, min_T_height, fused_bp ? s->xy_dev : nullptr,
-                            fused_bp ? s->span_off_dev : nullptr, fused_bp ? s->nbr_dev : nullptr, st) != 0)
-        return -1;
-    if (s && k > 0 && !fused_bp)  // degenerate sizes keep the reference's sequential loop (IRFileLoader.cpp:735-752)
-        if (launch_loader_bp(merged, s->xy_dev, s->mask_dev, k, w, hb, nframes, fpx, st) != 0) return -1;
-    if (motion) {
-        std::vector<double> sx((size_t)nframes), sy((size_t)nframes);
-        if (is_device_ptr(shift_x) || is_device_ptr(shift_y)) {
-            RIRB_CUDA_OK(cudaMemcpyAsync(sx.data(), shift_x, sizeof(double) * nframes, cudaMemcpyDefault, st));
-            RIRB_CUDA_OK(cudaMemcpyAsync(sy.data(), shift_y, sizeof(double) * nframes, cudaMemcpyDefault, st));
-            RIRB_CUDA_OK(cudaStreamSynchronize(st));
-        } else {
-            memcpy(sx.data(), shift_x, sizeof(double) * nframes);
-            memcpy(sy.data(), shift_y, sizeof(double) * nframes);
-        }
-        std::vector<float> fx((size_t)nframes), fy((size_t)nframes);
-        for (long long i = 0; i < nframes; ++i) {  // translate(..., -x[pos], -y[pos], ...) with float arguments (:621)
-            fx[i] = (float)(-sx[i]);
-            fy[i] = (float)(-sy[i]);
-        }
-        const float* d_dx = (const float*)stage_in(fx.data(), sizeof(float) * nframes, 4, st);
-        const float* d_dy = (const float*)stage_in(fy.data(), sizeof(float) * nframes, 5, st);
-        if (!d_dx || !d_dy) return -1;
+    if (!motion) {
+        u16* merged = (u16*)o.dev;
+        if (launch_loader_merge(d_lo, d_hi, merged, w, h, hb, nframes, fpx, min_T, min_T_height, fused_bp ? s->xy_dev : nullptr,
+                                fused_bp ? s->span_off_dev : nullptr, fused_bp ? s->nbr_dev : nullptr, st) != 0)
+            return -1;
+        if (s && k > 0 && !fused_bp)  // degenerate sizes keep the reference's sequential loop (IRFileLoader.cpp:735-752)
+            if (launch_loader_bp(merged, s->xy_dev, s->mask_dev, k, w, hb, nframes, fpx, st) != 0) return -1;
+        return finish_out(&o, 1, st);
+    }
+    // shifts: translate(..., -x[pos], -y[pos], ...) with float arguments (IRFileLoader.cpp:621)
+    std::vector<double> sx((size_t)nframes), sy((size_t)nframes);
+    if (is_device_ptr(shift_x) || is_device_ptr(shift_y)) {
+        RIRB_CUDA_OK(cudaMemcpyAsync(sx.data(), shift_x, sizeof(double) * nframes, cudaMemcpyDefault, st));
+        RIRB_CUDA_OK(cudaMemcpyAsync(sy.data(), shift_y, sizeof(double) * nframes, cudaMemcpyDefault, st));
+        RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    } else {
+        memcpy(sx.data(), shift_x, sizeof(double) * nframes);
+        memcpy(sy.data(), shift_y, sizeof(double) * nframes);
+    }
+    std::vector<float> fx((size_t)nframes), fy((size_t)nframes);
+    for (long long i = 0; i < nframes; ++i) {
+        fx[i] = (float)(-sx[i]);
+        fy[i] = (float)(-sy[i]);
+    }
+    const float* d_dx = (const float*)stage_in(fx.data(), sizeof(float) * nframes, 4, st);
+    const float* d_dy = (const float*)stage_in(fy.data(), sizeof(float) * nframes, 5, st);
+    if (!d_dx || !d_dy) return -1;
+    // one pass: planes -> merge -> += min_T -> medians -> motion translate (translate.cu, PLANES)
+    const int rows_t = (min_T == 0 || min_T_height < 0) ? 0 : (min_T_height > h ? h : min_T_height);
+    int rc = (s && k > 0 && !fused_bp)
+                 ? 1
+                 : launch_loader_fused(d_lo, d_hi, (u16*)o.dev, w, h, hb, nframes, min_T, rows_t, fused_bp ? s->xy_dev : nullptr,
+                                       fused_bp ? s->nbr_dev : nullptr, fused_bp ? s->row_off_dev : nullptr,
+                                       fused_bp ? s->mask_dev : nullptr, d_dx, d_dy, st);
+    if (rc < 0) return -1;
+    if (rc == 1) {  // layouts the fused kernel does not take: merge pass, then the motion pass through a scratch movie
+        u16* merged = (u16*)scratch(3, pbytes * 2);
+        if (!merged) return -1;
+        if (launch_loader_merge(d_lo, d_hi, merged, w, h, hb, nframes, fpx, min_T, min_T_height, fused_bp ? s->xy_dev : nullptr,
+                                fused_bp ? s->span_off_dev : nullptr, fused_bp ? s->nbr_dev : nullptr, st) != 0)
+            return -1;
+        if (s && k > 0 && !fused_bp)
+            if (launch_loader_bp(merged, s->xy_dev, s->mask_dev, k, w, hb, nframes, fpx, st) != 0) return -1;
         if (meta_rows > 0)  // the metadata rows are not translated
             RIRB_CUDA_OK(cudaMemcpy2DAsync((u16*)o.dev + (size_t)w * hb, fpx * 2, merged + (size_t)w * hb, fpx * 2,
                                            (size_t)w * meta_rows * 2, (size_t)nframes, cudaMemcpyDeviceToDevice, st));
         if (launch_translate_u16(merged, (u16*)o.dev, w, hb, nframes, fpx, fpx, d_dx, d_dy, 0.f, 0.f, STRAT_NEAREST, 0u, true, st) != 0)
             return -1;
-        if (o.host) RIRB_CUDA_OK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st));
-        RIRB_CUDA_OK(cudaStreamSynchronize(st));  // fx / fy are host vectors read by an async copy
-        return 0;
     }
-    return finish_out(&o, 1, st);
+    if (o.host) RIRB_CUDA_OK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st));
+    RIRB_CUDA_OK(cudaStreamSynchronize(st));  // fx / fy are host vectors read by an async copy
+    return 0;
 }
 
 // =================================================================================================

@@ -417,10 +417,7 @@ static int launch_gaussian(const TIN* src, float* dst, int w, int h, long long n
         RIRB_LAUNCH(gauss_generic_kernel<TIN>, grid, block, 0, st, src, dst, w, h, nframes, taps);
         return 0;
     }
-    static const bool tma_enabled = []() {  // RIRB_GAUSS_TMA=0 selects the warp-strip kernel (A/B measurements)
-        const char* e = getenv("RIRB_GAUSS_TMA");
-        return !(e && e[0] == '0');
-    }();
+    const bool tma_enabled = option_enabled(OPT_GAUSS_TMA);  // "gauss_tma" = 0 selects the warp-strip kernel (A/B measurements)
     const size_t esz = sizeof(TIN);
     const int tiles_x = (int)ceil_div(w, GT_W), tiles_y = (int)ceil_div(h, GT_H);
     const long long tgrid = nframes * tiles_x * tiles_y;

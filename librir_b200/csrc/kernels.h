@@ -30,6 +30,11 @@ int launch_loader_merge(const u8* lo, const u8* hi, u16* out, int w, int h, int 
                         int min_t, int min_t_height, const int* xy_dev, const int* span_off_dev, const int* nbr_dev,
                         cudaStream_t st);
 
+// translate.cu: the reader's chain fused into the motion translate; returns 1 if the layout cannot take it
+int launch_loader_fused(const u8* lo, const u8* hi, u16* out, int w, int h_full, int hb, long long nframes, int min_t, int t_rows,
+                        const int* xy_dev, const int* nbr_dev, const int* row_off_dev, const u8* mask_dev, const float* dxs,
+                        const float* dys, cudaStream_t st);
+
 // translate.cu
 int launch_translate(int type, const void* src, void* dst, int w, int h, long long nframes, const float* dxs, const float* dys,
                      float dx0, float dy0, int strategy, const void* background_host, cudaStream_t st);

@@ -36,7 +36,7 @@ int make_movie_tensor_map(CUtensorMap* map, const void* base, int elem_bytes, in
         set_error("cuTensorMapEncodeTiled is not available from this driver");
         return -1;
     }
-    if ((elem_bytes != 2 && elem_bytes != 4) || !tma_compatible(base, row_stride_bytes, frame_stride_bytes) || box_w > 256 ||
+    if ((elem_bytes != 1 && elem_bytes != 2 && elem_bytes != 4) || !tma_compatible(base, row_stride_bytes, frame_stride_bytes) || box_w > 256 ||
         box_h > 256 || (box_w * elem_bytes) % 16 != 0 || nframes <= 0) {
         set_error("tensor map: unsupported layout");
         return -1;
@@ -46,7 +46,7 @@ int make_movie_tensor_map(CUtensorMap* map, const void* base, int elem_bytes, in
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     // a one-frame movie must not carry a zero / unaligned outer stride
-    const CUresult r = enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+    const CUresult r = enc(map, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 3,
                            const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

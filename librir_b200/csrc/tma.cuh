@@ -22,7 +22,7 @@
 namespace rirb {
 
 // ---- host: tensor-map encoding through the driver entry point (no link against libcuda) ---------
-// elem_bytes 2 (uint16) or 4 (float32).  Strides in BYTES, multiples of 16; base 16-byte aligned;
+// elem_bytes 1 (uint8), 2 (uint16) or 4 (float32).  Strides in BYTES, multiples of 16; base 16-byte aligned;
 // box_w * elem_bytes a multiple of 16, box dims <= 256.  Returns 0 / -1 (set_error).
 int make_movie_tensor_map(CUtensorMap* map, const void* base, int elem_bytes, int w, int h, long long nframes,
                           size_t row_stride_bytes, size_t frame_stride_bytes, int box_w, int box_h);

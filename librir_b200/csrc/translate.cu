@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "sort9.cuh"
 #include "tma.cuh"
 
 namespace rirb {
@@ -476,11 +477,100 @@ __device__ __forceinline__ void fast_rows(uint32_t tbase, uint32_t rinfo, bool x
 constexpr int TT_STAGES = 2;
 constexpr unsigned TT_STAGE_BYTES = (TT_BH * TT_BW * 2 + 127u) & ~127u;
 
-template <bool MOTION>
+// ---- fused reader front end (PLANES) --------------------------------------------------------------
+// IRFileLoader::readImage's whole post-decode chain in ONE pass over HBM: the source
+// of a tile is not a uint16 frame but the decoder's two byte planes.  Per stage two TMA boxes (low
+// bytes, high bytes; uint8 boxes start on 16-pixel boundaries) land in shared memory; the CTA merges
+// them into the uint16 tile the blend reads (v = lo | hi << 8, h264.cpp:3030,3044; += min_T on the
+// rows that ask for it, IRFileLoader.cpp:1174-1179), patches the flagged pixels of the tile with the
+// loader's median (IRFileLoader.cpp:754-795) and then runs the motion translate (:617-627) exactly
+// as the plain kernel does.  2 B/px read + 2 B/px written instead of three round trips.
+constexpr int TP_BW = 160;                                      // plane box width (bytes = pixels)
+constexpr unsigned TP_BOX_BYTES = TP_BW * TT_BH;                // one plane, one stage
+constexpr unsigned TP_BOX_AL = (TP_BOX_BYTES + 127u) & ~127u;
+constexpr unsigned TP_STAGE_BYTES = 2 * TP_BOX_AL;              // lo box + hi box
+constexpr unsigned TP_SMEM_BYTES = TT_STAGES * TP_STAGE_BYTES + TT_STAGE_BYTES;  // + the merged uint16 tile
+
+struct PlaneSrc {
+    const u8* lo;            // [n][h_full][w] byte planes (global), for the medians and out-of-box reads
+    const u8* hi;
+    size_t plane_stride;     // h_full * w
+    const int* xy;           // bad-pixel list of the w x h image (nullptr: no correction)
+    const int* nbr;          // per entry: flagged cells of its shifted 3x3 window
+    const int* row_off;      // first list entry of each row, h + 1 entries
+    const u8* mask;          // bitmap (row stride (w + 7) / 8), used by out-of-box reads only
+    unsigned min_t;          // added (mod 2^16) on rows < t_rows
+    int t_rows;
+    int h_full;              // rows of the stored frame; rows [h, h_full) are metadata: merged, not translated
+};
+
+__device__ __forceinline__ unsigned plane_px(const u8* __restrict__ lo, const u8* __restrict__ hi, int w, int x, int y, const PlaneSrc& ps)
+{
+    const size_t i = (size_t)y * w + x;
+    return (((unsigned)lo[i] | ((unsigned)hi[i] << 8)) + (y < ps.t_rows ? ps.min_t : 0u)) & 0xFFFFu;
+}
+// the loader's median for flagged pixel (x, y) of the w x h image; false: no un-flagged cell (pixel stays)
+__device__ __forceinline__ bool plane_median(const u8* __restrict__ lo, const u8* __restrict__ hi, int w, int h, int x, int y, int flags,
+                                             const PlaneSrc& ps, unsigned& med)
+{
+    const int x0 = x == 0 ? 0 : (x == w - 1 ? w - 3 : x - 1);
+    const int y0 = y == 0 ? 0 : (y == h - 1 ? h - 3 : y - 1);
+    unsigned v[9];
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const unsigned val = plane_px(lo, hi, w, x0 + k / 3, y0 + k % 3, ps);
+        const bool ok = !((flags >> k) & 1);
+        v[k] = ok ? val : 0xFFFFFFFFu;
+        c += ok;
+    }
+    if (c == 0) return false;
+    sort9(v);
+    med = pick_mid(v, c);
+    return true;
+}
+// Source pixel of the corrected frame that is NOT in the staged tile (far clamped / wrapped reads): rebuilt from the planes.
+__device__ __noinline__ unsigned plane_corrected_px(const u8* __restrict__ lo, const u8* __restrict__ hi, int w, int h, int x, int y,
+                                                    const PlaneSrc& ps)
+{
+    unsigned v = plane_px(lo, hi, w, x, y, ps);
+    if (ps.xy != nullptr) {
+        const int mstride = (w + 7) >> 3;
+        if (ps.mask[(size_t)y * mstride + (x >> 3)] & (1u << (x & 7))) {
+            const int x0 = x == 0 ? 0 : (x == w - 1 ? w - 3 : x - 1);
+            const int y0 = y == 0 ? 0 : (y == h - 1 ? h - 3 : y - 1);
+            int flags = 0;
+            for (int k = 0; k < 9; ++k) {
+                const int xx = x0 + k / 3, yy = y0 + k % 3;
+                if (ps.mask[(size_t)yy * mstride + (xx >> 3)] & (1u << (xx & 7))) flags |= 1 << k;
+            }
+            unsigned med;
+            if (plane_median(lo, hi, w, h, x, y, flags, ps, med)) v = med;
+        }
+    }
+    return v;
+}
+struct PlaneTileSrc {
+    const u16* tile;  // merged [TT_BH][TT_BW], origin (xs, ys)
+    const u8* __restrict__ lo;
+    const u8* __restrict__ hi;
+    const PlaneSrc* ps;
+    int xs, ys, w, h;
+    __device__ __forceinline__ u16 operator()(long long row, long long col) const
+    {
+        const long long r = row - ys, c = col - xs;
+        if (r >= 0 && r < TT_BH && c >= 0 && c < TT_BW) return tile[r * TT_BW + c];
+        return (u16)plane_corrected_px(lo, hi, w, h, (int)col, (int)row, *ps);
+    }
+};
+
+// PLANES: tmap / tmap_hi describe the low / high byte planes and `src` is unused (see PlaneSrc).
+template <bool MOTION, bool PLANES>
 __global__ void __launch_bounds__(TT_THREADS, 3)
-translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __restrict__ src, u16* __restrict__ dst, int w, int h,
-                         size_t src_stride, size_t dst_stride, const float* __restrict__ dxs, const float* __restrict__ dys,
-                         float dx0, float dy0, int strategy, unsigned background, int tiles_y)
+translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_hi,
+                         const u16* __restrict__ src, u16* __restrict__ dst, int w, int h, size_t src_stride, size_t dst_stride,
+                         const float* __restrict__ dxs, const float* __restrict__ dys, float dx0, float dy0, int strategy,
+                         unsigned background, int tiles_y, const __grid_constant__ PlaneSrc ps)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar[TT_STAGES];
@@ -488,8 +578,8 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
     __shared__ unsigned slow_count[2];    // between the two barriers of tile ty
     __shared__ unsigned slowq[(TT_W / 8) * TT_H];
     __shared__ EdgeTable edge_tab[2];  // [0]: the image's first group of a row, [1]: its last
-    constexpr unsigned TILE_BYTES = TT_BH * TT_BW * 2;
-    constexpr unsigned STAGE_BYTES = TT_STAGE_BYTES;  // TMA destinations are 128-byte aligned
+    constexpr unsigned TILE_BYTES = PLANES ? 2 * TP_BOX_BYTES : TT_BH * TT_BW * 2;  // bytes one stage receives
+    constexpr unsigned STAGE_BYTES = PLANES ? TP_STAGE_BYTES : TT_STAGE_BYTES;      // TMA destinations are 128-byte aligned
     const int f = blockIdx.y;
     const int x0t = blockIdx.x * TT_W;
     const float dx = dxs ? dxs[f] : dx0;
@@ -501,6 +591,16 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
     const int sy = (int)fminf(fmaxf(floorf(-dy), -fh - 16.f), fh + 16.f);
     const int xs = (x0t + sx) & ~7;      // box origin: 16-byte aligned column
     const int xoff = (x0t + sx) - xs;    // 0..7, the same for every fast group of the CTA
+    const int xs16 = (x0t + sx) & ~15;   // PLANES: the uint8 boxes start on 16-pixel boundaries; xs - xs16 is 0 or 8
+    auto issue_boxes = [&](int s, int tile_row) {
+        mbar_expect_tx(&bar[s], TILE_BYTES);
+        if (PLANES) {
+            tma_load_box(smem_raw + s * STAGE_BYTES, &tmap, &bar[s], xs16, tile_row * TT_H + sy, f);
+            tma_load_box(smem_raw + s * STAGE_BYTES + TP_BOX_AL, &tmap_hi, &bar[s], xs16, tile_row * TT_H + sy, f);
+        } else {
+            tma_load_box(smem_raw + s * STAGE_BYTES, &tmap, &bar[s], xs, tile_row * TT_H + sy, f);
+        }
+    };
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < TT_STAGES; ++s) mbar_init(&bar[s], 1);
@@ -529,10 +629,7 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < TT_STAGES; ++s)
-            if (s < tiles_y) {
-                mbar_expect_tx(&bar[s], TILE_BYTES);
-                tma_load_box(smem_raw + s * STAGE_BYTES, &tmap, &bar[s], xs, s * TT_H + sy, f);
-            }
+            if (s < tiles_y) issue_boxes(s, s);
     }
 
     // ---- per-thread column constants (while the first boxes are in flight) -----------------------
@@ -553,7 +650,9 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
     }
     const bool clamp_rt = (l0 + 8 == w);
     const HWeights ca = make_hweights(u0), cb = make_hweights(u7);
-    const u16* frame = src + (size_t)f * src_stride;
+    const u16* frame = PLANES ? nullptr : src + (size_t)f * src_stride;
+    const u8* flo = PLANES ? ps.lo + (size_t)f * ps.plane_stride : nullptr;
+    const u8* fhi = PLANES ? ps.hi + (size_t)f * ps.plane_stride : nullptr;
     u16* oframe = dst + (size_t)f * dst_stride;
     const uint32_t rinfo = smem_addr(&rowinfo[0][ry]);
     const size_t row_step = (size_t)16 * w;
@@ -565,7 +664,43 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
         const int y0t = ty * TT_H, ys = y0t + sy;
         const int pp = ty & 1;  // which rowinfo / queue counter this tile uses
         mbar_wait(&bar[stage], parity);
-        const u16* tile = reinterpret_cast<const u16*>(smem_raw + stage * STAGE_BYTES);
+        const u16* tile = reinterpret_cast<const u16*>(smem_raw + (PLANES ? TT_STAGES * STAGE_BYTES : stage * STAGE_BYTES));
+        if (PLANES) {
+            // (1) merge the two byte boxes into the uint16 tile, 8 pixels per step
+            u16* merged = reinterpret_cast<u16*>(smem_raw + TT_STAGES * STAGE_BYTES);
+            const unsigned char* blo = smem_raw + stage * STAGE_BYTES + (xs - xs16);
+            const unsigned char* bhi = blo + TP_BOX_AL;
+            const unsigned t2 = ps.min_t | (ps.min_t << 16);
+            for (int v = threadIdx.x; v < TT_BH * (TT_BW / 8); v += TT_THREADS) {
+                const int r = v / (TT_BW / 8), c8 = v - r * (TT_BW / 8);
+                const uint2 l = *reinterpret_cast<const uint2*>(blo + r * TP_BW + 8 * c8);
+                const uint2 hh = *reinterpret_cast<const uint2*>(bhi + r * TP_BW + 8 * c8);
+                const int gy = ys + r;
+                const unsigned add = (gy >= 0 && gy < ps.t_rows) ? t2 : 0u;
+                uint4 o;
+                o.x = __vadd2(__byte_perm(l.x, hh.x, 0x5140), add);
+                o.y = __vadd2(__byte_perm(l.x, hh.x, 0x7362), add);
+                o.z = __vadd2(__byte_perm(l.y, hh.y, 0x5140), add);
+                o.w = __vadd2(__byte_perm(l.y, hh.y, 0x7362), add);
+                *reinterpret_cast<uint4*>(merged + r * TT_BW + 8 * c8) = o;
+            }
+            __syncthreads();
+            // (2) the loader's bad-pixel medians for the flagged pixels that fall into the tile
+            if (ps.xy != nullptr) {
+                const int gy0 = max(ys, 0), gy1 = min(ys + TT_BH, h);
+                if (gy0 < gy1) {
+                    const int a = ps.row_off[gy0], b = ps.row_off[gy1];
+                    for (int i = a + threadIdx.x; i < b; i += TT_THREADS) {
+                        const int2 p = reinterpret_cast<const int2*>(ps.xy)[i];
+                        const int cxl = p.x - xs;
+                        unsigned med;
+                        if (cxl >= 0 && cxl < TT_BW && plane_median(flo, fhi, w, h, p.x, p.y, ps.nbr[i], ps, med))
+                            merged[(p.y - ys) * TT_BW + cxl] = (u16)med;
+                    }
+                }
+            }
+            __syncthreads();
+        }
         u16* ocol = oframe + (size_t)(y0t + ry) * w + x0;
         const int rows_left = (x0 < w) ? h - y0t : 0;  // destination rows of this tile that exist (none for columns past the edge)
 
@@ -605,19 +740,29 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __
                                               (edge_tab[e].clamped >> gi) & 1u, edge_tab[e].wt[gi]);
                 continue;
             }
-            const TileSrc ts{tile, frame, xs, ys, w};
-            if (MOTION) {
+            if (PLANES) {
+                const PlaneTileSrc ts{tile, flo, fhi, &ps, xs, ys, w, h};
                 float r;
                 if (translate_pixel<u16, float>(ts, w, h, gx, gy, dx, dy, strategy, (float)background, r)) *o = (u16)r;
             } else {
-                u16 r;
-                if (translate_pixel<u16, u16>(ts, w, h, gx, gy, dx, dy, strategy, (u16)background, r)) *o = r;
+                const TileSrc ts{tile, frame, xs, ys, w};
+                if (MOTION) {
+                    float r;
+                    if (translate_pixel<u16, float>(ts, w, h, gx, gy, dx, dy, strategy, (float)background, r)) *o = (u16)r;
+                } else {
+                    u16 r;
+                    if (translate_pixel<u16, u16>(ts, w, h, gx, gy, dx, dy, strategy, (u16)background, r)) *o = r;
+                }
             }
         }
         __syncthreads();  // every warp is done with this stage and the queue; next tile's row parameters are visible
-        if (threadIdx.x == 0 && ty + TT_STAGES < tiles_y) {
-            mbar_expect_tx(&bar[stage], TILE_BYTES);
-            tma_load_box(smem_raw + stage * STAGE_BYTES, &tmap, &bar[stage], xs, (ty + TT_STAGES) * TT_H + sy, f);
+        if (threadIdx.x == 0 && ty + TT_STAGES < tiles_y) issue_boxes(stage, ty + TT_STAGES);
+    }
+    if (PLANES) {  // metadata rows [h, h_full): merged, never translated (IRFileLoader.cpp:1241-1243 pass h - 3)
+        const int nmeta = (ps.h_full - h) * TT_W;
+        for (int i = threadIdx.x; i < nmeta; i += TT_THREADS) {
+            const int yy = h + i / TT_W, xx = x0t + i % TT_W;
+            if (xx < w) oframe[(size_t)yy * w + xx] = (u16)plane_px(flo, fhi, w, xx, yy, ps);
         }
     }
 }
@@ -627,17 +772,14 @@ int launch_translate_u16(const u16* src, u16* dst, int w, int h, long long nfram
                          cudaStream_t st)
 {
     if (nframes <= 0 || w <= 0 || h <= 0) return 0;
-    static const bool tma_enabled = []() {  // RIRB_TRANSLATE_TMA=0 selects the plain kernel (A/B measurements)
-        const char* e = getenv("RIRB_TRANSLATE_TMA");
-        return !(e && e[0] == '0');
-    }();
+    const bool tma_enabled = option_enabled(OPT_TRANSLATE_TMA);  // "translate_tma" = 0 selects the plain kernel (A/B measurements)
     const int tiles_x = (int)ceil_div(w, TT_W), tiles_y = (int)ceil_div(h, TT_H);
     if (tma_enabled && (w % 8 == 0) && aligned16(dst) && (dst_stride % 8 == 0) && tma_compatible(src, (size_t)w * 2, src_stride * 2)) {
         const size_t smem = (size_t)TT_STAGES * TT_STAGE_BYTES;
         static bool attr_set = false;
         if (!attr_set) {
-            RIRB_CUDA_OK(cudaFuncSetAttribute(translate_u16_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            RIRB_CUDA_OK(cudaFuncSetAttribute(translate_u16_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RIRB_CUDA_OK(cudaFuncSetAttribute(translate_u16_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RIRB_CUDA_OK(cudaFuncSetAttribute(translate_u16_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
         // grid = (tile column, frame); gridDim.y <= 65535, so long movies go in several launches
@@ -650,12 +792,13 @@ int launch_translate_u16(const u16* src, u16* dst, int w, int h, long long nfram
             CUtensorMap tmap;
             if (make_movie_tensor_map(&tmap, s0, 2, w, h, n, (size_t)w * 2, src_stride * 2, TT_BW, TT_BH) != 0) return -1;
             const dim3 tgrid((unsigned)tiles_x, (unsigned)n);
+            const PlaneSrc none{};
             if (motion)
-                RIRB_LAUNCH(translate_u16_tma_kernel<true>, tgrid, TT_THREADS, smem, st, tmap, s0, d0, w, h, src_stride, dst_stride,
-                            dx_p, dy_p, dx0, dy0, strategy, background, tiles_y);
+                RIRB_LAUNCH((translate_u16_tma_kernel<true, false>), tgrid, TT_THREADS, smem, st, tmap, tmap, s0, d0, w, h, src_stride,
+                            dst_stride, dx_p, dy_p, dx0, dy0, strategy, background, tiles_y, none);
             else
-                RIRB_LAUNCH(translate_u16_tma_kernel<false>, tgrid, TT_THREADS, smem, st, tmap, s0, d0, w, h, src_stride, dst_stride,
-                            dx_p, dy_p, dx0, dy0, strategy, background, tiles_y);
+                RIRB_LAUNCH((translate_u16_tma_kernel<false, false>), tgrid, TT_THREADS, smem, st, tmap, tmap, s0, d0, w, h, src_stride,
+                            dst_stride, dx_p, dy_p, dx0, dy0, strategy, background, tiles_y, none);
         }
         return 0;
     }
@@ -667,6 +810,51 @@ int launch_translate_u16(const u16* src, u16* dst, int w, int h, long long nfram
     else
         RIRB_LAUNCH(translate_u16_kernel<false>, grid, block, 0, st, src, dst, w, h, nframes, src_stride, dst_stride, dxs, dys,
                     dx0, dy0, strategy, background);
+    return 0;
+}
+
+// The reader's chain in one pass: byte planes [n][h_full][w] -> corrected, registered uint16 frames.
+// Returns 1 when the layout cannot take this path (the caller then runs the two-pass chain), 0 / -1 otherwise.
+int launch_loader_fused(const u8* lo, const u8* hi, u16* out, int w, int h_full, int hb, long long nframes, int min_t, int t_rows,
+                        const int* xy_dev, const int* nbr_dev, const int* row_off_dev, const u8* mask_dev, const float* dxs,
+                        const float* dys, cudaStream_t st)
+{
+    // Off by default: measured on B200 (profiles/r1_loader_fused_ab.md) the one-pass kernel is instruction-bound
+    // (merge + medians + blend in one CTA) and only ties the two-pass chain at 640x512, losing on larger frames.
+    const bool enabled = option_enabled(OPT_LOADER_FUSED);
+    const size_t fpx = (size_t)w * h_full;
+    if (!enabled || (w % 16) != 0 || hb < 3 || !aligned16(out) || !tma_compatible(lo, (size_t)w, fpx) ||
+        !tma_compatible(hi, (size_t)w, fpx))
+        return 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RIRB_CUDA_OK(cudaFuncSetAttribute(translate_u16_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)TP_SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles_x = (int)ceil_div(w, TT_W), tiles_y = (int)ceil_div(hb, TT_H);
+    for (long long f0 = 0; f0 < nframes; f0 += 65535) {
+        const long long n = min(nframes - f0, 65535LL);
+        CUtensorMap map_lo, map_hi;
+        // the translated image is the first hb rows of every stored frame: rows >= hb must read as "outside"
+        if (make_movie_tensor_map(&map_lo, lo + f0 * fpx, 1, w, hb, n, (size_t)w, fpx, TP_BW, TT_BH) != 0 ||
+            make_movie_tensor_map(&map_hi, hi + f0 * fpx, 1, w, hb, n, (size_t)w, fpx, TP_BW, TT_BH) != 0)
+            return -1;
+        PlaneSrc ps;
+        ps.lo = lo + f0 * fpx;
+        ps.hi = hi + f0 * fpx;
+        ps.plane_stride = fpx;
+        ps.xy = xy_dev;
+        ps.nbr = nbr_dev;
+        ps.row_off = row_off_dev;
+        ps.mask = mask_dev;
+        ps.min_t = (unsigned)min_t & 0xFFFFu;
+        ps.t_rows = t_rows;
+        ps.h_full = h_full;
+        const dim3 tgrid((unsigned)tiles_x, (unsigned)n);
+        RIRB_LAUNCH((translate_u16_tma_kernel<true, true>), tgrid, TT_THREADS, TP_SMEM_BYTES, st, map_lo, map_hi, (const u16*)nullptr,
+                    out + f0 * fpx, w, hb, fpx, fpx, dxs + f0, dys + f0, 0.f, 0.f, STRAT_NEAREST, 0u, tiles_y, ps);
+    }
     return 0;
 }
 

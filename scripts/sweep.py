@@ -26,6 +26,9 @@ BYTES_PER_PX = {"bp_correct": 4, "gaussian_u16_f32": 6, "gaussian_f32_f32": 8, "
 
 
 def main():
+    # the reader chain is ONE pass over HBM (2 B/px in, 2 B/px out) when the fused kernel takes it,
+    # merge pass + motion pass (8 B/px) with RIRB_LOADER_FUSED=0
+    BYTES_PER_PX["loader_read_chain"] = 8 if os.environ.get("RIRB_LOADER_FUSED", "1").startswith("0") else 4
     import torch
     import torch.distributed as dist
 
@@ -35,6 +38,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gb", type=float, default=2.0, help="input bytes per kernel launch (GB) -- far beyond the 126 MB L2")
     ap.add_argument("--reps", type=int, default=7)
+    ap.add_argument("--only", default="", help="comma-separated kernel names to run (default: all)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -95,9 +99,10 @@ def main():
             "decode_delta_merge": lambda: vio.decode_movie(lo, hi, 50, True, 0, out=out16),
             "stats_minmax_hist": lambda: stats.update(frames),
         }
+        only = [x for x in args.only.split(",") if x]
         for name, fn in cases.items():
-            if name == "gaussian_f32_f32" and npx * n * 4 > 6e9:
-                pass
+            if only and name not in only:
+                continue
             for _ in range(3):
                 fn()
             times = []

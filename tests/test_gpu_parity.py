@@ -105,6 +105,24 @@ def test_translate_u16_odd_shapes(best, shape):
             np.testing.assert_array_equal(sp.translate(f, dx, dy, st, 9), best.translate(f, dx, dy, st, 9))
 
 
+def test_kernel_variant_switches():
+    """rirb_set_parameter: the register-only kernels behind "translate_tma" / "gauss_tma" = 0 give the same
+    results as the TMA-tiled ones (bit-exact translate; Gaussian within tolerance of each other)."""
+    f = ir_frame(96, 128, 5)
+    want_t = sp.translate(f, 1.3, -2.7, "nearest", 0)
+    want_g = sp.gaussian_filter(f, 1.0)
+    try:
+        _lib.set_parameter("translate_tma", 0)
+        _lib.set_parameter("gauss_tma", 0)
+        np.testing.assert_array_equal(sp.translate(f, 1.3, -2.7, "nearest", 0), want_t)
+        assert_gauss_close(sp.gaussian_filter(f, 1.0), want_g)
+    finally:
+        _lib.set_parameter("translate_tma", 1)
+        _lib.set_parameter("gauss_tma", 1)
+    with pytest.raises(RuntimeError):
+        _lib.set_parameter("no_such_switch", 1)
+
+
 @pytest.mark.parametrize("shape", [(8, 8), (1, 8), (3, 16), (64, 128), (65, 136), (129, 256), (130, 264), (200, 320), (70, 1032)])
 def test_translate_u16_tiled_shapes(best, shape):
     """Widths that are multiples of 8 take the TMA-tiled kernel: tile / stage boundaries (128 columns,
@@ -308,8 +326,16 @@ def test_remove_motion_golden_and_live(golden, best, port):
 # ---------------------------------------------------------------------------------------------
 # statistics
 # ---------------------------------------------------------------------------------------------
+@pytest.fixture(params=[0, 1], ids=["two_pass", "fused"])
+def loader_mode(request):
+    """rirb_loader_read_movie as merge pass + motion pass, and as the one-pass fused kernel."""
+    _lib.set_parameter("loader_fused", request.param)
+    yield request.param
+    _lib.set_parameter("loader_fused", 0)
+
+
 @pytest.mark.parametrize("shape", [(12, 67, 96), (5, 131, 80), (3, 40, 37), (4, 259, 640), (2, 5, 3)])
-def test_loader_read_movie_chain(port, best, shape):
+def test_loader_read_movie_chain(port, best, shape, loader_mode):
     """The reader's post-decode chain in one call (merge -> +min_T -> removeBadPixels -> removeMotion)
     against the restated reference chain, with each stage switched on and off."""
     n, h, w = shape
@@ -338,6 +364,27 @@ def test_loader_read_movie_chain(port, best, shape):
     if bp is not None:
         got_d = to_host(vio.read_movie(to_dev(lo), to_dev(hi), bp, c["min_T"], c["rows"], sx, sy))
         np.testing.assert_array_equal(got_d, vio.read_movie(lo, hi, bp, c["min_T"], c["rows"], sx, sy))
+
+
+def test_loader_read_movie_fused_large_shifts_and_edges(port, loader_mode):
+    """Fused reader kernel (w % 16 == 0): shifts far beyond the staged box (clamped reads rebuilt from the
+    planes, including flagged source pixels), integer shifts, image smaller than a tile, many flagged pixels."""
+    rng = np.random.default_rng(17)
+    for (n, h, w) in [(6, 70, 160), (4, 35, 16), (3, 200, 272)]:
+        mov = ir_movie(n, h, w, seed=3)
+        bad = rng.choice(h * w, h * w // 40, replace=False)  # 2.5 % stuck pixels, some adjacent, some on the borders
+        mov.reshape(n, -1)[:, bad] = 0
+        mov[:, 0, :8] = 0
+        mov[:, :, 0] = 16000
+        lo, hi = (mov & 0xFF).astype(np.uint8), (mov >> 8).astype(np.uint8)
+        bp = vio.LoaderBadPixels(mov[0])
+        xy = sp.bad_pixels_list(bp.handle)[0]
+        sx = np.array([0.0, 25.5, -30.25, 3.0, -2.0, 1e-7][:n])
+        sy = np.array([0.0, -40.75, 19.5, -3.0, 70.0, 0.99999][:n])
+        got = vio.read_movie(lo, hi, bp, 1000, h - 3, sx, sy)
+        for t in range(n):
+            want = port.loader_read_image(lo[t], hi[t], xy, 1000, h - 3, (sx[t], sy[t]))
+            np.testing.assert_array_equal(got[t], want, err_msg=f"{(n, h, w)} frame {t} shift {(sx[t], sy[t])}")
 
 
 def test_loader_read_movie_is_inverse_of_the_writer_split():
