@@ -62,6 +62,8 @@ def test_no_gpu_means_failure_not_fallback():
         lambda: sp.bad_pixels_create(img),
         lambda: vio.split_yuv444(img),
         lambda: vio.precode_movie(img[None]),
+        lambda: vio.read_movie(img[None].astype(np.uint8), img[None].astype(np.uint8)),
+        lambda: vio.remove_motion(img[None], [0.5], [0.5]),
     ):
         with pytest.raises(RuntimeError) as e:
             call()
@@ -86,6 +88,40 @@ def test_argument_errors_match_reference_conventions():
         sp.bad_pixels_correct(0, img)
     lib = _lib.load()
     assert lib.rirb_bad_pixels_count(12345) == -1
+
+
+def test_new_entries_argument_errors():
+    lib = _lib.load()
+    lo = np.zeros((2, 8, 16), np.uint8)
+    with pytest.raises(RuntimeError):  # planes of different shapes
+        vio.read_movie(lo, np.zeros((2, 8, 8), np.uint8))
+    with pytest.raises(RuntimeError):  # one shift per frame
+        vio.read_movie(lo, lo, None, 0, 0, [1.0], [1.0])
+    assert lib.rirb_loader_read_movie(0, None, None, 1, 16, 8, 0, 0, None, None, 3, None) == -1
+    assert lib.rirb_loader_read_movie(77, lo.ctypes.data, lo.ctypes.data, 2, 16, 8, 0, 0, None, None, 3, lo.ctypes.data) == -1
+    assert "unknown handle" in _lib.last_error()
+    assert lib.rirb_process_movie_host(0, None, 0, 1, 1, 1.0, None, None, b"nearest", 0, 50, 1, 0, None, None, None) == -1
+    assert lib.rirb_set_parameter(b"loader_fused", b"0") == 0
+    assert lib.rirb_set_parameter(b"bogus", b"1") == -1 and "unknown key" in _lib.last_error()
+
+
+def test_oracle_reader_chain_composition():
+    """oracle.loader_read_image is the composition of the pinned pieces, in readImage's order."""
+    from oracle import oracle as O
+
+    port = O.Port()
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 16384, (20, 24), dtype=np.uint16)
+    lo, hi = (img & 0xFF).astype(np.uint8), (img >> 8).astype(np.uint8)
+    np.testing.assert_array_equal(port.loader_read_image(lo, hi), img)
+    xy = np.array([[3, 4], [4, 4], [0, 0], [23, 16]], dtype=np.int32)
+    got = port.loader_read_image(lo, hi, xy, 100, 10, (1.5, -0.5))
+    step = img.copy()
+    step[:10] += 100
+    step[:17] = port.loader_remove_bad_pixels(step[:17], xy)
+    step[:17] = port.loader_remove_motion(step[:17], 1.5, -0.5)
+    np.testing.assert_array_equal(got, step)
+    np.testing.assert_array_equal(got[17:], img[17:])  # metadata rows: merged only (min_T rows end above them here)
 
 
 def test_forwarded_entries_fail_cleanly_without_forward_lib():

@@ -543,6 +543,29 @@ def test_process_movie_host_one_call_equals_the_staged_calls(port, best):
         movie.process_movie_host(bp, mov[:2], dx[:2], dy[:2], strategy="noborder")
 
 
+def test_more_frames_than_one_grid_dimension(port, best):
+    """66,000 tiny frames in one call: the translate grid carries the frame index in gridDim.y (<= 65,535),
+    so long movies go in several launches; every other kernel folds frames into a 1-D grid."""
+    n, h, w = 66000, 8, 16
+    rng = np.random.default_rng(8)
+    mov = rng.integers(0, 16384, (n, h, w), dtype=np.uint16)
+    dx = rng.uniform(-3, 3, n).astype(np.float32)
+    dy = rng.uniform(-3, 3, n).astype(np.float32)
+    d = to_dev(mov)
+    reg = to_host(sp.translate_batch(d, to_dev(dx), to_dev(dy), "nearest", 0))
+    sm = sp.gaussian_filter_batch(d, 1.0).cpu().numpy()
+    bp = sp.BadPixels(mov[0])
+    xy, clamp = sp.bad_pixels_list(bp.handle)
+    cor = to_host(bp.correct_batch(d))
+    lo, hi = vio.precode_movie(d, gop=50, delta=True)
+    back = to_host(vio.decode_movie(lo, hi, gop=50, delta=True))
+    np.testing.assert_array_equal(back, mov)
+    for t in [0, 1, 65534, 65535, 65536, 65537, n - 1]:
+        np.testing.assert_array_equal(reg[t], best.translate(mov[t], dx[t], dy[t], "nearest", 0), err_msg=f"translate frame {t}")
+        assert_gauss_close(sm[t], best.gaussian_filter(mov[t].astype(np.float32), 1.0))
+        np.testing.assert_array_equal(cor[t], port.bad_pixels_correct_with(xy, clamp, mov[t]), err_msg=f"bad pixels frame {t}")
+
+
 def test_full_size_c2_round_trip_and_checksums():
     """640x512x1000 (configs[1]): decode(precode(x)) == x with and without delta, and the byte
     planes carry exactly the movie's bytes (checksum of checksums)."""
