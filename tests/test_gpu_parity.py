@@ -566,6 +566,22 @@ def test_more_frames_than_one_grid_dimension(port, best):
         np.testing.assert_array_equal(cor[t], port.bad_pixels_correct_with(xy, clamp, mov[t]), err_msg=f"bad pixels frame {t}")
 
 
+def test_lossless_chain_with_host_zstd_round_trip_and_ratio():
+    """frames -> GPU pre-coder -> host zstd -> host zstd^-1 -> GPU inverse = frames (the lossless guarantee the
+    reference's tests pin, tests/python/test_IRMovie.py:46-49), and the pre-coder earns its keep: byte planes
+    compress better than raw frames, the temporal delta better still."""
+    from librir_b200 import entropy
+
+    mov = ir_movie(100, 128, 160)
+    sizes = {}
+    for delta in (False, True):
+        chunks = entropy.compress_movie(mov, gop=50, delta=delta, level=3)
+        np.testing.assert_array_equal(entropy.decompress_movie(chunks, 128, 160, gop=50, delta=delta), mov)
+        sizes[delta] = sum(len(c[2]) + len(c[3]) for c in chunks)
+    raw = sum(len(entropy.zstd_compress(mov[a:a + 50], 3)) for a in range(0, 100, 50))
+    assert sizes[True] < sizes[False] < raw, (raw, sizes)
+
+
 def test_full_size_c2_round_trip_and_checksums():
     """640x512x1000 (configs[1]): decode(precode(x)) == x with and without delta, and the byte
     planes carry exactly the movie's bytes (checksum of checksums)."""

@@ -69,3 +69,47 @@ def test_precoder_key_frame_bookkeeping_without_gpu(monkeypatch):
     assert keys == [True, False, False, False, True, False, False, False, True]
     with pytest.raises(RuntimeError):
         p.add_image(np.zeros((5, 8), np.uint16))
+
+
+# ---------------------------------------------------------------------------------------------
+# host entropy stage (zstd wrappers, tools.cpp:352-376)
+# ---------------------------------------------------------------------------------------------
+def test_zstd_wrappers_round_trip_and_garbage():
+    """Mirrors the reference's own test (tests/python/test_rir.py:47-74): round trip, and garbage raises."""
+    from librir_b200 import entropy as e
+
+    rng = np.random.default_rng(0)
+    for payload in (b"", b"toto" * 1000, rng.integers(0, 255, 10000, dtype=np.uint8).tobytes()):
+        for level in (0, 1, 3, 19):
+            c = e.zstd_compress(payload, level)
+            assert e.zstd_decompress_bound(c) == len(payload)
+            assert e.zstd_decompress(c) == payload
+    assert e.zstd_compress_bound(1000) >= 1000
+    with pytest.raises(RuntimeError):
+        e.zstd_decompress(b"definitely not a zstd frame")
+    a = np.arange(5000, dtype=np.uint16)
+    assert np.array_equal(np.frombuffer(e.zstd_decompress(e.zstd_compress(a, 3)), np.uint16), a)
+
+
+def test_zstd_wrappers_match_the_reference_build():
+    """Byte-identical to the reference's zstd_compress (libtools of oracle/_ref) at the same level."""
+    import ctypes as ct
+    import os
+
+    from librir_b200 import entropy as e
+
+    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libs", "libtools.so")
+    if not os.path.exists(lib):
+        pytest.skip("oracle/_ref not built")
+    tools = ct.CDLL(lib)
+    tools.zstd_compress.restype = ct.c_longlong
+    tools.zstd_compress.argtypes = [ct.c_char_p, ct.c_longlong, ct.c_char_p, ct.c_longlong, ct.c_int]
+    tools.zstd_compress_bound.restype = ct.c_longlong
+    tools.zstd_compress_bound.argtypes = [ct.c_longlong]
+    payload = (np.arange(40000) % 977).astype(np.uint16).tobytes()
+    for level in (1, 3, 9):
+        cap = tools.zstd_compress_bound(len(payload))
+        assert cap == e.zstd_compress_bound(len(payload))
+        out = ct.create_string_buffer(cap)
+        n = tools.zstd_compress(payload, len(payload), out, cap, level)
+        assert n > 0 and out.raw[:n] == e.zstd_compress(payload, level)
