@@ -456,7 +456,7 @@ __device__ __forceinline__ void fast_rows(uint32_t tbase, uint32_t rinfo, bool x
 {
     unsigned long long magic = 0x41C0000000000000ULL;
     asm volatile("" : "+l"(magic));  // opaque: otherwise ptxas ORs the constant into every column's high word
-#pragma unroll 2
+#pragma unroll
     for (int k = 0; k < TT_H / 16; ++k) {
         int B;
         unsigned rows;
