@@ -150,6 +150,20 @@ RIRB_API int rirb_decode_movie(const unsigned char* lo, const unsigned char* hi,
 /* key[t] = 1 iff frame t of a writer starting at frame 0 is a key frame (h264.cpp:1050-1061) */
 RIRB_API int rirb_key_frames(long long nframes, int gop, unsigned char* key);
 
+/* ---- lossy "bounded-error" pre-conditioner of the H.264 saver (H264_Saver::addImageLossyNoCamera,
+ *      h264.cpp:2253-2424; the frames it produces are what addImageLossLess then encodes) ----
+ * open: image size, stop_lossy_height (rows [0, stop) are lossy, the rest is copied), lowValueError /
+ * highValueError (reference defaults 6 / 2), stdFactor (5), runningAverage (32, <= 64, 0 = off), subtractMin,
+ * removeBadPixels -- the saver's string parameters (h264.cpp:1709-1781).  Returns a handle > 0, 0 on failure.
+ * add_images: nframes frames IN TIME ORDER (the state carries over between calls); out receives the
+ * pre-conditioned frames, errors (2 ints per frame, host or device, may be NULL) the per-frame
+ * BackgroundError / ForegroundError attributes.  Inputs must be in temperature already (the camera
+ * calibration of the "WithCamera" variant is outside this library). */
+RIRB_API int rirb_lossy_open(int w, int h, int stop_lossy_height, int low_error, int high_error, double std_factor,
+                             int running_average, int subtract_min, int remove_bad_pixels);
+RIRB_API int rirb_lossy_add_images(int handle, const unsigned short* frames, long long nframes, unsigned short* out, int* errors);
+RIRB_API void rirb_lossy_close(int handle);
+
 /* ---- the whole per-frame path on HOST buffers, one call (the end-to-end drop-in) ----
  * frames[nframes][h][w] (host) -> bad_pixels_correct (handle) -> gaussian_filter (sigma; result kept on
  * the device unless `smoothed` is non-NULL) -> translate by the per-frame shifts dx[t], dy[t] (host floats,

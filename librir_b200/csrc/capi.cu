@@ -961,6 +961,144 @@ int rirb_key_frames(long long nframes, int gop, unsigned char* key)
 }
 
 // =================================================================================================
+// lossy pre-conditioner (stateful, frames in time order)
+// =================================================================================================
+namespace {
+struct LossyState {
+    int w = 0, h = 0, stop_h = 0, low = 6, high = 2, ra = 32, subtract_min = 0, bp_enabled = 0, device = 0;
+    double std_factor = 5.0;
+    long long frames = 0;
+    int bp_handle = 0;
+    char* buf = nullptr;  // one allocation: lastDL | refT | prevT | tmp | tmpT | sums | cvalue | ccount | ring | scalars | errors
+    size_t o_lastDL = 0, o_refT = 0, o_prevT = 0, o_tmp = 0, o_tmpT = 0, o_sums = 0, o_cval = 0, o_ccnt = 0, o_ring = 0, o_scal = 0;
+    int* errors_dev = nullptr;
+    long long errors_cap = 0;
+    ~LossyState()
+    {
+        if (buf) cudaFree(buf);
+        if (errors_dev) cudaFree(errors_dev);
+        if (bp_handle) bad_pixels_destroy(bp_handle);
+    }
+};
+std::mutex g_lossy_mutex;
+std::map<int, std::shared_ptr<LossyState>> g_lossy;
+}  // namespace
+
+int rirb_lossy_open(int w, int h, int stop_lossy_height, int low_error, int high_error, double std_factor, int running_average,
+                    int subtract_min, int remove_bad_pixels)
+{
+    if (w <= 0 || h <= 0 || stop_lossy_height < 0 || stop_lossy_height > h || running_average < 0 || (long long)w * h > 0x7FFFFFFFLL) {
+        set_error("lossy_open: bad arguments");
+        return 0;
+    }
+    if (require_device() != 0) return 0;
+    auto s = std::make_shared<LossyState>();
+    s->w = w; s->h = h; s->stop_h = stop_lossy_height;
+    s->low = low_error; s->high = high_error; s->std_factor = std_factor;
+    s->ra = running_average > 64 ? 64 : running_average;  // setParameter clamps to 64 (h264.cpp:1774)
+    s->subtract_min = subtract_min != 0; s->bp_enabled = remove_bad_pixels != 0;
+    cudaGetDevice(&s->device);
+    const size_t n = (size_t)w * h, ns = (size_t)w * stop_lossy_height;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    s->o_lastDL = off; off += al(n * 2);
+    s->o_refT = off; off += al(n * 2);
+    s->o_prevT = off; off += al(n * 2);
+    s->o_tmp = off; off += al(n * 2);
+    s->o_tmpT = off; off += al(n * 2);
+    s->o_sums = off; off += al(ns * 4 + 4);
+    s->o_cval = off; off += al(ns * 2 + 2);
+    s->o_ccnt = off; off += al(ns * 2 + 2);
+    s->o_ring = off; off += al(ns * 2 * (size_t)(s->ra > 0 ? s->ra : 1) + 2);
+    s->o_scal = off; off += al(lossy_scalars_bytes());
+    if (cudaMalloc(&s->buf, off) != cudaSuccess || cudaMemset(s->buf, 0, off) != cudaSuccess) {
+        set_error("lossy_open: out of device memory (%zu bytes): %s", off, cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    std::lock_guard<std::mutex> lock(g_lossy_mutex);
+    int id = 1;
+    for (auto& kv : g_lossy) {
+        if (kv.first != id) break;
+        ++id;
+    }
+    g_lossy[id] = s;
+    return id;
+}
+
+void rirb_lossy_close(int handle)
+{
+    std::lock_guard<std::mutex> lock(g_lossy_mutex);
+    g_lossy.erase(handle);
+}
+
+int rirb_lossy_add_images(int handle, const unsigned short* frames, long long nframes, unsigned short* out, int* errors)
+{
+    std::shared_ptr<LossyState> s;
+    {
+        std::lock_guard<std::mutex> lock(g_lossy_mutex);
+        auto it = g_lossy.find(handle);
+        if (it != g_lossy.end()) s = it->second;
+    }
+    if (!s) {
+        set_error("lossy_add_images: unknown handle %d", handle);
+        return -1;
+    }
+    if (!frames || !out || nframes < 0) {
+        set_error("lossy_add_images: bad arguments");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const int w = s->w, h = s->h, n = w * h, ns = w * s->stop_h;
+    const size_t bytes = (size_t)n * 2 * (size_t)nframes;
+    const u16* d_in = (const u16*)stage_in(frames, bytes, 0, st);
+    if (!d_in) return -1;
+    StagedOut o;
+    if (!stage_out(o, out, bytes, 1, false, st)) return -1;
+    if (s->errors_cap < nframes) {
+        if (s->errors_dev) cudaFree(s->errors_dev);
+        s->errors_dev = nullptr;
+        s->errors_cap = 0;
+        RIRB_CUDA_OK(cudaMalloc(&s->errors_dev, sizeof(int) * 2 * (size_t)nframes));
+        s->errors_cap = nframes;
+    }
+    char* b = s->buf;
+    u16 *lastDL = (u16*)(b + s->o_lastDL), *refT = (u16*)(b + s->o_refT), *prevT = (u16*)(b + s->o_prevT), *tmp = (u16*)(b + s->o_tmp),
+        *tmpT = (u16*)(b + s->o_tmpT), *cval = (u16*)(b + s->o_cval), *ring = (u16*)(b + s->o_ring);
+    unsigned* sums = (unsigned*)(b + s->o_sums);
+    short* ccnt = (short*)(b + s->o_ccnt);
+    void* scal = b + s->o_scal;
+    for (long long f = 0; f < nframes; ++f) {
+        const u16* img = d_in + (size_t)f * n;
+        u16* dst = (u16*)o.dev + (size_t)f * n;
+        const u16* cur = img;  // "tmp" of the reference
+        if (s->bp_enabled && ns > 0) {  // bp.init on the first image's lossy rows, bp.correct on every image (:2259-2266)
+            if (s->frames == 0 && s->bp_handle == 0) {
+                s->bp_handle = bad_pixels_create((unsigned short*)img, w, s->stop_h);
+                if (s->bp_handle == 0) return -1;
+            }
+            auto bp = find_handle(s->bp_handle);
+            if (launch_bp_correct(img, tmp, bp->xy_dev, bp->span_off_dev, w, s->stop_h, bp->clamp_value, 1, (size_t)n, st) != 0) return -1;
+            if (n > ns) RIRB_CUDA_OK(cudaMemcpyAsync(tmp + ns, img + ns, (size_t)(n - ns) * 2, cudaMemcpyDeviceToDevice, st));
+            cur = tmp;
+        }
+        int rc;
+        if (s->frames == 0)
+            rc = launch_lossy_first(cur, dst, lastDL, refT, prevT, n, ns, s->subtract_min, scal, s->errors_dev + 2 * f, s->low, s->high, st);
+        else
+            rc = launch_lossy_frame(img, cur, tmpT, dst, lastDL, refT, prevT, sums, cval, ccnt, ring, n, ns, s->ra, s->subtract_min,
+                                    s->frames, s->low, s->high, s->std_factor, scal, s->errors_dev + 2 * f, st);
+        if (rc != 0) return -1;
+        ++s->frames;
+    }
+    if (errors) RIRB_CUDA_OK(cudaMemcpyAsync(errors, s->errors_dev, sizeof(int) * 2 * (size_t)nframes, cudaMemcpyDefault, st));
+    if (o.host) RIRB_CUDA_OK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st));
+    if (o.host || (errors && !is_device_ptr(errors))) RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// =================================================================================================
 // the whole path on host buffers
 // =================================================================================================
 namespace {

@@ -64,6 +64,14 @@ int launch_precode_movie(const u16* mov, long long nframes, int w, int h, int go
 int launch_decode_movie(const u8* lo, const u8* hi, long long nframes, int w, int h, int gop, int delta, long long first_frame,
                         u16* mov, cudaStream_t st);
 
+// lossy.cu (H264_Saver::addImageLossyNoCamera, h264.cpp:2253-2424)
+size_t lossy_scalars_bytes();
+int launch_lossy_first(const u16* tmp, u16* out, u16* lastDL, u16* refT, u16* prevT, int n, int ns, int subtract_min, void* scalars,
+                       int* errors_out_dev, int low0, int high0, cudaStream_t st);
+int launch_lossy_frame(const u16* img, const u16* tmp, u16* tmpT, u16* out, u16* lastDL, u16* refT, u16* prevT, unsigned* sums,
+                       u16* cvalue, short* ccount, u16* ring, int n, int ns, int ra, int subtract_min, long long frame_index,
+                       int low0, int high0, double std_factor, void* scalars, int* errors_out_dev, cudaStream_t st);
+
 // stats.cu
 // minmax[0] = min, minmax[1] = max (unsigned, device); hist = 65536 x u64 (device) or nullptr.
 // Accumulates INTO the outputs: callers zero hist / seed minmax with {65535, 0} first

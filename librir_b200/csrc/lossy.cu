@@ -1,0 +1,304 @@
+// librir_b200/csrc/lossy.cu -- the lossy "bounded-error" pre-conditioner of the H.264 saver.
+//
+// Reference: H264_Saver::addImageLossyNoCamera, h264.cpp:2253-2424 (input already in temperature),
+// with RunningAverage2 (:1526-1615), get_background (:1955-1991) and stdDev (:1993-2036).  Per frame:
+//   tmp  = bad-pixel-corrected input (optional)                                   :2259-2271
+//   tmpT = tmp - min (saturating, lossy rows only, optional)                      :2314-2328
+//   background = mode of the 16,384-bin histogram of tmp >> 2                      :2331
+//   (sd_back, sd_fore) = spread of |tmpT - prevT|, split by img > background once 40 frames are in   :2337-2340
+//   lowError / highError = defaults minus round(|sd - running mean| * stdFactor)   :2353-2376
+//   per pixel: if |tmpT - refT| <= error(class) and the integration-time bits did not change, the pixel is
+//              replaced by the running average (or refT), else refT restarts from it                :2392-2413
+//   prevT = output, lastDL = tmp, metadata rows copied                              :2415-2421
+// Time is sequential (every frame needs the previous frame's state and two global reductions of its
+// own), pixels are parallel: five small launches per frame on one stream.  All sums are exact integers
+// (the reference adds int products into doubles, exact below 2^53), the scalar decision is evaluated in
+// non-contracted fp64 by one thread, so the outputs are bit-identical to the restated reference.
+// State per pixel: sums u32, const (value u16, count i16), refT, prevT, lastDL u16 and a ring of
+// `running_average` frames -- 12 + 2 * running_average bytes.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rirb {
+
+struct LossyScalars {
+    unsigned minv;                  // m_data->min
+    unsigned background;
+    int low_error, high_error;      // of the current frame
+    unsigned long long sum[4];      // fore: sum_diff, sum_diff2; back: b_sum_diff, b_sum_diff2
+    unsigned cnt[2];                // fore, back pixel counts
+    double first[2];                // firstStdDevs[0]
+    double stds[40][2];             // stdDevs window (oldest first)
+    unsigned hist[16384];
+};
+
+__global__ void lossy_min_kernel(const u16* __restrict__ tmp, int ns, LossyScalars* sc)
+{
+    unsigned m = 65535u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) m = min(m, (unsigned)tmp[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(&sc->minv, m);
+}
+
+// first image (:2273-2311): lastDL = tmp, tmp -= min, out = tmp, refT = prevT = tmp
+__global__ void lossy_first_kernel(const u16* __restrict__ tmp, u16* __restrict__ out, u16* __restrict__ lastDL, u16* __restrict__ refT,
+                                   u16* __restrict__ prevT, int n, int ns, int subtract_min, const LossyScalars* __restrict__ sc)
+{
+    const unsigned mn = subtract_min ? sc->minv : 0u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned v = tmp[i];
+        lastDL[i] = (u16)v;
+        unsigned t = v;
+        if (i < ns) {
+            t = v < mn ? 0u : v - mn;
+            refT[i] = (u16)t;
+            prevT[i] = (u16)t;
+        }
+        out[i] = (u16)t;
+    }
+}
+
+// tmpT = tmp - min on the lossy rows; histogram of tmp >> 2 (get_background's, :1958-1962)
+__global__ void lossy_prep_kernel(const u16* __restrict__ tmp, u16* __restrict__ tmpT, int ns, int subtract_min, LossyScalars* sc)
+{
+    extern __shared__ unsigned sh[];  // 16,384 bins = 64 KB (dynamic: above the 48 KB static limit)
+    for (int i = threadIdx.x; i < 16384; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const unsigned mn = subtract_min ? sc->minv : 0u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
+        const unsigned v = tmp[i];
+        tmpT[i] = (u16)(v < mn ? 0u : v - mn);
+        atomicAdd(&sh[v >> 2], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16384; i += blockDim.x) {
+        const unsigned c = sh[i];
+        if (c) atomicAdd(&sc->hist[i], c);
+    }
+}
+
+// background = (first maximum bin << 2) + 1 (:1974-1990); clears the histogram and the sums for the next steps
+__global__ void __launch_bounds__(1024) lossy_background_kernel(LossyScalars* sc)
+{
+    __shared__ unsigned bv[1024];
+    __shared__ int bi[1024];
+    const int t = threadIdx.x;
+    unsigned best = 0;
+    int idx = 0x7FFFFFFF;
+    for (int k = 0; k < 16; ++k) {
+        const int bin = t * 16 + k;
+        const unsigned c = sc->hist[bin];
+        sc->hist[bin] = 0;
+        if (idx == 0x7FFFFFFF || c > best) {
+            best = c;
+            idx = bin;
+        }
+    }
+    bv[t] = best;
+    bi[t] = idx;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if (t < s && (bv[t + s] > bv[t] || (bv[t + s] == bv[t] && bi[t + s] < bi[t]))) {
+            bv[t] = bv[t + s];
+            bi[t] = bi[t + s];
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        sc->background = ((unsigned)bi[0] << 2) + 1u;
+        sc->sum[0] = sc->sum[1] = sc->sum[2] = sc->sum[3] = 0ull;
+        sc->cnt[0] = sc->cnt[1] = 0u;
+    }
+}
+
+// stdDev's sums (:1993-2036), always split by img > background (the un-split case is the sum of both halves)
+__global__ void lossy_sums_kernel(const u16* __restrict__ prevT, const u16* __restrict__ tmpT, const u16* __restrict__ img, int ns,
+                                  LossyScalars* sc)
+{
+    const unsigned back = sc->background;
+    unsigned long long sd = 0, sd2 = 0, bd = 0, bd2 = 0;
+    unsigned nf = 0, nb = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
+        const int d = abs((int)tmpT[i] - (int)prevT[i]);
+        const unsigned long long d2 = (unsigned long long)d * (unsigned long long)d;
+        if ((unsigned)img[i] > back) {
+            sd += d; sd2 += d2; ++nf;
+        } else {
+            bd += d; bd2 += d2; ++nb;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sd += __shfl_xor_sync(0xFFFFFFFFu, sd, o);
+        sd2 += __shfl_xor_sync(0xFFFFFFFFu, sd2, o);
+        bd += __shfl_xor_sync(0xFFFFFFFFu, bd, o);
+        bd2 += __shfl_xor_sync(0xFFFFFFFFu, bd2, o);
+        nf += __shfl_xor_sync(0xFFFFFFFFu, nf, o);
+        nb += __shfl_xor_sync(0xFFFFFFFFu, nb, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sc->sum[0], sd);
+        atomicAdd(&sc->sum[1], sd2);
+        atomicAdd(&sc->sum[2], bd);
+        atomicAdd(&sc->sum[3], bd2);
+        atomicAdd(&sc->cnt[0], nf);
+        atomicAdd(&sc->cnt[1], nb);
+    }
+}
+
+// The scalar part of the frame (:2337-2376), one thread, the reference's operation order in plain fp64.
+// nstds: size of the stdDevs window BEFORE this frame (0..40); first: this is the first non-initial frame.
+__global__ void lossy_decide_kernel(LossyScalars* sc, int ns, int nstds, int first, int low0, int high0, double std_factor,
+                                    int* __restrict__ errors_out)
+{
+    double sd0, sd1;
+    if (nstds < 40) {
+        const double s = (double)(sc->sum[0] + sc->sum[2]), s2 = (double)(sc->sum[1] + sc->sum[3]);
+        sd0 = sd1 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(s, s), s2)), (double)ns);
+    } else {
+        const double s = (double)sc->sum[0], s2 = (double)sc->sum[1], b = (double)sc->sum[2], b2 = (double)sc->sum[3];
+        sd0 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(b, b), b2)), (double)(int)sc->cnt[1]);
+        sd1 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(s, s), s2)), (double)(int)sc->cnt[0]);
+    }
+    if (first) {
+        sc->first[0] = sd0;
+        sc->first[1] = sd1;
+    }
+    int n = nstds;
+    if (n < 40) {
+        sc->stds[n][0] = sd0;
+        sc->stds[n][1] = sd1;
+        ++n;
+    } else {
+        for (int i = 0; i < 39; ++i) {
+            sc->stds[i][0] = sc->stds[i + 1][0];
+            sc->stds[i][1] = sc->stds[i + 1][1];
+        }
+        sc->stds[39][0] = sd0;
+        sc->stds[39][1] = sd1;
+    }
+    double m0 = sc->first[0], m1 = sc->first[1];
+    for (int i = 0; i < n; ++i) {
+        m0 = __dadd_rn(m0, sc->stds[i][0]);
+        m1 = __dadd_rn(m1, sc->stds[i][1]);
+    }
+    m0 = __ddiv_rn(m0, (double)(n + 1));
+    m1 = __ddiv_rn(m1, (double)(n + 1));
+    int high = high0 - (int)round(__dmul_rn(fabs(__dsub_rn(sd1, m1)), std_factor));
+    int low = low0 - (int)round(__dmul_rn(fabs(__dsub_rn(sd0, m0)), std_factor));
+    if (high < 0) high = 0;
+    if (low < high) low = high;
+    sc->low_error = low;
+    sc->high_error = high;
+    errors_out[0] = low;
+    errors_out[1] = high;
+}
+
+// Per-pixel update (:2392-2421) with RunningAverage2::addImage / pixel / resetPixel folded in.
+// len_before: frames in the ring before this one; slot_new: ring slot this frame is written to;
+// slot_old: slot of the oldest frame (read only when the ring is full).
+__global__ void lossy_update_kernel(const u16* __restrict__ tmp, const u16* __restrict__ tmpT, u16* __restrict__ out,
+                                    u16* __restrict__ lastDL, u16* __restrict__ refT, u16* __restrict__ prevT, unsigned* __restrict__ sums,
+                                    u16* __restrict__ cvalue, short* __restrict__ ccount, u16* __restrict__ ring, int n, int ns, int ra,
+                                    int len_before, int slot_new, int slot_old, const LossyScalars* __restrict__ sc)
+{
+    const unsigned back = sc->background;
+    const int low = sc->low_error, high = sc->high_error;
+    const unsigned len_after = (unsigned)(len_before < ra ? len_before + 1 : ra);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned v = tmp[i];
+        if (i >= ns) {  // metadata rows: copied (:2419)
+            out[i] = (u16)v;
+            lastDL[i] = (u16)v;
+            continue;
+        }
+        const unsigned t = tmpT[i];
+        unsigned s = 0;
+        short cc = 0;
+        if (ra > 0) {
+            s = sums[i] + t;
+            cc = ccount[i];
+            if (len_before == ra) {
+                if (cc) {
+                    --cc;
+                    s -= cvalue[i];
+                } else {
+                    s -= ring[(size_t)slot_old * ns + i];
+                }
+            }
+            ring[(size_t)slot_new * ns + i] = (u16)t;
+        }
+        const unsigned r = refT[i];
+        const int diff = abs((int)t - (int)r);
+        const int max_error = v > back ? high : low;
+        unsigned o;
+        if (diff <= max_error && ((unsigned)lastDL[i] >> 13) == (v >> 13)) {
+            o = ra > 0 ? ((s / len_after) & 0xFFFFu) : r;
+        } else {
+            o = t;
+            refT[i] = (u16)t;
+            if (ra > 0) {
+                cvalue[i] = (u16)t;
+                cc = (short)len_after;
+                s = t * len_after;
+            }
+        }
+        if (ra > 0) {
+            sums[i] = s;
+            ccount[i] = cc;
+        }
+        out[i] = (u16)o;
+        prevT[i] = (u16)o;
+        lastDL[i] = (u16)v;
+    }
+}
+
+// ---- launchers ----------------------------------------------------------------------------------
+size_t lossy_scalars_bytes() { return sizeof(LossyScalars); }
+
+int launch_lossy_first(const u16* tmp, u16* out, u16* lastDL, u16* refT, u16* prevT, int n, int ns, int subtract_min, void* scalars,
+                       int* errors_out_dev, int low0, int high0, cudaStream_t st)
+{
+    LossyScalars* sc = (LossyScalars*)scalars;
+    RIRB_CUDA_OK(cudaMemsetAsync(sc, 0, sizeof(LossyScalars), st));
+    const int grid = (int)min((long long)ceil_div(n, 256), (long long)sm_count() * 8);
+    if (subtract_min) {
+        const unsigned init = 65535u;
+        RIRB_CUDA_OK(cudaMemcpyAsync(&sc->minv, &init, sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        if (ns > 0) RIRB_LAUNCH(lossy_min_kernel, grid, 256, 0, st, tmp, ns, sc);
+    }
+    RIRB_LAUNCH(lossy_first_kernel, grid, 256, 0, st, tmp, out, lastDL, refT, prevT, n, ns, subtract_min, sc);
+    const int e[2] = {low0, high0};
+    RIRB_CUDA_OK(cudaMemcpyAsync(errors_out_dev, e, sizeof(e), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+int launch_lossy_frame(const u16* img, const u16* tmp, u16* tmpT, u16* out, u16* lastDL, u16* refT, u16* prevT, unsigned* sums,
+                       u16* cvalue, short* ccount, u16* ring, int n, int ns, int ra, int subtract_min, long long frame_index,
+                       int low0, int high0, double std_factor, void* scalars, int* errors_out_dev, cudaStream_t st)
+{
+    LossyScalars* sc = (LossyScalars*)scalars;
+    const int grid_s = (int)max(1LL, min((long long)ceil_div(ns, 256), (long long)sm_count() * 8));
+    const int grid_n = (int)max(1LL, min((long long)ceil_div(n, 256), (long long)sm_count() * 8));
+    // frame_index >= 1: frames already stored.  Window / ring sizes follow from it.
+    const long long prior = frame_index - 1;                 // non-initial frames before this one
+    const int nstds = (int)min(prior, 40LL);
+    const int len_before = (int)min(prior, (long long)ra);
+    const int slot_new = ra > 0 ? (int)(prior % ra) : 0;     // circular: the slot of the oldest frame once full
+    const int slot_old = slot_new;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RIRB_CUDA_OK(cudaFuncSetAttribute(lossy_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4));
+        attr_set = true;
+    }
+    RIRB_LAUNCH(lossy_prep_kernel, min(grid_s, sm_count() * 2), 512, 16384 * 4, st, tmp, tmpT, ns, subtract_min, sc);
+    RIRB_LAUNCH(lossy_background_kernel, 1, 1024, 0, st, sc);
+    RIRB_LAUNCH(lossy_sums_kernel, grid_s, 256, 0, st, prevT, tmpT, img, ns, sc);
+    RIRB_LAUNCH(lossy_decide_kernel, 1, 1, 0, st, sc, ns, nstds, prior == 0 ? 1 : 0, low0, high0, std_factor, errors_out_dev);
+    RIRB_LAUNCH(lossy_update_kernel, grid_n, 256, 0, st, tmp, tmpT, out, lastDL, refT, prevT, sums, cvalue, ccount, ring, n, ns, ra,
+                len_before, slot_new, slot_old, sc);
+    return 0;
+}
+
+}  // namespace rirb

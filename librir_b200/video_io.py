@@ -241,6 +241,45 @@ def read_movie(lo, hi, bad_pixels=None, min_T=0, min_T_height=0, shifts_x=None, 
     return out
 
 
+class LossyPreconditioner:
+    """``H264_Saver``'s lossy "bounded-error" pre-conditioner (``addImageLossyNoCamera``, h264.cpp:2253-2424):
+    frames in temperature, IN TIME ORDER -> the frames the lossless encoder then receives, pixels that stay
+    within the per-frame error bounds being frozen to a reference / running-average value.  Parameters are the
+    saver's string parameters (h264.cpp:1709-1781) with their defaults (PrivateData(), :1663-1665)."""
+
+    def __init__(self, width, height, lossy_height=None, lowValueError=6, highValueError=2, stdFactor=5.0, runningAverage=32,
+                 subtractMin=False, removeBadPixels=False):
+        lib = _lib.load()
+        self.width, self.height = int(width), int(height)
+        self.lossy_height = self.height if lossy_height is None else int(lossy_height)
+        self.handle = lib.rirb_lossy_open(self.width, self.height, self.lossy_height, int(lowValueError), int(highValueError),
+                                          float(stdFactor), int(runningAverage), int(bool(subtractMin)), int(bool(removeBadPixels)))
+        if self.handle <= 0:
+            raise RuntimeError(f"An error occured while calling 'lossy_open': {_lib.last_error()}")
+
+    def __del__(self):
+        try:
+            _lib.load().rirb_lossy_close(self.handle)
+        except Exception:
+            pass
+
+    def add_images(self, frames, out=None):
+        """``frames``: uint16 ``[n, h, w]`` (or one ``[h, w]`` frame), numpy or torch CUDA.  Returns
+        ``(out, errors)`` with ``errors[t] = (BackgroundError, ForegroundError)`` of frame t."""
+        lib = _lib.load()
+        _prepare_device_call(frames)
+        single = len(frames.shape) == 2
+        n = 1 if single else frames.shape[0]
+        if tuple(frames.shape[-2:]) != (self.height, self.width):
+            raise RuntimeError("lossy add_images: wrong image size")
+        if out is None:
+            out = _empty_like(frames)
+        errors = np.zeros((n, 2), dtype=np.int32)
+        r = lib.rirb_lossy_add_images(self.handle, _ptr(frames), n, _ptr(out), _ptr(errors))
+        _lib.check(r, "lossy_add_images")
+        return out, errors
+
+
 def load_translation_file(filename, nframes=None):
     """``IRFileLoader::loadTranslationFile`` (IRFileLoader.cpp:822-847): tab-separated file, one
     header line, 4 columns; shifts are columns 1 and 2.  Returns ``(x, y)`` float64 arrays."""
@@ -272,6 +311,7 @@ def save_translation_file(filename, x, y, confidence=None):
 
 __all__ = [
     "DEFAULT_GOP", "linesize", "key_frames", "split_yuv444", "merge_yuv444", "split_yuv420", "merge_yuv420",
-    "precode_movie", "decode_movie", "LosslessPrecoder", "LoaderBadPixels", "remove_motion", "read_movie", "load_translation_file",
+    "precode_movie", "decode_movie", "LosslessPrecoder", "LoaderBadPixels", "remove_motion", "read_movie", "LossyPreconditioner",
+    "load_translation_file",
     "save_translation_file",
 ]

@@ -585,3 +585,159 @@ ORC_API int orc_quantile_from_hist(const unsigned long long *hist65536, unsigned
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* f-2  lossy "bounded-error" pre-conditioner of the H.264 saver                         */
+/*      H264_Saver::addImageLossyNoCamera  h264.cpp:2253-2424                           */
+/*      RunningAverage2 h264.cpp:1526-1615, get_background :1955-1991, stdDev :1993-2036 */
+/*      PARITY UNPINNED BY EXECUTION: video_io cannot be compiled here (ffmpeg/x264), and */
+/*      the reference has no test of these values; this is a line-by-line restatement.   */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    int w, h, stop_h;           /* stop_h = stop_lossy_height: rows [0, stop_h) are lossy */
+    int low_error, high_error;  /* lowValueError (6) / highValueError (2), PrivateData() :1663 */
+    double std_factor;          /* 5 */
+    int running_average;        /* 32; 0 = off */
+    int subtract_min;
+    int bp_enabled;
+    /* state */
+    long frames;                /* m_data->attributes.size() */
+    unsigned short minv;
+    u16 *lastDL, *refT, *prevT, *tmp, *tmpT;
+    int *bp_xy; int bp_count; int bp_clamp;
+    double first_std[2]; int have_first;
+    double stds[40][2]; int nstds;
+    /* RunningAverage2 */
+    u16 *ring; int ring_len;    /* images: ring[k*len + i], oldest first (kept compact, like the vector) */
+    unsigned *sums; u16 *cvalue; short *ccount;
+} orc_lossy;
+
+ORC_API orc_lossy *orc_lossy_open(int w, int h, int stop_h, int low_error, int high_error, double std_factor, int running_average,
+                                  int subtract_min, int bp_enabled)
+{
+    orc_lossy *s = (orc_lossy *)calloc(1, sizeof(orc_lossy));
+    size_t n = (size_t)w * (size_t)h, ns = (size_t)w * (size_t)stop_h;
+    s->w = w; s->h = h; s->stop_h = stop_h;
+    s->low_error = low_error; s->high_error = high_error; s->std_factor = std_factor;
+    if (running_average > 64) running_average = 64; /* setParameter :1774 */
+    s->running_average = running_average; s->subtract_min = subtract_min; s->bp_enabled = bp_enabled;
+    s->lastDL = (u16 *)calloc(n, 2); s->refT = (u16 *)calloc(n, 2); s->prevT = (u16 *)calloc(n, 2);
+    s->tmp = (u16 *)calloc(n, 2); s->tmpT = (u16 *)calloc(n, 2);
+    s->ring = (u16 *)calloc(ns * (size_t)(running_average > 0 ? running_average : 1), 2);
+    s->sums = (unsigned *)calloc(ns ? ns : 1, 4); s->cvalue = (u16 *)calloc(ns ? ns : 1, 2); s->ccount = (short *)calloc(ns ? ns : 1, 2);
+    s->bp_xy = (int *)malloc(sizeof(int) * 2 * (ns ? ns : 1));
+    return s;
+}
+ORC_API void orc_lossy_close(orc_lossy *s)
+{
+    if (!s) return;
+    free(s->lastDL); free(s->refT); free(s->prevT); free(s->tmp); free(s->tmpT); free(s->ring);
+    free(s->sums); free(s->cvalue); free(s->ccount); free(s->bp_xy); free(s);
+}
+
+/* stdDev, h264.cpp:1993-2036: (first, second) = (background, foreground) spreads of |img - prev| */
+static void lossy_std_dev(const u16 *prev, const u16 *img, int n, const u16 *img_dl, const unsigned *back, double out[2])
+{
+    if (!back || !img_dl) {
+        double sum_diff2 = 0, sum_diff = 0;
+        for (int i = 0; i < n; ++i) {
+            int diff = abs((int)img[i] - (int)prev[i]);
+            sum_diff2 += diff * diff; /* int product, like the reference (overflows for |diff| >= 46341: UB there) */
+            sum_diff += diff;
+        }
+        double res = sqrt((sum_diff * sum_diff - sum_diff2)) / n;
+        out[0] = out[1] = res;
+    } else {
+        double sum_diff2 = 0, sum_diff = 0, b_sum_diff2 = 0, b_sum_diff = 0;
+        int b_sum = 0, sum = 0;
+        for (int i = 0; i < n; ++i) {
+            int diff = abs((int)img[i] - (int)prev[i]);
+            if (img_dl[i] > *back) { sum_diff2 += diff * diff; sum_diff += diff; sum++; }
+            else { b_sum_diff2 += diff * diff; b_sum_diff += diff; b_sum++; }
+        }
+        out[0] = sqrt((b_sum_diff * b_sum_diff - b_sum_diff2)) / b_sum;
+        out[1] = sqrt((sum_diff * sum_diff - sum_diff2)) / sum;
+    }
+}
+
+/* One frame in, one frame out (what addImageLossLess then receives).  errors[0] = BackgroundError
+ * (lowError), errors[1] = ForegroundError (highError) of this frame. */
+ORC_API void orc_lossy_add_image(orc_lossy *s, const u16 *img, u16 *out, int *errors)
+{
+    const int w = s->w, h = s->h;
+    const int n = w * h, ns = w * s->stop_h;
+    /* :2259-2271 bad pixels on the lossy rows, copy of the rest */
+    if (s->bp_enabled) {
+        if (s->frames == 0) {
+            int thr;
+            s->bp_count = orc_bad_pixels_detect(img, w, s->stop_h, 5.0, s->bp_xy, ns, &thr);
+            s->bp_clamp = orc_bad_pixels_clamp_value(img, w, s->stop_h);
+        }
+        orc_bad_pixels_correct(img, s->tmp, w, s->stop_h, s->bp_xy, s->bp_count, s->bp_clamp);
+        memcpy(s->tmp + ns, img + ns, (size_t)(n - ns) * 2);
+    } else {
+        memcpy(s->tmp, img, (size_t)n * 2);
+    }
+    if (s->frames == 0) { /* :2273-2311 first image */
+        memcpy(s->lastDL, s->tmp, (size_t)n * 2);
+        if (s->subtract_min) {
+            s->minv = 65535;
+            for (int i = 0; i < ns; ++i) if (s->tmp[i] < s->minv) s->minv = s->tmp[i];
+            for (int i = 0; i < ns; ++i) s->tmp[i] = (s->tmp[i] < s->minv) ? 0 : (u16)(s->tmp[i] - s->minv);
+        }
+        errors[0] = s->low_error; errors[1] = s->high_error;
+        memcpy(out, s->tmp, (size_t)n * 2);
+        memcpy(s->refT, s->tmp, (size_t)ns * 2);
+        memcpy(s->prevT, s->tmp, (size_t)ns * 2);
+        s->frames++;
+        return;
+    }
+    memcpy(s->tmpT, s->tmp, (size_t)n * 2); /* :2314 */
+    if (s->subtract_min)
+        for (int i = 0; i < ns; ++i) s->tmpT[i] = (s->tmpT[i] < s->minv) ? 0 : (u16)(s->tmpT[i] - s->minv);
+    unsigned background = orc_get_background(s->tmp, ns); /* :2331 */
+    int lowError = s->low_error, highError = s->high_error;
+    double sd[2];
+    const int running_average_frames = 40;
+    if (s->nstds < running_average_frames) lossy_std_dev(s->prevT, s->tmpT, ns, NULL, NULL, sd);
+    else lossy_std_dev(s->prevT, s->tmpT, ns, img, &background, sd);
+    if (!s->have_first) { s->first_std[0] = sd[0]; s->first_std[1] = sd[1]; s->have_first = 1; }
+    if (s->nstds < running_average_frames) { s->stds[s->nstds][0] = sd[0]; s->stds[s->nstds][1] = sd[1]; s->nstds++; }
+    else { memmove(&s->stds[0], &s->stds[1], sizeof(double) * 2 * (running_average_frames - 1)); s->stds[39][0] = sd[0]; s->stds[39][1] = sd[1]; }
+    double mean0 = s->first_std[0], mean1 = s->first_std[1]; /* :2353-2365 */
+    for (int i = 0; i < s->nstds; ++i) { mean0 += s->stds[i][0]; mean1 += s->stds[i][1]; }
+    mean0 /= (s->nstds + 1); mean1 /= (s->nstds + 1);
+    highError -= (int)round(fabs(sd[1] - mean1) * s->std_factor);
+    lowError -= (int)round(fabs(sd[0] - mean0) * s->std_factor);
+    if (highError < 0) highError = 0;
+    if (lowError < highError) lowError = highError;
+    errors[0] = lowError; errors[1] = highError;
+    /* RunningAverage2::addImage :1560-1594 */
+    const int ra = s->running_average;
+    if (ra > 0) {
+        for (int i = 0; i < ns; ++i) {
+            s->sums[i] += s->tmpT[i];
+            if (s->ring_len == ra) {
+                if (s->ccount[i]) { --s->ccount[i]; s->sums[i] -= s->cvalue[i]; }
+                else if (s->ring_len > 0) s->sums[i] -= s->ring[i];
+            }
+        }
+        if (s->ring_len < ra) { memcpy(s->ring + (size_t)s->ring_len * ns, s->tmpT, (size_t)ns * 2); s->ring_len++; }
+        else { memmove(s->ring, s->ring + ns, (size_t)(ra - 1) * ns * 2); memcpy(s->ring + (size_t)(ra - 1) * ns, s->tmpT, (size_t)ns * 2); }
+    }
+    for (int i = 0; i < ns; ++i) { /* :2397-2413 */
+        int diff = abs((int)s->tmpT[i] - (int)s->refT[i]);
+        int max_error = s->tmp[i] > background ? highError : lowError;
+        if (diff <= max_error && (s->lastDL[i] >> 13) == (s->tmp[i] >> 13)) {
+            s->tmpT[i] = ra > 0 ? (u16)(s->sums[i] / (unsigned long)s->ring_len) : s->refT[i];
+        } else {
+            s->refT[i] = s->tmpT[i];
+            if (ra > 0) { s->cvalue[i] = s->tmpT[i]; s->ccount[i] = (short)s->ring_len; s->sums[i] = (unsigned)s->tmpT[i] * (unsigned)s->ring_len; }
+        }
+    }
+    memcpy(s->prevT, s->tmpT, (size_t)ns * 2);
+    memcpy(s->lastDL, s->tmp, (size_t)n * 2);
+    memcpy(s->tmpT + ns, s->tmp + ns, (size_t)(n - ns) * 2);
+    memcpy(out, s->tmpT, (size_t)n * 2);
+    s->frames++;
+}

@@ -216,6 +216,31 @@ class Port(_Base):
         f(_p(img), w, h, float(shift_x), float(shift_y))
         return img
 
+    def lossy_open(self, w, h, stop_h, low_error=6, high_error=2, std_factor=5.0, running_average=32, subtract_min=False,
+                   bp_enabled=False):
+        """H264_Saver::addImageLossyNoCamera state (h264.cpp:2253-2424); returns an opaque state for lossy_add."""
+        f = self.lib.orc_lossy_open
+        f.restype = ct.c_void_p
+        f.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_double, ct.c_int, ct.c_int, ct.c_int]
+        return ct.c_void_p(f(w, h, stop_h, low_error, high_error, std_factor, running_average, int(subtract_min), int(bp_enabled)))
+
+    def lossy_add(self, state, image):
+        """One frame through the pre-conditioner: returns (frame handed to the lossless encoder, (lowError, highError))."""
+        img = _c(image, np.uint16)
+        out = np.empty_like(img)
+        err = np.zeros(2, dtype=np.int32)
+        f = self.lib.orc_lossy_add_image
+        f.restype = None
+        f.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p]
+        f(state, _p(img), _p(out), _p(err))
+        return out, (int(err[0]), int(err[1]))
+
+    def lossy_close(self, state):
+        f = self.lib.orc_lossy_close
+        f.restype = None
+        f.argtypes = [ct.c_void_p]
+        f(state)
+
     def loader_read_image(self, lo, hi, xy=None, min_T=0, min_T_height=0, shift=None, meta_rows=3):
         """IRFileLoader::readImage after the decoder, calibration == 0 (IRFileLoader.cpp:1168-1247):
         toArray's merge (h264.cpp:3016-3051) -> += min_T on the first min_T_height rows (:1174-1179)

@@ -582,6 +582,47 @@ def test_lossless_chain_with_host_zstd_round_trip_and_ratio():
     assert sizes[True] < sizes[False] < raw, (raw, sizes)
 
 
+def lossy_movie(n, h, w, seed=0):
+    """IR-like movie for the lossy pre-conditioner: static background + noise (pixels that freeze), a hot spot
+    that moves (pixels that restart), integration-time bits (>> 13) that flip in a patch, metadata rows."""
+    rng = np.random.default_rng(seed)
+    mov = ir_movie(n, h, w, seed=seed + 1, drift=0.7).astype(np.int64)
+    mov[n // 3:, 5:12, 5:20] += 8192          # integration time changes at frame n/3 in a patch
+    mov[:, : h // 2] += rng.integers(-1, 2, (n, h // 2, w))
+    mov[:, -3:] = rng.integers(0, 65536, (n, 3, w))
+    return np.clip(mov, 0, 65535).astype(np.uint16)
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(runningAverage=0), dict(runningAverage=5, subtractMin=True),
+                                 dict(removeBadPixels=True, lowValueError=12, highValueError=5),
+                                 dict(runningAverage=64, subtractMin=True, removeBadPixels=True, stdFactor=2.0)])
+def test_lossy_preconditioner_matches_restated_reference(port, cfg):
+    """rirb_lossy_* against the line-by-line restatement of addImageLossyNoCamera, frame by frame and with the
+    state carried across calls: the frozen / restarted pixels, the running average ring wrapping, the switch to
+    background-split spreads after 40 frames, the per-frame error attributes."""
+    n, h, w = 90, 43, 64
+    mov = lossy_movie(n, h, w)
+    stop = h - 3
+    st = port.lossy_open(w, h, stop, cfg.get("lowValueError", 6), cfg.get("highValueError", 2), cfg.get("stdFactor", 5.0),
+                         cfg.get("runningAverage", 32), cfg.get("subtractMin", False), cfg.get("removeBadPixels", False))
+    want, werr = [], []
+    for t in range(n):
+        o, e = port.lossy_add(st, mov[t])
+        want.append(o)
+        werr.append(e)
+    port.lossy_close(st)
+    want, werr = np.stack(want), np.array(werr)
+    pre = vio.LossyPreconditioner(w, h, stop, **cfg)
+    got_a, err_a = pre.add_images(mov[:37])            # host frames, several calls
+    got_b, err_b = pre.add_images(to_dev(mov[37:]))    # device frames
+    got = np.concatenate([got_a, to_host(got_b)])
+    err = np.concatenate([err_a, err_b])
+    np.testing.assert_array_equal(err, werr)
+    for t in range(n):
+        np.testing.assert_array_equal(got[t], want[t], err_msg=f"{cfg} frame {t}")
+    assert (got != mov).any() and (got[:, -3:] == mov[:, -3:]).all()  # something was frozen; metadata rows untouched
+
+
 def test_full_size_c2_round_trip_and_checksums():
     """640x512x1000 (configs[1]): decode(precode(x)) == x with and without delta, and the byte
     planes carry exactly the movie's bytes (checksum of checksums)."""
