@@ -28,7 +28,7 @@ struct LossyScalars {
     unsigned long long sum[4];      // fore: sum_diff, sum_diff2; back: b_sum_diff, b_sum_diff2
     unsigned cnt[2];                // fore, back pixel counts
     double first[2];                // firstStdDevs[0]
-    double stds[40][2];             // stdDevs window (oldest first)
+    double stds[40][2];             // stdDevs window, circular: the oldest entry is stds[head] once 40 are in
     unsigned hist[16384];
 };
 
@@ -137,52 +137,83 @@ __global__ void lossy_sums_kernel(const u16* __restrict__ prevT, const u16* __re
         nf += __shfl_xor_sync(0xFFFFFFFFu, nf, o);
         nb += __shfl_xor_sync(0xFFFFFFFFu, nb, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&sc->sum[0], sd);
-        atomicAdd(&sc->sum[1], sd2);
-        atomicAdd(&sc->sum[2], bd);
-        atomicAdd(&sc->sum[3], bd2);
-        atomicAdd(&sc->cnt[0], nf);
-        atomicAdd(&sc->cnt[1], nb);
+    // one set of global atomics per CTA, not per warp: they all land on the same six words
+    __shared__ unsigned long long part[32][4];
+    __shared__ unsigned pcnt[32][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (lane == 0) {
+        part[warp][0] = sd; part[warp][1] = sd2; part[warp][2] = bd; part[warp][3] = bd2;
+        pcnt[warp][0] = nf; pcnt[warp][1] = nb;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        unsigned long long a = 0;
+        for (int k = 0; k < nwarps; ++k) a += part[k][threadIdx.x];
+        atomicAdd(&sc->sum[threadIdx.x], a);
+    } else if (threadIdx.x < 6) {
+        unsigned a = 0;
+        for (int k = 0; k < nwarps; ++k) a += pcnt[k][threadIdx.x - 4];
+        atomicAdd(&sc->cnt[threadIdx.x - 4], a);
     }
 }
 
-// The scalar part of the frame (:2337-2376), one thread, the reference's operation order in plain fp64.
-// nstds: size of the stdDevs window BEFORE this frame (0..40); first: this is the first non-initial frame.
-__global__ void lossy_decide_kernel(LossyScalars* sc, int ns, int nstds, int first, int low0, int high0, double std_factor,
-                                    int* __restrict__ errors_out)
+// The scalar part of the frame (:2337-2376): the reference's operation order in plain fp64, by ONE thread -- the
+// other 63 only fetch the window into shared memory with independent loads (a lone thread walking global
+// memory pays a full round trip per entry: 40 us per frame in the first version of this kernel).
+// nstds: size of the stdDevs window BEFORE this frame (0..40); head: slot of its oldest entry when full;
+// first: this is the first non-initial frame.
+__global__ void __launch_bounds__(64) lossy_decide_kernel(LossyScalars* sc, int ns, int nstds, int head, int first, int low0, int high0,
+                                                          double std_factor, int* __restrict__ errors_out)
 {
+    __shared__ double win[40][2];
+    __shared__ unsigned long long sums[4];
+    __shared__ unsigned cnts[2];
+    const int t = threadIdx.x;
+    if (t < 40) {  // window in time order: oldest first
+        const int slot = nstds < 40 ? t : (head + t) % 40;
+        win[t][0] = sc->stds[slot][0];
+        win[t][1] = sc->stds[slot][1];
+    } else if (t < 44) {
+        sums[t - 40] = sc->sum[t - 40];
+    } else if (t < 46) {
+        cnts[t - 44] = sc->cnt[t - 44];
+    }
+    __syncthreads();
+    if (t != 0) return;
     double sd0, sd1;
     if (nstds < 40) {
-        const double s = (double)(sc->sum[0] + sc->sum[2]), s2 = (double)(sc->sum[1] + sc->sum[3]);
+        const double s = (double)(sums[0] + sums[2]), s2 = (double)(sums[1] + sums[3]);
         sd0 = sd1 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(s, s), s2)), (double)ns);
     } else {
-        const double s = (double)sc->sum[0], s2 = (double)sc->sum[1], b = (double)sc->sum[2], b2 = (double)sc->sum[3];
-        sd0 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(b, b), b2)), (double)(int)sc->cnt[1]);
-        sd1 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(s, s), s2)), (double)(int)sc->cnt[0]);
+        const double s = (double)sums[0], s2 = (double)sums[1], b = (double)sums[2], b2 = (double)sums[3];
+        sd0 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(b, b), b2)), (double)(int)cnts[1]);
+        sd1 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(s, s), s2)), (double)(int)cnts[0]);
     }
+    double f0 = sc->first[0], f1 = sc->first[1];
     if (first) {
-        sc->first[0] = sd0;
-        sc->first[1] = sd1;
+        sc->first[0] = f0 = sd0;
+        sc->first[1] = f1 = sd1;
     }
-    int n = nstds;
-    if (n < 40) {
-        sc->stds[n][0] = sd0;
-        sc->stds[n][1] = sd1;
-        ++n;
+    // push (window not full) or drop the oldest and append (:2343-2351); the sum below runs oldest -> newest
+    int n, from;
+    if (nstds < 40) {
+        sc->stds[nstds][0] = sd0;
+        sc->stds[nstds][1] = sd1;
+        n = nstds + 1;
+        from = 0;
     } else {
-        for (int i = 0; i < 39; ++i) {
-            sc->stds[i][0] = sc->stds[i + 1][0];
-            sc->stds[i][1] = sc->stds[i + 1][1];
-        }
-        sc->stds[39][0] = sd0;
-        sc->stds[39][1] = sd1;
+        sc->stds[head][0] = sd0;  // the oldest slot becomes the newest
+        sc->stds[head][1] = sd1;
+        n = 40;
+        from = 1;
     }
-    double m0 = sc->first[0], m1 = sc->first[1];
-    for (int i = 0; i < n; ++i) {
-        m0 = __dadd_rn(m0, sc->stds[i][0]);
-        m1 = __dadd_rn(m1, sc->stds[i][1]);
+    double m0 = f0, m1 = f1;
+    for (int i = from; i < (nstds < 40 ? nstds : 40); ++i) {
+        m0 = __dadd_rn(m0, win[i][0]);
+        m1 = __dadd_rn(m1, win[i][1]);
     }
+    m0 = __dadd_rn(m0, sd0);
+    m1 = __dadd_rn(m1, sd1);
     m0 = __ddiv_rn(m0, (double)(n + 1));
     m1 = __ddiv_rn(m1, (double)(n + 1));
     int high = high0 - (int)round(__dmul_rn(fabs(__dsub_rn(sd1, m1)), std_factor));
@@ -292,10 +323,12 @@ int launch_lossy_frame(const u16* img, const u16* tmp, u16* tmpT, u16* out, u16*
         RIRB_CUDA_OK(cudaFuncSetAttribute(lossy_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4));
         attr_set = true;
     }
-    RIRB_LAUNCH(lossy_prep_kernel, min(grid_s, sm_count() * 2), 512, 16384 * 4, st, tmp, tmpT, ns, subtract_min, sc);
+    const int grid_r = (int)max(1LL, min((long long)ceil_div(ns, 1024 * 4), (long long)sm_count()));  // reductions: few, fat CTAs
+    const int head = (int)(prior % 40);  // circular stdDevs window: slot of the oldest entry once 40 are in
+    RIRB_LAUNCH(lossy_prep_kernel, grid_r, 1024, 16384 * 4, st, tmp, tmpT, ns, subtract_min, sc);
     RIRB_LAUNCH(lossy_background_kernel, 1, 1024, 0, st, sc);
-    RIRB_LAUNCH(lossy_sums_kernel, grid_s, 256, 0, st, prevT, tmpT, img, ns, sc);
-    RIRB_LAUNCH(lossy_decide_kernel, 1, 1, 0, st, sc, ns, nstds, prior == 0 ? 1 : 0, low0, high0, std_factor, errors_out_dev);
+    RIRB_LAUNCH(lossy_sums_kernel, grid_r, 1024, 0, st, prevT, tmpT, img, ns, sc);
+    RIRB_LAUNCH(lossy_decide_kernel, 1, 64, 0, st, sc, ns, nstds, head, prior == 0 ? 1 : 0, low0, high0, std_factor, errors_out_dev);
     RIRB_LAUNCH(lossy_update_kernel, grid_n, 256, 0, st, tmp, tmpT, out, lastDL, refT, prevT, sums, cvalue, ccount, ring, n, ns, ra,
                 len_before, slot_new, slot_old, sc);
     return 0;
