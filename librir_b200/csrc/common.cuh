@@ -50,6 +50,20 @@ bool option_enabled(int which);
         }                                                                                     \
     } while (0)
 
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per device (the attribute belongs to the
+// function in one context; a process may drive several GPUs).  Usage: RIRB_SMEM_ATTR(kernel, bytes).
+#define RIRB_SMEM_ATTR(kern, bytes)                                                                        \
+    do {                                                                                                   \
+        static std::atomic<unsigned long long> _done{0};                                                   \
+        int _dev = 0;                                                                                      \
+        cudaGetDevice(&_dev);                                                                              \
+        const unsigned long long _bit = 1ull << (_dev & 63);                                               \
+        if (!(_done.load(std::memory_order_relaxed) & _bit)) {                                             \
+            RIRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            _done.fetch_or(_bit, std::memory_order_relaxed);                                               \
+        }                                                                                                  \
+    } while (0)
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 

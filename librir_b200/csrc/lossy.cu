@@ -11,7 +11,8 @@
 //              replaced by the running average (or refT), else refT restarts from it                :2392-2413
 //   prevT = output, lastDL = tmp, metadata rows copied                              :2415-2421
 // Time is sequential (every frame needs the previous frame's state and two global reductions of its
-// own), pixels are parallel: five small launches per frame on one stream.  All sums are exact integers
+// own), pixels are parallel: three small launches per frame on one stream (the two scalar steps run in the
+// last CTA of the reduction that feeds them).  All sums are exact integers
 // (the reference adds int products into doubles, exact below 2^53), the scalar decision is evaluated in
 // non-contracted fp64 by one thread, so the outputs are bit-identical to the restated reference.
 // State per pixel: sums u32, const (value u16, count i16), refT, prevT, lastDL u16 and a ring of
@@ -29,7 +30,8 @@ struct LossyScalars {
     unsigned cnt[2];                // fore, back pixel counts
     double first[2];                // firstStdDevs[0]
     double stds[40][2];             // stdDevs window, circular: the oldest entry is stds[head] once 40 are in
-    unsigned hist[16384];
+    alignas(16) unsigned hist[16384];
+    unsigned ticket[2];             // "last CTA done" counters of the two reduction kernels
 };
 
 __global__ void lossy_min_kernel(const u16* __restrict__ tmp, int ns, LossyScalars* sc)
@@ -59,42 +61,31 @@ __global__ void lossy_first_kernel(const u16* __restrict__ tmp, u16* __restrict_
     }
 }
 
-// tmpT = tmp - min on the lossy rows; histogram of tmp >> 2 (get_background's, :1958-1962)
-__global__ void lossy_prep_kernel(const u16* __restrict__ tmp, u16* __restrict__ tmpT, int ns, int subtract_min, LossyScalars* sc)
-{
-    extern __shared__ unsigned sh[];  // 16,384 bins = 64 KB (dynamic: above the 48 KB static limit)
-    for (int i = threadIdx.x; i < 16384; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    const unsigned mn = subtract_min ? sc->minv : 0u;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
-        const unsigned v = tmp[i];
-        tmpT[i] = (u16)(v < mn ? 0u : v - mn);
-        atomicAdd(&sh[v >> 2], 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 16384; i += blockDim.x) {
-        const unsigned c = sh[i];
-        if (c) atomicAdd(&sc->hist[i], c);
-    }
-}
-
-// background = (first maximum bin << 2) + 1 (:1974-1990); clears the histogram and the sums for the next steps
-__global__ void __launch_bounds__(1024) lossy_background_kernel(LossyScalars* sc)
+// background = (first maximum bin << 2) + 1 (:1974-1990); clears the histogram and the sums for the next steps.
+// Run by all 1024 threads of ONE CTA: the last CTA of lossy_prep_kernel to finish (no separate launch).
+__device__ __forceinline__ void lossy_background_body(LossyScalars* sc)
 {
     __shared__ unsigned bv[1024];
     __shared__ int bi[1024];
     const int t = threadIdx.x;
-    unsigned best = 0;
-    int idx = 0x7FFFFFFF;
-    for (int k = 0; k < 16; ++k) {
-        const int bin = t * 16 + k;
-        const unsigned c = sc->hist[bin];
-        sc->hist[bin] = 0;
-        if (idx == 0x7FFFFFFF || c > best) {
-            best = c;
-            idx = bin;
+    // 16 consecutive bins per thread: four independent 128-bit loads at L2 (the counts were written by other
+    // CTAs' atomics), then the zeroing stores -- interleaving them would serialise sixteen L2 round trips
+    uint4* hv = reinterpret_cast<uint4*>(&sc->hist[t * 16]);
+    uint4 q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = __ldcg(hv + k);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hv[k] = make_uint4(0u, 0u, 0u, 0u);
+    const unsigned c16[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w,
+                              q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
+    unsigned best = c16[0];
+    int idx = t * 16;
+#pragma unroll
+    for (int k = 1; k < 16; ++k)
+        if (c16[k] > best) {  // strict: the first maximum wins, like the reference's scan (:1976-1983)
+            best = c16[k];
+            idx = t * 16 + k;
         }
-    }
     bv[t] = best;
     bi[t] = idx;
     __syncthreads();
@@ -112,58 +103,49 @@ __global__ void __launch_bounds__(1024) lossy_background_kernel(LossyScalars* sc
     }
 }
 
-// stdDev's sums (:1993-2036), always split by img > background (the un-split case is the sum of both halves)
-__global__ void lossy_sums_kernel(const u16* __restrict__ prevT, const u16* __restrict__ tmpT, const u16* __restrict__ img, int ns,
-                                  LossyScalars* sc)
+// true in every thread of the CTA that finishes last (its global writes being ordered before the ticket)
+__device__ __forceinline__ bool lossy_last_cta(unsigned* ticket)
 {
-    const unsigned back = sc->background;
-    unsigned long long sd = 0, sd2 = 0, bd = 0, bd2 = 0;
-    unsigned nf = 0, nb = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
-        const int d = abs((int)tmpT[i] - (int)prevT[i]);
-        const unsigned long long d2 = (unsigned long long)d * (unsigned long long)d;
-        if ((unsigned)img[i] > back) {
-            sd += d; sd2 += d2; ++nf;
-        } else {
-            bd += d; bd2 += d2; ++nb;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sd += __shfl_xor_sync(0xFFFFFFFFu, sd, o);
-        sd2 += __shfl_xor_sync(0xFFFFFFFFu, sd2, o);
-        bd += __shfl_xor_sync(0xFFFFFFFFu, bd, o);
-        bd2 += __shfl_xor_sync(0xFFFFFFFFu, bd2, o);
-        nf += __shfl_xor_sync(0xFFFFFFFFu, nf, o);
-        nb += __shfl_xor_sync(0xFFFFFFFFu, nb, o);
-    }
-    // one set of global atomics per CTA, not per warp: they all land on the same six words
-    __shared__ unsigned long long part[32][4];
-    __shared__ unsigned pcnt[32][2];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    if (lane == 0) {
-        part[warp][0] = sd; part[warp][1] = sd2; part[warp][2] = bd; part[warp][3] = bd2;
-        pcnt[warp][0] = nf; pcnt[warp][1] = nb;
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+        if (last) *ticket = 0;  // ready for the next frame
     }
     __syncthreads();
-    if (threadIdx.x < 4) {
-        unsigned long long a = 0;
-        for (int k = 0; k < nwarps; ++k) a += part[k][threadIdx.x];
-        atomicAdd(&sc->sum[threadIdx.x], a);
-    } else if (threadIdx.x < 6) {
-        unsigned a = 0;
-        for (int k = 0; k < nwarps; ++k) a += pcnt[k][threadIdx.x - 4];
-        atomicAdd(&sc->cnt[threadIdx.x - 4], a);
-    }
+    if (last) __threadfence();
+    return last;
 }
 
-// The scalar part of the frame (:2337-2376): the reference's operation order in plain fp64, by ONE thread -- the
-// other 63 only fetch the window into shared memory with independent loads (a lone thread walking global
+// tmpT = tmp - min on the lossy rows; histogram of tmp >> 2 (get_background's, :1958-1962)
+__global__ void __launch_bounds__(1024) lossy_prep_kernel(const u16* __restrict__ tmp, u16* __restrict__ tmpT, int ns, int subtract_min, LossyScalars* sc)
+{
+    extern __shared__ unsigned sh[];  // 16,384 bins = 64 KB (dynamic: above the 48 KB static limit)
+    for (int i = threadIdx.x; i < 16384; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const unsigned mn = subtract_min ? sc->minv : 0u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
+        const unsigned v = tmp[i];
+        tmpT[i] = (u16)(v < mn ? 0u : v - mn);
+        atomicAdd(&sh[v >> 2], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16384; i += blockDim.x) {
+        const unsigned c = sh[i];
+        if (c) atomicAdd(&sc->hist[i], c);
+    }
+    if (lossy_last_cta(&sc->ticket[0])) lossy_background_body(sc);
+}
+
+// The scalar part of the frame (:2337-2376), run by the last CTA of lossy_sums_kernel to finish: the reference's
+// operation order in plain fp64, by ONE thread -- the others only fetch the window into shared memory with independent loads (a lone thread walking global
 // memory pays a full round trip per entry: 40 us per frame in the first version of this kernel).
 // nstds: size of the stdDevs window BEFORE this frame (0..40); head: slot of its oldest entry when full;
 // first: this is the first non-initial frame.
-__global__ void __launch_bounds__(64) lossy_decide_kernel(LossyScalars* sc, int ns, int nstds, int head, int first, int low0, int high0,
-                                                          double std_factor, int* __restrict__ errors_out)
+__device__ __forceinline__ void lossy_decide_body(LossyScalars* sc, int ns, int nstds, int head, int first, int low0, int high0,
+                                                  double std_factor, int* __restrict__ errors_out)
 {
     __shared__ double win[40][2];
     __shared__ unsigned long long sums[4];
@@ -174,9 +156,9 @@ __global__ void __launch_bounds__(64) lossy_decide_kernel(LossyScalars* sc, int 
         win[t][0] = sc->stds[slot][0];
         win[t][1] = sc->stds[slot][1];
     } else if (t < 44) {
-        sums[t - 40] = sc->sum[t - 40];
+        sums[t - 40] = __ldcg(&sc->sum[t - 40]);  // other CTAs' atomics: read at L2
     } else if (t < 46) {
-        cnts[t - 44] = sc->cnt[t - 44];
+        cnts[t - 44] = __ldcg(&sc->cnt[t - 44]);
     }
     __syncthreads();
     if (t != 0) return;
@@ -224,6 +206,53 @@ __global__ void __launch_bounds__(64) lossy_decide_kernel(LossyScalars* sc, int 
     sc->high_error = high;
     errors_out[0] = low;
     errors_out[1] = high;
+}
+
+// stdDev's sums (:1993-2036), always split by img > background (the un-split case is the sum of both halves)
+__global__ void __launch_bounds__(1024)
+lossy_sums_kernel(const u16* __restrict__ prevT, const u16* __restrict__ tmpT, const u16* __restrict__ img, int ns, LossyScalars* sc,
+                  int nstds, int head, int first, int low0, int high0, double std_factor, int* __restrict__ errors_out)
+{
+    const unsigned back = sc->background;
+    unsigned long long sd = 0, sd2 = 0, bd = 0, bd2 = 0;
+    unsigned nf = 0, nb = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
+        const int d = abs((int)tmpT[i] - (int)prevT[i]);
+        const unsigned long long d2 = (unsigned long long)d * (unsigned long long)d;
+        if ((unsigned)img[i] > back) {
+            sd += d; sd2 += d2; ++nf;
+        } else {
+            bd += d; bd2 += d2; ++nb;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sd += __shfl_xor_sync(0xFFFFFFFFu, sd, o);
+        sd2 += __shfl_xor_sync(0xFFFFFFFFu, sd2, o);
+        bd += __shfl_xor_sync(0xFFFFFFFFu, bd, o);
+        bd2 += __shfl_xor_sync(0xFFFFFFFFu, bd2, o);
+        nf += __shfl_xor_sync(0xFFFFFFFFu, nf, o);
+        nb += __shfl_xor_sync(0xFFFFFFFFu, nb, o);
+    }
+    // one set of global atomics per CTA, not per warp: they all land on the same six words
+    __shared__ unsigned long long part[32][4];
+    __shared__ unsigned pcnt[32][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (lane == 0) {
+        part[warp][0] = sd; part[warp][1] = sd2; part[warp][2] = bd; part[warp][3] = bd2;
+        pcnt[warp][0] = nf; pcnt[warp][1] = nb;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        unsigned long long a = 0;
+        for (int k = 0; k < nwarps; ++k) a += part[k][threadIdx.x];
+        atomicAdd(&sc->sum[threadIdx.x], a);
+    } else if (threadIdx.x < 6) {
+        unsigned a = 0;
+        for (int k = 0; k < nwarps; ++k) a += pcnt[k][threadIdx.x - 4];
+        atomicAdd(&sc->cnt[threadIdx.x - 4], a);
+    }
+    if (lossy_last_cta(&sc->ticket[1])) lossy_decide_body(sc, ns, nstds, head, first, low0, high0, std_factor, errors_out);
 }
 
 // Per-pixel update (:2392-2421) with RunningAverage2::addImage / pixel / resetPixel folded in.
@@ -318,17 +347,13 @@ int launch_lossy_frame(const u16* img, const u16* tmp, u16* tmpT, u16* out, u16*
     const int len_before = (int)min(prior, (long long)ra);
     const int slot_new = ra > 0 ? (int)(prior % ra) : 0;     // circular: the slot of the oldest frame once full
     const int slot_old = slot_new;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RIRB_CUDA_OK(cudaFuncSetAttribute(lossy_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4));
-        attr_set = true;
-    }
+    RIRB_SMEM_ATTR(lossy_prep_kernel, 16384 * 4);
     const int grid_r = (int)max(1LL, min((long long)ceil_div(ns, 1024 * 4), (long long)sm_count()));  // reductions: few, fat CTAs
     const int head = (int)(prior % 40);  // circular stdDevs window: slot of the oldest entry once 40 are in
+    // three launches per frame: the two scalar steps run in the last CTA of the reduction before them
     RIRB_LAUNCH(lossy_prep_kernel, grid_r, 1024, 16384 * 4, st, tmp, tmpT, ns, subtract_min, sc);
-    RIRB_LAUNCH(lossy_background_kernel, 1, 1024, 0, st, sc);
-    RIRB_LAUNCH(lossy_sums_kernel, grid_r, 1024, 0, st, prevT, tmpT, img, ns, sc);
-    RIRB_LAUNCH(lossy_decide_kernel, 1, 64, 0, st, sc, ns, nstds, head, prior == 0 ? 1 : 0, low0, high0, std_factor, errors_out_dev);
+    RIRB_LAUNCH(lossy_sums_kernel, grid_r, 1024, 0, st, prevT, tmpT, img, ns, sc, nstds, head, prior == 0 ? 1 : 0, low0, high0, std_factor,
+                errors_out_dev);
     RIRB_LAUNCH(lossy_update_kernel, grid_n, 256, 0, st, tmp, tmpT, out, lastDL, refT, prevT, sums, cvalue, ccount, ring, n, ns, ra,
                 len_before, slot_new, slot_old, sc);
     return 0;

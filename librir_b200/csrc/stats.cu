@@ -130,7 +130,7 @@ int launch_movie_stats(const u16* mov, size_t n, const u8* mask, unsigned* minma
     if (grid < 1) grid = 1;
     if (hist) {
         const size_t smem = HIST_SMEM_BINS * sizeof(unsigned);
-        RIRB_CUDA_OK(cudaFuncSetAttribute(movie_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RIRB_SMEM_ATTR(movie_stats_kernel<true>, smem);
         RIRB_LAUNCH(movie_stats_kernel<true>, (unsigned)grid, ST_THREADS, smem, st, mov, n, mask, minmax, hist);
     } else {
         RIRB_LAUNCH(movie_stats_kernel<false>, (unsigned)(grid * 2), ST_THREADS, 0, st, mov, n, mask, minmax, hist);

@@ -776,12 +776,8 @@ int launch_translate_u16(const u16* src, u16* dst, int w, int h, long long nfram
     const int tiles_x = (int)ceil_div(w, TT_W), tiles_y = (int)ceil_div(h, TT_H);
     if (tma_enabled && (w % 8 == 0) && aligned16(dst) && (dst_stride % 8 == 0) && tma_compatible(src, (size_t)w * 2, src_stride * 2)) {
         const size_t smem = (size_t)TT_STAGES * TT_STAGE_BYTES;
-        static bool attr_set = false;
-        if (!attr_set) {
-            RIRB_CUDA_OK(cudaFuncSetAttribute(translate_u16_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            RIRB_CUDA_OK(cudaFuncSetAttribute(translate_u16_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
+        RIRB_SMEM_ATTR((translate_u16_tma_kernel<true, false>), smem);
+        RIRB_SMEM_ATTR((translate_u16_tma_kernel<false, false>), smem);
         // grid = (tile column, frame); gridDim.y <= 65535, so long movies go in several launches
         for (long long f0 = 0; f0 < nframes; f0 += 65535) {
             const long long n = min(nframes - f0, 65535LL);
@@ -826,12 +822,7 @@ int launch_loader_fused(const u8* lo, const u8* hi, u16* out, int w, int h_full,
     if (!enabled || (w % 16) != 0 || hb < 3 || !aligned16(out) || !tma_compatible(lo, (size_t)w, fpx) ||
         !tma_compatible(hi, (size_t)w, fpx))
         return 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RIRB_CUDA_OK(cudaFuncSetAttribute(translate_u16_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)TP_SMEM_BYTES));
-        attr_set = true;
-    }
+    RIRB_SMEM_ATTR((translate_u16_tma_kernel<true, true>), TP_SMEM_BYTES);
     const int tiles_x = (int)ceil_div(w, TT_W), tiles_y = (int)ceil_div(hb, TT_H);
     for (long long f0 = 0; f0 < nframes; f0 += 65535) {
         const long long n = min(nframes - f0, 65535LL);

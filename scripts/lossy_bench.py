@@ -24,15 +24,17 @@ def main():
     out = torch.empty_like(frames)
     rows = []
     for cfg in (dict(), dict(runningAverage=0), dict(removeBadPixels=True, subtractMin=True)):
-        pre = vio.LossyPreconditioner(W, H, H - 3, **cfg)
-        pre.add_images(frames[:50], out=out[:50])  # warm-up (also the first-image branch)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        pre.add_images(frames[50:], out=out[50:])
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms = None
+        for attempt in range(2):  # the first pass of a process pays one-time allocations: report the second
+            pre = vio.LossyPreconditioner(W, H, H - 3, **cfg)
+            pre.add_images(frames[:50], out=out[:50])  # the first-image branch and the window filling up
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pre.add_images(frames[50:], out=out[50:])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
         frozen = float((out[50:].view(torch.int16) != frames[50:].view(torch.int16)).float().mean())
         # CPU: the restated reference, one core
         port = O.Port()
