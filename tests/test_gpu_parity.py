@@ -150,6 +150,32 @@ def test_translate_u16_random_shifts_full_size(best):
             np.testing.assert_array_equal(got[t], best.translate(mov[t], dx[t], dy[t], "nearest", 0), err_msg=f"{h}x{w} frame {t}")
 
 
+def test_translate_u16_randomized(best):
+    """150 random (shape, shift, strategy) cases: widths on and off the TMA path, shifts from sub-ulp to beyond the
+    image, exact integers, halves and values one float ulp away from an integer."""
+    rng = np.random.default_rng(2026)
+    specials = [0.0, 1.0, -1.0, 0.5, -0.5, 8.0, -8.0, 7.9999995, -7.9999995, 1.0000001, 127.5, -128.0, 1e-20, -1e-20, 0.25, 63.75]
+    for case in range(150):
+        w = int(rng.choice([8, 16, 24, 40, 64, 96, 128, 136, 200, 264, 7, 33, 130]))
+        h = int(rng.integers(1, 150))
+        f = rng.integers(0, 65536, (h, w), dtype=np.uint16)
+        if case % 3 == 0:
+            f = (f >> 6).astype(np.uint16)  # small values: exact-integer results are common
+        def pick(extent):
+            k = rng.integers(0, 4)
+            if k == 0:
+                return float(rng.choice(specials))
+            if k == 1:
+                return float(np.float32(rng.uniform(-3, 3)))
+            if k == 2:
+                return float(np.float32(rng.uniform(-extent - 5, extent + 5)))
+            return float(np.float32(rng.integers(-extent, extent + 1)) + np.float32(rng.choice([0, 2 ** -20, -2 ** -20, 0.5])))
+        dx, dy = pick(w), pick(h)
+        st = ["nearest", "background", "wrap", ""][case % 4]
+        np.testing.assert_array_equal(sp.translate(f, dx, dy, st, 321), best.translate(f, dx, dy, st, 321),
+                                      err_msg=f"case {case}: {h}x{w} {st!r} dx={dx!r} dy={dy!r}")
+
+
 def test_translate_batch_per_frame_shifts_device(best):
     mov = ir_movie(9, 96, 128)
     rng = np.random.default_rng(777)
@@ -225,6 +251,25 @@ def test_gaussian_tiled_shapes_u16_and_f32(best, shape, sigma):
     got = sp.gaussian_filter_batch(to_dev(np.stack([f, f])), sigma).cpu().numpy()
     assert_gauss_close(got[0], want)
     assert_gauss_close(got[1], want)
+
+
+def test_gaussian_randomized(best):
+    """60 random (shape, sigma, dtype) cases through both input types."""
+    rng = np.random.default_rng(77)
+    for case in range(60):
+        w = int(rng.choice([8, 12, 16, 40, 64, 128, 132, 136, 200, 264, 7, 33]))
+        h = int(rng.integers(1, 140))
+        sigma = float(rng.choice([0.3, 0.5, 0.8, 1.0, 1.3, 1.7, 2.0, 2.49, 3.1]))
+        if case % 2:
+            img = rng.integers(0, 16384, (h, w), dtype=np.uint16)
+            want = best.gaussian_filter(img.astype(np.float32), sigma)
+        else:
+            img = (rng.random((h, w)) * 5000 - 1000).astype(np.float32)
+            want = best.gaussian_filter(img, sigma)
+        got = sp.gaussian_filter(img, sigma)
+        tol = 1e-5 * np.abs(want) + 1e-6 * float(np.abs(want).max() + 1e-30)
+        bad = np.abs(got.astype(np.float64) - want.astype(np.float64)) > tol
+        assert not bad.any(), f"case {case}: {h}x{w} sigma {sigma}: {bad.sum()} pixels out of tolerance"
 
 
 def test_gaussian_constant_image_stays_constant():
