@@ -27,9 +27,10 @@ struct ThreadState {
     char err[512] = {0};
     cudaStream_t stream = 0;
     // grow-only device scratch slots for host-pointer callers (never shared between threads)
-    void* dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t cap[6] = {0, 0, 0, 0, 0, 0};
-    int dev_of[6] = {-1, -1, -1, -1, -1, -1};
+    // slots 0-5: operands of the entry that is running; 6-7: bad_pixels_create, which other entries call
+    void* dev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int dev_of[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
 };
 static thread_local ThreadState tls;
 
@@ -443,10 +444,10 @@ int bad_pixels_create(unsigned short* first_image, int width, int height)
         set_error("bad_pixels_create: %s: %s", what, cudaGetErrorString(cudaGetLastError()));
         return 0;
     };
-    const u16* d_img = (const u16*)stage_in(first_image, n * 2, 0, st);
+    const u16* d_img = (const u16*)stage_in(first_image, n * 2, 6, st);
     if (!d_img) return 0;
     // (i) frame histogram -> median (sorted[N/2]) and spread, as Filters.h:145-160 / BadPixels.cpp:19-31
-    unsigned* d_hist = (unsigned*)scratch(1, 65536 * sizeof(unsigned));
+    unsigned* d_hist = (unsigned*)scratch(7, 65536 * sizeof(unsigned));
     if (!d_hist) return 0;
     if (launch_hist_frame(d_img, n, d_hist, st) != 0) return 0;
     std::vector<unsigned> hist(65536);
