@@ -56,46 +56,58 @@ def shard_frames(nframes: int, world: int, rank: int, gop: int = vio.DEFAULT_GOP
 class MovieStats:
     """min / max / 65,536-bin histogram of a movie shard, kept on the device and reduced across
     ranks in place.  ``quantile`` follows ``find_median_pixel`` (Filters.cpp:56-72) and
-    ``background`` follows ``get_background`` (h264.cpp:1955-1991) on the reduced histogram."""
+    ``background`` follows ``get_background`` (h264.cpp:1955-1991) on the reduced histogram.
+
+    Layout: one int64 buffer ``[hist[65536] | count]`` so that the reduction is ONE ``SUM``
+    all-reduce, and ``minmax`` = ``[min, max]`` reduced as ONE ``MIN`` all-reduce of ``[min, -max]``;
+    nothing in ``update`` / ``all_reduce`` waits for the device."""
 
     def __init__(self, device):
         import torch
 
         self.device = torch.device(device)
         self.minmax = torch.empty(2, dtype=torch.int32, device=self.device)   # viewed as uint32 by the kernel
-        self.hist = torch.empty(65536, dtype=torch.int64, device=self.device)  # viewed as uint64
-        self.count = 0
+        self._sums = torch.zeros(65537, dtype=torch.int64, device=self.device)  # hist (viewed as uint64) + pixel count
+        self.hist = self._sums[:65536]
         self._fresh = True
+
+    @property
+    def count(self) -> int:
+        return int(self._sums[65536].item())
+
+    @count.setter
+    def count(self, v: int) -> None:
+        self._sums[65536] = int(v)
 
     def update(self, frames) -> None:
         """Fold a chunk of uint16 frames (torch CUDA tensor) into the statistics."""
         lib = _lib.load()
         sp._prepare_device_call(frames)
         n = frames.numel()
+        if self._fresh:
+            self._sums[65536] = 0
         r = lib.rirb_movie_stats(sp._ptr(frames), n, ct.c_void_p(self.minmax.data_ptr()), ct.c_void_p(self.hist.data_ptr()),
                                  0 if self._fresh else 1)
         _lib.check(r, "movie_stats")
         self._fresh = False
-        self.count += n
+        self._sums[65536] += n
 
     def all_reduce(self, group=None) -> None:
-        """The path's only collective: min (MIN), max (MAX), histogram and count (SUM)."""
+        """The path's only collective: min (MIN), max (MAX), histogram and count (SUM) -- two NCCL calls."""
         import torch
         import torch.distributed as dist
 
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
-        mn, mx = self.minmax[0:1], self.minmax[1:2]
-        cnt = torch.tensor([self.count], dtype=torch.int64, device=self.device)
         if self._fresh:  # an empty shard contributes the identities
             self.minmax[0], self.minmax[1] = 65535, 0
-            self.hist.zero_()
+            self._sums.zero_()
             self._fresh = False
-        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-        dist.all_reduce(self.hist, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
-        self.count = int(cnt.item())
+        mm = torch.stack((self.minmax[0], -self.minmax[1]))  # max(x) = -min(-x): one MIN reduction for both
+        dist.all_reduce(mm, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(self._sums, op=dist.ReduceOp.SUM, group=group)
+        self.minmax[0] = mm[0]
+        self.minmax[1] = -mm[1]
 
     # host-side views -------------------------------------------------------------------
     def min(self) -> int:
