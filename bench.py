@@ -36,7 +36,9 @@ SIGMA = 1.0
 METRIC = "frames/s at 640x512 u16 (full per-frame pipeline: bad-pixel correct + gaussian + translate + pre-coder)"
 # algorithmic bytes per pixel of each kernel: every input byte read once, every
 # output byte written once
-BYTES_PER_PX = {"bp_correct": 4, "gaussian_u16_f32": 6, "translate_u16": 4, "precode_delta_split": 4, "stats_minmax_hist": 2}
+BYTES_PER_PX = {"bp_correct": 4, "gaussian_u16_f32": 6, "translate_u16": 4, "precode_delta_split": 4, "stats_minmax_hist": 2,
+                # the statistics ride along in the pre-coder's pass: the frames are read once, the planes written once
+                "precode_delta_split_stats": 4}
 
 
 def ncu_traffic(kernel, frames):
@@ -254,7 +256,7 @@ def workload_config(chunk, n_gpus):
         "workload": "C3 (BASELINE.json configs[2]): WEST-style 640x512 uint16 movie, full per-frame pipeline, "
                     "frame-sharded; one step = one chunk per GPU",
         "frame": [W, H], "frames_per_step_per_gpu": chunk, "global_frames_per_step": chunk * n_gpus, "gop": GOP,
-        "sigma": SIGMA, "translate": "per-frame shifts U(-3,3), nearest border", "precoder": "temporal delta + byte-plane split",
+        "sigma": SIGMA, "translate": "per-frame shifts U(-3,3), nearest border", "precoder": "temporal delta + byte-plane split (+ min/max/histogram of the same frames)",
         "sharding": f"contiguous GOP-aligned frame ranges over {n_gpus} rank(s)",
         "l2": "inputs larger than L2 (each stage streams >= 2.7 GB per step)",
     }
@@ -284,7 +286,8 @@ def run_ours(args, out):
         print(f"bench.py: note: WORLD_SIZE={world} but --gpus {args.gpus}; using {world}", file=sys.stderr)
 
     chunk = args.chunk
-    cfg = movie.PipelineConfig(width=W, height=H, sigma=SIGMA, strategy="nearest", gop=GOP, delta=True, chunk_frames=chunk)
+    cfg = movie.PipelineConfig(width=W, height=H, sigma=SIGMA, strategy="nearest", gop=GOP, delta=True, chunk_frames=chunk,
+                               fuse_stats=not args.unfused_stats)
     pipe = movie.FramePipeline(cfg, dev)
     # this rank's shard of the (virtual) movie: chunk frames per step, GOP-aligned
     shard = movie.shard_frames(chunk * world, world, rank, GOP)
@@ -394,7 +397,7 @@ def run_ours(args, out):
                          "frac": kernels[dom]["frac_of_peak"], "traffic": ncu_traffic(dom, chunk),
                          "traffic_source": "profiles/ncu_traffic.json (ncu --set full, one launch, scaled per frame)",
                          "algorithmic_bytes": kernels[dom]["algorithmic_bytes_per_launch"], "peak_source": peak_src,
-                         "pipeline_achieved": sum(BYTES_PER_PX.values()) * npx * chunk / (sum(per_stage) * 1e-3) / 1e9},
+                         "pipeline_achieved": sum(BYTES_PER_PX[k] for k in pipe.STAGES) * npx * chunk / (sum(per_stage) * 1e-3) / 1e9},
             "kernels": kernels,
             "e2e": {"value": e2e_n * world * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": e2e_n * (npx * 2 + 8), "d2h_bytes_per_step": e2e_n * npx * 2,
@@ -449,6 +452,7 @@ def main():
     ap.add_argument("--e2e-sub", type=int, default=100, help="frames per sub-chunk of the host path (rounded to whole GOPs)")
     ap.add_argument("--cpu-frames", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--unfused-stats", action="store_true", help="statistics as their own kernel instead of inside the pre-coder's pass")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     with JsonOnlyStdout() as out:

@@ -145,6 +145,11 @@ RIRB_API int rirb_merge_yuv420(const unsigned char* y_plane, int ls_y, const uns
  * first_frame must be a multiple of gop (shards start on key frames). */
 RIRB_API int rirb_precode_movie(const unsigned short* movie, long long nframes, int w, int h, int gop, int delta,
                                 long long first_frame, unsigned char* lo, unsigned char* hi);
+/* rirb_precode_movie and rirb_movie_stats of the same frames in ONE pass over them (the pre-coder is purely
+ * bandwidth-bound, the histogram rides along): minmax / hist / accumulate as in rirb_movie_stats. */
+RIRB_API int rirb_precode_movie_stats(const unsigned short* movie, long long nframes, int w, int h, int gop, int delta,
+                                      long long first_frame, unsigned char* lo, unsigned char* hi, unsigned int* minmax,
+                                      unsigned long long* hist, int accumulate);
 RIRB_API int rirb_decode_movie(const unsigned char* lo, const unsigned char* hi, long long nframes, int w, int h, int gop,
                                int delta, long long first_frame, unsigned short* movie);
 /* key[t] = 1 iff frame t of a writer starting at frame 0 is a key frame (h264.cpp:1050-1061) */

@@ -67,6 +67,7 @@ SIGNATURES = {
     "rirb_split_yuv420": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i]),
     "rirb_merge_yuv420": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "rirb_precode_movie": (_i, [_vp, _ll, _i, _i, _i, _i, _ll, _vp, _vp]),
+    "rirb_precode_movie_stats": (_i, [_vp, _ll, _i, _i, _i, _i, _ll, _vp, _vp, _vp, _vp, _i]),
     "rirb_decode_movie": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _ll, _vp]),
     "rirb_key_frames": (_i, [_ll, _i, _vp]),
     "rirb_lossy_open": (_i, [_i, _i, _i, _i, _i, ct.c_double, _i, _i, _i]),

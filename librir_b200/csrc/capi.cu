@@ -925,6 +925,34 @@ int rirb_precode_movie(const unsigned short* movie, long long nframes, int w, in
     return finish_out(o, 2, st);
 }
 
+int rirb_precode_movie_stats(const unsigned short* movie, long long nframes, int w, int h, int gop, int delta, long long first_frame,
+                             unsigned char* lo, unsigned char* hi, unsigned int* minmax, unsigned long long* hist, int accumulate)
+{
+    if (!movie || !lo || !hi || !minmax || !hist || w <= 0 || h <= 0 || nframes < 0 || gop < 1) {
+        set_error("precode_movie_stats: bad arguments");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const size_t n = (size_t)w * h * (size_t)nframes;
+    const u16* d_mov = (const u16*)stage_in(movie, n * 2, 0, st);
+    if (!d_mov) return -1;
+    StagedOut o[4];
+    if (!stage_out(o[0], lo, n, 1, false, st) || !stage_out(o[1], hi, n, 2, false, st)) return -1;
+    if (!stage_out(o[2], minmax, 2 * sizeof(unsigned), 3, accumulate != 0, st)) return -1;
+    if (!stage_out(o[3], hist, 65536 * sizeof(unsigned long long), 4, accumulate != 0, st)) return -1;
+    if (!accumulate && launch_stats_init((unsigned*)o[2].dev, (unsigned long long*)o[3].dev, st) != 0) return -1;
+    const int rc = launch_precode_movie_stats(d_mov, nframes, w, h, gop, delta, first_frame, (u8*)o[0].dev, (u8*)o[1].dev,
+                                              (unsigned*)o[2].dev, (unsigned long long*)o[3].dev, st);
+    if (rc < 0) return -1;
+    if (rc == 1) {  // layouts the fused kernel does not take: the two kernels
+        if (launch_precode_movie(d_mov, nframes, w, h, gop, delta, first_frame, (u8*)o[0].dev, (u8*)o[1].dev, st) != 0) return -1;
+        if (launch_movie_stats(d_mov, n, nullptr, (unsigned*)o[2].dev, (unsigned long long*)o[3].dev, st) != 0) return -1;
+    }
+    return finish_out(o, 4, st);
+}
+
 int rirb_decode_movie(const unsigned char* lo, const unsigned char* hi, long long nframes, int w, int h, int gop, int delta,
                       long long first_frame, unsigned short* movie)
 {

@@ -61,6 +61,8 @@ int launch_merge_planes(const u8* y_plane, const u8* u_plane, const u8* v_plane,
                         u16* img, u8* it, cudaStream_t st);
 int launch_precode_movie(const u16* mov, long long nframes, int w, int h, int gop, int delta, long long first_frame, u8* lo,
                          u8* hi, cudaStream_t st);
+int launch_precode_movie_stats(const u16* mov, long long nframes, int w, int h, int gop, int delta, long long first_frame, u8* lo,
+                               u8* hi, unsigned* minmax, unsigned long long* hist, cudaStream_t st);
 int launch_decode_movie(const u8* lo, const u8* hi, long long nframes, int w, int h, int gop, int delta, long long first_frame,
                         u16* mov, cudaStream_t st);
 

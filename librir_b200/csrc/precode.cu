@@ -15,6 +15,7 @@
 //                              every frame is read from HBM once although it is used twice.
 //   split_rows / merge_rows    the per-frame AVFrame layouts with row padding (linesize).
 #include "common.cuh"
+#include "hist.cuh"
 #include "kernels.h"
 
 namespace rirb {
@@ -223,6 +224,85 @@ __global__ void delta_merge_scalar_kernel(const u8* __restrict__ lo, const u8* _
 static bool movie_vectorizable(const void* mov, const void* lo, const void* hi, size_t npx)
 {
     return (npx % 16 == 0) && aligned32(mov) && aligned16(lo) && aligned16(hi);
+}
+
+// ---- pre-coder fused with the movie statistics ---------------------------------------------------
+// The frames the pre-coder reads are the frames the statistics are taken of (the registered movie), and
+// the pre-coder leaves four fifths of the issue slots idle (it is purely bandwidth-bound), so one kernel
+// does both: persistent, one 1024-thread CTA per SM with the 49,152-bin shared histogram of stats.cu,
+// work items = (1024 vector positions, one GOP).  4 B/px for both results instead of 4 + 2.
+constexpr int PS_THREADS = 1024;
+
+template <bool DELTA>
+__global__ void __launch_bounds__(PS_THREADS, 1)
+split_stats_kernel(const u16* __restrict__ mov, u8* __restrict__ lo, u8* __restrict__ hi, size_t vec_per_frame, long long nframes,
+                   int gop, unsigned* __restrict__ minmax, unsigned long long* __restrict__ hist)
+{
+    extern __shared__ unsigned sh[];
+    for (unsigned i = threadIdx.x; i < HIST_SMEM_BINS; i += PS_THREADS) sh[i] = 0;
+    __syncthreads();
+    const long long ngop = (nframes + gop - 1) / gop;
+    const long long blocks = (long long)((vec_per_frame + PS_THREADS - 1) / PS_THREADS);
+    unsigned lo2 = 0xFFFFFFFFu, hi2 = 0u;  // packed per-halfword min / max
+    for (long long item = blockIdx.x; item < blocks * ngop; item += gridDim.x) {
+        const long long g = item / blocks;
+        const size_t i = (size_t)(item - g * blocks) * PS_THREADS + threadIdx.x;
+        if (i >= vec_per_frame) continue;
+        const long long t0 = g * gop, t1 = min(nframes, t0 + gop);
+        U32x8 prev;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) prev.v[k] = 0;
+        for (long long t = t0; t < t1; t += PC_UNROLL) {
+            U32x8 cur[PC_UNROLL];
+#pragma unroll
+            for (int k = 0; k < PC_UNROLL; ++k)
+                if (t + k < t1) cur[k] = ld_stream256(mov + ((size_t)(t + k) * vec_per_frame + i) * 16);
+#pragma unroll
+            for (int k = 0; k < PC_UNROLL; ++k)
+                if (t + k < t1) {
+                    const LoHi r = split16(DELTA ? sub16(cur[k], prev) : cur[k]);
+                    if (DELTA) prev = cur[k];
+                    const size_t o = (size_t)(t + k) * vec_per_frame + i;
+                    st_stream(reinterpret_cast<uint4*>(lo) + o, r.lo);
+                    st_stream(reinterpret_cast<uint4*>(hi) + o, r.hi);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const unsigned w2 = cur[k].v[q];
+                        lo2 = __vminu2(lo2, w2);
+                        hi2 = __vmaxu2(hi2, w2);
+                        count_px(w2 & 0xFFFFu, sh, hist);
+                        count_px(w2 >> 16, sh, hist);
+                    }
+                }
+        }
+    }
+    hist_flush(min(lo2 & 0xFFFFu, lo2 >> 16), max(hi2 & 0xFFFFu, hi2 >> 16), sh, minmax, hist, true);
+}
+
+// returns 1 when the layout cannot take the fused kernel (caller runs the two kernels)
+int launch_precode_movie_stats(const u16* mov, long long nframes, int w, int h, int gop, int delta, long long first_frame, u8* lo,
+                               u8* hi, unsigned* minmax, unsigned long long* hist, cudaStream_t st)
+{
+    if (nframes <= 0 || w <= 0 || h <= 0) return 0;
+    const size_t npx = (size_t)w * h;
+    if (gop < 1) gop = 1;
+    if (!movie_vectorizable(mov, lo, hi, npx) || !hist || !minmax) return 1;
+    if (delta && first_frame % gop != 0) {
+        set_error("precode: with delta on, a shard must start on a key frame (first_frame %lld, GOP %d)", first_frame, gop);
+        return -1;
+    }
+    const size_t vpf = npx / 16;
+    const size_t smem = HIST_SMEM_BINS * sizeof(unsigned);
+    const long long items = ceil_div((long long)vpf, PS_THREADS) * ceil_div(nframes, gop);
+    const unsigned grid = (unsigned)min((long long)sm_count(), items);
+    if (delta) {
+        RIRB_SMEM_ATTR(split_stats_kernel<true>, smem);
+        RIRB_LAUNCH(split_stats_kernel<true>, grid, PS_THREADS, smem, st, mov, lo, hi, vpf, nframes, gop, minmax, hist);
+    } else {
+        RIRB_SMEM_ATTR(split_stats_kernel<false>, smem);
+        RIRB_LAUNCH(split_stats_kernel<false>, grid, PS_THREADS, smem, st, mov, lo, hi, vpf, nframes, gop, minmax, hist);
+    }
+    return 0;
 }
 
 int launch_precode_movie(const u16* mov, long long nframes, int w, int h, int gop, int delta, long long first_frame, u8* lo,

@@ -11,12 +11,12 @@
 // straight to the global u64 histogram.  At the end each CTA adds its non-zero bins to the global
 // histogram.  Algorithmic traffic: 2 B/px read.
 #include "common.cuh"
+#include "hist.cuh"
 #include "kernels.h"
 
 namespace rirb {
 
 constexpr int ST_THREADS = 1024;
-constexpr unsigned HIST_SMEM_BINS = 49152;
 
 __global__ void stats_init_kernel(unsigned* minmax, unsigned long long* hist)
 {
@@ -32,14 +32,6 @@ int launch_stats_init(unsigned* minmax, unsigned long long* hist, cudaStream_t s
 {
     RIRB_LAUNCH(stats_init_kernel, 65536 / 256, 256, 0, st, minmax, hist);
     return 0;
-}
-
-__device__ __forceinline__ void count_px(unsigned v, unsigned* sh, unsigned long long* hist)
-{
-    if (v < HIST_SMEM_BINS)
-        atomicAdd(&sh[v], 1u);
-    else
-        atomicAdd(&hist[v], 1ull);
 }
 
 template <bool HIST>
@@ -100,25 +92,7 @@ movie_stats_kernel(const u16* __restrict__ p, size_t n, const u8* __restrict__ m
             if (HIST) count_px(v, sh, hist);
         }
     }
-    // min / max: warp shuffle reduction, one global atomic per warp
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
-        hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
-    }
-    if ((threadIdx.x & 31) == 0 && minmax) {
-        if (lo <= hi) {  // this warp saw at least one pixel
-            atomicMin(&minmax[0], lo);
-            atomicMax(&minmax[1], hi);
-        }
-    }
-    if (HIST) {
-        __syncthreads();
-        for (unsigned i = threadIdx.x; i < HIST_SMEM_BINS; i += ST_THREADS) {
-            const unsigned c = sh[i];
-            if (c) atomicAdd(&hist[i], (unsigned long long)c);
-        }
-    }
+    hist_flush(lo, hi, sh, minmax, hist, HIST);
 }
 
 int launch_movie_stats(const u16* mov, size_t n, const u8* mask, unsigned* minmax, unsigned long long* hist, cudaStream_t st)

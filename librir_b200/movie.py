@@ -142,6 +142,7 @@ class PipelineConfig:
     gop: int = vio.DEFAULT_GOP
     delta: bool = True                 # temporal delta in the pre-coder
     chunk_frames: int = 4096           # frames per batched launch (buffers are reused per chunk)
+    fuse_stats: bool = True            # statistics ride along in the pre-coder's pass instead of their own
 
 
 class FramePipeline:
@@ -169,7 +170,11 @@ class FramePipeline:
         """Bad-pixel detection on the movie's frame 0 (every rank is handed the same frame)."""
         self.bad_pixels = sp.BadPixels(first_frame)
 
-    STAGES = ("bp_correct", "gaussian_u16_f32", "translate_u16", "precode_delta_split", "stats_minmax_hist")
+    @property
+    def STAGES(self):
+        if self.cfg.fuse_stats:
+            return ("bp_correct", "gaussian_u16_f32", "translate_u16", "precode_delta_split_stats")
+        return ("bp_correct", "gaussian_u16_f32", "translate_u16", "precode_delta_split", "stats_minmax_hist")
 
     def process_chunk(self, frames, dx, dy, first_frame: int, with_stats: bool = True, events=None):
         """Run the stages on ``frames[n, h, w]`` (torch CUDA uint16, n <= chunk_frames).
@@ -192,11 +197,15 @@ class FramePipeline:
         mark(2)
         sp.translate_batch(c, dx, dy, self.cfg.strategy, background=0, out=r)
         mark(3)
-        vio.precode_movie(r, self.cfg.gop, self.cfg.delta, first_frame, out=(lo, hi))
-        mark(4)
-        if with_stats:
-            self.stats.update(r)
-        mark(5)
+        if self.cfg.fuse_stats:
+            vio.precode_movie(r, self.cfg.gop, self.cfg.delta, first_frame, out=(lo, hi), stats=self.stats if with_stats else None)
+            mark(4)
+        else:
+            vio.precode_movie(r, self.cfg.gop, self.cfg.delta, first_frame, out=(lo, hi))
+            mark(4)
+            if with_stats:
+                self.stats.update(r)
+            mark(5)
         return c, s, r, lo, hi
 
     def process_host(self, frames_host, dx_host, dy_host, first_frame: int, lo_host, hi_host, sub_frames: int = 256,

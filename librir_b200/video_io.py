@@ -99,15 +99,28 @@ def merge_yuv420(y, width, u=None):
 # ----------------------------------------------------------------------------------------
 # whole movies (dense planes)
 # ----------------------------------------------------------------------------------------
-def precode_movie(movie, gop=DEFAULT_GOP, delta=False, first_frame=0, out=None):
+def precode_movie(movie, gop=DEFAULT_GOP, delta=False, first_frame=0, out=None, stats=None):
     """Byte-plane split (+ optional temporal delta) of ``movie[t, h, w]`` (numpy or torch CUDA
-    uint16).  Returns ``(lo, hi)`` uint8 ``[t, h, w]``."""
+    uint16).  Returns ``(lo, hi)`` uint8 ``[t, h, w]``.  ``stats``: a :class:`librir_b200.movie.MovieStats`
+    to fold the same frames into (min / max / histogram) in the same pass over them."""
     lib = _lib.load()
     if len(movie.shape) != 3:
         raise RuntimeError("precode_movie: wrong input dimension")
     _prepare_device_call(movie)
     t, h, w = movie.shape
     lo, hi = out if out is not None else (_empty_like(movie, np.uint8), _empty_like(movie, np.uint8))
+    if stats is not None:
+        import ctypes as ct
+
+        if stats._fresh:
+            stats._sums[65536] = 0
+        r = lib.rirb_precode_movie_stats(_ptr(movie), t, w, h, gop, int(bool(delta)), first_frame, _ptr(lo), _ptr(hi),
+                                         ct.c_void_p(stats.minmax.data_ptr()), ct.c_void_p(stats.hist.data_ptr()),
+                                         0 if stats._fresh else 1)
+        _lib.check(r, "precode_movie_stats")
+        stats._fresh = False
+        stats._sums[65536] += t * h * w
+        return lo, hi
     r = lib.rirb_precode_movie(_ptr(movie), t, w, h, gop, int(bool(delta)), first_frame, _ptr(lo), _ptr(hi))
     _lib.check(r, "precode_movie")
     return lo, hi

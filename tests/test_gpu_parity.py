@@ -533,6 +533,36 @@ def test_precode_movie_vs_oracle(port, shape, delta):
         assert torch.equal(vio.decode_movie(dlo, dhi, gop, delta).view(torch.int16), d.view(torch.int16))
 
 
+@pytest.mark.parametrize("shape", [(23, 20, 32), (120, 64, 96), (7, 5, 3), (260, 16, 16)])
+@pytest.mark.parametrize("delta", [False, True])
+def test_precode_movie_fused_with_stats(port, shape, delta):
+    """rirb_precode_movie_stats: the planes of the plain pre-coder and the statistics of rirb_movie_stats, from one
+    pass; accumulation over two calls; values above the shared-memory histogram's range; odd sizes (fallback)."""
+    from librir_b200 import movie
+
+    rng = np.random.default_rng(12)
+    mov = ir_movie(*shape)
+    mov[0, 0, 0] = 65535
+    mov[-1, -1, -1] = 50000          # beyond the 49,152 shared bins
+    mov.reshape(-1)[rng.choice(mov.size, 5, replace=False)] = 0
+    d = to_dev(mov)
+    st = movie.MovieStats("cuda")
+    half = (shape[0] // 2) // 5 * 5
+    if half:
+        lo_a, hi_a = vio.precode_movie(d[:half], 5, delta, 0, stats=st)
+        lo_b, hi_b = vio.precode_movie(d[half:], 5, delta, half, stats=st)
+        lo = torch.cat([lo_a, lo_b]).cpu().numpy()
+        hi = torch.cat([hi_a, hi_b]).cpu().numpy()
+    else:
+        lo, hi = (x.cpu().numpy() for x in vio.precode_movie(d, 5, delta, 0, stats=st))
+    wlo, whi = port.precode_movie(mov, gop=5, delta=delta)
+    np.testing.assert_array_equal(lo, wlo)
+    np.testing.assert_array_equal(hi, whi)
+    mn, mx, hist = port.movie_stats(mov)
+    assert (st.min(), st.max(), st.count) == (mn, mx, mov.size)
+    np.testing.assert_array_equal(st.histogram(), hist)
+
+
 def test_precode_delta_needs_key_frame_aligned_shards():
     mov = ir_movie(10, 16, 16)
     with pytest.raises(RuntimeError):
