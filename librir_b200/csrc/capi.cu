@@ -127,13 +127,86 @@ static void* scratch(int slot, size_t bytes)
     return tls.dev[slot];
 }
 
+// ---- pageable host buffers --------------------------------------------------------------------
+// A device->host cudaMemcpyAsync into pageable memory is staged by the driver at ~5 GB/s for one
+// 640x512 frame (measured: profiles/r1_percall.md).  Host-pointer callers are the reference's own
+// one-frame-per-call seam, so the library keeps a small per-thread ring of pinned chunks and
+// pipelines  DMA | memcpy(pinned -> host)  itself; pinned or registered caller buffers
+// (cudaMemoryTypeHost) skip the ring and are written in place.
+constexpr size_t PIN_CHUNK = 256u << 10;
+constexpr int PIN_NB = 4;
+constexpr size_t PIN_MAX_BYTES = 64u << 20;  // beyond this the driver's own pageable path is as good
+struct PinRing {
+    char* buf[PIN_NB] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[PIN_NB] = {nullptr, nullptr, nullptr, nullptr};
+    int state = 0;  // 0 not tried, 1 ready, -1 unavailable (fall back to plain copies)
+};
+static thread_local PinRing pin;
+
+static bool pin_ready()
+{
+    if (pin.state == 0) {
+        pin.state = 1;
+        for (int i = 0; i < PIN_NB && pin.state == 1; ++i)
+            if (cudaMallocHost((void**)&pin.buf[i], PIN_CHUNK) != cudaSuccess ||
+                cudaEventCreateWithFlags(&pin.ev[i], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                pin.state = -1;
+            }
+    }
+    return pin.state == 1;
+}
+
+static bool is_pageable(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Uploads stay with the driver: its pageable host->device path already runs at the speed of one
+// host memcpy (~10 GB/s here), the ring was no faster at 640x512 and 20 % slower at 1280x1024.
+static cudaError_t copy_h2d(void* dev, const void* host, size_t bytes, cudaStream_t st)
+{
+    return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st);
+}
+
+// Returns with the bytes in `host` (synchronous for pageable destinations).
+static cudaError_t copy_d2h(void* host, const void* dev, size_t bytes, cudaStream_t st)
+{
+    if (bytes > PIN_MAX_BYTES || !is_pageable(host) || !pin_ready()) return cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaSuccess;
+    const size_t nchunks = (bytes + PIN_CHUNK - 1) / PIN_CHUNK;
+    auto enqueue = [&](size_t k) -> cudaError_t {
+        const size_t off = k * PIN_CHUNK;
+        const size_t len = bytes - off < PIN_CHUNK ? bytes - off : PIN_CHUNK;
+        const int i = (int)(k % PIN_NB);
+        cudaError_t r = cudaMemcpyAsync(pin.buf[i], (const char*)dev + off, len, cudaMemcpyDeviceToHost, st);
+        if (r == cudaSuccess) r = cudaEventRecord(pin.ev[i], st);
+        return r;
+    };
+    for (size_t k = 0; k < nchunks && k < (size_t)PIN_NB && e == cudaSuccess; ++k) e = enqueue(k);
+    for (size_t k = 0; k < nchunks && e == cudaSuccess; ++k) {
+        const size_t off = k * PIN_CHUNK;
+        const size_t len = bytes - off < PIN_CHUNK ? bytes - off : PIN_CHUNK;
+        const int i = (int)(k % PIN_NB);
+        if ((e = cudaEventSynchronize(pin.ev[i])) != cudaSuccess) break;
+        memcpy((char*)host + off, pin.buf[i], len);
+        if (k + PIN_NB < nchunks) e = enqueue(k + PIN_NB);
+    }
+    return e;
+}
+
 // Input operand: device pointer as is, host pointer uploaded into scratch slot `slot`.
 static const void* stage_in(const void* p, size_t bytes, int slot, cudaStream_t st)
 {
     if (is_device_ptr(p)) return p;
     void* d = scratch(slot, bytes);
     if (!d) return nullptr;
-    if (cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    if (copy_h2d(d, p, bytes, st) != cudaSuccess) {
         set_error("host->device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
@@ -158,7 +231,7 @@ static bool stage_out(StagedOut& o, void* p, size_t bytes, int slot, bool preloa
     o.host = p;
     o.dev = scratch(slot, bytes);
     if (!o.dev) return false;
-    if (preload && cudaMemcpyAsync(o.dev, p, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    if (preload && copy_h2d(o.dev, p, bytes, st) != cudaSuccess) {
         set_error("host->device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         return false;
     }
@@ -170,7 +243,7 @@ static int finish_out(StagedOut* outs, int n, cudaStream_t st)
     bool any = false;
     for (int i = 0; i < n; ++i)
         if (outs[i].host && outs[i].bytes) {
-            RIRB_CUDA_OK(cudaMemcpyAsync(outs[i].host, outs[i].dev, outs[i].bytes, cudaMemcpyDeviceToHost, st));
+            RIRB_CUDA_OK(copy_d2h(outs[i].host, outs[i].dev, outs[i].bytes, st));
             any = true;
         }
     if (any) RIRB_CUDA_OK(cudaStreamSynchronize(st));
@@ -705,7 +778,7 @@ int rirb_loader_remove_motion(const unsigned short* in, unsigned short* out, int
                              true, st) != 0)
         return -1;
     if (o.host) {
-        RIRB_CUDA_OK(cudaMemcpyAsync(o.host, o.dev, bytes, cudaMemcpyDeviceToHost, st));
+        RIRB_CUDA_OK(copy_d2h(o.host, o.dev, bytes, st));
     }
     // fx/fy are stack-owned host vectors read by an async copy: always wait before returning
     RIRB_CUDA_OK(cudaStreamSynchronize(st));
@@ -797,7 +870,7 @@ int rirb_loader_read_movie(int handle, const unsigned char* lo, const unsigned c
         if (launch_translate_u16(merged, (u16*)o.dev, w, hb, nframes, fpx, fpx, d_dx, d_dy, 0.f, 0.f, STRAT_NEAREST, 0u, true, st) != 0)
             return -1;
     }
-    if (o.host) RIRB_CUDA_OK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st));
+    if (o.host) RIRB_CUDA_OK(copy_d2h(o.host, o.dev, o.bytes, st));
     RIRB_CUDA_OK(cudaStreamSynchronize(st));  // fx / fy are host vectors read by an async copy
     return 0;
 }
@@ -1122,7 +1195,7 @@ int rirb_lossy_add_images(int handle, const unsigned short* frames, long long nf
         ++s->frames;
     }
     if (errors) RIRB_CUDA_OK(cudaMemcpyAsync(errors, s->errors_dev, sizeof(int) * 2 * (size_t)nframes, cudaMemcpyDefault, st));
-    if (o.host) RIRB_CUDA_OK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st));
+    if (o.host) RIRB_CUDA_OK(copy_d2h(o.host, o.dev, o.bytes, st));
     if (o.host || (errors && !is_device_ptr(errors))) RIRB_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }

@@ -76,7 +76,7 @@ def _empty_like(x, dtype=None):
         tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.uint16): torch.uint16, np.dtype(np.uint8): torch.uint8}[
             np.dtype(dtype)]
         return torch.empty(x.shape, dtype=tdt, device=x.device)
-    return np.zeros(x.shape, dtype=dtype or x.dtype)
+    return np.empty(x.shape, dtype=dtype or x.dtype)
 
 
 def _prepare_device_call(x):
@@ -108,8 +108,9 @@ def translate(image, dx, dy, strategy=str(), background=None):
     strategy = toCharP(strategy)
     if strategy == b"constant":
         strategy = b"background"
-    img = np.copy(image, "C")
-    res = np.copy(image, "C")  # "noborder" pixels keep the source value
+    img = np.ascontiguousarray(image)
+    # "noborder" pixels keep the source value; the other strategies write every pixel
+    res = np.copy(img, "C") if strategy in (b"", b"noborder") else np.empty_like(img)
     _back = np.zeros((1), dtype=img.dtype)
     if background is not None:
         _back[0] = background
@@ -167,9 +168,15 @@ def gaussian_filter(image, sigma=1.0):
     lib = _lib.load()
     if len(image.shape) != 2:
         raise RuntimeError("gaussian_filter: wrong input image dimension")
-    img = np.array(image, dtype=np.float32, order="C")
-    res = np.zeros(image.shape, dtype=np.float32)
-    r = lib.gaussian_filter(_ptr(img), _ptr(res), img.shape[1], img.shape[0], sigma)
+    res = np.empty(image.shape, dtype=np.float32)
+    if image.dtype == np.uint16:
+        # the uint16 -> float32 conversion of the reference wrapper (rir_signal_processing.py:100) happens
+        # in the kernel: half the upload, no host pass (the conversion is exact either way)
+        img = np.ascontiguousarray(image)
+        r = lib.rirb_gaussian_filter_u16_batch(_ptr(img), _ptr(res), img.shape[1], img.shape[0], 1, sigma)
+    else:
+        img = np.ascontiguousarray(image, dtype=np.float32)
+        r = lib.gaussian_filter(_ptr(img), _ptr(res), img.shape[1], img.shape[0], sigma)
     _lib.check(r, "gaussian_filter")
     return res
 
@@ -246,8 +253,8 @@ def bad_pixels_correct(handle, img):
     Corrects input image from bad pixels and returns the result.
     """
     lib = _lib.load()
-    img = np.array(img, dtype=np.uint16, order="C")
-    out = np.zeros(img.shape, dtype=np.uint16)
+    img = np.ascontiguousarray(img, dtype=np.uint16)
+    out = np.empty(img.shape, dtype=np.uint16)
     res = lib.bad_pixels_correct(handle, _ptr(img), _ptr(out))
     if res < 0:
         raise RuntimeError("'bad_pixels_correct': unknown error")
