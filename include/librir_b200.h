@@ -192,6 +192,57 @@ RIRB_API int rirb_hist_quantile(const unsigned long long* hist, long long count,
 /* get_background (h264.cpp:1955-1991) of one image */
 RIRB_API int rirb_get_background(const unsigned short* pixels, int size);
 
+/* ===================== Part 3: the file formats either side of the path (host code) ========
+ * SURVEY.md 8f-3.  No kernels here: the entropy stage is zstd on the host by design.  What is added
+ * over the reference: a run of frames is (de)compressed by a pool of host threads with the records
+ * kept in order, and frame buffers may be device pointers. */
+
+/* ---- attribute trailer: replaces attrs_*, tools.h:96-179 / tools.cpp:87-350 (rir::FileAttributes,
+ *      FileAttributes.cpp).  Same arguments and status codes: handle > 0 or 0; getters return 0, -1 on a bad
+ *      handle / index, -2 with *len set when the buffer is too small; changes are written when the handle is
+ *      closed or flushed.  Like the reference, open_file creates a missing (or < 30-byte) file, a file
+ *      without a trailer gets one on close, and attrs_discard WRITES (tools.cpp:124-131 calls close());
+ *      rirb_attrs_abandon is the entry that drops the changes. */
+RIRB_API int rirb_attrs_open_file(const char* filename);
+RIRB_API int rirb_attrs_open_from_memory(const void* ptr, long long size);
+RIRB_API void rirb_attrs_close(int handle);
+RIRB_API void rirb_attrs_discard(int handle);
+RIRB_API void rirb_attrs_abandon(int handle);
+RIRB_API int rirb_attrs_flush(int handle);
+RIRB_API int rirb_attrs_image_count(int handle);
+RIRB_API int rirb_attrs_global_attribute_count(int handle);
+RIRB_API int rirb_attrs_global_attribute_name(int handle, int pos, char* name, int* len);
+RIRB_API int rirb_attrs_global_attribute_value(int handle, int pos, char* value, int* len);
+RIRB_API int rirb_attrs_frame_attribute_count(int handle, int frame);
+RIRB_API int rirb_attrs_frame_attribute_name(int handle, int frame, int pos, char* name, int* len);
+RIRB_API int rirb_attrs_frame_attribute_value(int handle, int frame, int pos, char* value, int* len);
+RIRB_API int rirb_attrs_frame_timestamp(int handle, int frame, long long* time);
+RIRB_API int rirb_attrs_timestamps(int handle, long long* times);
+RIRB_API int rirb_attrs_set_times(int handle, const long long* times, int size);
+RIRB_API int rirb_attrs_set_time(int handle, int pos, long long time);
+RIRB_API int rirb_attrs_set_frame_attributes(int handle, int pos, const char* keys, const int* key_lens, const char* values,
+                                             const int* value_lens, int count);
+RIRB_API int rirb_attrs_set_global_attributes(int handle, const char* keys, const int* key_lens, const char* values,
+                                              const int* value_lens, int count);
+
+/* ---- zstd movie file: replaces z_open_file_write / z_write_image / z_close_file / z_open_file_read /
+ *      z_image_count / z_image_size / z_read_image / z_get_timestamps, ZFile.h:16-52 / ZFile.cpp (the
+ *      BIN_FILE_Z_COMPRESSED branch of IRFileLoader, IRFileLoader.cpp:331-370,540-541).  Files are
+ *      byte-compatible both ways with the reference's.  Handles are ints (the reference hands out pointers);
+ *      method must be 1 (zstd of the raw image: the only one ZFile.cpp implements).  The *_images entries take
+ *      frames[n][h][w] as host or device pointers and use `threads` host threads (0 = all cores). */
+RIRB_API int rirb_z_open_file_write(const char* filename, int width, int height, int rate, int method, int clevel);
+RIRB_API int rirb_z_write_image(int handle, const unsigned short* img, long long timestamp);
+RIRB_API int rirb_z_write_images(int handle, const unsigned short* frames, long long nframes, const long long* timestamps,
+                                 int threads);
+RIRB_API long long rirb_z_close_file(int handle);
+RIRB_API int rirb_z_open_file_read(const char* filename);
+RIRB_API int rirb_z_image_count(int handle);
+RIRB_API int rirb_z_image_size(int handle, int* width, int* height);
+RIRB_API int rirb_z_get_timestamps(int handle, long long* times);
+RIRB_API int rirb_z_read_image(int handle, int pos, unsigned short* img, long long* timestamp);
+RIRB_API int rirb_z_read_images(int handle, int pos, int count, unsigned short* out, long long* timestamps, int threads);
+
 #ifdef __cplusplus
 }
 #endif

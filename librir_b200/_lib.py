@@ -77,6 +77,36 @@ SIGNATURES = {
     "rirb_movie_stats": (_i, [_vp, _sz, _vp, _vp, _i]),
     "rirb_hist_quantile": (_i, [_vp, _ll, _f]),
     "rirb_get_background": (_i, [_vp, _i]),
+    # Part 3: file formats (host code)
+    "rirb_attrs_open_file": (_i, [ct.c_char_p]),
+    "rirb_attrs_open_from_memory": (_i, [_vp, _ll]),
+    "rirb_attrs_close": (None, [_i]),
+    "rirb_attrs_discard": (None, [_i]),
+    "rirb_attrs_abandon": (None, [_i]),
+    "rirb_attrs_flush": (_i, [_i]),
+    "rirb_attrs_image_count": (_i, [_i]),
+    "rirb_attrs_global_attribute_count": (_i, [_i]),
+    "rirb_attrs_global_attribute_name": (_i, [_i, _i, _vp, _vp]),
+    "rirb_attrs_global_attribute_value": (_i, [_i, _i, _vp, _vp]),
+    "rirb_attrs_frame_attribute_count": (_i, [_i, _i]),
+    "rirb_attrs_frame_attribute_name": (_i, [_i, _i, _i, _vp, _vp]),
+    "rirb_attrs_frame_attribute_value": (_i, [_i, _i, _i, _vp, _vp]),
+    "rirb_attrs_frame_timestamp": (_i, [_i, _i, _vp]),
+    "rirb_attrs_timestamps": (_i, [_i, _vp]),
+    "rirb_attrs_set_times": (_i, [_i, _vp, _i]),
+    "rirb_attrs_set_time": (_i, [_i, _i, _ll]),
+    "rirb_attrs_set_frame_attributes": (_i, [_i, _i, _vp, _vp, _vp, _vp, _i]),
+    "rirb_attrs_set_global_attributes": (_i, [_i, _vp, _vp, _vp, _vp, _i]),
+    "rirb_z_open_file_write": (_i, [ct.c_char_p, _i, _i, _i, _i, _i]),
+    "rirb_z_write_image": (_i, [_i, _vp, _ll]),
+    "rirb_z_write_images": (_i, [_i, _vp, _ll, _vp, _i]),
+    "rirb_z_close_file": (_ll, [_i]),
+    "rirb_z_open_file_read": (_i, [ct.c_char_p]),
+    "rirb_z_image_count": (_i, [_i]),
+    "rirb_z_image_size": (_i, [_i, _vp, _vp]),
+    "rirb_z_get_timestamps": (_i, [_i, _vp]),
+    "rirb_z_read_image": (_i, [_i, _i, _vp, _vp]),
+    "rirb_z_read_images": (_i, [_i, _i, _i, _vp, _vp, _i]),
 }
 
 _lib = None

@@ -39,4 +39,10 @@ if [ ! "$OUT/libs/libref_shim.so" -nt "$HERE/ref_shim.cpp" ] || [ -n "${FORCE:-}
   echo "build_ref: libref_shim.so"
   $CXX $FLAGS $INC "$HERE/ref_shim.cpp" -L"$OUT/libs" -lsignal_processing -ltools -Wl,-rpath,'$ORIGIN' -o "$OUT/libs/libref_shim.so"
 fi
+# the zstd movie file (ZFile.cpp is the one video_io source that needs nothing but the tools library)
+if [ ! "$OUT/libs/libref_zfile.so" -nt "$HERE/zfile_shim.cpp" ] || [ ! "$OUT/libs/libref_zfile.so" -nt "$0" ] || [ -n "${FORCE:-}" ]; then
+  echo "build_ref: libref_zfile.so"
+  $CXX $FLAGS -DBUILD_IO_LIB $INC -I$R/src/cpp/video_io "$R/src/cpp/video_io/ZFile.cpp" "$HERE/zfile_shim.cpp" \
+      -L"$OUT/libs" -ltools -Wl,-rpath,'$ORIGIN' -o "$OUT/libs/libref_zfile.so"
+fi
 echo "build_ref: done -> $OUT/libs"
