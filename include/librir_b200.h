@@ -243,6 +243,31 @@ RIRB_API int rirb_z_get_timestamps(int handle, long long* times);
 RIRB_API int rirb_z_read_image(int handle, int pos, unsigned short* img, long long* timestamp);
 RIRB_API int rirb_z_read_images(int handle, int pos, int count, unsigned short* out, long long* timestamps, int threads);
 
+/* ===================== Part 4: the registration front end ==================
+ * MaskedRegistratorECC.compute, librir/registration/masked_registration_ecc.py:105-191: quantile clamp,
+ * min/max normalisation and cv2.findTransformECC(template, image, warp, MOTION_TRANSLATION,
+ * (COUNT|EPS, iterations, eps), mask, gaussFiltSize = 1) -- OpenCV 4.13's iteration, including warpAffine's
+ * fixed-point (1/32 pixel) coordinates -- on float windows that stay in device memory.  A handle owns one
+ * w x h problem: the reference window, the current window, the optional mask and all scratch.
+ * set_image: which = 0 reference / 1 current; img = first pixel of the window inside a float image whose rows
+ *            are `stride` floats apart (host or device pointer).
+ * set_mask : which = 0 the mask findTransformECC gets, 1 the mask of the quantile thresholds (w x h bytes, host or
+ *            device, NULL = none).  Two masks because the reference's wrapper hands find_median_pixel a non-contiguous
+ *            view of a full-size uint8 mask uncompacted (rir_signal_processing.py:134-136); the Python mirror reproduces it.
+ * quantile : find_median_pixel(window.astype(uint16), percent[, mask 1]) of the reference (0) or current (1) window.
+ * compute  : thresh = the clamp of :147-151 (+inf / NaN: none); shift[2] = {tx, ty} warm start in, result out
+ *            (warp_matrix[0,2], warp_matrix[1,2]); returns 0, or 1 ("NaN encountered.") / 2 ("The algorithm
+ *            stopped before its convergence...") where cv2 raises cv2.error, -1 on a bad call.
+ * reset_reference: reference = translate(current, dx, dy), the rule of :182-185. */
+RIRB_API int rirb_ecc_open(int width, int height);
+RIRB_API void rirb_ecc_close(int handle);
+RIRB_API int rirb_ecc_set_mask(int handle, int which, const unsigned char* mask);
+RIRB_API int rirb_ecc_set_image(int handle, int which, const float* img, int stride);
+RIRB_API int rirb_ecc_reset_reference(int handle, float dx, float dy);
+RIRB_API int rirb_ecc_quantile(int handle, int which, float percent, int use_mask);
+RIRB_API int rirb_ecc_compute(int handle, float thresh, int use_mask, int max_iterations, double eps, float* shift, double* rho,
+                              int* iterations);
+
 #ifdef __cplusplus
 }
 #endif

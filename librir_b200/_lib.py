@@ -107,6 +107,14 @@ SIGNATURES = {
     "rirb_z_get_timestamps": (_i, [_i, _vp]),
     "rirb_z_read_image": (_i, [_i, _i, _vp, _vp]),
     "rirb_z_read_images": (_i, [_i, _i, _i, _vp, _vp, _i]),
+    # Part 4: registration front end
+    "rirb_ecc_open": (_i, [_i, _i]),
+    "rirb_ecc_close": (None, [_i]),
+    "rirb_ecc_set_mask": (_i, [_i, _i, _vp]),
+    "rirb_ecc_set_image": (_i, [_i, _i, _vp, _i]),
+    "rirb_ecc_reset_reference": (_i, [_i, _f, _f]),
+    "rirb_ecc_quantile": (_i, [_i, _i, _f, _i]),
+    "rirb_ecc_compute": (_i, [_i, _f, _i, _i, ct.c_double, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -41,6 +41,7 @@
 
 #include "../../include/librir_b200.h"
 #include "common.cuh"
+#include "handles.h"
 #include "kernels.h"
 
 namespace rirb {
@@ -312,33 +313,6 @@ static void attrs_write_if_dirty(AttrsFile& a)
     a.file_table_size = a.table_size;
 }
 
-// ---- handle tables (lowest free positive id, like tools.cpp:40-85) --------------------------------
-template <typename T> struct Table {
-    std::mutex mu;
-    std::map<int, std::shared_ptr<T>> items;
-    int add(const std::shared_ptr<T>& p)
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        int id = 1;
-        for (auto& kv : items) {
-            if (kv.first != id) break;
-            ++id;
-        }
-        items[id] = p;
-        return id;
-    }
-    std::shared_ptr<T> get(int id)
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        auto it = items.find(id);
-        return it == items.end() ? nullptr : it->second;
-    }
-    void remove(int id)
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        items.erase(id);
-    }
-};
 static Table<AttrsFile> g_attrs;
 
 static int copy_out(const std::string& s, char* dst, int* len)

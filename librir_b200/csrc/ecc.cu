@@ -1,0 +1,469 @@
+// librir_b200/csrc/ecc.cu -- the registration front end on the GPU.
+//
+// Reference: MaskedRegistratorECC.compute, librir/registration/masked_registration_ecc.py:105-191 --
+//   crop of the Gaussian-filtered frame, optional quantile clamp of template and image (:143-151),
+//   min/max normalisation of both (:153-160), then
+//   cv2.findTransformECC(template, image, warp, MOTION_TRANSLATION, (COUNT|EPS, 500, 1e-3), mask, 1) (:165-167).
+// The ECC iteration is OpenCV's (4.13.0, video/src/ecc.cpp), third-party to librir: restated in
+// oracle/ecc.py, which is pinned against cv2 itself; this file follows that restatement.
+//
+// What OpenCV does per iteration, and what it becomes here:
+//   warpAffine x4 (image, d/dx, d/dy bilinear; mask nearest)   -> for a pure translation warpAffine's fixed-point
+//       coordinates (10 fractional bits, rounded to 1/32 px) give EVERY pixel the same integer offset and the same four
+//       float weights, so the warp is a 4-tap stencil with launch-constant weights, evaluated on the fly;
+//   meanStdDev x2, subtract x2, 7 dot products over full images   -> ONE pass that accumulates 15 raw sums in fp64
+//       (products of two floats are exact in fp64) from which every masked, zero-meaned quantity follows
+//       algebraically; no intermediate image is ever written;
+//   2x2 inverse, lambda, parameter update                         -> the last CTA to finish does it (one thread, same
+//       float / double types as OpenCV's Mats) and publishes the new shift, rho and the stop flag in device memory.
+// The host enqueues a few iteration launches back to back (a finished problem makes the remaining ones return at
+// once) and reads the 40-byte result back; nothing else crosses PCIe per frame.
+// Traffic per iteration: template, image, two gradients (float) + mask, all L2-resident (3 MB at 448 x 358): the loop
+// is bound by launch latency, not by memory.
+#include <math.h>
+#include <string.h>
+
+#include <memory>
+#include <mutex>
+
+#include "../../include/librir_b200.h"
+#include "common.cuh"
+#include "handles.h"
+#include "kernels.h"
+
+namespace rirb {
+
+enum { A_N, A_I, A_T, A_II, A_TT, A_IT, A_H11, A_H12, A_H22, A_B1, A_B2, A_C1, A_C2, A_D1, A_D2, NACC };
+
+struct EccDev {
+    double acc[NACC];
+    double rho, last_rho, eps;
+    unsigned ticket;
+    unsigned mm[4];  // order-preserving keys: template min, max, image min, max
+    float tx, ty;
+    int it, max_it, done, status;  // status: 0 ok, 1 NaN (cv2: "NaN encountered."), 2 correlation about to be minimised
+};
+
+struct EccResult {  // what the host reads back
+    double rho;
+    float tx, ty;
+    int it, done, status;
+};
+
+__device__ __forceinline__ unsigned fkey(float f)
+{
+    const unsigned b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k)
+{
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+
+// masked_registration_ecc.py:147-151: where EITHER image exceeds the threshold, BOTH are set to it
+__device__ __forceinline__ float clamp_pair(float own, float other, float th) { return (own > th || other > th) ? th : own; }
+
+__global__ void ecc_begin_kernel(EccDev* d, float tx, float ty, int max_it, double eps)
+{
+    for (int i = 0; i < NACC; ++i) d->acc[i] = 0.0;
+    d->ticket = 0;
+    d->mm[0] = d->mm[2] = 0xFFFFFFFFu;
+    d->mm[1] = d->mm[3] = 0u;
+    d->tx = tx;
+    d->ty = ty;
+    d->rho = -1.0;        // ecc.cpp: rho = -1, last_rho = -termination_eps
+    d->last_rho = -eps;
+    d->eps = eps;
+    d->it = 0;
+    d->max_it = max_it;
+    d->done = (max_it <= 0) || !(fabs(-1.0 + eps) >= eps);
+    d->status = 0;
+}
+
+constexpr int ECC_THREADS = 256;
+
+__global__ void __launch_bounds__(ECC_THREADS) ecc_minmax_kernel(const float* __restrict__ ref, const float* __restrict__ cur, int n,
+                                                                  float thresh, EccDev* d)
+{
+    unsigned k[4] = {0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float r = ref[i], c = cur[i];
+        const unsigned kr = fkey(clamp_pair(r, c, thresh)), kc = fkey(clamp_pair(c, r, thresh));
+        k[0] = min(k[0], kr);
+        k[1] = max(k[1], kr);
+        k[2] = min(k[2], kc);
+        k[3] = max(k[3], kc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        k[0] = min(k[0], __shfl_down_sync(0xFFFFFFFFu, k[0], o));
+        k[1] = max(k[1], __shfl_down_sync(0xFFFFFFFFu, k[1], o));
+        k[2] = min(k[2], __shfl_down_sync(0xFFFFFFFFu, k[2], o));
+        k[3] = max(k[3], __shfl_down_sync(0xFFFFFFFFu, k[3], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&d->mm[0], k[0]);
+        atomicMax(&d->mm[1], k[1]);
+        atomicMin(&d->mm[2], k[2]);
+        atomicMax(&d->mm[3], k[3]);
+    }
+}
+
+// numpy float32: (im - mi) / (ma - mi), two roundings
+__device__ __forceinline__ float normalise(float v, float mi, float span) { return __fdiv_rn(__fsub_rn(v, mi), span); }
+
+// T = normalised template, I = normalised image, gx / gy = its [-0.5 0 0.5] derivatives (reflect-101 at the window's
+// edge, ecc.cpp's filter2D) times the 0/1 mask.
+__global__ void __launch_bounds__(ECC_THREADS)
+ecc_normalise_kernel(const float* __restrict__ ref, const float* __restrict__ cur, const u8* __restrict__ mask, int w, int h,
+                     float thresh, const EccDev* __restrict__ d, float* __restrict__ T, float* __restrict__ I, float* __restrict__ gx,
+                     float* __restrict__ gy)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w) return;
+    const float mi_t = fkey_inv(d->mm[0]), span_t = __fsub_rn(fkey_inv(d->mm[1]), mi_t);
+    const float mi_i = fkey_inv(d->mm[2]), span_i = __fsub_rn(fkey_inv(d->mm[3]), mi_i);
+    auto img = [&](int xx, int yy) {
+        const int i = yy * w + xx;
+        return normalise(clamp_pair(cur[i], ref[i], thresh), mi_i, span_i);
+    };
+    const int i = y * w + x;
+    T[i] = normalise(clamp_pair(ref[i], cur[i], thresh), mi_t, span_t);
+    I[i] = img(x, y);
+    const int xm = x == 0 ? (w > 1 ? 1 : 0) : x - 1, xp = x == w - 1 ? (w > 1 ? w - 2 : 0) : x + 1;
+    const int ym = y == 0 ? (h > 1 ? 1 : 0) : y - 1, yp = y == h - 1 ? (h > 1 ? h - 2 : 0) : y + 1;
+    const float m = (mask == nullptr || mask[i] != 0) ? 1.0f : 0.0f;
+    gx[i] = __fmul_rn(__fsub_rn(__fmul_rn(0.5f, img(xp, y)), __fmul_rn(0.5f, img(xm, y))), m);
+    gy[i] = __fmul_rn(__fsub_rn(__fmul_rn(0.5f, img(x, yp)), __fmul_rn(0.5f, img(x, ym))), m);
+}
+
+__global__ void ecc_cast_u16_kernel(const float* __restrict__ src, u16* __restrict__ dst, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (u16)__float2int_rz(src[i]);  // numpy astype(uint16) on in-range values
+}
+
+// One ECC iteration (ecc.cpp, the body of the for loop) -- see the header of this file.
+__global__ void __launch_bounds__(ECC_THREADS)
+ecc_iter_kernel(const float* __restrict__ T, const float* __restrict__ I, const float* __restrict__ gx, const float* __restrict__ gy,
+                const u8* __restrict__ mask, int w, int h, EccDev* d)
+{
+    if (d->done) return;  // written by the previous launch's last CTA only
+    __shared__ double red[ECC_THREADS / 32][NACC];
+    __shared__ bool last;
+    // warpAffine's fixed point (imgwarp.cpp): AB_BITS = 10, INTER_BITS = 5; M = [1 0 tx; 0 1 ty], WARP_INVERSE_MAP
+    const int SX = __double2int_rn((double)d->tx * 1024.0), SY = __double2int_rn((double)d->ty * 1024.0);
+    const int ox = (SX + 16) >> 10, oy = (SY + 16) >> 10;              // bilinear: round_delta = 1024 / 32 / 2
+    const float fx = (float)(((SX + 16) >> 5) & 31) * 0.03125f, fy = (float)(((SY + 16) >> 5) & 31) * 0.03125f;
+    const int oxn = (SX + 512) >> 10, oyn = (SY + 512) >> 10;          // nearest: round_delta = 1024 / 2
+    const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx), w10 = __fmul_rn(fy, 1.0f - fx), w11 = __fmul_rn(fy, fx);
+
+    double a[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) a[k] = 0.0;
+    const int npx = w * h;
+    for (int p = blockIdx.x * ECC_THREADS + threadIdx.x; p < npx; p += gridDim.x * ECC_THREADS) {
+        const int y = p / w, x = p - y * w;
+        const int ix = x + ox, iy = y + oy;
+        const bool x0 = ix >= 0 && ix < w, x1 = ix + 1 >= 0 && ix + 1 < w, y0 = iy >= 0 && iy < h, y1 = iy + 1 >= 0 && iy + 1 < h;
+        const int i00 = iy * w + ix;
+        auto warp = [&](const float* __restrict__ s) {  // remapBilinear: S[0]*w0 + S[1]*w1 + S[step]*w2 + S[step+1]*w3, border 0
+            const float s00 = (x0 && y0) ? s[i00] : 0.f, s01 = (x1 && y0) ? s[i00 + 1] : 0.f;
+            const float s10 = (x0 && y1) ? s[i00 + w] : 0.f, s11 = (x1 && y1) ? s[i00 + w + 1] : 0.f;
+            return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)), __fmul_rn(s11, w11));
+        };
+        const double Iw = warp(I), Gx = warp(gx), Gy = warp(gy);
+        const int mx = x + oxn, my = y + oyn;
+        const bool m = mx >= 0 && mx < w && my >= 0 && my < h && (mask == nullptr || mask[my * w + mx] != 0);
+        const double t = T[p];
+        a[A_H11] += Gx * Gx;
+        a[A_H12] += Gx * Gy;
+        a[A_H22] += Gy * Gy;
+        a[A_B1] += Gx * Iw;
+        a[A_B2] += Gy * Iw;
+        if (m) {
+            a[A_N] += 1.0;
+            a[A_I] += Iw;
+            a[A_T] += t;
+            a[A_II] += Iw * Iw;
+            a[A_TT] += t * t;
+            a[A_IT] += Iw * t;
+            a[A_C1] += Gx;
+            a[A_C2] += Gy;
+            a[A_D1] += Gx * t;
+            a[A_D2] += Gy * t;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NACC; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_down_sync(0xFFFFFFFFu, a[k], o);
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) red[wi][k] = a[k];
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        double s = 0.0;
+        for (int q = 0; q < ECC_THREADS / 32; ++q) s += red[q][threadIdx.x];
+        atomicAdd(&d->acc[threadIdx.x], s);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&d->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last || threadIdx.x != 0) return;
+    __threadfence();
+    volatile double* acc = d->acc;
+    const double n = acc[A_N], sI = acc[A_I], sT = acc[A_T], sII = acc[A_II], sTT = acc[A_TT], sIT = acc[A_IT];
+    const double h11 = acc[A_H11], h12 = acc[A_H12], h22 = acc[A_H22], b1 = acc[A_B1], b2 = acc[A_B2];
+    const double c1 = acc[A_C1], c2 = acc[A_C2], d1 = acc[A_D1], d2 = acc[A_D2];
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    d->ticket = 0;
+    const int it = d->it + 1;
+    d->it = it;
+    int status = 0;
+    double rho = d->rho;
+    if (n <= 0.0) {
+        status = 1;
+    } else {
+        // meanStdDev under the warped mask; subtract(image, mean) works in the image's type: the mean is rounded to float
+        const double meanI = sI / n, meanT = sT / n;
+        const double varI = fmax(sII / n - meanI * meanI, 0.0), varT = fmax(sTT / n - meanT * meanT, 0.0);
+        const double img_norm = sqrt(n * varI), tmp_norm = sqrt(n * varT);
+        const double muI = (double)(float)meanI, muT = (double)(float)meanT;
+        const float H11 = (float)h11, H12 = (float)h12, H22 = (float)h22;  // Mat hessian is CV_32F
+        // cv::invert of a 2 x 2 float matrix: closed form evaluated in double
+        const double det = (double)H11 * H22 - (double)H12 * H12;
+        const double id = det != 0.0 ? 1.0 / det : 0.0;
+        const float Hi11 = (float)(H22 * id), Hi22 = (float)(H11 * id), Hi12 = (float)(-(double)H12 * id);
+        const double corr = sIT - muT * sI - muI * sT + muI * muT * n;  // templateZM . imageWarped
+        d->last_rho = rho;
+        rho = corr / (img_norm * tmp_norm);
+        if (isnan(rho) || det == 0.0) {
+            status = 1;
+        } else {
+            const double pI1 = b1 - muI * c1, pI2 = b2 - muI * c2;  // J^T (I - mean), exact sums
+            const double pT1 = d1 - muT * c1, pT2 = d2 - muT * c2;  // J^T (T - mean)
+            const float ip1 = (float)pI1, ip2 = (float)pI2, tp1 = (float)pT1, tp2 = (float)pT2;  // CV_32F projections
+            const float iph1 = (float)((double)Hi11 * ip1 + (double)Hi12 * ip2), iph2 = (float)((double)Hi12 * ip1 + (double)Hi22 * ip2);
+            const double lam_n = img_norm * img_norm - ((double)ip1 * iph1 + (double)ip2 * iph2);
+            const double lam_d = corr - ((double)tp1 * iph1 + (double)tp2 * iph2);
+            if (lam_d <= 0.0) {
+                rho = -1.0;
+                status = 2;
+            } else {
+                const double lam = lam_n / lam_d;
+                const float e1 = (float)(lam * pT1 - pI1), e2 = (float)(lam * pT2 - pI2);  // J^T (lambda T - I)
+                const float dp1 = (float)((double)Hi11 * e1 + (double)Hi12 * e2), dp2 = (float)((double)Hi12 * e1 + (double)Hi22 * e2);
+                d->tx = __fadd_rn(d->tx, dp1);
+                d->ty = __fadd_rn(d->ty, dp2);
+            }
+        }
+    }
+    d->rho = rho;
+    d->status = status;
+    d->done = status != 0 || it >= d->max_it || !(fabs(rho - d->last_rho) >= d->eps);
+    __threadfence();
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+struct EccState {
+    int w = 0, h = 0, dev = 0;
+    float *ref = nullptr, *cur = nullptr, *T = nullptr, *I = nullptr, *gx = nullptr, *gy = nullptr;
+    u8 *mask = nullptr, *qmask = nullptr;  // ECC mask; mask of the quantile thresholds (see rirb_ecc_set_mask)
+    bool have_mask = false, have_qmask = false, have_ref = false, have_cur = false;
+    u16* q16 = nullptr;               // quantile scratch: the crop cast to uint16
+    unsigned long long* hist = nullptr;
+    unsigned* mm = nullptr;
+    int* qout = nullptr;
+    EccDev* d = nullptr;
+    std::mutex mu;
+    ~EccState()
+    {
+        void* ptrs[] = {ref, cur, T, I, gx, gy, mask, qmask, q16, hist, mm, qout, d};
+        for (void* p : ptrs)
+            if (p) cudaFree(p);
+    }
+};
+static Table<EccState> g_ecc;
+
+static int ecc_need_device()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("no usable CUDA device: librir_b200 computes on the GPU only and has no CPU fallback");
+        return -1;
+    }
+    return 0;
+}
+
+static int ecc_load_window(EccState& s, float* dst, const float* src, int stride, cudaStream_t st)
+{
+    if (!src || stride < s.w) {
+        set_error("ecc: bad image pointer or row stride");
+        return -1;
+    }
+    RIRB_CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)s.w * 4, src, (size_t)stride * 4, (size_t)s.w * 4, (size_t)s.h, cudaMemcpyDefault, st));
+    return 0;
+}
+
+}  // namespace rirb
+
+using namespace rirb;
+
+extern "C" {
+
+int rirb_ecc_open(int width, int height)
+{
+    if (width < 2 || height < 2 || (long long)width * height > (1LL << 28)) {
+        set_error("ecc_open: bad window size %d x %d", width, height);
+        return 0;
+    }
+    if (ecc_need_device() != 0) return 0;
+    auto s = std::make_shared<EccState>();
+    s->w = width;
+    s->h = height;
+    cudaGetDevice(&s->dev);
+    const size_t n = (size_t)width * height;
+    bool ok = true;
+    for (float** p : {&s->ref, &s->cur, &s->T, &s->I, &s->gx, &s->gy}) ok = ok && cudaMalloc((void**)p, n * 4) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s->mask, n) == cudaSuccess && cudaMalloc((void**)&s->qmask, n) == cudaSuccess &&
+         cudaMalloc((void**)&s->q16, n * 2) == cudaSuccess &&
+         cudaMalloc((void**)&s->hist, 65536 * sizeof(unsigned long long)) == cudaSuccess &&
+         cudaMalloc((void**)&s->mm, 2 * sizeof(unsigned)) == cudaSuccess && cudaMalloc((void**)&s->qout, sizeof(int)) == cudaSuccess &&
+         cudaMalloc((void**)&s->d, sizeof(EccDev)) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        set_error("ecc_open: out of device memory");
+        return 0;
+    }
+    return g_ecc.add(s);
+}
+
+void rirb_ecc_close(int handle) { g_ecc.remove(handle); }
+
+// mask: w x h bytes (non-zero = use), host or device; NULL removes it.  which = 0: the mask findTransformECC gets;
+// which = 1: the mask of the quantile thresholds.  They are two because the reference hands find_median_pixel a
+// non-contiguous view of the full-size mask without compacting it (rir_signal_processing.py:134-136), so with a
+// uint8 mask its thresholds are taken under a different pixel set than the one ECC uses; the Python mirror reproduces that.
+int rirb_ecc_set_mask(int handle, int which, const unsigned char* mask)
+{
+    auto s = g_ecc.get(handle);
+    if (!s || (which != 0 && which != 1)) {
+        set_error("ecc: unknown handle %d or mask selector", handle);
+        return -1;
+    }
+    std::lock_guard<std::mutex> lock(s->mu);
+    (which ? s->have_qmask : s->have_mask) = mask != nullptr;
+    if (mask) RIRB_CUDA_OK(cudaMemcpyAsync(which ? s->qmask : s->mask, mask, (size_t)s->w * s->h, cudaMemcpyDefault, current_stream()));
+    return 0;
+}
+
+// which: 0 = the reference window, 1 = the current image window.  img points at the window's first pixel inside a
+// float image whose rows are `stride` floats apart (host or device).
+int rirb_ecc_set_image(int handle, int which, const float* img, int stride)
+{
+    auto s = g_ecc.get(handle);
+    if (!s || (which != 0 && which != 1)) {
+        set_error("ecc: unknown handle %d or image selector", handle);
+        return -1;
+    }
+    std::lock_guard<std::mutex> lock(s->mu);
+    if (ecc_load_window(*s, which ? s->cur : s->ref, img, stride, current_stream()) != 0) return -1;
+    (which ? s->have_cur : s->have_ref) = true;
+    return 0;
+}
+
+// The reference-image reset of MaskedRegistratorECC.compute (:182-185): reference = translate(current, dx, dy)
+// with translate's default ("noborder") strategy, on the un-normalised float window.
+int rirb_ecc_reset_reference(int handle, float dx, float dy)
+{
+    auto s = g_ecc.get(handle);
+    if (!s || !s->have_cur) {
+        set_error("ecc_reset_reference: unknown handle or no current image");
+        return -1;
+    }
+    std::lock_guard<std::mutex> lock(s->mu);
+    cudaStream_t st = current_stream();
+    const size_t bytes = (size_t)s->w * s->h * 4;
+    RIRB_CUDA_OK(cudaMemcpyAsync(s->ref, s->cur, bytes, cudaMemcpyDeviceToDevice, st));  // untouched pixels keep the source value
+    const float zero = 0.f;
+    if (launch_translate('f', s->cur, s->ref, s->w, s->h, 1, nullptr, nullptr, dx, dy, STRAT_NOBORDER, &zero, st) != 0) return -1;
+    s->have_ref = true;
+    return 0;
+}
+
+// find_median_pixel(window.astype(uint16), percent, mask) of the reference (0) or current (1) window (:144-145)
+int rirb_ecc_quantile(int handle, int which, float percent, int use_mask)
+{
+    auto s = g_ecc.get(handle);
+    if (!s || (which != 0 && which != 1) || !(which ? s->have_cur : s->have_ref)) {
+        set_error("ecc_quantile: unknown handle or image not set");
+        return -1;
+    }
+    std::lock_guard<std::mutex> lock(s->mu);
+    cudaStream_t st = current_stream();
+    const int n = s->w * s->h;
+    RIRB_LAUNCH(ecc_cast_u16_kernel, (unsigned)ceil_div(n, 256), 256, 0, st, which ? s->cur : s->ref, s->q16, n);
+    const bool masked = use_mask && s->have_qmask;
+    if (launch_stats_init(s->mm, s->hist, st) != 0) return -1;
+    if (launch_movie_stats(s->q16, (size_t)n, masked ? s->qmask : nullptr, s->mm, s->hist, st) != 0) return -1;
+    if (launch_hist_quantile(s->hist, masked ? -1 : (long long)n, percent, masked ? 1 : 0, s->qout, st) != 0) return -1;
+    int r = 0;
+    RIRB_CUDA_OK(cudaMemcpyAsync(&r, s->qout, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    return r;
+}
+
+// cv2.findTransformECC(reference, current, [[1,0,tx],[0,1,ty]], MOTION_TRANSLATION, (COUNT|EPS, max_iterations, eps), mask, 1)
+// after the quantile clamp (thresh; pass +inf or NaN for none) and the min/max normalisation of both windows.
+// shift[2] = {tx, ty}: warm start in, result out (unchanged on failure).  Returns 0; 1 = "NaN encountered";
+// 2 = "the correlation is going to be minimized" (both are cv2.error in the reference); -1 = bad call.
+int rirb_ecc_compute(int handle, float thresh, int use_mask, int max_iterations, double eps, float* shift, double* rho, int* iterations)
+{
+    auto s = g_ecc.get(handle);
+    if (!s || !s->have_ref || !s->have_cur || !shift) {
+        set_error("ecc_compute: unknown handle, or reference / current image not set");
+        return -1;
+    }
+    std::lock_guard<std::mutex> lock(s->mu);
+    cudaStream_t st = current_stream();
+    const int n = s->w * s->h;
+    const float th = isnan(thresh) ? INFINITY : thresh;
+    const u8* mask = (use_mask && s->have_mask) ? s->mask : nullptr;
+    RIRB_LAUNCH(ecc_begin_kernel, 1, 1, 0, st, s->d, shift[0], shift[1], max_iterations, eps);
+    const int blocks = (int)min((long long)ceil_div(n, ECC_THREADS), (long long)sm_count() * 2);
+    RIRB_LAUNCH(ecc_minmax_kernel, (unsigned)blocks, ECC_THREADS, 0, st, s->ref, s->cur, n, th, s->d);
+    RIRB_LAUNCH(ecc_normalise_kernel, dim3((unsigned)ceil_div(s->w, ECC_THREADS), (unsigned)s->h), ECC_THREADS, 0, st, s->ref, s->cur,
+                mask, s->w, s->h, th, s->d, s->T, s->I, s->gx, s->gy);
+    EccResult r;
+    memset(&r, 0, sizeof(r));
+    int launched = 0;
+    while (!r.done && launched < max_iterations) {
+        const int burst = min(launched == 0 ? 6 : 12, max_iterations - launched);  // a converged problem turns the rest into no-ops
+        for (int k = 0; k < burst; ++k)
+            RIRB_LAUNCH(ecc_iter_kernel, (unsigned)blocks, ECC_THREADS, 0, st, s->T, s->I, s->gx, s->gy, mask, s->w, s->h, s->d);
+        launched += burst;
+        EccDev hd;
+        RIRB_CUDA_OK(cudaMemcpyAsync(&hd, s->d, sizeof(EccDev), cudaMemcpyDeviceToHost, st));
+        RIRB_CUDA_OK(cudaStreamSynchronize(st));
+        r.rho = hd.rho;
+        r.tx = hd.tx;
+        r.ty = hd.ty;
+        r.it = hd.it;
+        r.done = hd.done;
+        r.status = hd.status;
+    }
+    if (iterations) *iterations = r.it;
+    if (rho) *rho = r.rho;
+    if (r.status == 0) {
+        shift[0] = r.tx;
+        shift[1] = r.ty;
+    }
+    return r.status;
+}
+
+}  // extern "C"

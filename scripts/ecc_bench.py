@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""scripts/ecc_bench.py -- frames/s of the registration front end on a synthetic 640x512 movie:
+the product (librir_b200.registration.MaskedRegistratorECC: Gaussian + normalisation + OpenCV's ECC iteration on the GPU)
+next to the restated reference class driven by OpenCV itself on the host (oracle/ecc.py with cv2.findTransformECC and the
+oracle's Gaussian: what librir runs, minus its pandas bookkeeping).  Evidence for profiles/, not a bench.py line.
+
+    python scripts/ecc_bench.py [--frames 200] > gpurun_out/ecc_bench.jsonl
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=200)
+    args = ap.parse_args()
+    import torch
+
+    from librir_b200 import registration as rg
+    from oracle import ecc as oe, oracle as O  # baseline / checker only
+    from tests import ecc_cases as ec
+
+    n = args.frames
+    base, _, _ = ec.movie(40)
+    mov = np.concatenate([base, base[::-1]] * ((n + 79) // 80))[:n]  # the camera wanders out and back
+    rows = []
+
+    def rec(impl, secs, extra=None):
+        row = {"impl": impl, "frames": n, "frame": [640, 512], "seconds": round(secs, 4), "frames_per_s": round((n - 1) / secs, 1)}
+        row.update(extra or {})
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+
+    ref_xy = None
+    try:
+        import cv2  # noqa: F401
+
+        reg = oe.MaskedRegistratorECC(O.Ref() if O.have_ref() else O.Port(), ecc=oe.cv2_ecc)
+        reg.start(mov[0])
+        m = min(n, 60)
+        t0 = time.perf_counter()
+        for t in range(1, m):
+            reg.compute(mov[t])
+        el = time.perf_counter() - t0
+        rec("reference class (cv2.findTransformECC + reference Gaussian, 1 host thread)", el * (n - 1) / (m - 1),
+            {"sample": f"first {m} frames, scaled"})
+        ref_xy = np.array([reg.x, reg.y])
+        below = np.nonzero(np.array(reg.confidences) < (reg.conf_thresh if reg.conf_thresh is not None else -1))[0]
+        first_reset = int(below[0]) if len(below) else m
+    except ImportError:
+        pass
+    for name, frames in (("product, numpy frames (one upload per frame)", mov),
+                         ("product, frames in HBM", torch.from_numpy(mov.view(np.int16)).cuda().view(torch.uint16))):
+        for rep in range(2):
+            reg = rg.MaskedRegistratorECC()
+            reg.start(frames[0])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for t in range(1, n):
+                reg.compute(frames[t])
+            el = time.perf_counter() - t0
+        extra = {"mean_iterations": round(float(np.mean(reg.iterations)), 2)}
+        if ref_xy is not None:
+            k = ref_xy.shape[1]
+            d = np.abs(np.array([reg.x[:k], reg.y[:k]]) - ref_xy)
+            # chained reference resets amplify rounding differences: report both regimes
+            extra["max_abs_diff_vs_reference_px_before_first_reset"] = float(np.max(d[:, :first_reset + 1]))
+            extra["max_abs_diff_vs_reference_px_all"] = float(np.max(d))
+            extra["first_reset_frame"] = first_reset
+        rec(name, el, extra)
+
+
+if __name__ == "__main__":
+    main()
