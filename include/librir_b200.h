@@ -80,6 +80,8 @@ RIRB_API const char* rirb_version(void);
 /* string key/value switches, the reference's *_set_parameter convention (h264.cpp:1709-1781); process-wide.
  * "translate_tma" / "gauss_tma" (default 1): TMA-tiled kernels vs the register-only ones;
  * "loader_fused" (default 0): rirb_loader_read_movie as one fused pass instead of merge pass + motion pass.
+ * "ecc_fused" (default 1): rirb_ecc_compute as ONE cooperative launch (grid barriers between the phases and the
+ *   iterations) instead of one launch per iteration.
  * Initial values can also come from RIRB_TRANSLATE_TMA / RIRB_GAUSS_TMA / RIRB_LOADER_FUSED.  -1: unknown key. */
 RIRB_API int rirb_set_parameter(const char* key, const char* value);
 
@@ -267,6 +269,21 @@ RIRB_API int rirb_ecc_reset_reference(int handle, float dx, float dy);
 RIRB_API int rirb_ecc_quantile(int handle, int which, float percent, int use_mask);
 RIRB_API int rirb_ecc_compute(int handle, float thresh, int use_mask, int max_iterations, double eps, float* shift, double* rho,
                               int* iterations);
+/* The class's whole tracking loop without leaving the library (start :89-103, compute :105-191,
+ * manage_computation_and_tries :229-260).  track_config: sigma / median of the constructor; fixed_ref != 0 keeps the
+ * reference window set with rirb_ecc_set_image(handle, 0, ...) for good; clears the history.
+ * track: frames[nframes][full_h][full_w], type 'H' (uint16) or 'f' (float32), host or device, in time order; window origin
+ *   (x0, y0).  The first frame the handle sees is start() (0, 0, confidence 1), the others compute(): Gaussian, window,
+ *   quantile clamp, normalisation, ECC with the previous shift as warm start, and the confidence rule that replaces the
+ *   reference (confidence < min - 2 std of the first 21).  max_try = 0: an ECC failure stops the call and is returned
+ *   (1 / 2, *processed = frames done); max_try > 0: the manage rule (median lowered by 0.01 per attempt, then the previous
+ *   estimate repeated; a median < 1 returns to 1 after a success).  x / y / conf (and iters, may be NULL): nframes entries.
+ * track_state: current median, confidence threshold (NaN until it exists), warm start, frames seen. */
+RIRB_API int rirb_ecc_track_config(int handle, float sigma, double median, int fixed_ref);
+RIRB_API int rirb_ecc_track_set_median(int handle, double median); /* the class's public attribute; keeps the history */
+RIRB_API int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, int full_w, int full_h, int x0, int y0,
+                            int use_mask, int max_try, double* x, double* y, double* conf, int* iters, long long* processed);
+RIRB_API int rirb_ecc_track_state(int handle, double* median, double* conf_thresh, float* start, long long* count);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,10 @@ SIGNATURES = {
     "rirb_ecc_reset_reference": (_i, [_i, _f, _f]),
     "rirb_ecc_quantile": (_i, [_i, _i, _f, _i]),
     "rirb_ecc_compute": (_i, [_i, _f, _i, _i, ct.c_double, _vp, _vp, _vp]),
+    "rirb_ecc_track_config": (_i, [_i, _f, ct.c_double, _i]),
+    "rirb_ecc_track_set_median": (_i, [_i, ct.c_double]),
+    "rirb_ecc_track": (_i, [_i, _i, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rirb_ecc_track_state": (_i, [_i, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -134,7 +138,7 @@ def load() -> ct.CDLL:
 
 
 def set_parameter(key: str, value) -> None:
-    """``rirb_set_parameter``: process-wide kernel-variant switches ("translate_tma", "gauss_tma", "loader_fused")."""
+    """``rirb_set_parameter``: process-wide kernel-variant switches ("translate_tma", "gauss_tma", "loader_fused", "ecc_fused")."""
     check(load().rirb_set_parameter(key.encode(), str(int(value)).encode()), "set_parameter")
 
 

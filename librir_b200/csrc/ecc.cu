@@ -20,11 +20,13 @@
 // once) and reads the 40-byte result back; nothing else crosses PCIe per frame.
 // Traffic per iteration: template, image, two gradients (float) + mask, all L2-resident (3 MB at 448 x 358): the loop
 // is bound by launch latency, not by memory.
+#include <cooperative_groups.h>
 #include <math.h>
 #include <string.h>
 
 #include <memory>
 #include <mutex>
+#include <vector>
 
 #include "../../include/librir_b200.h"
 #include "common.cuh"
@@ -101,11 +103,15 @@ __global__ void __launch_bounds__(ECC_THREADS) ecc_minmax_kernel(const float* __
         k[2] = min(k[2], __shfl_down_sync(0xFFFFFFFFu, k[2], o));
         k[3] = max(k[3], __shfl_down_sync(0xFFFFFFFFu, k[3], o));
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(&d->mm[0], k[0]);
-        atomicMax(&d->mm[1], k[1]);
-        atomicMin(&d->mm[2], k[2]);
-        atomicMax(&d->mm[3], k[3]);
+    __shared__ unsigned kred[ECC_THREADS / 32][4];
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) kred[threadIdx.x >> 5][q] = k[q];
+    __syncthreads();
+    if (threadIdx.x < 4) {  // one atomic per value and CTA
+        unsigned v = kred[0][threadIdx.x];
+        for (int q = 1; q < ECC_THREADS / 32; ++q) v = (threadIdx.x & 1) ? max(v, kred[q][threadIdx.x]) : min(v, kred[q][threadIdx.x]);
+        if (threadIdx.x & 1) atomicMax(&d->mm[threadIdx.x], v); else atomicMin(&d->mm[threadIdx.x], v);
     }
 }
 
@@ -138,43 +144,56 @@ ecc_normalise_kernel(const float* __restrict__ ref, const float* __restrict__ cu
     gy[i] = __fmul_rn(__fsub_rn(__fmul_rn(0.5f, img(x, yp)), __fmul_rn(0.5f, img(x, ym))), m);
 }
 
+__global__ void ecc_u16_to_f32_kernel(const u16* __restrict__ src, float* __restrict__ dst, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
+}
+
 __global__ void ecc_cast_u16_kernel(const float* __restrict__ src, u16* __restrict__ dst, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = (u16)__float2int_rz(src[i]);  // numpy astype(uint16) on in-range values
 }
 
-// One ECC iteration (ecc.cpp, the body of the for loop) -- see the header of this file.
-__global__ void __launch_bounds__(ECC_THREADS)
-ecc_iter_kernel(const float* __restrict__ T, const float* __restrict__ I, const float* __restrict__ gx, const float* __restrict__ gy,
-                const u8* __restrict__ mask, int w, int h, EccDev* d)
-{
-    if (d->done) return;  // written by the previous launch's last CTA only
-    __shared__ double red[ECC_THREADS / 32][NACC];
-    __shared__ bool last;
-    // warpAffine's fixed point (imgwarp.cpp): AB_BITS = 10, INTER_BITS = 5; M = [1 0 tx; 0 1 ty], WARP_INVERSE_MAP
-    const int SX = __double2int_rn((double)d->tx * 1024.0), SY = __double2int_rn((double)d->ty * 1024.0);
-    const int ox = (SX + 16) >> 10, oy = (SY + 16) >> 10;              // bilinear: round_delta = 1024 / 32 / 2
-    const float fx = (float)(((SX + 16) >> 5) & 31) * 0.03125f, fy = (float)(((SY + 16) >> 5) & 31) * 0.03125f;
-    const int oxn = (SX + 512) >> 10, oyn = (SY + 512) >> 10;          // nearest: round_delta = 1024 / 2
-    const float w00 = __fmul_rn(1.0f - fy, 1.0f - fx), w01 = __fmul_rn(1.0f - fy, fx), w10 = __fmul_rn(fy, 1.0f - fx), w11 = __fmul_rn(fy, fx);
+// ---- one ECC iteration (ecc.cpp, the body of the for loop), in pieces shared by the two drivers below -----------
+struct EccShift {  // warpAffine's fixed point (imgwarp.cpp): AB_BITS = 10, INTER_BITS = 5; M = [1 0 tx; 0 1 ty], WARP_INVERSE_MAP
+    int ox, oy, oxn, oyn;
+    float w00, w01, w10, w11;
+    __device__ EccShift(float tx, float ty)
+    {
+        const int SX = __double2int_rn((double)tx * 1024.0), SY = __double2int_rn((double)ty * 1024.0);
+        ox = (SX + 16) >> 10;  // bilinear: round_delta = 1024 / 32 / 2, then 5 fractional bits
+        oy = (SY + 16) >> 10;
+        const float fx = (float)(((SX + 16) >> 5) & 31) * 0.03125f, fy = (float)(((SY + 16) >> 5) & 31) * 0.03125f;
+        oxn = (SX + 512) >> 10;  // nearest: round_delta = 1024 / 2
+        oyn = (SY + 512) >> 10;
+        w00 = __fmul_rn(1.0f - fy, 1.0f - fx);
+        w01 = __fmul_rn(1.0f - fy, fx);
+        w10 = __fmul_rn(fy, 1.0f - fx);
+        w11 = __fmul_rn(fy, fx);
+    }
+};
 
-    double a[NACC];
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) a[k] = 0.0;
+// the 15 sums of pixels p0, p0 + stride, ... < w * h
+__device__ __forceinline__ void ecc_accumulate(const float* __restrict__ T, const float* __restrict__ I, const float* __restrict__ gx,
+                                               const float* __restrict__ gy, const u8* __restrict__ mask, int w, int h, const EccShift& sh,
+                                               int p0, int stride, double (&a)[NACC])
+{
     const int npx = w * h;
-    for (int p = blockIdx.x * ECC_THREADS + threadIdx.x; p < npx; p += gridDim.x * ECC_THREADS) {
+    for (int p = p0; p < npx; p += stride) {
         const int y = p / w, x = p - y * w;
-        const int ix = x + ox, iy = y + oy;
+        const int ix = x + sh.ox, iy = y + sh.oy;
         const bool x0 = ix >= 0 && ix < w, x1 = ix + 1 >= 0 && ix + 1 < w, y0 = iy >= 0 && iy < h, y1 = iy + 1 >= 0 && iy + 1 < h;
         const int i00 = iy * w + ix;
         auto warp = [&](const float* __restrict__ s) {  // remapBilinear: S[0]*w0 + S[1]*w1 + S[step]*w2 + S[step+1]*w3, border 0
             const float s00 = (x0 && y0) ? s[i00] : 0.f, s01 = (x1 && y0) ? s[i00 + 1] : 0.f;
             const float s10 = (x0 && y1) ? s[i00 + w] : 0.f, s11 = (x1 && y1) ? s[i00 + w + 1] : 0.f;
-            return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)), __fmul_rn(s11, w11));
+            return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, sh.w00), __fmul_rn(s01, sh.w01)), __fmul_rn(s10, sh.w10)),
+                             __fmul_rn(s11, sh.w11));
         };
         const double Iw = warp(I), Gx = warp(gx), Gy = warp(gy);
-        const int mx = x + oxn, my = y + oyn;
+        const int mx = x + sh.oxn, my = y + sh.oyn;
         const bool m = mx >= 0 && mx < w && my >= 0 && my < h && (mask == nullptr || mask[my * w + mx] != 0);
         const double t = T[p];
         a[A_H11] += Gx * Gx;
@@ -195,6 +214,12 @@ ecc_iter_kernel(const float* __restrict__ T, const float* __restrict__ I, const 
             a[A_D2] += Gy * t;
         }
     }
+}
+
+// CTA-wide sum of the 15 values into this CTA's slot of `partials` ([gridDim.x][NACC]).  No atomics anywhere on the way to
+// the result: the order of every addition is fixed, so a frame gives the same bits on every run and in every batching.
+__device__ __forceinline__ void ecc_block_partial(double (&a)[NACC], double (*red)[NACC], double* partials)
+{
 #pragma unroll
     for (int k = 0; k < NACC; ++k)
 #pragma unroll
@@ -207,26 +232,43 @@ ecc_iter_kernel(const float* __restrict__ T, const float* __restrict__ I, const 
     if (threadIdx.x < NACC) {
         double s = 0.0;
         for (int q = 0; q < ECC_THREADS / 32; ++q) s += red[q][threadIdx.x];
-        atomicAdd(&d->acc[threadIdx.x], s);
+        partials[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
     }
-    __threadfence();
+}
+
+// Sum of all CTAs' slots, 8 threads per value (strided, then a fixed shuffle tree); result in sums[NACC] (shared).
+__device__ __forceinline__ void ecc_sum_partials(const double* partials, int nblk, double* sums)
+{
+    static_assert(NACC * 8 <= ECC_THREADS, "8 threads per accumulated value");
+    const bool active = threadIdx.x < NACC * 8;
+    const int k = threadIdx.x >> 3, j = threadIdx.x & 7;
+    double v = 0.0;
+    if (active)
+        for (int b = j; b < nblk; b += 8) v += __ldcg(&partials[(size_t)b * NACC + k]);
+    v += __shfl_down_sync(0xFFFFFFFFu, v, 4, 8);
+    v += __shfl_down_sync(0xFFFFFFFFu, v, 2, 8);
+    v += __shfl_down_sync(0xFFFFFFFFu, v, 1, 8);
+    if (active && j == 0) sums[k] = v;
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(&d->ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last || threadIdx.x != 0) return;
-    __threadfence();
-    volatile double* acc = d->acc;
+}
+
+struct EccIterate {  // the scalar state of the loop
+    float tx, ty;
+    double rho, last_rho;
+    int it, status, done;
+};
+
+// From the sums to the next shift: means / norms under the warped mask, 2 x 2 Hessian inverse, rho, lambda, update --
+// in the float / double types OpenCV's Mats have.
+__device__ __forceinline__ void ecc_update(const double* acc, EccIterate& s, int max_it, double eps)
+{
     const double n = acc[A_N], sI = acc[A_I], sT = acc[A_T], sII = acc[A_II], sTT = acc[A_TT], sIT = acc[A_IT];
     const double h11 = acc[A_H11], h12 = acc[A_H12], h22 = acc[A_H22], b1 = acc[A_B1], b2 = acc[A_B2];
     const double c1 = acc[A_C1], c2 = acc[A_C2], d1 = acc[A_D1], d2 = acc[A_D2];
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    d->ticket = 0;
-    const int it = d->it + 1;
-    d->it = it;
-    int status = 0;
-    double rho = d->rho;
+    s.it += 1;
+    s.status = 0;
     if (n <= 0.0) {
-        status = 1;
+        s.status = 1;
     } else {
         // meanStdDev under the warped mask; subtract(image, mean) works in the image's type: the mean is rounded to float
         const double meanI = sI / n, meanT = sT / n;
@@ -239,10 +281,10 @@ ecc_iter_kernel(const float* __restrict__ T, const float* __restrict__ I, const 
         const double id = det != 0.0 ? 1.0 / det : 0.0;
         const float Hi11 = (float)(H22 * id), Hi22 = (float)(H11 * id), Hi12 = (float)(-(double)H12 * id);
         const double corr = sIT - muT * sI - muI * sT + muI * muT * n;  // templateZM . imageWarped
-        d->last_rho = rho;
-        rho = corr / (img_norm * tmp_norm);
-        if (isnan(rho) || det == 0.0) {
-            status = 1;
+        s.last_rho = s.rho;
+        s.rho = corr / (img_norm * tmp_norm);
+        if (isnan(s.rho) || det == 0.0) {
+            s.status = 1;
         } else {
             const double pI1 = b1 - muI * c1, pI2 = b2 - muI * c2;  // J^T (I - mean), exact sums
             const double pT1 = d1 - muT * c1, pT2 = d2 - muT * c2;  // J^T (T - mean)
@@ -251,21 +293,155 @@ ecc_iter_kernel(const float* __restrict__ T, const float* __restrict__ I, const 
             const double lam_n = img_norm * img_norm - ((double)ip1 * iph1 + (double)ip2 * iph2);
             const double lam_d = corr - ((double)tp1 * iph1 + (double)tp2 * iph2);
             if (lam_d <= 0.0) {
-                rho = -1.0;
-                status = 2;
+                s.rho = -1.0;
+                s.status = 2;
             } else {
                 const double lam = lam_n / lam_d;
                 const float e1 = (float)(lam * pT1 - pI1), e2 = (float)(lam * pT2 - pI2);  // J^T (lambda T - I)
                 const float dp1 = (float)((double)Hi11 * e1 + (double)Hi12 * e2), dp2 = (float)((double)Hi12 * e1 + (double)Hi22 * e2);
-                d->tx = __fadd_rn(d->tx, dp1);
-                d->ty = __fadd_rn(d->ty, dp2);
+                s.tx = __fadd_rn(s.tx, dp1);
+                s.ty = __fadd_rn(s.ty, dp2);
             }
         }
     }
-    d->rho = rho;
-    d->status = status;
-    d->done = status != 0 || it >= d->max_it || !(fabs(rho - d->last_rho) >= d->eps);
+    s.done = s.status != 0 || s.it >= max_it || !(fabs(s.rho - s.last_rho) >= eps);
+}
+
+// Driver 1: one launch per iteration; the last CTA to finish adds up the slots and runs the update (used when a
+// cooperative launch is not possible).
+__global__ void __launch_bounds__(ECC_THREADS)
+ecc_iter_kernel(const float* __restrict__ T, const float* __restrict__ I, const float* __restrict__ gx, const float* __restrict__ gy,
+                const u8* __restrict__ mask, int w, int h, EccDev* d, double* partials)
+{
+    if (d->done) return;  // written by the previous launch's last CTA only
+    __shared__ double red[ECC_THREADS / 32][NACC];
+    __shared__ double sums[NACC];
+    __shared__ bool last;
+    const EccShift sh(d->tx, d->ty);
+    double a[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) a[k] = 0.0;
+    ecc_accumulate(T, I, gx, gy, mask, w, h, sh, blockIdx.x * ECC_THREADS + threadIdx.x, gridDim.x * ECC_THREADS, a);
+    ecc_block_partial(a, red, partials);
     __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&d->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    ecc_sum_partials(partials, (int)gridDim.x, sums);
+    if (threadIdx.x != 0) return;
+    EccIterate s{d->tx, d->ty, d->rho, d->last_rho, d->it, 0, 0};
+    ecc_update(sums, s, d->max_it, d->eps);
+    d->ticket = 0;
+    d->tx = s.tx;
+    d->ty = s.ty;
+    d->rho = s.rho;
+    d->last_rho = s.last_rho;
+    d->it = s.it;
+    d->status = s.status;
+    d->done = s.done;
+    __threadfence();
+}
+
+// Driver 2: the whole solve in ONE cooperative launch (one CTA per SM, all co-resident): min/max -> grid barrier ->
+// normalisation + gradients -> grid barrier -> iterations, one grid barrier each.  After the barrier every CTA reads
+// every CTA's 15 partial sums in the same fixed order and runs the same scalar update itself (identical inputs, identical
+// arithmetic, identical result), so no second barrier is needed to publish the new shift.  The slots are double-buffered
+// by iteration parity: a fast CTA writes iteration it + 1's sums into the other buffer while a slow one still reads it's.
+__global__ void __launch_bounds__(ECC_THREADS)
+ecc_solve_kernel(const float* __restrict__ ref, const float* __restrict__ cur, const u8* __restrict__ mask, int w, int h, float thresh,
+                 float* __restrict__ T, float* __restrict__ I, float* __restrict__ gx, float* __restrict__ gy, EccDev* d, double* partials,
+                 float tx0, float ty0, int max_it, double eps)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red[ECC_THREADS / 32][NACC];
+    __shared__ double sums[NACC];
+    __shared__ unsigned kred[ECC_THREADS / 32][4];
+    __shared__ EccIterate shared_state;
+    const int npx = w * h;
+    const int gtid = blockIdx.x * ECC_THREADS + threadIdx.x, gthreads = gridDim.x * ECC_THREADS;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+
+    // ---- min / max of the clamped windows (d->mm was initialised by the host before the launch) ----
+    {
+        unsigned k[4] = {0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u};
+        for (int i = gtid; i < npx; i += gthreads) {
+            const float r = ref[i], c = cur[i];
+            const unsigned kr = fkey(clamp_pair(r, c, thresh)), kc = fkey(clamp_pair(c, r, thresh));
+            k[0] = min(k[0], kr);
+            k[1] = max(k[1], kr);
+            k[2] = min(k[2], kc);
+            k[3] = max(k[3], kc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            k[0] = min(k[0], __shfl_down_sync(0xFFFFFFFFu, k[0], o));
+            k[1] = max(k[1], __shfl_down_sync(0xFFFFFFFFu, k[1], o));
+            k[2] = min(k[2], __shfl_down_sync(0xFFFFFFFFu, k[2], o));
+            k[3] = max(k[3], __shfl_down_sync(0xFFFFFFFFu, k[3], o));
+        }
+        if (lane == 0)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) kred[wi][q] = k[q];
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            unsigned v = kred[0][threadIdx.x];
+            for (int q = 1; q < ECC_THREADS / 32; ++q) v = (threadIdx.x & 1) ? max(v, kred[q][threadIdx.x]) : min(v, kred[q][threadIdx.x]);
+            if (threadIdx.x & 1) atomicMax(&d->mm[threadIdx.x], v); else atomicMin(&d->mm[threadIdx.x], v);
+        }
+    }
+    grid.sync();
+    // ---- normalisation + gradients ----
+    {
+        const float mi_t = fkey_inv(d->mm[0]), span_t = __fsub_rn(fkey_inv(d->mm[1]), mi_t);
+        const float mi_i = fkey_inv(d->mm[2]), span_i = __fsub_rn(fkey_inv(d->mm[3]), mi_i);
+        auto img = [&](int xx, int yy) {
+            const int i = yy * w + xx;
+            return normalise(clamp_pair(cur[i], ref[i], thresh), mi_i, span_i);
+        };
+        for (int i = gtid; i < npx; i += gthreads) {
+            const int y = i / w, x = i - y * w;
+            T[i] = normalise(clamp_pair(ref[i], cur[i], thresh), mi_t, span_t);
+            I[i] = img(x, y);
+            const int xm = x == 0 ? 1 : x - 1, xp = x == w - 1 ? w - 2 : x + 1;  // w, h >= 2 (rirb_ecc_open)
+            const int ym = y == 0 ? 1 : y - 1, yp = y == h - 1 ? h - 2 : y + 1;
+            const float m = (mask == nullptr || mask[i] != 0) ? 1.0f : 0.0f;
+            gx[i] = __fmul_rn(__fsub_rn(__fmul_rn(0.5f, img(xp, y)), __fmul_rn(0.5f, img(xm, y))), m);
+            gy[i] = __fmul_rn(__fsub_rn(__fmul_rn(0.5f, img(x, yp)), __fmul_rn(0.5f, img(x, ym))), m);
+        }
+    }
+    grid.sync();
+    // ---- iterations ----
+    EccIterate s{tx0, ty0, -1.0, -eps, 0, 0, 0};  // ecc.cpp: rho = -1, last_rho = -termination_eps
+    s.done = (max_it <= 0) || !(fabs(s.rho - s.last_rho) >= eps);
+    while (!s.done) {
+        double* slots = partials + (size_t)(s.it & 1) * gridDim.x * NACC;
+        const EccShift sh(s.tx, s.ty);
+        double a[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] = 0.0;
+        ecc_accumulate(T, I, gx, gy, mask, w, h, sh, gtid, gthreads, a);
+        ecc_block_partial(a, red, slots);
+        grid.sync();
+        ecc_sum_partials(slots, (int)gridDim.x, sums);
+        if (threadIdx.x == 0) {
+            ecc_update(sums, s, max_it, eps);
+            shared_state = s;
+        }
+        __syncthreads();
+        s = shared_state;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        d->tx = s.tx;
+        d->ty = s.ty;
+        d->rho = s.rho;
+        d->last_rho = s.last_rho;
+        d->it = s.it;
+        d->status = s.status;
+        d->done = 1;
+    }
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -279,10 +455,22 @@ struct EccState {
     unsigned* mm = nullptr;
     int* qout = nullptr;
     EccDev* d = nullptr;
-    std::mutex mu;
+    double* partials = nullptr;  // per-CTA partial sums, two buffers of [max grid][NACC]
+    int max_grid = 0;
+    int coop_grid = 0;       // CTAs of the cooperative launch (0: not available)
+    // ---- tracking state of MaskedRegistratorECC (rirb_ecc_track*) ----
+    bool started = false, fixed_ref = false, have_thresh = false;
+    float sigma = 0.5f;
+    double median = 1.0, conf_thresh = 0.0, last_x = 0.0, last_y = 0.0, last_conf = 1.0;
+    float start[2] = {0.f, 0.f};  // warp_matrix[0,2], warp_matrix[1,2]: the warm start of the next frame
+    std::vector<double> confs;
+    void* stage = nullptr;        // one full frame uploaded from the host
+    float* filtered = nullptr;    // one full frame, Gaussian-filtered / converted to float
+    size_t stage_cap = 0, filtered_cap = 0;
+    std::recursive_mutex mu;
     ~EccState()
     {
-        void* ptrs[] = {ref, cur, T, I, gx, gy, mask, qmask, q16, hist, mm, qout, d};
+        void* ptrs[] = {ref, cur, T, I, gx, gy, mask, qmask, q16, hist, mm, qout, d, partials, stage, filtered};
         for (void* p : ptrs)
             if (p) cudaFree(p);
     }
@@ -298,6 +486,16 @@ static int ecc_need_device()
         return -1;
     }
     return 0;
+}
+
+static bool is_device_pointer(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
 static int ecc_load_window(EccState& s, float* dst, const float* src, int stride, cudaStream_t st)
@@ -335,11 +533,19 @@ int rirb_ecc_open(int width, int height)
          cudaMalloc((void**)&s->hist, 65536 * sizeof(unsigned long long)) == cudaSuccess &&
          cudaMalloc((void**)&s->mm, 2 * sizeof(unsigned)) == cudaSuccess && cudaMalloc((void**)&s->qout, sizeof(int)) == cudaSuccess &&
          cudaMalloc((void**)&s->d, sizeof(EccDev)) == cudaSuccess;
+    s->max_grid = sm_count() * 2;
+    ok = ok && cudaMalloc((void**)&s->partials, (size_t)2 * s->max_grid * NACC * sizeof(double)) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         set_error("ecc_open: out of device memory");
         return 0;
     }
+    // the one-launch solver needs every CTA resident at once: one per SM, if the device can launch cooperatively
+    int coop = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->dev) == cudaSuccess && coop &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ecc_solve_kernel, ECC_THREADS, 0) == cudaSuccess && per_sm >= 1)
+        s->coop_grid = (int)min((long long)sm_count(), (long long)ceil_div((long long)n, ECC_THREADS));
+    cudaGetLastError();
     return g_ecc.add(s);
 }
 
@@ -356,7 +562,7 @@ int rirb_ecc_set_mask(int handle, int which, const unsigned char* mask)
         set_error("ecc: unknown handle %d or mask selector", handle);
         return -1;
     }
-    std::lock_guard<std::mutex> lock(s->mu);
+    std::lock_guard<std::recursive_mutex> lock(s->mu);
     (which ? s->have_qmask : s->have_mask) = mask != nullptr;
     if (mask) RIRB_CUDA_OK(cudaMemcpyAsync(which ? s->qmask : s->mask, mask, (size_t)s->w * s->h, cudaMemcpyDefault, current_stream()));
     return 0;
@@ -371,7 +577,7 @@ int rirb_ecc_set_image(int handle, int which, const float* img, int stride)
         set_error("ecc: unknown handle %d or image selector", handle);
         return -1;
     }
-    std::lock_guard<std::mutex> lock(s->mu);
+    std::lock_guard<std::recursive_mutex> lock(s->mu);
     if (ecc_load_window(*s, which ? s->cur : s->ref, img, stride, current_stream()) != 0) return -1;
     (which ? s->have_cur : s->have_ref) = true;
     return 0;
@@ -386,7 +592,7 @@ int rirb_ecc_reset_reference(int handle, float dx, float dy)
         set_error("ecc_reset_reference: unknown handle or no current image");
         return -1;
     }
-    std::lock_guard<std::mutex> lock(s->mu);
+    std::lock_guard<std::recursive_mutex> lock(s->mu);
     cudaStream_t st = current_stream();
     const size_t bytes = (size_t)s->w * s->h * 4;
     RIRB_CUDA_OK(cudaMemcpyAsync(s->ref, s->cur, bytes, cudaMemcpyDeviceToDevice, st));  // untouched pixels keep the source value
@@ -404,7 +610,7 @@ int rirb_ecc_quantile(int handle, int which, float percent, int use_mask)
         set_error("ecc_quantile: unknown handle or image not set");
         return -1;
     }
-    std::lock_guard<std::mutex> lock(s->mu);
+    std::lock_guard<std::recursive_mutex> lock(s->mu);
     cudaStream_t st = current_stream();
     const int n = s->w * s->h;
     RIRB_LAUNCH(ecc_cast_u16_kernel, (unsigned)ceil_div(n, 256), 256, 0, st, which ? s->cur : s->ref, s->q16, n);
@@ -429,25 +635,24 @@ int rirb_ecc_compute(int handle, float thresh, int use_mask, int max_iterations,
         set_error("ecc_compute: unknown handle, or reference / current image not set");
         return -1;
     }
-    std::lock_guard<std::mutex> lock(s->mu);
+    std::lock_guard<std::recursive_mutex> lock(s->mu);
     cudaStream_t st = current_stream();
     const int n = s->w * s->h;
     const float th = isnan(thresh) ? INFINITY : thresh;
     const u8* mask = (use_mask && s->have_mask) ? s->mask : nullptr;
     RIRB_LAUNCH(ecc_begin_kernel, 1, 1, 0, st, s->d, shift[0], shift[1], max_iterations, eps);
-    const int blocks = (int)min((long long)ceil_div(n, ECC_THREADS), (long long)sm_count() * 2);
-    RIRB_LAUNCH(ecc_minmax_kernel, (unsigned)blocks, ECC_THREADS, 0, st, s->ref, s->cur, n, th, s->d);
-    RIRB_LAUNCH(ecc_normalise_kernel, dim3((unsigned)ceil_div(s->w, ECC_THREADS), (unsigned)s->h), ECC_THREADS, 0, st, s->ref, s->cur,
-                mask, s->w, s->h, th, s->d, s->T, s->I, s->gx, s->gy);
     EccResult r;
     memset(&r, 0, sizeof(r));
-    int launched = 0;
-    while (!r.done && launched < max_iterations) {
-        const int burst = min(launched == 0 ? 6 : 12, max_iterations - launched);  // a converged problem turns the rest into no-ops
-        for (int k = 0; k < burst; ++k)
-            RIRB_LAUNCH(ecc_iter_kernel, (unsigned)blocks, ECC_THREADS, 0, st, s->T, s->I, s->gx, s->gy, mask, s->w, s->h, s->d);
-        launched += burst;
-        EccDev hd;
+    EccDev hd;
+    if (s->coop_grid > 0 && option_enabled(OPT_ECC_FUSED)) {
+        // the whole solve in one cooperative launch ("ecc_fused" = 0 selects the launch-per-iteration driver)
+        const float* ref = s->ref;
+        const float* cur = s->cur;
+        int w = s->w, h = s->h;
+        float th_arg = th, tx0 = shift[0], ty0 = shift[1];
+        void* args[] = {&ref, &cur, &mask, &w, &h, &th_arg, &s->T, &s->I, &s->gx, &s->gy, &s->d, &s->partials, &tx0, &ty0, &max_iterations, &eps};
+        RIRB_CUDA_OK(cudaLaunchCooperativeKernel((const void*)ecc_solve_kernel, dim3((unsigned)s->coop_grid), dim3(ECC_THREADS), args, 0, st));
+        g_launches.fetch_add(1);
         RIRB_CUDA_OK(cudaMemcpyAsync(&hd, s->d, sizeof(EccDev), cudaMemcpyDeviceToHost, st));
         RIRB_CUDA_OK(cudaStreamSynchronize(st));
         r.rho = hd.rho;
@@ -456,6 +661,26 @@ int rirb_ecc_compute(int handle, float thresh, int use_mask, int max_iterations,
         r.it = hd.it;
         r.done = hd.done;
         r.status = hd.status;
+    } else {
+        const int blocks = (int)min((long long)ceil_div(n, ECC_THREADS), (long long)s->max_grid);
+        RIRB_LAUNCH(ecc_minmax_kernel, (unsigned)blocks, ECC_THREADS, 0, st, s->ref, s->cur, n, th, s->d);
+        RIRB_LAUNCH(ecc_normalise_kernel, dim3((unsigned)ceil_div(s->w, ECC_THREADS), (unsigned)s->h), ECC_THREADS, 0, st, s->ref, s->cur,
+                    mask, s->w, s->h, th, s->d, s->T, s->I, s->gx, s->gy);
+        int launched = 0;
+        while (!r.done && launched < max_iterations) {
+            const int burst = min(launched == 0 ? 4 : 12, max_iterations - launched);  // a converged problem turns the rest into no-ops
+            for (int k = 0; k < burst; ++k)
+                RIRB_LAUNCH(ecc_iter_kernel, (unsigned)blocks, ECC_THREADS, 0, st, s->T, s->I, s->gx, s->gy, mask, s->w, s->h, s->d, s->partials);
+            launched += burst;
+            RIRB_CUDA_OK(cudaMemcpyAsync(&hd, s->d, sizeof(EccDev), cudaMemcpyDeviceToHost, st));
+            RIRB_CUDA_OK(cudaStreamSynchronize(st));
+            r.rho = hd.rho;
+            r.tx = hd.tx;
+            r.ty = hd.ty;
+            r.it = hd.it;
+            r.done = hd.done;
+            r.status = hd.status;
+        }
     }
     if (iterations) *iterations = r.it;
     if (rho) *rho = r.rho;
@@ -464,6 +689,194 @@ int rirb_ecc_compute(int handle, float thresh, int use_mask, int max_iterations,
         shift[1] = r.ty;
     }
     return r.status;
+}
+
+// ---- the tracking loop of MaskedRegistratorECC, frame after frame, without leaving the library ---------------------
+// (masked_registration_ecc.py: start :89-103, compute :105-191, manage_computation_and_tries :229-260)
+
+// sigma / median as in the class constructor; fixed_ref != 0: the reference window set with rirb_ecc_set_image(0) is kept
+// for good (the class's `ref` argument) and the confidence rule never replaces it.  Clears the tracking history.
+int rirb_ecc_track_config(int handle, float sigma, double median, int fixed_ref)
+{
+    auto s = g_ecc.get(handle);
+    if (!s || !(sigma >= 0.f)) {
+        set_error("ecc_track_config: unknown handle or negative sigma");
+        return -1;
+    }
+    std::lock_guard<std::recursive_mutex> lock(s->mu);
+    s->sigma = sigma;
+    s->median = median;
+    s->fixed_ref = fixed_ref != 0;
+    s->started = false;
+    s->have_thresh = false;
+    s->confs.clear();
+    s->start[0] = s->start[1] = 0.f;
+    s->last_x = s->last_y = 0.0;
+    s->last_conf = 1.0;
+    return 0;
+}
+
+// The class's `median` attribute is public: a caller may change it between frames without losing the history.
+int rirb_ecc_track_set_median(int handle, double median)
+{
+    auto s = g_ecc.get(handle);
+    if (!s) {
+        set_error("ecc_track_set_median: unknown handle");
+        return -1;
+    }
+    std::lock_guard<std::recursive_mutex> lock(s->mu);
+    s->median = median;
+    return 0;
+}
+
+// median (the manage rule changes it), conf_thresh (NaN until it exists), start[2], frames seen so far
+int rirb_ecc_track_state(int handle, double* median, double* conf_thresh, float* start, long long* count)
+{
+    auto s = g_ecc.get(handle);
+    if (!s) {
+        set_error("ecc_track_state: unknown handle");
+        return -1;
+    }
+    std::lock_guard<std::recursive_mutex> lock(s->mu);
+    if (median) *median = s->median;
+    if (conf_thresh) *conf_thresh = s->have_thresh ? s->conf_thresh : NAN;
+    if (start) {
+        start[0] = s->start[0];
+        start[1] = s->start[1];
+    }
+    if (count) *count = (long long)s->confs.size();
+    return 0;
+}
+
+// frames[nframes][full_h][full_w], type 'H' (uint16) or 'f' (float32), host or device, IN TIME ORDER; the registration
+// window starts at (x0, y0).  The first frame the handle ever sees is the class's start() (outputs 0, 0, 1); every other
+// frame is compute().  max_try = 0: a frame on which ECC fails stops the call, which returns the failure's status (1 / 2)
+// with *processed = frames done before it.  max_try > 0: manage_computation_and_tries -- up to max_try attempts with the
+// median lowered by 0.01 each time, then the previous estimate is repeated; after a success a median < 1 goes back to 1.
+// x / y / conf / iters: nframes entries each (iters may be NULL; 0 for the start frame, -1 for a repeated estimate).
+int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, int full_w, int full_h, int x0, int y0, int use_mask,
+                   int max_try, double* x, double* y, double* conf, int* iters, long long* processed)
+{
+    auto s = g_ecc.get(handle);
+    if (processed) *processed = 0;
+    if (!s || !frames || nframes < 0 || !x || !y || !conf || (type != 'H' && type != 'f') || x0 < 0 || y0 < 0 || x0 + s->w > full_w ||
+        y0 + s->h > full_h) {
+        set_error("ecc_track: unknown handle, bad pointers / dtype, or the window does not fit the frame");
+        return -1;
+    }
+    std::lock_guard<std::recursive_mutex> lock(s->mu);
+    if (s->fixed_ref && s->median < 1.0) {
+        set_error("ecc_track: median < 1 together with a fixed reference image is not supported");
+        return -1;
+    }
+    cudaStream_t st = current_stream();
+    const size_t fpx = (size_t)full_w * full_h, esz = type == 'H' ? 2 : 4;
+    const bool on_device = is_device_pointer(frames);
+    if (!on_device && s->stage_cap < fpx * esz) {
+        if (s->stage) cudaFree(s->stage);
+        s->stage = nullptr;
+        s->stage_cap = 0;
+        RIRB_CUDA_OK(cudaMalloc(&s->stage, fpx * esz));
+        s->stage_cap = fpx * esz;
+    }
+    if (s->filtered_cap < fpx * 4) {
+        if (s->filtered) cudaFree(s->filtered);
+        s->filtered = nullptr;
+        s->filtered_cap = 0;
+        RIRB_CUDA_OK(cudaMalloc((void**)&s->filtered, fpx * 4));
+        s->filtered_cap = fpx * 4;
+    }
+    GaussTaps taps;
+    if (s->sigma > 0.f && gaussian_taps_host(s->sigma, &taps) != 0) return -1;
+    for (long long t = 0; t < nframes; ++t) {
+        const char* src = (const char*)frames + (size_t)t * fpx * esz;
+        if (!on_device) {
+            RIRB_CUDA_OK(cudaMemcpyAsync(s->stage, src, fpx * esz, cudaMemcpyHostToDevice, st));
+            src = (const char*)s->stage;
+        }
+        const float* full = s->filtered;
+        if (s->sigma > 0.f) {
+            if ((type == 'H' ? launch_gaussian_u16((const u16*)src, s->filtered, full_w, full_h, 1, taps, st)
+                             : launch_gaussian_f32((const float*)src, s->filtered, full_w, full_h, 1, taps, st)) != 0)
+                return -1;
+        } else if (type == 'H') {
+            RIRB_LAUNCH(ecc_u16_to_f32_kernel, (unsigned)ceil_div((long long)fpx, 256), 256, 0, st, (const u16*)src, s->filtered, (int)fpx);
+        } else {
+            full = (const float*)src;
+        }
+        const float* window = full + (size_t)y0 * full_w + x0;
+        if (!s->started) {  // start(): the first window is the reference (unless one was given), shifts 0, confidence 1
+            if (ecc_load_window(*s, s->fixed_ref ? s->cur : s->ref, window, full_w, st) != 0) return -1;
+            (s->fixed_ref ? s->have_cur : s->have_ref) = true;
+            s->started = true;
+            s->confs.push_back(1.0);
+            x[t] = y[t] = 0.0;
+            conf[t] = 1.0;
+            if (iters) iters[t] = 0;
+            if (processed) *processed = t + 1;
+            continue;
+        }
+        if (ecc_load_window(*s, s->cur, window, full_w, st) != 0) return -1;
+        s->have_cur = true;
+        int tries = 0, status = 0, its = 0;
+        double rho = 0.0;
+        float shift[2];
+        for (;;) {
+            float thresh = INFINITY;
+            if (s->median < 1.0) {
+                const int t1 = rirb_ecc_quantile(handle, 1, (float)s->median, use_mask);
+                const int t2 = rirb_ecc_quantile(handle, 0, (float)s->median, use_mask);
+                if (t1 < 0 || t2 < 0) return -1;
+                thresh = (float)(t1 > t2 ? t1 : t2);
+            }
+            shift[0] = s->start[0];
+            shift[1] = s->start[1];
+            status = rirb_ecc_compute(handle, thresh, use_mask, 500, 1e-3, shift, &rho, &its);
+            if (status < 0) return -1;
+            if (status == 0) {
+                if (max_try > 0 && s->median < 1.0) s->median = 1.0;
+                break;
+            }
+            if (max_try <= 0) return status;
+            s->median -= 0.01;
+            if (++tries >= max_try) break;
+        }
+        if (status != 0) {  // append_last_coordinates_and_confidence
+            x[t] = s->last_x;
+            y[t] = s->last_y;
+            conf[t] = s->last_conf;
+            s->confs.push_back(s->last_conf);
+            if (iters) iters[t] = -1;
+            if (processed) *processed = t + 1;
+            continue;
+        }
+        s->start[0] = shift[0];
+        s->start[1] = shift[1];
+        x[t] = s->last_x = (double)shift[0];
+        y[t] = s->last_y = (double)shift[1];
+        conf[t] = s->last_conf = rho;
+        if (iters) iters[t] = its;
+        s->confs.push_back(rho);
+        if (s->confs.size() > 20 && !s->fixed_ref) {  // :176-186
+            if (!s->have_thresh) {  // np.min(c) - 2 * np.std(c), population std, once
+                double mn = s->confs[0], mean = 0.0, var = 0.0;
+                for (double c : s->confs) {
+                    mn = c < mn ? c : mn;
+                    mean += c;
+                }
+                mean /= (double)s->confs.size();
+                for (double c : s->confs) var += (c - mean) * (c - mean);
+                s->conf_thresh = mn - 2.0 * sqrt(var / (double)s->confs.size());
+                s->have_thresh = true;
+            }
+            if (rho < s->conf_thresh) {
+                if (rirb_ecc_reset_reference(handle, -shift[0], -shift[1]) != 0) return -1;
+                s->start[0] = s->start[1] = 0.f;
+            }
+        }
+        if (processed) *processed = t + 1;
+    }
+    return 0;
 }
 
 }  // extern "C"

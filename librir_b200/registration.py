@@ -67,7 +67,9 @@ class MaskedRegistratorECC:
 
     Same behaviour as librir's class (masked_registration_ecc.py:20-226): the first image goes to ``start()``, the others
     to ``compute()``; results accumulate in ``x``, ``y`` (translations from the first image) and ``confidences``; the
-    reference image is replaced when the confidence drops below min - 2 std of the first 21 confidences.
+    reference image is replaced when the confidence drops below min - 2 std of the first 21 confidences.  The loop itself
+    (warm start, confidence rule, retry rule) lives in the library (``rirb_ecc_track``); ``compute_movie`` hands it a whole
+    stack of frames in one call.
     """
 
     def __init__(self, window_factorh=0.7, window_factorv=0.7, sigma=0.5, mask=None, median=1, ref=None, pre_process=None, view=None,
@@ -79,6 +81,7 @@ class MaskedRegistratorECC:
         self.iterations = []
         self.window_factorH = window_factorh
         self.window_factorV = window_factorv
+        self.shape = tuple(shape)
         self.subW = int(shape[1] * self.window_factorH)  # the reference hard-codes shape = (512, 640), :77
         self.subH = int(shape[0] * self.window_factorV)
         self.startX = int((shape[1] - self.subW) / 2)
@@ -95,13 +98,15 @@ class MaskedRegistratorECC:
             raise RuntimeError(f"MaskedRegistratorECC: {_lib.last_error()}")
         self._fixed_ref = ref is not None
         self._started = False
+        _lib.check(self._lib.rirb_ecc_track_config(self._h, float(sigma), float(median), int(self._fixed_ref)), "ecc_track_config")
         if ref is not None:
             if pre_process is not None:
                 ref = pre_process(ref)
             g = self._filtered(ref)
             if tuple(g.shape) != (self.subH, self.subW):
                 raise RuntimeError("MaskedRegistratorECC: a fixed `ref` must have the size of the registration window")
-            self._set(0, g, 0, 0)
+            _lib.use_torch_stream()
+            _lib.check(self._lib.rirb_ecc_set_image(self._h, 0, ct.c_void_p(g.data_ptr()), int(g.shape[1])), "ecc_set_image")
 
     def __del__(self):
         try:
@@ -111,16 +116,14 @@ class MaskedRegistratorECC:
         except Exception:  # noqa: BLE001
             pass
 
-    # ---- device helpers -----------------------------------------------------------------------------
+    # ---- helpers ----------------------------------------------------------------------------------------
     def _filtered(self, img):
-        """img (numpy or torch, any dtype) -> float32 CUDA tensor [h, w], Gaussian-filtered when sigma > 0."""
+        """img (numpy or torch, any dtype) -> float32 CUDA tensor [h, w], Gaussian-filtered when sigma > 0 (fixed `ref` only)."""
         torch = _torch()
         if not sp._is_torch(img):
             a = np.ascontiguousarray(img)
-            if a.dtype == np.uint16:
-                img = torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
-            else:
-                img = torch.from_numpy(a.astype(np.float32, copy=False)).cuda()
+            img = torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16) if a.dtype == np.uint16 else torch.from_numpy(
+                a.astype(np.float32, copy=False)).cuda()
         elif not img.is_cuda:
             img = img.cuda()
         if img.dtype not in (torch.uint16, torch.float32):
@@ -129,71 +132,102 @@ class MaskedRegistratorECC:
             return sp.gaussian_filter_batch(img[None], self.sigma)[0]
         return img.to(torch.float32)
 
-    def _set(self, which, g, x0, y0):
-        _lib.use_torch_stream()
-        ptr = g.data_ptr() + 4 * (y0 * g.shape[1] + x0)
-        _lib.check(self._lib.rirb_ecc_set_image(self._h, which, ct.c_void_p(ptr), int(g.shape[1])), "ecc_set_image")
-
-    # ---- the reference's interface ----------------------------------------------------------------------
-    def start(self, img):
-        if self.pre_process is not None:
-            img = self.pre_process(img)
-        g = self._filtered(img)
-        if not self._fixed_ref:
-            self._set(0, g, self.startX, self.startY)
+    def _frames(self, frames):
+        """-> (ctypes pointer, dtype code, n, keep-alive): a stack [n, h, w] (or one frame [h, w]) of uint16 / float32."""
+        if sp._is_torch(frames):
+            torch = _torch()
+            t = frames if frames.dtype in (torch.uint16, torch.float32) else frames.to(torch.float32)
+            t = t.contiguous()
+            if t.is_cuda:
+                _lib.use_torch_stream()
+            shape, code, ptr = tuple(t.shape), ("H" if t.dtype == torch.uint16 else "f"), ct.c_void_p(t.data_ptr())
         else:
-            self._set(1, g, self.startX, self.startY)
-        if self.mask is not None:
+            t = np.asarray(frames)
+            t = np.ascontiguousarray(t if t.dtype in (np.uint16, np.float32) else t.astype(np.float32))
+            shape, code, ptr = t.shape, ("H" if t.dtype == np.uint16 else "f"), t.ctypes.data_as(ct.c_void_p)
+        if len(shape) == 2:
+            shape = (1,) + tuple(shape)
+        if len(shape) != 3 or tuple(shape[1:]) != self.shape:
+            raise RuntimeError(f"MaskedRegistratorECC: frames must be {self.shape[0]} x {self.shape[1]} images")
+        return ptr, ord(code), int(shape[0]), t
+
+    def _track(self, frames, max_try):
+        if self.pre_process is not None:
+            if sp._is_torch(frames) or np.asarray(frames).ndim == 3:
+                frames = np.stack([np.asarray(self.pre_process(f)) for f in frames])
+            else:
+                frames = self.pre_process(frames)
+        if not self._started and self.mask is not None:
             full = np.asarray(self.mask)
             self.mask = full[self.startY:self.startY + self.subH, self.startX:self.startX + self.subW]
             ecc_mask = np.ascontiguousarray(self.mask).astype(np.uint8)
             qmask = quantile_mask_like_reference(full, self.startX, self.startY, self.subW, self.subH)
             _lib.check(self._lib.rirb_ecc_set_mask(self._h, 0, ecc_mask.ctypes.data_as(ct.c_void_p)), "ecc_set_mask")
             _lib.check(self._lib.rirb_ecc_set_mask(self._h, 1, qmask.ctypes.data_as(ct.c_void_p)), "ecc_set_mask")
-        self._started = True
-        self.x.append(0)
-        self.y.append(0)
-        self.confidences.append(1)
+        ptr, code, n, keep = self._frames(frames)
+        x, y, c = np.zeros(n), np.zeros(n), np.zeros(n)
+        its = np.zeros(n, dtype=np.int32)
+        done = ct.c_longlong(0)
+        if self.median != self._lib_median():  # the attribute is public in the reference: honour a value the user changed
+            self._set_median(self.median)
+        status = self._lib.rirb_ecc_track(self._h, code, ptr, n, self.shape[1], self.shape[0], self.startX, self.startY,
+                                          1 if self.mask is not None else 0, int(max_try), x.ctypes.data_as(ct.c_void_p),
+                                          y.ctypes.data_as(ct.c_void_p), c.ctypes.data_as(ct.c_void_p), its.ctypes.data_as(ct.c_void_p),
+                                          ct.byref(done))
+        del keep
+        k = done.value
+        first = 0
+        if not self._started and k > 0:  # start(): integer zeros and a confidence of 1, like the reference's lists
+            self.x.append(0)
+            self.y.append(0)
+            self.confidences.append(1)
+            self._started = True
+            first = 1
+        for i in range(first, k):
+            self.x.append(np.float32(x[i]))
+            self.y.append(np.float32(y[i]))
+            self.confidences.append(float(c[i]))
+            self.iterations.append(int(its[i]))
+        self._sync_state()
+        if status < 0:
+            raise RuntimeError(f"An error occured while calling 'ecc_track': {_lib.last_error()}")
+        if status > 0:
+            raise ECCError(_MESSAGES.get(status, "findTransformECC failed"))
+        return k
+
+    def _lib_median(self):
+        m = ct.c_double(0.0)
+        self._lib.rirb_ecc_track_state(self._h, ct.byref(m), None, None, None)
+        return m.value
+
+    def _set_median(self, median):
+        _lib.check(self._lib.rirb_ecc_track_set_median(self._h, float(median)), "ecc_track_set_median")
+
+    def _sync_state(self):
+        m, th, n = ct.c_double(0.0), ct.c_double(0.0), ct.c_longlong(0)
+        st = (ct.c_float * 2)()
+        self._lib.rirb_ecc_track_state(self._h, ct.byref(m), ct.byref(th), st, ct.byref(n))
+        self.median = 1 if m.value == 1.0 else m.value
+        self.conf_thresh = None if np.isnan(th.value) else th.value
+        self.start_mat = np.eye(2, 3, dtype=np.float32)
+        self.start_mat[0, 2], self.start_mat[1, 2] = st[0], st[1]
+
+    # ---- the reference's interface ----------------------------------------------------------------------
+    def start(self, img):
+        if self._started:
+            raise RuntimeError("MaskedRegistratorECC.start: already started")
+        self._track(img, 0)
 
     def compute(self, img):
         if not self._started:
             raise RuntimeError("MaskedRegistratorECC.compute: call start() with the first image")
-        if self.pre_process is not None:
-            img = self.pre_process(img)
-        g = self._filtered(img)
-        self._set(1, g, self.startX, self.startY)
-        use_mask = 1 if self.mask is not None else 0
-        thresh = float("inf")
-        if self.median < 1:
-            if self._fixed_ref:
-                raise NotImplementedError("median < 1 together with a fixed `ref` image")
-            t1 = _lib.check(self._lib.rirb_ecc_quantile(self._h, 1, float(self.median), use_mask), "ecc_quantile")
-            t2 = _lib.check(self._lib.rirb_ecc_quantile(self._h, 0, float(self.median), use_mask), "ecc_quantile")
-            thresh = float(max(t1, t2))
-        shift = np.array([self.start_mat[0, 2], self.start_mat[1, 2]], dtype=np.float32)
-        rho, its = ct.c_double(0.0), ct.c_int(0)
-        status = self._lib.rirb_ecc_compute(self._h, thresh, use_mask, 500, 1e-3, shift.ctypes.data_as(ct.c_void_p), ct.byref(rho),
-                                            ct.byref(its))
-        if status < 0:
-            raise RuntimeError(f"An error occured while calling 'ecc_compute': {_lib.last_error()}")
-        if status > 0:
-            raise ECCError(_MESSAGES.get(status, "findTransformECC failed"))
-        warp_matrix = np.eye(2, 3, dtype=np.float32)
-        warp_matrix[0, 2], warp_matrix[1, 2] = shift[0], shift[1]
-        self.start_mat = warp_matrix
-        shift = [warp_matrix[1, 2], warp_matrix[0, 2]]
-        confidence = rho.value
-        self.iterations.append(its.value)
-        self.confidences.append(confidence)
-        self.x.append(shift[1])
-        self.y.append(shift[0])
-        if len(self.confidences) > 20 and not self._fixed_ref:
-            if self.conf_thresh is None:
-                self.conf_thresh = np.min(self.confidences) - 2 * np.std(self.confidences)
-            if confidence < self.conf_thresh:
-                _lib.check(self._lib.rirb_ecc_reset_reference(self._h, float(-shift[1]), float(-shift[0])), "ecc_reset_reference")
-                self.start_mat = np.eye(2, 3, dtype=np.float32)
-        return shift
+        self._track(img, 0)
+        return [self.y[-1], self.x[-1]]
+
+    def compute_movie(self, frames, max_try=5):
+        """All of ``frames`` ([n, h, w], numpy or torch CUDA) in one call: start() on the first frame if the object is new,
+        then manage_computation_and_tries for every other frame (``max_try=0``: plain compute(), raising on a failure)."""
+        return self._track(frames, max_try)
 
     def append_last_coordinates_and_confidence(self):
         self.x.append(self.x[-1])
@@ -216,18 +250,6 @@ class MaskedRegistratorECC:
 
 def manage_computation_and_tries(img, regis_obj: MaskedRegistratorECC):
     """masked_registration_ecc.py:229-260: up to five tries with the median lowered by 0.01 each time, then the previous
-    estimate."""
-    nb_try = 0
-    max_try = 5
-    compute = False
-    while nb_try < max_try and not compute:
-        try:
-            regis_obj.compute(img)
-            compute = True
-            regis_obj.median = 1 if regis_obj.median < 1 else regis_obj.median
-        except ECCError:
-            regis_obj.median -= 0.01
-            nb_try += 1
-    if nb_try >= max_try:
-        regis_obj.append_last_coordinates_and_confidence()
+    estimate; a median < 1 goes back to 1 after a success."""
+    regis_obj._track(img, 5)
     return regis_obj

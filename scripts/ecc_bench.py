@@ -76,6 +76,21 @@ def main():
             extra["max_abs_diff_vs_reference_px_all"] = float(np.max(d))
             extra["first_reset_frame"] = first_reset
         rec(name, el, extra)
+    # the whole movie in one call: the tracking loop stays inside the library
+    d = torch.from_numpy(mov.view(np.int16)).cuda().view(torch.uint16)
+    for name, frames in (("product, one call for the movie, numpy frames", mov), ("product, one call for the movie, frames in HBM", d)):
+        for rep in range(2):
+            reg = rg.MaskedRegistratorECC()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reg.compute_movie(frames, max_try=5)
+            el = time.perf_counter() - t0
+        extra = {"mean_iterations": round(float(np.mean([i for i in reg.iterations if i > 0])), 2)}
+        if ref_xy is not None:
+            k = ref_xy.shape[1]
+            dd = np.abs(np.array([reg.x[:k], reg.y[:k]], dtype=np.float64) - ref_xy)
+            extra["max_abs_diff_vs_reference_px_before_first_reset"] = float(np.max(dd[:, :first_reset + 1]))
+        rec(name, el, extra)
 
 
 if __name__ == "__main__":

@@ -129,8 +129,17 @@ def _solve(lib, t, i, tx0=0.0, ty0=0.0, mask=None, iters=500):
         lib.rirb_ecc_close(hd)
 
 
+@pytest.fixture(params=["one cooperative launch", "launch per iteration"])
+def ecc_driver(request):
+    from librir_b200 import _lib
+
+    _lib.set_parameter("ecc_fused", request.param == "one cooperative launch")
+    yield request.param
+    _lib.set_parameter("ecc_fused", 1)
+
+
 @pytest.mark.gpu
-def test_product_solver_matches_port_and_cv2():
+def test_product_solver_matches_port_and_cv2(ecc_driver):
     from librir_b200 import _lib
 
     lib = _lib.load()
@@ -166,7 +175,7 @@ def test_product_solver_matches_port_and_cv2():
 
 
 @pytest.mark.gpu
-def test_product_class_matches_port_and_reference_golden():
+def test_product_class_matches_port_and_reference_golden(ecc_driver):
     from librir_b200 import registration as rg
 
     mov, sx, sy = ec.movie(30)
@@ -178,6 +187,16 @@ def test_product_class_matches_port_and_reference_golden():
     assert reg.iterations == port.iterations
     _close(a, GOLD["seq_default"], SHIFT_TOL_CV2, RHO_TOL_CV2)
     assert np.array(reg.stabilisation_data).shape == (30, 3)
+    # the whole movie in one call (frames in HBM) gives the same numbers as frame-by-frame calls
+    import torch
+
+    whole = rg.MaskedRegistratorECC()
+    assert whole.compute_movie(torch.from_numpy(mov.view(np.int16)).cuda().view(torch.uint16), max_try=0) == 30
+    assert np.array_equal(np.array([whole.x, whole.y, whole.confidences], dtype=np.float64), a) and whole.iterations == reg.iterations
+    half = rg.MaskedRegistratorECC()  # and so does any split into several calls, numpy or torch
+    half.compute_movie(mov[:7])
+    half.compute_movie(mov[7:])
+    assert np.array_equal(np.array([half.x, half.y, half.confidences], dtype=np.float64), a)
     static = np.ones(mov[0].shape, np.uint8)
     static[:, :140] = 0
     a = _run(rg.MaskedRegistratorECC(mask=static, median=0.9), mov, 16)
