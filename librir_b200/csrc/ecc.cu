@@ -13,13 +13,15 @@
 //       float weights, so the warp is a 4-tap stencil with launch-constant weights, evaluated on the fly;
 //   meanStdDev x2, subtract x2, 7 dot products over full images   -> ONE pass that accumulates 15 raw sums in fp64
 //       (products of two floats are exact in fp64) from which every masked, zero-meaned quantity follows
-//       algebraically; no intermediate image is ever written;
-//   2x2 inverse, lambda, parameter update                         -> the last CTA to finish does it (one thread, same
-//       float / double types as OpenCV's Mats) and publishes the new shift, rho and the stop flag in device memory.
-// The host enqueues a few iteration launches back to back (a finished problem makes the remaining ones return at
-// once) and reads the 40-byte result back; nothing else crosses PCIe per frame.
+//       algebraically; no intermediate image is ever written; per-CTA partial sums are added in a fixed order (no
+//       atomics), so results are reproducible bit for bit;
+//   2x2 inverse, lambda, parameter update                         -> one thread, in the float / double types of OpenCV's
+//       Mats.
+// The whole solve (min/max, normalisation + gradients, all iterations) is ONE cooperative launch with grid barriers
+// between the phases (ecc_solve_kernel); a launch-per-iteration driver (ecc_iter_kernel, "last CTA done" epilogue) is
+// the fallback.  The host reads 40 bytes back per frame; nothing else crosses PCIe.
 // Traffic per iteration: template, image, two gradients (float) + mask, all L2-resident (3 MB at 448 x 358): the loop
-// is bound by launch latency, not by memory.
+// is bound by launch / barrier latency, not by memory.
 #include <cooperative_groups.h>
 #include <math.h>
 #include <string.h>
@@ -38,7 +40,6 @@ namespace rirb {
 enum { A_N, A_I, A_T, A_II, A_TT, A_IT, A_H11, A_H12, A_H22, A_B1, A_B2, A_C1, A_C2, A_D1, A_D2, NACC };
 
 struct EccDev {
-    double acc[NACC];
     double rho, last_rho, eps;
     unsigned ticket;
     unsigned mm[4];  // order-preserving keys: template min, max, image min, max
@@ -67,7 +68,6 @@ __device__ __forceinline__ float clamp_pair(float own, float other, float th) { 
 
 __global__ void ecc_begin_kernel(EccDev* d, float tx, float ty, int max_it, double eps)
 {
-    for (int i = 0; i < NACC; ++i) d->acc[i] = 0.0;
     d->ticket = 0;
     d->mm[0] = d->mm[2] = 0xFFFFFFFFu;
     d->mm[1] = d->mm[3] = 0u;
@@ -464,7 +464,14 @@ struct EccState {
     double median = 1.0, conf_thresh = 0.0, last_x = 0.0, last_y = 0.0, last_conf = 1.0;
     float start[2] = {0.f, 0.f};  // warp_matrix[0,2], warp_matrix[1,2]: the warm start of the next frame
     std::vector<double> confs;
-    void* stage = nullptr;        // one full frame uploaded from the host
+    EccDev* result = nullptr;     // pinned host copy of the device state
+    int launched = 0;             // iteration launches enqueued for the solve in flight
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    void* pinned[2] = {nullptr, nullptr};  // host frames: pinned staging ...
+    void* stage2[2] = {nullptr, nullptr};  // ... and their device copies (double-buffered)
+    size_t pin_cap[2] = {0, 0};
+    void* stage = nullptr;        // (unused since the prefetch path)
     float* filtered = nullptr;    // one full frame, Gaussian-filtered / converted to float
     size_t stage_cap = 0, filtered_cap = 0;
     std::recursive_mutex mu;
@@ -473,6 +480,13 @@ struct EccState {
         void* ptrs[] = {ref, cur, T, I, gx, gy, mask, qmask, q16, hist, mm, qout, d, partials, stage, filtered};
         for (void* p : ptrs)
             if (p) cudaFree(p);
+        for (int i = 0; i < 2; ++i) {
+            if (stage2[i]) cudaFree(stage2[i]);
+            if (pinned[i]) cudaFreeHost(pinned[i]);
+            if (copied[i]) cudaEventDestroy(copied[i]);
+        }
+        if (result) cudaFreeHost(result);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 };
 static Table<EccState> g_ecc;
@@ -505,6 +519,90 @@ static int ecc_load_window(EccState& s, float* dst, const float* src, int stride
         return -1;
     }
     RIRB_CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)s.w * 4, src, (size_t)stride * 4, (size_t)s.w * 4, (size_t)s.h, cudaMemcpyDefault, st));
+    return 0;
+}
+
+// The solve in two halves, so that a caller can do host work (fetching the next frame) while the GPU is busy.
+// enqueue: everything up to and including the copy of the result towards the host; collect: wait, and for the
+// launch-per-iteration driver keep launching until the problem reports done.
+static int ecc_enqueue(EccState& s, float thresh, int use_mask, int max_iterations, double eps, const float* shift)
+{
+    cudaStream_t st = current_stream();
+    const int n = s.w * s.h;
+    const float th = isnan(thresh) ? INFINITY : thresh;
+    const u8* mask = (use_mask && s.have_mask) ? s.mask : nullptr;
+    if (!s.result) RIRB_CUDA_OK(cudaMallocHost((void**)&s.result, sizeof(EccDev)));  // pinned: the copy back does not stall the host
+    RIRB_LAUNCH(ecc_begin_kernel, 1, 1, 0, st, s.d, shift[0], shift[1], max_iterations, eps);
+    s.launched = 0;
+    if (s.coop_grid > 0 && option_enabled(OPT_ECC_FUSED)) {
+        // the whole solve in one cooperative launch ("ecc_fused" = 0 selects the launch-per-iteration driver)
+        const float* ref = s.ref;
+        const float* cur = s.cur;
+        int w = s.w, h = s.h;
+        float th_arg = th, tx0 = shift[0], ty0 = shift[1];
+        void* args[] = {&ref, &cur, &mask, &w, &h, &th_arg, &s.T, &s.I, &s.gx, &s.gy, &s.d, &s.partials, &tx0, &ty0, &max_iterations, &eps};
+        RIRB_CUDA_OK(cudaLaunchCooperativeKernel((const void*)ecc_solve_kernel, dim3((unsigned)s.coop_grid), dim3(ECC_THREADS), args, 0, st));
+        g_launches.fetch_add(1);
+        s.launched = max_iterations;
+    } else {
+        const int blocks = (int)min((long long)ceil_div(n, ECC_THREADS), (long long)s.max_grid);
+        RIRB_LAUNCH(ecc_minmax_kernel, (unsigned)blocks, ECC_THREADS, 0, st, s.ref, s.cur, n, th, s.d);
+        RIRB_LAUNCH(ecc_normalise_kernel, dim3((unsigned)ceil_div(s.w, ECC_THREADS), (unsigned)s.h), ECC_THREADS, 0, st, s.ref, s.cur, mask,
+                    s.w, s.h, th, s.d, s.T, s.I, s.gx, s.gy);
+        const int burst = min(4, max_iterations);  // a converged problem turns the rest into no-ops
+        for (int k = 0; k < burst; ++k)
+            RIRB_LAUNCH(ecc_iter_kernel, (unsigned)blocks, ECC_THREADS, 0, st, s.T, s.I, s.gx, s.gy, mask, s.w, s.h, s.d, s.partials);
+        s.launched = burst;
+    }
+    RIRB_CUDA_OK(cudaMemcpyAsync(s.result, s.d, sizeof(EccDev), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+static int ecc_collect(EccState& s, int use_mask, int max_iterations, float* shift, double* rho, int* iterations)
+{
+    cudaStream_t st = current_stream();
+    const u8* mask = (use_mask && s.have_mask) ? s.mask : nullptr;
+    RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    while (!s.result->done && s.launched < max_iterations) {  // launch-per-iteration driver only
+        const int blocks = (int)min((long long)ceil_div(s.w * s.h, ECC_THREADS), (long long)s.max_grid);
+        const int burst = min(12, max_iterations - s.launched);
+        for (int k = 0; k < burst; ++k)
+            RIRB_LAUNCH(ecc_iter_kernel, (unsigned)blocks, ECC_THREADS, 0, st, s.T, s.I, s.gx, s.gy, mask, s.w, s.h, s.d, s.partials);
+        s.launched += burst;
+        RIRB_CUDA_OK(cudaMemcpyAsync(s.result, s.d, sizeof(EccDev), cudaMemcpyDeviceToHost, st));
+        RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    const EccDev& r = *s.result;
+    if (iterations) *iterations = r.it;
+    if (rho) *rho = r.rho;
+    if (r.status == 0) {
+        shift[0] = r.tx;
+        shift[1] = r.ty;
+    }
+    return r.status;
+}
+
+// Frames that live in host memory: frame t + 1 is copied into a pinned buffer and sent on its own stream while the GPU
+// solves frame t (two buffers, two events).
+static int ecc_prefetch(EccState& s, const void* src, size_t bytes, int slot)
+{
+    if (!s.copy_stream) {
+        RIRB_CUDA_OK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) RIRB_CUDA_OK(cudaEventCreateWithFlags(&s.copied[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 2; ++i)
+        if (s.pin_cap[i] < bytes) {
+            if (s.pinned[i]) cudaFreeHost(s.pinned[i]);
+            if (s.stage2[i]) cudaFree(s.stage2[i]);
+            s.pinned[i] = s.stage2[i] = nullptr;
+            s.pin_cap[i] = 0;
+            RIRB_CUDA_OK(cudaMallocHost(&s.pinned[i], bytes));
+            RIRB_CUDA_OK(cudaMalloc(&s.stage2[i], bytes));
+            s.pin_cap[i] = bytes;
+        }
+    memcpy(s.pinned[slot], src, bytes);
+    RIRB_CUDA_OK(cudaMemcpyAsync(s.stage2[slot], s.pinned[slot], bytes, cudaMemcpyHostToDevice, s.copy_stream));
+    RIRB_CUDA_OK(cudaEventRecord(s.copied[slot], s.copy_stream));
     return 0;
 }
 
@@ -636,59 +734,8 @@ int rirb_ecc_compute(int handle, float thresh, int use_mask, int max_iterations,
         return -1;
     }
     std::lock_guard<std::recursive_mutex> lock(s->mu);
-    cudaStream_t st = current_stream();
-    const int n = s->w * s->h;
-    const float th = isnan(thresh) ? INFINITY : thresh;
-    const u8* mask = (use_mask && s->have_mask) ? s->mask : nullptr;
-    RIRB_LAUNCH(ecc_begin_kernel, 1, 1, 0, st, s->d, shift[0], shift[1], max_iterations, eps);
-    EccResult r;
-    memset(&r, 0, sizeof(r));
-    EccDev hd;
-    if (s->coop_grid > 0 && option_enabled(OPT_ECC_FUSED)) {
-        // the whole solve in one cooperative launch ("ecc_fused" = 0 selects the launch-per-iteration driver)
-        const float* ref = s->ref;
-        const float* cur = s->cur;
-        int w = s->w, h = s->h;
-        float th_arg = th, tx0 = shift[0], ty0 = shift[1];
-        void* args[] = {&ref, &cur, &mask, &w, &h, &th_arg, &s->T, &s->I, &s->gx, &s->gy, &s->d, &s->partials, &tx0, &ty0, &max_iterations, &eps};
-        RIRB_CUDA_OK(cudaLaunchCooperativeKernel((const void*)ecc_solve_kernel, dim3((unsigned)s->coop_grid), dim3(ECC_THREADS), args, 0, st));
-        g_launches.fetch_add(1);
-        RIRB_CUDA_OK(cudaMemcpyAsync(&hd, s->d, sizeof(EccDev), cudaMemcpyDeviceToHost, st));
-        RIRB_CUDA_OK(cudaStreamSynchronize(st));
-        r.rho = hd.rho;
-        r.tx = hd.tx;
-        r.ty = hd.ty;
-        r.it = hd.it;
-        r.done = hd.done;
-        r.status = hd.status;
-    } else {
-        const int blocks = (int)min((long long)ceil_div(n, ECC_THREADS), (long long)s->max_grid);
-        RIRB_LAUNCH(ecc_minmax_kernel, (unsigned)blocks, ECC_THREADS, 0, st, s->ref, s->cur, n, th, s->d);
-        RIRB_LAUNCH(ecc_normalise_kernel, dim3((unsigned)ceil_div(s->w, ECC_THREADS), (unsigned)s->h), ECC_THREADS, 0, st, s->ref, s->cur,
-                    mask, s->w, s->h, th, s->d, s->T, s->I, s->gx, s->gy);
-        int launched = 0;
-        while (!r.done && launched < max_iterations) {
-            const int burst = min(launched == 0 ? 4 : 12, max_iterations - launched);  // a converged problem turns the rest into no-ops
-            for (int k = 0; k < burst; ++k)
-                RIRB_LAUNCH(ecc_iter_kernel, (unsigned)blocks, ECC_THREADS, 0, st, s->T, s->I, s->gx, s->gy, mask, s->w, s->h, s->d, s->partials);
-            launched += burst;
-            RIRB_CUDA_OK(cudaMemcpyAsync(&hd, s->d, sizeof(EccDev), cudaMemcpyDeviceToHost, st));
-            RIRB_CUDA_OK(cudaStreamSynchronize(st));
-            r.rho = hd.rho;
-            r.tx = hd.tx;
-            r.ty = hd.ty;
-            r.it = hd.it;
-            r.done = hd.done;
-            r.status = hd.status;
-        }
-    }
-    if (iterations) *iterations = r.it;
-    if (rho) *rho = r.rho;
-    if (r.status == 0) {
-        shift[0] = r.tx;
-        shift[1] = r.ty;
-    }
-    return r.status;
+    if (ecc_enqueue(*s, thresh, use_mask, max_iterations, eps, shift) != 0) return -1;
+    return ecc_collect(*s, use_mask, max_iterations, shift, rho, iterations);
 }
 
 // ---- the tracking loop of MaskedRegistratorECC, frame after frame, without leaving the library ---------------------
@@ -772,13 +819,7 @@ int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, 
     cudaStream_t st = current_stream();
     const size_t fpx = (size_t)full_w * full_h, esz = type == 'H' ? 2 : 4;
     const bool on_device = is_device_pointer(frames);
-    if (!on_device && s->stage_cap < fpx * esz) {
-        if (s->stage) cudaFree(s->stage);
-        s->stage = nullptr;
-        s->stage_cap = 0;
-        RIRB_CUDA_OK(cudaMalloc(&s->stage, fpx * esz));
-        s->stage_cap = fpx * esz;
-    }
+    if (!on_device && nframes > 0 && ecc_prefetch(*s, frames, fpx * esz, 0) != 0) return -1;
     if (s->filtered_cap < fpx * 4) {
         if (s->filtered) cudaFree(s->filtered);
         s->filtered = nullptr;
@@ -790,9 +831,15 @@ int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, 
     if (s->sigma > 0.f && gaussian_taps_host(s->sigma, &taps) != 0) return -1;
     for (long long t = 0; t < nframes; ++t) {
         const char* src = (const char*)frames + (size_t)t * fpx * esz;
+        bool next_fetched = on_device || t + 1 >= nframes;
+        auto fetch_next = [&]() -> int {  // called once per frame, as soon as the GPU has work queued
+            if (next_fetched) return 0;
+            next_fetched = true;
+            return ecc_prefetch(*s, (const char*)frames + (size_t)(t + 1) * fpx * esz, fpx * esz, (int)((t + 1) & 1));
+        };
         if (!on_device) {
-            RIRB_CUDA_OK(cudaMemcpyAsync(s->stage, src, fpx * esz, cudaMemcpyHostToDevice, st));
-            src = (const char*)s->stage;
+            RIRB_CUDA_OK(cudaStreamWaitEvent(st, s->copied[t & 1], 0));
+            src = (const char*)s->stage2[t & 1];
         }
         const float* full = s->filtered;
         if (s->sigma > 0.f) {
@@ -814,6 +861,8 @@ int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, 
             conf[t] = 1.0;
             if (iters) iters[t] = 0;
             if (processed) *processed = t + 1;
+            if (fetch_next() != 0) return -1;
+            RIRB_CUDA_OK(cudaStreamSynchronize(st));  // the staged frame is free again
             continue;
         }
         if (ecc_load_window(*s, s->cur, window, full_w, st) != 0) return -1;
@@ -831,7 +880,9 @@ int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, 
             }
             shift[0] = s->start[0];
             shift[1] = s->start[1];
-            status = rirb_ecc_compute(handle, thresh, use_mask, 500, 1e-3, shift, &rho, &its);
+            if (ecc_enqueue(*s, thresh, use_mask, 500, 1e-3, shift) != 0) return -1;
+            if (fetch_next() != 0) return -1;  // host memcpy + upload of frame t + 1 while the GPU solves frame t
+            status = ecc_collect(*s, use_mask, 500, shift, &rho, &its);
             if (status < 0) return -1;
             if (status == 0) {
                 if (max_try > 0 && s->median < 1.0) s->median = 1.0;

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 TAG="${TAG:-r1}"
 ECC="python scripts/ecc_bench.py --frames 40"
 $ECC > gpurun_out/ecc_plain_${TAG}.jsonl 2> gpurun_out/ecc_plain_${TAG}.err &&
-ncu --set full --clock-control none --import-source on -k "regex:ecc_iter_kernel|ecc_normalise_kernel|ecc_minmax_kernel" -s 300 -c 8 -f \
+ncu --set full --clock-control none --import-source on -k "regex:ecc_solve_kernel|ecc_iter_kernel" -s 60 -c 4 -f \
     -o gpurun_out/prof_ecc_${TAG} $ECC > gpurun_out/ncu_ecc_${TAG}.log 2>&1
 echo "ecc capture rc=$?"
 tail -2 gpurun_out/ncu_ecc_${TAG}.log

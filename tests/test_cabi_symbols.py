@@ -68,6 +68,15 @@ def test_no_gpu_means_failure_not_fallback():
         with pytest.raises(RuntimeError) as e:
             call()
         assert "no CPU fallback" in str(e.value) or "no usable CUDA device" in str(e.value)
+    # the registration front end and the lossy pre-conditioner refuse to open
+    lib = _lib.load()
+    assert lib.rirb_ecc_open(448, 358) == 0 and "no CPU fallback" in _lib.last_error()
+    from librir_b200 import registration
+
+    with pytest.raises(RuntimeError) as e:
+        registration.MaskedRegistratorECC()
+    assert "no CPU fallback" in str(e.value)
+    assert lib.rirb_lossy_open(64, 48, 45, 6, 2, 5.0, 32, 0, 0) == 0 and "no" in _lib.last_error()
 
 
 def test_argument_errors_match_reference_conventions():
