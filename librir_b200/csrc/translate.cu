@@ -56,10 +56,20 @@ __device__ __forceinline__ double blend4(double p1, double p2, double p3, double
 }
 
 // Source accessors: where translate_pixel reads src[row][col] from.
+// The reference indexes the image flat, src[col + row * w], and its in-range branch can produce col = w + 1 or
+// row = h + 1: when px (py) lies within half a float ulp below w (h), px + 1.0f rounds UP to the next integer, the
+// `rt == w` clamp does not fire, and Filters.h:300-310 reads one pixel into the next row -- or, on the last row(s),
+// past the end of the buffer (undefined there).  Every accessor keeps the flat meaning (so the defined cases match
+// the reference bit for bit) and clamps the index to the frame's last pixel (so the undefined ones stay in bounds).
 template <typename T> struct GlobalSrc {
     const T* __restrict__ p;
     int w;
-    __device__ __forceinline__ T operator()(long long row, long long col) const { return p[row * w + col]; }
+    long long npx;  // w * h
+    __device__ __forceinline__ T operator()(long long row, long long col) const
+    {
+        const long long i = row * w + col;
+        return p[i < npx ? i : npx - 1];
+    }
 };
 
 // One destination pixel, any strategy.  Returns false when dst must be left untouched.
@@ -112,7 +122,7 @@ template <typename T, typename U>
 __device__ __forceinline__ bool translate_pixel(const T* __restrict__ src, int w, int h, int x, int y, float dx, float dy,
                                                 int strategy, U background, U& result)
 {
-    return translate_pixel<T, U>(GlobalSrc<T>{src, w}, w, h, x, y, dx, dy, strategy, background, result);
+    return translate_pixel<T, U>(GlobalSrc<T>{src, w, (long long)w * h}, w, h, x, y, dx, dy, strategy, background, result);
 }
 
 template <typename T>
@@ -378,12 +388,14 @@ __device__ __forceinline__ void blend_group(uint32_t rowb, uint32_t rowt, unsign
 struct TileSrc {
     const u16* tile;  // [TT_BH][TT_BW], box origin (xs, ys)
     const u16* __restrict__ frame;
-    int xs, ys, w;
+    int xs, ys, w, h;
     __device__ __forceinline__ u16 operator()(long long row, long long col) const
     {
         const long long r = row - ys, c = col - xs;
-        if (r >= 0 && r < TT_BH && c >= 0 && c < TT_BW) return tile[r * TT_BW + c];
-        return frame[row * w + col];
+        // col >= w / row >= h: the flat index of GlobalSrc (the box holds the hardware's zero fill there)
+        if (col < w && row < h && r >= 0 && r < TT_BH && c >= 0 && c < TT_BW) return tile[r * TT_BW + c];
+        const long long i = row * w + col, npx = (long long)w * h;
+        return frame[i < npx ? i : npx - 1];
     }
 };
 
@@ -559,8 +571,11 @@ struct PlaneTileSrc {
     __device__ __forceinline__ u16 operator()(long long row, long long col) const
     {
         const long long r = row - ys, c = col - xs;
-        if (r >= 0 && r < TT_BH && c >= 0 && c < TT_BW) return tile[r * TT_BW + c];
-        return (u16)plane_corrected_px(lo, hi, w, h, (int)col, (int)row, *ps);
+        if (col < w && row < h && r >= 0 && r < TT_BH && c >= 0 && c < TT_BW) return tile[r * TT_BW + c];
+        long long i = row * w + col;  // flat meaning, clamped to the image (see GlobalSrc)
+        const long long npx = (long long)w * h;
+        i = i < npx ? i : npx - 1;
+        return (u16)plane_corrected_px(lo, hi, w, h, (int)(i % w), (int)(i / w), *ps);
     }
 };
 
@@ -745,7 +760,7 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                 float r;
                 if (translate_pixel<u16, float>(ts, w, h, gx, gy, dx, dy, strategy, (float)background, r)) *o = (u16)r;
             } else {
-                const TileSrc ts{tile, frame, xs, ys, w};
+                const TileSrc ts{tile, frame, xs, ys, w, h};
                 if (MOTION) {
                     float r;
                     if (translate_pixel<u16, float>(ts, w, h, gx, gy, dx, dy, strategy, (float)background, r)) *o = (u16)r;

@@ -273,6 +273,7 @@ static inline uint64_t wrap_idx(uint64_t v, uint64_t n) { return (v + n) % n; }
 
 /* One generic body; T = storage type, U = destination type, TODBL converts a pixel to the
  * double it is promoted to in the blend, CAST is detail::cast<U> (Filters.h:232-235). */
+#define ORC_FLAT(i) ((i) < w * h ? (i) : w * h - 1)
 #define ORC_DEFINE_TRANSLATE(NAME, T, U, CAST)                                                 \
     static void NAME(const T *src, U *dst, U background, size_t w, size_t h, float dx,        \
                      float dy, int strategy)                                                   \
@@ -312,8 +313,11 @@ static inline uint64_t wrap_idx(uint64_t v, uint64_t n) { return (v + n) % n; }
                     u = (double)(px - (float)l);                                               \
                     v = (double)((float)b - py);                                               \
                 }                                                                              \
-                double p1 = (double)src[b * w + l], p2 = (double)src[t * w + l];               \
-                double p3 = (double)src[b * w + rt], p4 = (double)src[t * w + rt];             \
+                /* px (py) within half a float ulp below w (h): px + 1 rounds up to w + 1, the clamp above does   \
+                 * not fire and the reference reads into the next row -- or past the buffer on the last row(s),  \
+                 * which is undefined; there this restatement (and the CUDA path) reads the last pixel. */         \
+                double p1 = (double)src[ORC_FLAT(b * w + l)], p2 = (double)src[ORC_FLAT(t * w + l)];               \
+                double p3 = (double)src[ORC_FLAT(b * w + rt)], p4 = (double)src[ORC_FLAT(t * w + rt)];             \
                 double val = (p1 * (1 - v) + p2 * v) * (1 - u) + (p3 * (1 - v) + p4 * v) * u;  \
                 dst[x + y * w] = CAST(val);                                                    \
             }                                                                                  \

@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star): bit-exact for bad pixels, pre-coder, statistics
 the blend is evaluated in the reference's fp64 order, for integer translate as well (the
 allowed +-1 LSB is not used); 1e-5 relative (+1e-6*max floor) for float32 Gaussian output.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -29,6 +31,12 @@ def to_dev(a):
     if a.dtype == np.uint16:
         return torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
     return torch.from_numpy(a).cuda()
+
+
+# One-off fuzzing on the GPU box: RIRB_FUZZ_SEED shifts the seeds of the randomised tests, RIRB_FUZZ_SCALE multiplies
+# their case counts (defaults: the committed, deterministic cases).
+FUZZ_SEED = int(os.environ.get("RIRB_FUZZ_SEED", "0"))
+FUZZ_SCALE = max(1, int(os.environ.get("RIRB_FUZZ_SCALE", "1")))
 
 
 def rand_u16(shape, seed, high=16384):
@@ -150,12 +158,25 @@ def test_translate_u16_random_shifts_full_size(best):
             np.testing.assert_array_equal(got[t], best.translate(mov[t], dx[t], dy[t], "nearest", 0), err_msg=f"{h}x{w} frame {t}")
 
 
-def test_translate_u16_randomized(best):
+def reference_reads_past_the_buffer(h, w, dx, dy):
+    """Pixels for which the reference's in-range branch indexes past the end of the image (Filters.h:300-310 with
+    px + 1.0f or py + 1.0f rounded up beyond the clamp): undefined in the reference, last-pixel reads here."""
+    px = np.broadcast_to(np.arange(w, dtype=np.float32)[None, :] - np.float32(dx), (h, w))
+    py = np.broadcast_to(np.arange(h, dtype=np.float32)[:, None] - np.float32(dy), (h, w))
+    inr = (px >= 0) & (px < w) & (py >= 0) & (py < h)
+    rt = np.where(inr, px + np.float32(1), np.float32(0)).astype(np.int64)
+    b = np.where(inr, py + np.float32(1), np.float32(0)).astype(np.int64)
+    rt = np.where(rt == w, w - 1, rt)  # clamped onto l
+    b = np.where(b == h, h - 1, b)     # clamped onto t
+    return inr & (b * w + rt >= h * w)
+
+
+def test_translate_u16_randomized(best, port):
     """150 random (shape, shift, strategy) cases: widths on and off the TMA path, shifts from sub-ulp to beyond the
     image, exact integers, halves and values one float ulp away from an integer."""
-    rng = np.random.default_rng(2026)
+    rng = np.random.default_rng(2026 + FUZZ_SEED)
     specials = [0.0, 1.0, -1.0, 0.5, -0.5, 8.0, -8.0, 7.9999995, -7.9999995, 1.0000001, 127.5, -128.0, 1e-20, -1e-20, 0.25, 63.75]
-    for case in range(150):
+    for case in range(150 * FUZZ_SCALE):
         w = int(rng.choice([8, 16, 24, 40, 64, 96, 128, 136, 200, 264, 7, 33, 130]))
         h = int(rng.integers(1, 150))
         f = rng.integers(0, 65536, (h, w), dtype=np.uint16)
@@ -172,8 +193,36 @@ def test_translate_u16_randomized(best):
             return float(np.float32(rng.integers(-extent, extent + 1)) + np.float32(rng.choice([0, 2 ** -20, -2 ** -20, 0.5])))
         dx, dy = pick(w), pick(h)
         st = ["nearest", "background", "wrap", ""][case % 4]
-        np.testing.assert_array_equal(sp.translate(f, dx, dy, st, 321), best.translate(f, dx, dy, st, 321),
-                                      err_msg=f"case {case}: {h}x{w} {st!r} dx={dx!r} dy={dy!r}")
+        got, want = sp.translate(f, dx, dy, st, 321), best.translate(f, dx, dy, st, 321)
+        undefined = reference_reads_past_the_buffer(h, w, dx, dy)
+        if undefined.any():  # there the compiled reference returns whatever follows its buffer: the restatement decides
+            want = np.where(undefined, port.translate(f, dx, dy, st, 321), want)
+        np.testing.assert_array_equal(got, want, err_msg=f"case {case}: {h}x{w} {st!r} dx={dx!r} dy={dy!r}")
+
+
+@pytest.mark.parametrize("h,w,st,dx,dy", [
+    (46, 16, "nearest", -4.999999046325684, -14.0), (121, 8, "nearest", -7.9999995, 0.0),
+    (33, 16, "wrap", -6.999999046325684, -2.654136896133423), (40, 136, "background", -7.9999995, -15.999999),
+    (64, 128, "", 0.25, -31.999998), (70, 264, "nearest", -127.99999, -5.9999995), (9, 7, "nearest", -2.9999998, -3.9999998)])
+def test_translate_source_index_one_past_the_clamp(best, port, h, w, st, dx, dy):
+    """px (py) within half a float ulp below w (h): px + 1.0f rounds up to w + 1, the reference's `== w` clamp does not
+    fire and it reads the first pixels of the NEXT row (found by fuzzing: the staged box holds zeros there).  Defined
+    pixels must equal the compiled reference; the ones whose read leaves the buffer follow the restatement's clamp."""
+    rng = np.random.default_rng(h * 1000 + w)
+    f = rng.integers(0, 65536, (h, w), dtype=np.uint16)
+    undefined = reference_reads_past_the_buffer(h, w, dx, dy)
+    want = np.where(undefined, port.translate(f, dx, dy, st, 321), best.translate(f, dx, dy, st, 321))
+    np.testing.assert_array_equal(sp.translate(f, dx, dy, st, 321), want)
+    mov = np.stack([f, f[::-1].copy(), f])  # batched: every frame keeps its own "last pixel"
+    got = sp.translate_batch(mov, dx, dy, st, 321)
+    for k in range(3):
+        und_k = port.translate(mov[k], dx, dy, st, 321)
+        np.testing.assert_array_equal(got[k], np.where(undefined, und_k, best.translate(mov[k], dx, dy, st, 321)))
+    # the reader's motion variant takes the same route (u16 -> float -> u16)
+    moved = vio.remove_motion(mov, [-dx] * 3, [-dy] * 3, meta_rows=0)
+    for k in range(3):
+        want_k = port.loader_remove_motion(mov[k], -dx, -dy)
+        np.testing.assert_array_equal(moved[k][~undefined], want_k[~undefined])
 
 
 def test_translate_batch_per_frame_shifts_device(best):
@@ -255,8 +304,8 @@ def test_gaussian_tiled_shapes_u16_and_f32(best, shape, sigma):
 
 def test_gaussian_randomized(best):
     """60 random (shape, sigma, dtype) cases through both input types."""
-    rng = np.random.default_rng(77)
-    for case in range(60):
+    rng = np.random.default_rng(77 + FUZZ_SEED)
+    for case in range(60 * FUZZ_SCALE):
         w = int(rng.choice([8, 12, 16, 40, 64, 128, 132, 136, 200, 264, 7, 33]))
         h = int(rng.integers(1, 140))
         sigma = float(rng.choice([0.3, 0.5, 0.8, 1.0, 1.3, 1.7, 2.0, 2.49, 3.1]))
