@@ -538,19 +538,23 @@ int bad_pixels_create(unsigned short* first_image, int width, int height)
             }
         }
     }
-    // sum of int squares, exact (the reference adds int products into a double, which stays
-    // exact below 2^53); beyond |d| >= 46341 the reference's int product overflows (UB)
-    unsigned long long ssum = 0;
+    // Sum of int squares (the reference adds int products into a double, which stays exact below 2^53).  For
+    // |d| >= 46341 -- a saturated 65535 pixel over an 8000-count background -- the reference's int product overflows:
+    // undefined in C++, a wrap modulo 2^32 in every x86-64 build of it (oracle/_ref agrees on 300 extreme frames).
+    // Real movies contain such pixels, so the wrap is reproduced, as are the x86 float->integer conversions below.
+    long long ssum = 0;
     for (int v = 0; v < 65536; ++v) {
-        long long d = (long long)v - median;
-        ssum += (unsigned long long)(d * d) * hist[v];
+        const int d = v - median;
+        ssum += (long long)(int)((unsigned)d * (unsigned)d) * (long long)hist[v];
     }
-    double gstd = sqrt((double)ssum / (double)(int)n);
+    const double gstd = sqrt((double)ssum / (double)(int)n);  // NaN when the wrapped sum is negative
     const double std_factor = 5.0;
-    double cutd = gstd * std_factor;
-    unsigned cut = cutd >= 65535.0 ? 65535u : (unsigned)cutd;  // (T)(double) truncation
-    unsigned gthr = ((unsigned)median > cut) ? (unsigned)median - cut : 0u;
-    int clamp_value = median - (int)(gstd * 2);
+    const double cutd = gstd * std_factor;
+    // (unsigned short)(double): cvttsd2si to a 32-bit int, low 16 bits kept; NaN / out of int range -> 0x80000000 -> 0
+    const unsigned cut = (cutd > -2147483649.0 && cutd < 2147483648.0) ? ((unsigned)(int)cutd & 0xFFFFu) : 0u;
+    const unsigned gthr = ((unsigned)median > cut) ? (unsigned)median - cut : 0u;
+    const double twice = gstd * 2;
+    const int clamp_value = (twice > -2147483649.0 && twice < 2147483648.0) ? median - (int)twice : -1;  // <= 0: no clamp
 
     auto state = std::make_shared<BadPixelState>();
     state->w = width;

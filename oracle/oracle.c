@@ -56,8 +56,30 @@ static u16 kth_smallest(u16 *v, int n, int k)
 
 /* Frame median (upper median, sorted[N/2]) and the spread around it as the reference
  * computes them: Filters.h:145-156 and BadPixels.cpp:19-30.  The squared difference is an
- * int product there; it is exact here as long as |p - median| < 46341 (the reference
- * overflows beyond that). */
+ * int product there: for |p - median| >= 46341 -- a saturated pixel at 65535 over an 8000-count
+ * background is enough -- it overflows, which is undefined in C++ and wraps modulo 2^32 in the
+ * reference as every x86-64 compiler builds it (checked against oracle/_ref).  Real movies have such
+ * pixels, so the wrap is part of the behaviour to reproduce; it is written out with unsigned
+ * arithmetic here so that this file itself has no undefined behaviour. */
+/* (unsigned short)(double) as x86-64 evaluates it (cvttsd2si to a 32-bit int, low 16 bits kept; NaN and
+ * values beyond int range give the "integer indefinite" 0x80000000, whose low half is 0): defined for the
+ * in-range values real frames produce, and spelled out for the rest instead of left undefined. */
+static u16 orc_trunc_u16(double v)
+{
+    if (!(v > -2147483649.0 && v < 2147483648.0))
+        return 0;
+    return (u16)(unsigned)(int)v;
+}
+/* median - (int)(2 * std) with the same conversion rule; a NaN spread (negative wrapped sum) makes the
+ * reference's result negative in practice, i.e. "no clamp". */
+static int orc_clamp_value(int median, double gstd)
+{
+    double v = gstd * 2;
+    if (!(v > -2147483649.0 && v < 2147483648.0))
+        return -1;
+    return median - (int)v;
+}
+
 static void frame_median_std(const u16 *img, size_t n, int *median, double *std_out)
 {
     u16 *tmp = (u16 *)malloc(n * sizeof(u16));
@@ -67,7 +89,7 @@ static void frame_median_std(const u16 *img, size_t n, int *median, double *std_
     double sum = 0;
     for (size_t i = 0; i < n; ++i) {
         int d = (int)tmp[i] - m;
-        sum += (double)(d * d);
+        sum += (double)(int)((unsigned)d * (unsigned)d);
     }
     free(tmp);
     sum /= (double)(int)n;
@@ -89,7 +111,7 @@ ORC_API int orc_bad_pixels_detect(const u16 *img, int w, int h, double std_facto
     int median;
     double gstd;
     frame_median_std(img, n, &median, &gstd);
-    u16 cut = (u16)(gstd * std_factor); /* (T)(double): truncation, Filters.h:157 */
+    u16 cut = orc_trunc_u16(gstd * std_factor); /* (T)(double): truncation, Filters.h:157 */
     u16 gthr = ((u16)median > cut) ? (u16)(median - cut) : 0;
     if (global_thr)
         *global_thr = gthr;
@@ -133,7 +155,7 @@ ORC_API int orc_bad_pixels_clamp_value(const u16 *img, int w, int h)
     int median;
     double gstd;
     frame_median_std(img, (size_t)w * (size_t)h, &median, &gstd);
-    return median - (int)(gstd * 2);
+    return orc_clamp_value(median, gstd);
 }
 
 /* ------------------------------------------------------------------------------------ */

@@ -1,0 +1,165 @@
+"""Randomised parity of the remaining entries (bad pixels, reader chain, pre-coder, statistics, lossy pre-conditioner)
+against the oracle, through the C ABI.  The committed case counts are small; on the GPU box
+``RIRB_FUZZ_SEED=<n> RIRB_FUZZ_SCALE=<k> pytest tests/test_gpu_fuzz.py -m gpu`` runs k times as many cases from other
+seeds (the translate / Gaussian fuzzers live in test_gpu_parity.py and take the same variables).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import ir_frame, ir_movie
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from librir_b200 import movie  # noqa: E402
+from librir_b200 import signal_processing as sp  # noqa: E402
+from librir_b200 import video_io as vio  # noqa: E402
+
+SEED = int(os.environ.get("RIRB_FUZZ_SEED", "0"))
+SCALE = max(1, int(os.environ.get("RIRB_FUZZ_SCALE", "1")))
+WIDTHS = [1, 2, 3, 5, 7, 8, 15, 16, 17, 24, 31, 32, 33, 40, 48, 63, 64, 65, 96, 127, 128, 129, 136, 144, 160, 200, 256, 264, 272]
+
+
+def to_dev(a):
+    return torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
+
+
+def random_frame(rng, h, w):
+    """Includes frames with pixels more than 46,340 counts from the median, where the reference's int product wraps
+    (the restatement and the library reproduce the x86-64 behaviour, pinned by tests/golden/bp_extreme_golden.npz)."""
+    kind = rng.integers(0, 4)
+    if kind == 0:
+        return rng.integers(0, 65536, (h, w), dtype=np.uint16)
+    if kind == 1:
+        return rng.integers(7000, 9000, (h, w), dtype=np.uint16)
+    f = ir_frame(h, w, int(rng.integers(0, 1 << 30))) if h >= 8 and w >= 8 else rng.integers(0, 16384, (h, w), dtype=np.uint16)
+    if kind == 3:  # clusters of stuck pixels, borders included
+        n = max(1, h * w // 30)
+        f = f.copy()
+        f.reshape(-1)[rng.choice(h * w, n, replace=False)] = rng.choice([0, 65535, 16000])
+        f[0, :] = rng.choice([0, f[0, 0]])
+    return f
+
+
+def test_fuzz_bad_pixels(port):
+    """Detection list + clamp value and the corrected frames, bit for bit, on random shapes and contents."""
+    rng = np.random.default_rng(501 + SEED)
+    for case in range(30 * SCALE):
+        w = int(rng.choice(WIDTHS))
+        h = int(rng.integers(1, 90))
+        first = random_frame(rng, h, w)
+        oxy, _thr, oclamp = port.bad_pixels_detect(first)
+        handle = sp.bad_pixels_create(first)
+        assert handle > 0
+        xy, clamp = sp.bad_pixels_list(handle)
+        np.testing.assert_array_equal(xy, oxy, err_msg=f"case {case}: {h}x{w} list")
+        assert clamp == oclamp, f"case {case}: {h}x{w} clamp"
+        mov = np.stack([random_frame(rng, h, w) for _ in range(3)])
+        want = np.stack([port.bad_pixels_correct_with(oxy, oclamp, f) for f in mov])
+        np.testing.assert_array_equal(sp.bad_pixels_correct_batch(handle, mov), want, err_msg=f"case {case}: {h}x{w} correct")
+        np.testing.assert_array_equal(sp.bad_pixels_correct(handle, mov[1]), want[1])
+        sp.bad_pixels_destroy(handle)
+
+
+def test_fuzz_reader_chain(port):
+    """merge -> + min_T -> loader medians -> motion, each stage on or off, random sizes / shifts / offsets."""
+    from librir_b200 import _lib
+
+    rng = np.random.default_rng(502 + SEED)
+    for case in range(24 * SCALE):
+        w = int(rng.choice([w for w in WIDTHS if w >= 3]))
+        h = int(rng.integers(6, 100))
+        n = int(rng.integers(1, 5))
+        mov = np.stack([random_frame(rng, h, w) for _ in range(n)])
+        lo, hi = (mov & 0xFF).astype(np.uint8), (mov >> 8).astype(np.uint8)
+        big = rng.integers(0, 3) == 0
+        sx = rng.uniform(-w - 3, w + 3, n) if big else rng.uniform(-3, 3, n)
+        sy = rng.uniform(-h - 3, h + 3, n) if big else rng.uniform(-3, 3, n)
+        if rng.integers(0, 3) == 0:
+            sx, sy = np.round(sx), np.round(sy * 2) / 2
+        use_bp, use_motion = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        min_T = int(rng.choice([0, 273, -7, 40000, 65535]))
+        rows = int(rng.integers(0, h + 1))
+        bp = vio.LoaderBadPixels(mov[0]) if use_bp else None
+        xy = sp.bad_pixels_list(bp.handle)[0] if bp is not None else None
+        _lib.set_parameter("loader_fused", int(rng.integers(0, 2)))
+        try:
+            got = vio.read_movie(lo, hi, bp, min_T, rows, sx if use_motion else None, sy if use_motion else None)
+        finally:
+            _lib.set_parameter("loader_fused", 0)
+        for t in range(n):
+            want = port.loader_read_image(lo[t], hi[t], xy, min_T, rows, (sx[t], sy[t]) if use_motion else None)
+            np.testing.assert_array_equal(got[t], want, err_msg=f"case {case}: {n}x{h}x{w} bp={use_bp} motion={use_motion} "
+                                          f"min_T={min_T} rows={rows} shift=({sx[t]!r},{sy[t]!r})")
+
+
+def test_fuzz_precoder_and_stats(port):
+    """Byte planes (+ temporal delta), their inverse, and the fused statistics, on random shapes / GOPs / offsets."""
+    rng = np.random.default_rng(503 + SEED)
+    for case in range(24 * SCALE):
+        w = int(rng.choice(WIDTHS))
+        h = int(rng.integers(1, 70))
+        n = int(rng.integers(1, 40))
+        gop = int(rng.choice([1, 2, 3, 5, 7, 50]))
+        delta = bool(rng.integers(0, 2))
+        mov = rng.integers(0, 65536, (n, h, w), dtype=np.uint16) if rng.integers(0, 2) else np.stack(
+            [random_frame(rng, h, w) for _ in range(n)])
+        first = int(rng.integers(0, 4)) * gop
+        lo, hi = vio.precode_movie(mov, gop, delta, first)
+        olo, ohi = port.precode_movie(mov, gop, delta)  # the key-frame pattern repeats every gop: any aligned offset gives the same planes
+        np.testing.assert_array_equal(lo, olo, err_msg=f"case {case}: {n}x{h}x{w} gop {gop} delta {delta}")
+        np.testing.assert_array_equal(hi, ohi)
+        np.testing.assert_array_equal(vio.decode_movie(lo, hi, gop, delta, first), mov)
+        st = movie.MovieStats("cuda")
+        dlo, dhi = vio.precode_movie(to_dev(mov), gop, delta, first, stats=st)
+        np.testing.assert_array_equal(dlo.cpu().numpy(), olo)
+        np.testing.assert_array_equal(dhi.cpu().numpy(), ohi)
+        mn, mx, hist = port.movie_stats(mov)
+        assert (st.min(), st.max(), st.count) == (mn, mx, mov.size), f"case {case}"
+        np.testing.assert_array_equal(st.histogram(), hist)
+
+
+def test_fuzz_quantiles(port):
+    rng = np.random.default_rng(504 + SEED)
+    for case in range(40 * SCALE):
+        w = int(rng.choice(WIDTHS))
+        h = int(rng.integers(1, 60))
+        img = random_frame(rng, h, w)
+        pc = float(rng.choice([0.0, 1.0, 0.5, 1e-6, 0.999999, float(np.float32(rng.random()))]))
+        assert sp.find_median_pixel(img, pc) == port.find_median_pixel(img, pc), f"case {case}: {h}x{w} {pc}"
+        mask = (rng.random((h, w)) < rng.choice([0.0, 0.1, 0.5, 1.0])).astype(np.uint8)
+        assert sp.find_median_pixel(img, pc, mask) == port.find_median_pixel(img, pc, mask), f"case {case}: masked {h}x{w} {pc}"
+
+
+def test_fuzz_lossy_preconditioner(port):
+    rng = np.random.default_rng(505 + SEED)
+    for case in range(3 * SCALE):
+        w = int(rng.choice([16, 40, 64, 96, 136]))
+        h = int(rng.integers(8, 60))
+        n = int(rng.integers(5, 70))
+        stop = int(rng.integers(1, h + 1))
+        cfg = dict(low_error=int(rng.integers(0, 12)), high_error=int(rng.integers(0, 6)), std_factor=float(rng.choice([2.0, 5.0, 9.5])),
+                   running_average=int(rng.choice([0, 1, 8, 32, 64])), subtract_min=bool(rng.integers(0, 2)),
+                   bp_enabled=bool(rng.integers(0, 2)))
+        mov = ir_movie(n, h, w, seed=int(rng.integers(0, 1 << 20)), drift=0.7)
+        mov = (mov.astype(np.int64) + rng.integers(-40, 40, mov.shape)).clip(0, 16383).astype(np.uint16)
+        state = port.lossy_open(w, h, stop, **cfg)
+        want, werr = [], []
+        for f in mov:
+            o, e = port.lossy_add(state, f)
+            want.append(o)
+            werr.append(e)
+        port.lossy_close(state)
+        pre = vio.LossyPreconditioner(w, h, stop, lowValueError=cfg["low_error"], highValueError=cfg["high_error"],
+                                      stdFactor=cfg["std_factor"], runningAverage=cfg["running_average"], subtractMin=cfg["subtract_min"],
+                                      removeBadPixels=cfg["bp_enabled"])
+        k = int(rng.integers(1, n))
+        out_a, err_a = pre.add_images(mov[:k])
+        out_b, err_b = pre.add_images(mov[k:])
+        np.testing.assert_array_equal(np.concatenate([out_a, out_b]), np.stack(want), err_msg=f"case {case}: {n}x{h}x{w} {cfg} stop {stop}")
+        np.testing.assert_array_equal(np.concatenate([err_a, err_b]), np.array(werr))

@@ -340,6 +340,21 @@ def test_bad_pixels_golden(golden, k):
     np.testing.assert_array_equal(bp.correct(other), golden[f"bp_{k}_other_out"])
 
 
+@pytest.mark.parametrize("k", range(5))
+def test_bad_pixels_beyond_the_int_product_range(k):
+    """Saturated / dead pixels more than 46,340 counts from the median (found by fuzzing): the reference's int product
+    wraps; list, clamp and corrected frames must equal the compiled reference's (tests/golden/bp_extreme_golden.npz)."""
+    from tests import bp_extreme_cases as bc
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bp_extreme_golden.npz"))
+    first = bc.frames()[k]
+    bp = sp.BadPixels(first)
+    xy, _clamp = sp.bad_pixels_list(bp.handle)
+    np.testing.assert_array_equal(xy, g[f"xy_{k}"])
+    np.testing.assert_array_equal(bp.correct(first), g[f"first_out_{k}"])
+    np.testing.assert_array_equal(bp.correct(bc.second_frame(first, k)), g[f"other_out_{k}"])
+
+
 @pytest.mark.parametrize("shape", [(512, 640), (256, 320), (100, 101), (1, 1), (2, 2), (7, 40)])
 def test_bad_pixels_live(port, shape):
     h, w = shape

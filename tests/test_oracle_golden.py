@@ -53,6 +53,22 @@ def test_bad_pixels(golden, port, k):
     np.testing.assert_array_equal(port.loader_remove_motion(first, 1.3, -2.7), golden[f"bp_{k}_motion"])
 
 
+@pytest.mark.parametrize("k", range(5))
+def test_bad_pixels_beyond_the_int_product_range(port, k):
+    """Saturated / dead pixels far from the median: the reference's int product wraps (x86-64 builds); the compiled
+    reference's answers are in tests/golden/bp_extreme_golden.npz and the restatement spells the wrap out."""
+    import os
+
+    from tests import bp_extreme_cases as bc
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bp_extreme_golden.npz"))
+    first = bc.frames()[k]
+    xy, _thr, clamp = port.bad_pixels_detect(first)
+    np.testing.assert_array_equal(np.asarray(xy).reshape(-1, 2), g[f"xy_{k}"])
+    np.testing.assert_array_equal(port.bad_pixels_correct_with(xy, clamp, first), g[f"first_out_{k}"])
+    np.testing.assert_array_equal(port.bad_pixels_correct_with(xy, clamp, bc.second_frame(first, k)), g[f"other_out_{k}"])
+
+
 def test_find_median_pixel(golden, port):
     f, m = golden["mp_in"], golden["mp_mask"]
     for p, want, want_m in zip(golden["mp_percents"], golden["mp_out"], golden["mp_out_mask"]):
