@@ -29,6 +29,13 @@ def to_dev(a):
     return torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
 
 
+@pytest.fixture(scope="module")
+def best():
+    from oracle import oracle as O
+
+    return O.best()
+
+
 def random_frame(rng, h, w):
     """Includes frames with pixels more than 46,340 counts from the median, where the reference's int product wraps
     (the restatement and the library reproduce the x86-64 behaviour, pinned by tests/golden/bp_extreme_golden.npz)."""
@@ -163,3 +170,29 @@ def test_fuzz_lossy_preconditioner(port):
         out_b, err_b = pre.add_images(mov[k:])
         np.testing.assert_array_equal(np.concatenate([out_a, out_b]), np.stack(want), err_msg=f"case {case}: {n}x{h}x{w} {cfg} stop {stop}")
         np.testing.assert_array_equal(np.concatenate([err_a, err_b]), np.array(werr))
+
+
+def test_fuzz_translate_all_dtypes(best, port):
+    """The generic translate kernel (every numpy dtype the facade accepts) on random shapes, shifts and strategies,
+    bit for bit against the compiled reference (the restatement where the reference's read leaves its buffer)."""
+    from tests.golden.make_golden import DTYPES, typed_image
+    from tests.test_gpu_parity import reference_reads_past_the_buffer
+
+    rng = np.random.default_rng(506 + SEED)
+    specials = [0.0, 1.0, -1.0, 0.5, -0.5, 7.9999995, -7.9999995, 1.0000001, -2.9999998, 1e-20, 0.25, 15.999999]
+    for case in range(60 * SCALE):
+        dt = DTYPES[int(rng.integers(0, len(DTYPES)))]
+        w = int(rng.choice([w for w in WIDTHS if w <= 144]))
+        h = int(rng.integers(1, 60))
+        img = typed_image(dt, h, w, rng)
+        k = rng.integers(0, 3)
+        dx = float(rng.choice(specials)) if k == 0 else float(np.float32(rng.uniform(-w - 2, w + 2) if k == 1 else rng.uniform(-3, 3)))
+        k = rng.integers(0, 3)
+        dy = float(rng.choice(specials)) if k == 0 else float(np.float32(rng.uniform(-h - 2, h + 2) if k == 1 else rng.uniform(-3, 3)))
+        st = ["nearest", "background", "wrap", ""][case % 4]
+        got, want = sp.translate(img, dx, dy, st, 1), best.translate(img, dx, dy, st, 1)
+        undefined = reference_reads_past_the_buffer(h, w, dx, dy)
+        if undefined.any():
+            want = np.where(undefined, port.translate(img, dx, dy, st, 1), want)
+        assert got.dtype == want.dtype
+        np.testing.assert_array_equal(got, want, err_msg=f"case {case}: {dt} {h}x{w} {st!r} dx={dx!r} dy={dy!r}")
