@@ -269,3 +269,90 @@ def test_zfile_device_frames(tmp_path):
     with tools.ZFileReader(p) as r:
         r.read_images(0, 40, out=out)
     assert torch.equal(out.view(torch.int16), d.view(torch.int16))
+
+
+# ---- randomised: product, port and (when built) the compiled reference on the same random content -------------------
+FUZZ_SEED = int(os.environ.get("RIRB_FUZZ_SEED", "0"))
+FUZZ_SCALE = max(1, int(os.environ.get("RIRB_FUZZ_SCALE", "1")))
+
+
+def _random_attrs(rng, nframes):
+    def blob(maxlen):
+        n = int(rng.choice([0, 1, 7, 999, 1000, 1001, 1500, maxlen]))
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            return bytes(rng.integers(0, 256, n, dtype=np.uint8))            # incompressible
+        if kind == 1:
+            return (b"abc" * (n // 3 + 1))[:n]                                # compressible
+        return bytes(rng.integers(0, 4, n, dtype=np.uint8))                   # compressible, with NULs
+
+    g = {}
+    for i in range(int(rng.integers(0, 6))):
+        g[b"k%d" % i + bytes(rng.integers(97, 123, int(rng.integers(0, 5)), dtype=np.uint8))] = blob(4000)
+    frames = []
+    for _ in range(nframes):
+        frames.append({b"f%d" % j: blob(1200) for j in range(int(rng.integers(0, 3)))})
+    return g, frames
+
+
+def test_fuzz_trailers_product_vs_port_vs_reference(tmp_path):
+    rng = np.random.default_rng(900 + FUZZ_SEED)
+    for case in range(25 * FUZZ_SCALE):
+        n = int(rng.integers(0, 12))
+        times = rng.integers(-2 ** 62, 2 ** 62, n, dtype=np.int64)
+        g, frames = _random_attrs(rng, n)
+        payload = bytes(rng.integers(0, 256, int(rng.choice([0, 5, 29, 30, 31, 600])), dtype=np.uint8))
+        a = tmp_path / f"a{case}.bin"
+        a.write_bytes(payload)
+        h = tools.attrs_open_file(a)
+        assert h > 0
+        tools.attrs_set_times(h, times)
+        tools.attrs_set_global_attributes(h, g)
+        for i, m in enumerate(frames):
+            tools.attrs_set_frame_attributes(h, i, m)
+        tools.attrs_close(h)
+        # FileAttributes::open truncates a file shorter than a trailer (30 bytes) before appending (FileAttributes.cpp:364-371)
+        kept = payload if len(payload) >= 30 else b""
+        assert read(a) == kept + oc.build_trailer(g, frames, times), f"case {case}"
+        G, F, T, _ = oc.parse_trailer(read(a))
+        assert G == g and F == frames and np.array_equal(T, times)
+        fa = tools.FileAttributes.from_buffer(read(a)) if len(read(a)) else None
+        assert fa is not None and fa.frame_count() == n
+        assert [fa.frame_attributes(i) for i in range(n)] == [{k.decode(): v for k, v in m.items()} for m in frames]
+        _lib.load().rirb_attrs_abandon(fa.handle)
+        fa.handle = 0
+        if oc.have_ref():
+            b = tmp_path / f"b{case}.bin"
+            b.write_bytes(payload)
+            oc.ref_write_attrs(b, g, frames, times)
+            assert read(a) == read(b), f"case {case}: differs from the compiled reference"
+
+
+def test_fuzz_zfiles_product_vs_port_vs_reference(tmp_path):
+    rng = np.random.default_rng(901 + FUZZ_SEED)
+    for case in range(10 * FUZZ_SCALE):
+        h, w = int(rng.integers(1, 70)), int(rng.integers(1, 90))
+        n = int(rng.integers(0, 150 if case % 5 == 0 else 20))
+        kind = rng.integers(0, 3)
+        mov = (rng.integers(0, 65536, (n, h, w), dtype=np.uint16) if kind == 0 else
+               np.full((n, h, w), int(rng.integers(0, 65536)), np.uint16) if kind == 1 else
+               (rng.integers(8000, 8100, (n, h, w)) + np.arange(w)).astype(np.uint16))
+        ts = np.sort(rng.integers(0, 2 ** 60, n, dtype=np.int64))
+        clevel = int(rng.choice([1, 2, 3, 9]))
+        p = tmp_path / f"p{case}.bin"
+        with tools.ZFileWriter(p, w, h, rate=int(rng.integers(1, 999)), clevel=clevel, threads=int(rng.choice([0, 1, 3]))) as wr:
+            k = int(rng.integers(0, n + 1))
+            if k:
+                wr.add_images(mov[:k], ts[:k])
+            if n - k:
+                wr.add_images(mov[k:], ts[k:])
+        frames, times, _ = oc.read_zfile(p)
+        assert np.array_equal(frames, mov) and np.array_equal(times, ts), f"case {case}"
+        with tools.ZFileReader(p, threads=int(rng.choice([0, 1, 5]))) as rd:
+            assert len(rd) == n and np.array_equal(rd.timestamps, ts)
+            if n:
+                a, b = sorted(rng.integers(0, n + 1, 2))
+                assert np.array_equal(rd.read_images(a, b - a), mov[a:b])
+        if oc.have_ref() and n:
+            f2, t2 = oc.ref_read_zfile(p)
+            assert np.array_equal(f2, mov) and np.array_equal(t2, ts)
