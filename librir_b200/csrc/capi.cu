@@ -1247,8 +1247,14 @@ int rirb_process_movie_host(int handle, const unsigned short* frames, long long 
     if (gaussian_taps_host(sigma, &taps) != 0) return -1;
     RIRB_REQUIRE_DEVICE();
     const size_t fpx = (size_t)w * h;
-    // sub-chunk: whole GOPs, about 64 MB of input
-    long long sub = (long long)((64u << 20) / (fpx * 2));
+    // sub-chunk: whole GOPs, about 64 MB of input (RIRB_HOST_SUB_BYTES overrides the size: tests use it to make
+    // small movies rotate through all the slots)
+    long long sub_bytes = 64ll << 20;
+    if (const char* e = getenv("RIRB_HOST_SUB_BYTES")) {
+        const long long v = atoll(e);
+        if (v > 0) sub_bytes = v;
+    }
+    long long sub = sub_bytes / (long long)(fpx * 2);
     sub = sub / gop * gop;
     if (sub < gop) sub = gop;
     // per-slot layout (every section 256-byte aligned)

@@ -257,3 +257,49 @@ def test_fuzz_ecc_solver(port):
             continue
         assert st == 0 and its.value == want[3], what + f" -> {st}, {its.value} iterations vs {want[3]}"
         assert abs(rho.value - want[0]) < 1e-7 and abs(shift[0] - want[1]) < 2e-5 and abs(shift[1] - want[2]) < 2e-5, what
+
+
+def test_fuzz_process_movie_host(port):
+    """The one-call host path with sub-chunks shrunk (RIRB_HOST_SUB_BYTES) so that small movies rotate through all three
+    stream slots: ragged tails, GOP-aligned offsets, pageable and pinned buffers -- against the staged device calls."""
+    rng = np.random.default_rng(508 + SEED)
+    old = os.environ.get("RIRB_HOST_SUB_BYTES")
+    try:
+        for case in range(10 * SCALE):
+            w = int(rng.choice([16, 24, 40, 64, 96, 128, 136, 33, 7]))
+            h = int(rng.integers(3, 70))
+            n = int(rng.integers(1, 260))
+            gop = int(rng.choice([1, 3, 7, 50]))
+            delta = bool(rng.integers(0, 2))
+            first = int(rng.integers(0, 5)) * gop
+            sigma = float(rng.choice([0.5, 1.0, 1.7]))
+            st = str(rng.choice(["nearest", "background", "wrap"]))
+            mov = np.stack([random_frame(rng, h, w) for _ in range(min(n, 6))])[rng.integers(0, min(n, 6), n)]
+            mov = np.ascontiguousarray(mov)
+            dx = rng.uniform(-3, 3, n).astype(np.float32)
+            dy = rng.uniform(-3, 3, n).astype(np.float32)
+            os.environ["RIRB_HOST_SUB_BYTES"] = str(int(rng.choice([1, 4096, 50000, 300000, 1 << 26])))
+            bp = sp.BadPixels(mov[0])
+            smoothed = np.empty((n, h, w), np.float32) if rng.integers(0, 2) else None
+            frames = mov
+            if rng.integers(0, 2):
+                frames = torch.from_numpy(mov.view(np.int16)).pin_memory().view(torch.uint16)
+            lo, hi = movie.process_movie_host(bp, frames, dx, dy, sigma, st, 321, gop=gop, delta=delta, first_frame=first, smoothed=smoothed)
+            corr = bp.correct_batch(mov)
+            reg = sp.translate_batch(corr, dx, dy, st, 321)
+            wlo, whi = vio.precode_movie(reg, gop=gop, delta=delta, first_frame=first)
+            what = f"case {case}: {n}x{h}x{w} gop {gop} delta {delta} first {first} sub {os.environ['RIRB_HOST_SUB_BYTES']}"
+            np.testing.assert_array_equal(lo, wlo, err_msg=what)
+            np.testing.assert_array_equal(hi, whi, err_msg=what)
+            if smoothed is not None:
+                np.testing.assert_array_equal(smoothed, sp.gaussian_filter_batch(corr, sigma), err_msg=what)
+            t = int(rng.integers(0, n))  # and one frame against the oracle chain
+            oxy, _thr, oclamp = port.bad_pixels_detect(mov[0])
+            oc_ = port.bad_pixels_correct_with(oxy, oclamp, mov[t])
+            np.testing.assert_array_equal(corr[t], oc_, err_msg=what)
+            np.testing.assert_array_equal(reg[t], port.translate(oc_, dx[t], dy[t], st, 321), err_msg=what)
+    finally:
+        if old is None:
+            os.environ.pop("RIRB_HOST_SUB_BYTES", None)
+        else:
+            os.environ["RIRB_HOST_SUB_BYTES"] = old
