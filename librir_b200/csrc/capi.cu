@@ -141,7 +141,22 @@ struct PinRing {
     cudaEvent_t ev[PIN_NB] = {nullptr, nullptr, nullptr, nullptr};
     int state = 0;  // 0 not tried, 1 ready, -1 unavailable (fall back to plain copies)
 };
-static thread_local PinRing pin;
+// Events belong to the device that was current when they were created, so a thread that moves between devices
+// (rirb_set_device) gets one ring per device.
+constexpr int PIN_MAX_DEVICES = 16;
+static thread_local PinRing pin_rings[PIN_MAX_DEVICES];
+static thread_local PinRing pin_none;
+#define pin (*pin_current())
+static PinRing* pin_current()
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) cudaGetLastError();
+    if (dev < 0 || dev >= PIN_MAX_DEVICES) {
+        pin_none.state = -1;  // plain copies
+        return &pin_none;
+    }
+    return &pin_rings[dev];
+}
 
 static bool pin_ready()
 {
@@ -199,6 +214,8 @@ static cudaError_t copy_d2h(void* host, const void* dev, size_t bytes, cudaStrea
     }
     return e;
 }
+
+#undef pin
 
 // Input operand: device pointer as is, host pointer uploaded into scratch slot `slot`.
 static const void* stage_in(const void* p, size_t bytes, int slot, cudaStream_t st)
@@ -312,6 +329,24 @@ static std::shared_ptr<BadPixelState> find_handle(int id)
     std::lock_guard<std::mutex> lock(g_handles_mutex);
     auto it = g_handles.find(id);
     return it == g_handles.end() ? nullptr : it->second;
+}
+
+// A handle's tables live in the memory of the device it was created on: entries that launch kernels refuse a handle
+// from another device instead of faulting on its pointers.
+static std::shared_ptr<BadPixelState> find_handle_here(int id, const char* what)
+{
+    auto s = find_handle(id);
+    if (!s) {
+        set_error("%s: unknown handle %d", what, id);
+        return nullptr;
+    }
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) cudaGetLastError();
+    if (dev != s->device) {
+        set_error("%s: handle %d belongs to CUDA device %d, the calling thread is on device %d", what, id, s->device, dev);
+        return nullptr;
+    }
+    return s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -640,11 +675,8 @@ int bad_pixels_create(unsigned short* first_image, int width, int height)
 
 int rirb_bad_pixels_correct_batch(int handle, const unsigned short* in, unsigned short* out, long long nframes)
 {
-    auto s = find_handle(handle);
-    if (!s) {
-        set_error("bad_pixels_correct: unknown handle %d", handle);
-        return -1;
-    }
+    auto s = find_handle_here(handle, "bad_pixels_correct");
+    if (!s) return -1;
     if (!in || !out || nframes < 0) {
         set_error("bad_pixels_correct: bad arguments");
         return -1;
@@ -709,11 +741,8 @@ int rirb_bad_pixels_get(int handle, int* xy, int capacity, int* clamp_value)
 
 int rirb_loader_remove_bad_pixels(int handle, unsigned short* frames, long long nframes, size_t frame_stride)
 {
-    auto s = find_handle(handle);
-    if (!s) {
-        set_error("remove_bad_pixels: unknown handle %d", handle);
-        return -1;
-    }
+    auto s = find_handle_here(handle, "remove_bad_pixels");
+    if (!s) return -1;
     if (!frames || nframes < 0 || frame_stride < (size_t)s->w * s->h) {
         set_error("remove_bad_pixels: bad arguments");
         return -1;
@@ -803,11 +832,8 @@ int rirb_loader_read_movie(int handle, const unsigned char* lo, const unsigned c
     const int hb = h - meta_rows;
     std::shared_ptr<BadPixelState> s;
     if (handle != 0) {
-        s = find_handle(handle);
-        if (!s) {
-            set_error("loader_read_movie: unknown handle %d", handle);
-            return -1;
-        }
+        s = find_handle_here(handle, "loader_read_movie");
+        if (!s) return -1;
         if (s->w != w || s->h != hb) {
             set_error("loader_read_movie: the handle was created on a %dx%d image, expected %dx%d", s->w, s->h, w, hb);
             return -1;
@@ -1225,11 +1251,8 @@ int rirb_process_movie_host(int handle, const unsigned short* frames, long long 
                             const float* dy, const char* strategy, unsigned int background, int gop, int delta,
                             long long first_frame, unsigned char* lo, unsigned char* hi, float* smoothed)
 {
-    auto s = find_handle(handle);
-    if (!s) {
-        set_error("process_movie_host: unknown handle %d", handle);
-        return -1;
-    }
+    auto s = find_handle_here(handle, "process_movie_host");
+    if (!s) return -1;
     const int strat = strategy_code(strategy);
     if (!frames || !dx || !dy || !lo || !hi || w != s->w || h != s->h || nframes < 0 || gop < 1 || strat < 0 ||
         (delta && first_frame % gop != 0)) {

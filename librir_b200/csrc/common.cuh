@@ -34,6 +34,7 @@ bool option_enabled(int which);
         cudaError_t _e = (expr);                                                              \
         if (_e != cudaSuccess) {                                                              \
             ::rirb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            (void)cudaGetLastError(); /* do not leave it for the next launch check to find */ \
             return -1;                                                                        \
         }                                                                                     \
     } while (0)

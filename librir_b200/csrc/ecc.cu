@@ -491,6 +491,23 @@ struct EccState {
 };
 static Table<EccState> g_ecc;
 
+// Buffers live on the device the handle was opened on: refuse calls from a thread that is on another one.
+static std::shared_ptr<EccState> ecc_get(int handle, const char* what)
+{
+    auto s = g_ecc.get(handle);
+    if (!s) {
+        set_error("%s: unknown handle %d", what, handle);
+        return nullptr;
+    }
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) cudaGetLastError();
+    if (dev != s->dev) {
+        set_error("%s: handle %d belongs to CUDA device %d, the calling thread is on device %d", what, handle, s->dev, dev);
+        return nullptr;
+    }
+    return s;
+}
+
 static int ecc_need_device()
 {
     int n = 0;
@@ -655,7 +672,8 @@ void rirb_ecc_close(int handle) { g_ecc.remove(handle); }
 // uint8 mask its thresholds are taken under a different pixel set than the one ECC uses; the Python mirror reproduces that.
 int rirb_ecc_set_mask(int handle, int which, const unsigned char* mask)
 {
-    auto s = g_ecc.get(handle);
+    auto s = ecc_get(handle, "ecc_set_mask");
+    if (!s) return -1;
     if (!s || (which != 0 && which != 1)) {
         set_error("ecc: unknown handle %d or mask selector", handle);
         return -1;
@@ -670,7 +688,8 @@ int rirb_ecc_set_mask(int handle, int which, const unsigned char* mask)
 // float image whose rows are `stride` floats apart (host or device).
 int rirb_ecc_set_image(int handle, int which, const float* img, int stride)
 {
-    auto s = g_ecc.get(handle);
+    auto s = ecc_get(handle, "ecc_set_image");
+    if (!s) return -1;
     if (!s || (which != 0 && which != 1)) {
         set_error("ecc: unknown handle %d or image selector", handle);
         return -1;
@@ -685,7 +704,8 @@ int rirb_ecc_set_image(int handle, int which, const float* img, int stride)
 // with translate's default ("noborder") strategy, on the un-normalised float window.
 int rirb_ecc_reset_reference(int handle, float dx, float dy)
 {
-    auto s = g_ecc.get(handle);
+    auto s = ecc_get(handle, "ecc_reset_reference");
+    if (!s) return -1;
     if (!s || !s->have_cur) {
         set_error("ecc_reset_reference: unknown handle or no current image");
         return -1;
@@ -703,7 +723,8 @@ int rirb_ecc_reset_reference(int handle, float dx, float dy)
 // find_median_pixel(window.astype(uint16), percent, mask) of the reference (0) or current (1) window (:144-145)
 int rirb_ecc_quantile(int handle, int which, float percent, int use_mask)
 {
-    auto s = g_ecc.get(handle);
+    auto s = ecc_get(handle, "ecc_quantile");
+    if (!s) return -1;
     if (!s || (which != 0 && which != 1) || !(which ? s->have_cur : s->have_ref)) {
         set_error("ecc_quantile: unknown handle or image not set");
         return -1;
@@ -728,7 +749,8 @@ int rirb_ecc_quantile(int handle, int which, float percent, int use_mask)
 // 2 = "the correlation is going to be minimized" (both are cv2.error in the reference); -1 = bad call.
 int rirb_ecc_compute(int handle, float thresh, int use_mask, int max_iterations, double eps, float* shift, double* rho, int* iterations)
 {
-    auto s = g_ecc.get(handle);
+    auto s = ecc_get(handle, "ecc_compute");
+    if (!s) return -1;
     if (!s || !s->have_ref || !s->have_cur || !shift) {
         set_error("ecc_compute: unknown handle, or reference / current image not set");
         return -1;
@@ -804,7 +826,8 @@ int rirb_ecc_track_state(int handle, double* median, double* conf_thresh, float*
 int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, int full_w, int full_h, int x0, int y0, int use_mask,
                    int max_try, double* x, double* y, double* conf, int* iters, long long* processed)
 {
-    auto s = g_ecc.get(handle);
+    auto s = ecc_get(handle, "ecc_track");
+    if (!s) return -1;
     if (processed) *processed = 0;
     if (!s || !frames || nframes < 0 || !x || !y || !conf || (type != 'H' && type != 'f') || x0 < 0 || y0 < 0 || x0 + s->w > full_w ||
         y0 + s->h > full_h) {

@@ -831,3 +831,28 @@ def test_full_size_pipeline_matches_oracle_on_sampled_frames(port):
     assert (pipe.stats.min(), pipe.stats.max()) == (glo, ghi)
     np.testing.assert_array_equal(pipe.stats.histogram(), ghist)
     assert pipe.stats.quantile(0.5) == port.quantile_from_hist(ghist, 0.5)
+
+
+def test_handles_refuse_another_device():
+    """Handles own memory on the device they were created on; a call from a thread that moved to another device must be
+    refused with a message, not fault.  Needs two GPUs (skipped on the single-GPU box)."""
+    lib = _lib.load()
+    if lib.rirb_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    img = ir_frame(64, 96, 5)
+    assert lib.rirb_set_device(0) == 0
+    bp = sp.BadPixels(img)
+    ecc = lib.rirb_ecc_open(64, 48)
+    assert ecc > 0
+    try:
+        assert lib.rirb_set_device(1) == 0
+        with pytest.raises(RuntimeError) as e:
+            bp.correct(img)
+        assert "belongs to CUDA device 0" in _lib.last_error() or "device" in str(e.value)
+        f = np.zeros((48, 64), np.float32)
+        assert lib.rirb_ecc_set_image(ecc, 0, sp._ptr(f), 64) == -1 and "belongs to CUDA device 0" in _lib.last_error()
+        other = sp.BadPixels(img)  # a handle made here works here
+        np.testing.assert_array_equal(other.correct(img), (lib.rirb_set_device(0), bp.correct(img), lib.rirb_set_device(1))[1])
+    finally:
+        lib.rirb_set_device(0)
+        lib.rirb_ecc_close(ecc)
