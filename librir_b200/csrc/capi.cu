@@ -1181,6 +1181,14 @@ int rirb_lossy_add_images(int handle, const unsigned short* frames, long long nf
     }
     if (nframes == 0) return 0;
     RIRB_REQUIRE_DEVICE();
+    {
+        int dev = -1;
+        if (cudaGetDevice(&dev) != cudaSuccess) cudaGetLastError();
+        if (dev != s->device) {
+            set_error("lossy_add_images: handle %d belongs to CUDA device %d, the calling thread is on device %d", handle, s->device, dev);
+            return -1;
+        }
+    }
     cudaStream_t st = tls.stream;
     const int w = s->w, h = s->h, n = w * h, ns = w * s->stop_h;
     const size_t bytes = (size_t)n * 2 * (size_t)nframes;
