@@ -856,3 +856,38 @@ def test_handles_refuse_another_device():
     finally:
         lib.rirb_set_device(0)
         lib.rirb_ecc_close(ecc)
+
+
+def test_entries_are_reentrant_across_threads(best):
+    """ctypes releases the GIL, so the reference's callers may be in several entries at once (threading):
+    eight threads hammer the per-frame calls -- one shared bad-pixel handle, per-thread scratch -- and every result must
+    equal the single-threaded one."""
+    import threading
+
+    mov = ir_movie(16, 96, 136)
+    bp = sp.BadPixels(mov[0])
+    want_c = [bp.correct(f) for f in mov]
+    want_t = [sp.translate(f, 1.3 + 0.1 * i, -0.7, "nearest") for i, f in enumerate(mov)]
+    want_g = [sp.gaussian_filter(f, 1.0) for f in mov]
+    want_q = [sp.find_median_pixel(f, 0.5) for f in mov]
+    errors = []
+
+    def work(k):
+        try:
+            for rep in range(6):
+                for i in range(k, len(mov), 4):
+                    assert np.array_equal(bp.correct(mov[i]), want_c[i])
+                    assert np.array_equal(sp.translate(mov[i], 1.3 + 0.1 * i, -0.7, "nearest"), want_t[i])
+                    assert np.array_equal(sp.gaussian_filter(mov[i], 1.0), want_g[i])
+                    assert sp.find_median_pixel(mov[i], 0.5) == want_q[i]
+                    lo, hi = vio.precode_movie(mov[i:i + 2], gop=1)
+                    assert np.array_equal(lo.astype(np.uint16) | (hi.astype(np.uint16) << 8), mov[i:i + 2])
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(k % 4,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
