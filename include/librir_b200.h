@@ -98,6 +98,11 @@ RIRB_API int rirb_gaussian_filter_u16_batch(const unsigned short* src, float* ds
                                             float sigma);
 
 RIRB_API int rirb_bad_pixels_correct_batch(int handle, const unsigned short* in, unsigned short* out, long long nframes);
+/* bad_pixels_correct + gaussian_filter of the corrected frames in ONE pass over the movie: corrected[n][h][w] (uint16) and
+ * smoothed[n][h][w] (float32) are both written, the raw frames are read once (8 B/px instead of 4 + 6).  Same results as
+ * the two calls; layouts the tiled kernel cannot take fall back to them internally. */
+RIRB_API int rirb_bad_pixels_correct_gaussian_batch(int handle, const unsigned short* in, unsigned short* corrected, float* smoothed,
+                                                    long long nframes, float sigma);
 /* introspection of a handle: number of flagged pixels; raster-ordered (x,y) list; clamp level */
 RIRB_API int rirb_bad_pixels_count(int handle);
 RIRB_API int rirb_bad_pixels_get(int handle, int* xy, int capacity, int* clamp_value);

@@ -57,6 +57,7 @@ SIGNATURES = {
     "rirb_gaussian_filter_batch": (_i, [_vp, _vp, _i, _i, _ll, _f]),
     "rirb_gaussian_filter_u16_batch": (_i, [_vp, _vp, _i, _i, _ll, _f]),
     "rirb_bad_pixels_correct_batch": (_i, [_i, _vp, _vp, _ll]),
+    "rirb_bad_pixels_correct_gaussian_batch": (_i, [_i, _vp, _vp, _vp, _ll, _f]),
     "rirb_bad_pixels_count": (_i, [_i]),
     "rirb_bad_pixels_get": (_i, [_i, _vp, _i, _vp]),
     "rirb_loader_remove_bad_pixels": (_i, [_i, _vp, _ll, _sz]),

@@ -29,32 +29,6 @@ namespace rirb {
 //           clean pixels, which is what made the band-in-shared-memory version ALU-bound
 //           (profiles/r1_v1_ncu_summary.md: 64 % ALU at 29 % of HBM peak).
 // The two passes touch the same output address from different threads: __syncthreads orders them.
-__device__ __forceinline__ unsigned median3x3_global(const u16* __restrict__ frame, int w, int h, int x, int y)
-{
-    unsigned v[9];
-    if (x > 0 && y > 0 && x < w - 1 && y < h - 1) {  // interior: 9 unconditional loads
-        const u16* p = frame + (size_t)(y - 1) * w + (x - 1);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) v[r * 3 + c] = p[(size_t)r * w + c];
-        sort9(v);
-        return v[4];
-    }
-    int c = 0;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int xx = x + dx, yy = y + dy;
-            const bool ok = xx >= 0 && yy >= 0 && xx < w && yy < h;
-            v[(dy + 1) * 3 + dx + 1] = ok ? (unsigned)frame[(size_t)yy * w + xx] : 0xFFFFFFFFu;
-            c += ok;
-        }
-    sort9(v);
-    return pick_mid(v, c);
-}
-
 constexpr int BP_THREADS = 256;
 constexpr int BP_UNROLL = BP_SPAN / (BP_THREADS * 16);  // 256-bit vectors per thread
 static_assert(BP_UNROLL * BP_THREADS * 16 == BP_SPAN, "BP_SPAN must be a multiple of one CTA-wide row of vectors");

@@ -702,6 +702,40 @@ int rirb_bad_pixels_correct_batch(int handle, const unsigned short* in, unsigned
     return finish_out(&o, 1, st);
 }
 
+// bad_pixels_correct + gaussian_filter of the corrected frames, reading the movie once (gaussian.cu, BpFuse):
+// corrected[n][h][w] uint16 and smoothed[n][h][w] float32 are both produced.  Layouts the tiled kernel cannot take
+// (w % 8 != 0, unaligned buffers, radius > 4) run the two kernels instead; results are the same either way.
+int rirb_bad_pixels_correct_gaussian_batch(int handle, const unsigned short* in, unsigned short* corrected, float* smoothed,
+                                           long long nframes, float sigma)
+{
+    auto s = find_handle_here(handle, "bad_pixels_correct_gaussian");
+    if (!s) return -1;
+    if (!in || !corrected || !smoothed || nframes < 0 || in == corrected) {
+        set_error("bad_pixels_correct_gaussian: bad arguments (in-place correction is not supported here)");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    GaussTaps taps;
+    if (gaussian_taps_host(sigma, &taps) != 0) return -1;
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const size_t fpx = (size_t)s->w * s->h;
+    const u16* d_in = (const u16*)stage_in(in, fpx * 2 * (size_t)nframes, 0, st);
+    if (!d_in) return -1;
+    StagedOut o[2];
+    if (!stage_out(o[0], corrected, fpx * 2 * (size_t)nframes, 1, false, st)) return -1;
+    if (!stage_out(o[1], smoothed, fpx * 4 * (size_t)nframes, 2, false, st)) return -1;
+    const int rc = launch_gaussian_bp_u16(d_in, (u16*)o[0].dev, (float*)o[1].dev, s->w, s->h, nframes, taps, s->xy_dev, s->row_off_dev,
+                                          s->clamp_value, st);
+    if (rc < 0) return -1;
+    if (rc == 1) {
+        if (launch_bp_correct(d_in, (u16*)o[0].dev, s->xy_dev, s->span_off_dev, s->w, s->h, s->clamp_value, nframes, fpx, st) != 0 ||
+            launch_gaussian_u16((const u16*)o[0].dev, (float*)o[1].dev, s->w, s->h, nframes, taps, st) != 0)
+            return -1;
+    }
+    return finish_out(o, 2, st);
+}
+
 int bad_pixels_correct(int handle, unsigned short* in, unsigned short* out)
 {
     return rirb_bad_pixels_correct_batch(handle, in, out, 1);

@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "sort9.cuh"
 #include "tma.cuh"
 
 namespace rirb {
@@ -244,10 +245,23 @@ __device__ __forceinline__ void load4(const float* p, float (&a)[4])
     a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
 }
 
-template <int R, typename TIN>
+// Bad-pixel correction fused in front of the filter (uint16 input only): the box arrives RAW, the flagged pixels that
+// fall into it (halo included) are replaced in shared memory by BadPixels::correct's median -- taken from the raw frame
+// in global memory, so neighbouring flagged pixels do not see each other's replacement -- every pixel is raised to the
+// clamp level, the corrected interior is stored (it is what translate reads next) and the filter runs on the corrected
+// tile.  The movie is then read once for correction + filter: 8 B/px (2 in, 2 + 4 out) instead of 4 + 6.
+struct BpFuse {
+    const u16* raw;       // the movie the tensor map describes
+    const int* xy;        // flagged pixels, raster order (x, y)
+    const int* row_off;   // first list entry of each image row, h + 1 entries
+    u16* corrected;       // [n][h][w] output of the correction
+    unsigned clamp;       // 0: none
+};
+
+template <int R, typename TIN, bool BP>
 __global__ void __launch_bounds__(GT_WARPS * 32)
 gauss_tile_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ dst, int w, int h, int tiles_x, int tiles_y,
-                  GaussTaps taps)
+                  GaussTaps taps, BpFuse bf)
 {
     constexpr int BH = GT_H + 2 * R;
     constexpr int HALO = GtBox<TIN>::HALO;
@@ -302,7 +316,61 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ 
 #pragma unroll
     for (int i = 0; i <= 2 * R; ++i) ring[i][0] = ring[i][1] = make_float2(0.f, 0.f);
 
-    mbar_wait(&bar, 0);
+    if (BP) {
+        static_assert(!BP || sizeof(TIN) == 2, "the fused correction is for uint16 frames");
+        static_assert(BH <= GT_WARPS * 32, "one thread per box row");
+        constexpr int BW = GtBox<TIN>::BW;
+        u16* t16 = reinterpret_cast<u16*>(&tile[0][0]);
+        const u16* rawf = bf.raw + (size_t)f * w * h;
+        const int bx0 = x0t - HALO, by = y0t - R + (int)threadIdx.x;  // this thread's box row
+        // the row's flagged pixels inside the box; the first one's median is gathered while the box is in flight
+        int a = 0, b = 0, first_x = -1;
+        unsigned first_v = 0;
+        if ((int)threadIdx.x < BH && by >= 0 && by < h) {
+            a = bf.row_off[by];
+            b = bf.row_off[by + 1];
+            for (; a < b; ++a) {
+                const int x = bf.xy[2 * a];
+                if (x >= bx0 + BW) {
+                    a = b;
+                    break;
+                }
+                if (x >= bx0) {
+                    first_x = x;
+                    first_v = median3x3_global(rawf, w, h, x, by);
+                    ++a;
+                    break;
+                }
+            }
+        }
+        mbar_wait(&bar, 0);
+        if (first_x >= 0) t16[threadIdx.x * BW + (first_x - bx0)] = (u16)first_v;
+        for (; a < b; ++a) {  // further flagged pixels of the row: rare
+            const int x = bf.xy[2 * a];
+            if (x >= bx0 + BW) break;
+            t16[threadIdx.x * BW + (x - bx0)] = (u16)median3x3_global(rawf, w, h, x, by);
+        }
+        __syncthreads();
+        // clamp the whole box, store the corrected interior: 8 pixels (16 bytes) per step
+        const unsigned c2 = bf.clamp | (bf.clamp << 16);
+        u16* cframe = bf.corrected + (size_t)f * w * h;
+        for (int v = threadIdx.x; v < BH * (BW / 8); v += GT_WARPS * 32) {
+            const int r = v / (BW / 8), c8 = v - r * (BW / 8);
+            const int gy = y0t - R + r, gx = bx0 + 8 * c8;
+            if (gy < 0 || gy >= h || gx < 0 || gx >= w) continue;  // outside the image the box keeps the hardware's zeros
+            uint4* p = reinterpret_cast<uint4*>(t16 + r * BW + 8 * c8);  // w % 8 == 0 on this path: a vector is in or out
+            uint4 q = *p;
+            q.x = vmaxu2(q.x, c2);
+            q.y = vmaxu2(q.y, c2);
+            q.z = vmaxu2(q.z, c2);
+            q.w = vmaxu2(q.w, c2);
+            *p = q;
+            if (r >= R && r < R + GT_H && c8 >= 1 && c8 <= GT_W / 8) st_stream(reinterpret_cast<uint4*>(cframe + (size_t)gy * w + gx), q);
+        }
+        __syncthreads();
+    } else {
+        mbar_wait(&bar, 0);
+    }
 
 #pragma unroll
     for (int rr = 0; rr < GT_RG + 2 * R; ++rr) {
@@ -405,6 +473,41 @@ gauss_generic_kernel(const TIN* __restrict__ src, float* __restrict__ dst, int w
     }
 }
 
+// bad_pixels_correct + gaussian_filter in one pass over the raw movie (see BpFuse).  Returns 1 when the layout cannot
+// take the tiled path (the caller then runs the two kernels), 0 / -1 otherwise.
+int launch_gaussian_bp_u16(const u16* raw, u16* corrected, float* dst, int w, int h, long long nframes, const GaussTaps& taps,
+                           const int* xy_dev, const int* row_off_dev, int clamp_value, cudaStream_t st)
+{
+    if (nframes <= 0 || w <= 0 || h <= 0) return 0;
+    const int r = taps.radius;
+    const int tiles_x = (int)ceil_div(w, GT_W), tiles_y = (int)ceil_div(h, GT_H);
+    const long long tgrid = nframes * tiles_x * tiles_y;
+    if (r > 4 || (w % 8) != 0 || !aligned16(dst) || !aligned16(corrected) || !option_enabled(OPT_GAUSS_TMA) ||
+        !tma_compatible(raw, (size_t)w * 2, (size_t)w * h * 2) || nframes > 0x7FFFFFFFLL || tgrid > 0x7FFFFFFFLL)
+        return 1;
+    BpFuse bf;
+    bf.raw = raw;
+    bf.xy = xy_dev;
+    bf.row_off = row_off_dev;
+    bf.corrected = corrected;
+    bf.clamp = clamp_value > 0 ? (unsigned)clamp_value & 0xFFFFu : 0u;
+    CUtensorMap tmap;
+#define RIRB_GTB(RR)                                                                                                              \
+    do {                                                                                                                          \
+        if (make_movie_tensor_map(&tmap, raw, 2, w, h, nframes, (size_t)w * 2, (size_t)w * h * 2, GtBox<u16>::BW, GT_H + 2 * RR) != 0) \
+            return -1;                                                                                                            \
+        RIRB_LAUNCH((gauss_tile_kernel<RR, u16, true>), (unsigned)tgrid, GT_WARPS * 32, 0, st, tmap, dst, w, h, tiles_x, tiles_y, taps, bf); \
+    } while (0)
+    switch (r) {
+    case 1: RIRB_GTB(1); break;
+    case 2: RIRB_GTB(2); break;
+    case 3: RIRB_GTB(3); break;
+    default: RIRB_GTB(4); break;
+    }
+#undef RIRB_GTB
+    return 0;
+}
+
 template <typename TIN>
 static int launch_gaussian(const TIN* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st)
 {
@@ -428,7 +531,7 @@ static int launch_gaussian(const TIN* src, float* dst, int w, int h, long long n
         if (make_movie_tensor_map(&tmap, src, (int)esz, w, h, nframes, (size_t)w * esz, (size_t)w * h * esz, GtBox<TIN>::BW, \
                                   GT_H + 2 * RR) != 0)                                                                       \
             return -1;                                                                                                       \
-        RIRB_LAUNCH((gauss_tile_kernel<RR, TIN>), (unsigned)tgrid, GT_WARPS * 32, 0, st, tmap, dst, w, h, tiles_x, tiles_y, taps); \
+        RIRB_LAUNCH((gauss_tile_kernel<RR, TIN, false>), (unsigned)tgrid, GT_WARPS * 32, 0, st, tmap, dst, w, h, tiles_x, tiles_y, taps, BpFuse{}); \
     } while (0)
         switch (r) {
         case 1: RIRB_GT(1); break;

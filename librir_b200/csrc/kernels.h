@@ -53,6 +53,9 @@ struct GaussTaps {
 int gaussian_taps_host(float sigma, GaussTaps* taps);
 int launch_gaussian_f32(const float* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st);
 int launch_gaussian_u16(const u16* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st);
+// correction + filter in one pass (gaussian.cu, BpFuse); 1: layout not eligible, run the two kernels
+int launch_gaussian_bp_u16(const u16* raw, u16* corrected, float* dst, int w, int h, long long nframes, const GaussTaps& taps,
+                           const int* xy_dev, const int* row_off_dev, int clamp_value, cudaStream_t st);
 
 // precode.cu
 int launch_split_planes(const u16* img, const u8* it, int w, int h, u8* y_plane, u8* u_plane, u8* v_plane, int ls_y, int ls_u,

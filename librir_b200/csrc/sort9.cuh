@@ -35,4 +35,32 @@ __device__ __forceinline__ unsigned pick_mid(const unsigned (&v)[9], int c)
 }
 
 
+// BadPixels::correct's replacement value for pixel (x, y): the (c/2)-th smallest of the c in-bounds cells of its 3x3
+// neighbourhood, read from the UNCORRECTED frame (BadPixels.cpp:41-59).
+__device__ __forceinline__ unsigned median3x3_global(const u16* __restrict__ frame, int w, int h, int x, int y)
+{
+    unsigned v[9];
+    if (x > 0 && y > 0 && x < w - 1 && y < h - 1) {  // interior: 9 unconditional loads
+        const u16* p = frame + (size_t)(y - 1) * w + (x - 1);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[r * 3 + c] = p[(size_t)r * w + c];
+        sort9(v);
+        return v[4];
+    }
+    int c = 0;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx, yy = y + dy;
+            const bool ok = xx >= 0 && yy >= 0 && xx < w && yy < h;
+            v[(dy + 1) * 3 + dx + 1] = ok ? (unsigned)frame[(size_t)yy * w + xx] : 0xFFFFFFFFu;
+            c += ok;
+        }
+    sort9(v);
+    return pick_mid(v, c);
+}
+
 }  // namespace rirb

@@ -241,6 +241,22 @@ def bad_pixels_create(first_image):
     return ret
 
 
+def bad_pixels_correct_gaussian_batch(handle, frames, sigma=1.0, out=None, smoothed=None):
+    """``bad_pixels_correct_batch`` followed by ``gaussian_filter_batch`` of the corrected frames, in one pass over the
+    movie: returns ``(corrected uint16 [n,h,w], smoothed float32 [n,h,w])``."""
+    lib = _lib.load()
+    if len(frames.shape) != 3:
+        raise RuntimeError("bad_pixels_correct_gaussian_batch: wrong input dimension")
+    _prepare_device_call(frames)
+    if out is None:
+        out = _empty_like(frames)
+    if smoothed is None:
+        smoothed = _empty_like(frames, np.float32)
+    res = lib.rirb_bad_pixels_correct_gaussian_batch(handle, _ptr(frames), _ptr(out), _ptr(smoothed), frames.shape[0], float(sigma))
+    _lib.check(res, "bad_pixels_correct_gaussian")
+    return out, smoothed
+
+
 def bad_pixels_destroy(handle):
     """
     Destroy bad pixel object
@@ -304,6 +320,9 @@ class BadPixels:
     def correct_batch(self, frames, out=None):
         return bad_pixels_correct_batch(self.handle, frames, out)
 
+    def correct_gaussian_batch(self, frames, sigma=1.0, out=None, smoothed=None):
+        return bad_pixels_correct_gaussian_batch(self.handle, frames, sigma, out, smoothed)
+
 
 __all__ = [
     "translate",
@@ -314,6 +333,7 @@ __all__ = [
     "bad_pixels_create",
     "bad_pixels_correct",
     "bad_pixels_correct_batch",
+    "bad_pixels_correct_gaussian_batch",
     "bad_pixels_destroy",
     "bad_pixels_list",
     "BadPixels",

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 SIZES = [(320, 256), (640, 512), (1024, 1024), (1280, 1024), (2048, 2048)]
-BYTES_PER_PX = {"bp_correct": 4, "gaussian_u16_f32": 6, "gaussian_f32_f32": 8, "translate_u16": 4, "loader_motion_u16": 4, "loader_merge_minT_bp": 4, "loader_read_chain": 8,
+BYTES_PER_PX = {"bp_correct": 4, "bp_correct_gaussian_fused": 8, "gaussian_u16_f32": 6, "gaussian_f32_f32": 8, "translate_u16": 4, "loader_motion_u16": 4, "loader_merge_minT_bp": 4, "loader_read_chain": 8,
                 "precode_split": 4, "precode_delta_split": 4, "decode_delta_merge": 4, "stats_minmax_hist": 2}
 
 
@@ -88,6 +88,7 @@ def main():
 
         cases = {
             "bp_correct": lambda: bp.correct_batch(frames, out=out16),
+            "bp_correct_gaussian_fused": lambda: bp.correct_gaussian_batch(frames, 1.0, out=out16, smoothed=out32),
             "gaussian_u16_f32": lambda: sp.gaussian_filter_batch(frames, 1.0, out=out32),
             "gaussian_f32_f32": run_f32,
             "translate_u16": lambda: sp.translate_batch(frames, dx, dy, "nearest", background=0, out=out16),

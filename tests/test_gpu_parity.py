@@ -891,3 +891,31 @@ def test_entries_are_reentrant_across_threads(best):
     for t in threads:
         t.join()
     assert not errors, errors[:3]
+
+
+@pytest.mark.parametrize("shape", [(5, 64, 128), (3, 200, 264), (4, 70, 136), (2, 5, 8), (3, 130, 640), (2, 33, 20), (2, 64, 127)])
+@pytest.mark.parametrize("sigma", [0.5, 1.0, 1.7, 2.2])
+def test_bad_pixels_correct_gaussian_fused(port, shape, sigma):
+    """rirb_bad_pixels_correct_gaussian_batch = the two separate calls, bit for bit (corrected frames AND filter output):
+    tile seams, images smaller than a tile, flagged pixels on borders / in halos / adjacent to each other, a clamp level
+    that really clamps, widths off the tiled path (fallback), host and device buffers."""
+    n, h, w = shape
+    rng = np.random.default_rng(h * w)
+    mov = ir_movie(n, h, w, seed=5)
+    bad = rng.choice(h * w, max(3, h * w // 25), replace=False)      # 4 % stuck pixels: clusters are common
+    mov.reshape(n, -1)[:, bad[: len(bad) // 2]] = 0
+    mov.reshape(n, -1)[:, bad[len(bad) // 2:]] = 16000
+    mov[:, 0, :] = 0                                                   # a dead first row
+    mov[1:, h // 2, : w // 2] = 3000                                   # below the clamp level in later frames
+    bp = sp.BadPixels(mov[0])
+    want_c = bp.correct_batch(mov)
+    want_g = sp.gaussian_filter_batch(want_c, sigma)
+    got_c, got_g = bp.correct_gaussian_batch(mov, sigma)
+    np.testing.assert_array_equal(got_c, want_c)
+    np.testing.assert_array_equal(got_g, want_g)
+    oxy, _thr, oclamp = port.bad_pixels_detect(mov[0])
+    np.testing.assert_array_equal(got_c[-1], port.bad_pixels_correct_with(oxy, oclamp, mov[-1]))
+    d = to_dev(mov)
+    dc, dg = bp.correct_gaussian_batch(d, sigma)
+    np.testing.assert_array_equal(to_host(dc), want_c)
+    np.testing.assert_array_equal(dg.cpu().numpy(), want_g)
