@@ -303,3 +303,73 @@ def test_fuzz_process_movie_host(port):
             os.environ.pop("RIRB_HOST_SUB_BYTES", None)
         else:
             os.environ["RIRB_HOST_SUB_BYTES"] = old
+
+
+def test_fuzz_split_merge_and_loader_pieces(port):
+    """The writer's / reader's single-frame plane layouts with random line sizes and integration-time images, the in-place
+    loader correction and the stand-alone motion step."""
+    rng = np.random.default_rng(509 + SEED)
+    for case in range(30 * SCALE):
+        w = int(rng.choice(WIDTHS))
+        h = int(rng.integers(1, 80))
+        img = random_frame(rng, h, w)
+        it = rng.integers(0, 256, (h, w), dtype=np.uint8) if rng.integers(0, 2) else None
+        ls = int(w + rng.choice([0, 1, 7, 32, 63])) if rng.integers(0, 2) else None
+        what = f"case {case}: {h}x{w} ls {ls} it {it is not None}"
+        for got, want in zip(vio.split_yuv444(img, it, ls), port.split_444(img, it, ls)):
+            w_ = want.copy()
+            w_[:, w:] = 0  # the oracle marks untouched padding with 0xAA, the wrapper starts from zeros
+            np.testing.assert_array_equal(got, w_, err_msg=what)
+        y, u, v = vio.split_yuv444(img, it, ls)
+        back, it_back = vio.merge_yuv444(y, u, v, w)
+        np.testing.assert_array_equal(back, img, err_msg=what)
+        if it is not None:
+            np.testing.assert_array_equal(it_back, it, err_msg=what)
+        want420 = port.split_420(img, ls)
+        p = vio.split_yuv420(img, None, ls)
+        np.testing.assert_array_equal(p[:, :w], want420[:, :w], err_msg=what)
+        np.testing.assert_array_equal(vio.merge_yuv420(p, w), port.merge_420(want420, w), err_msg=what)
+        # loader pieces on a stack with 3 metadata rows
+        if h >= 6 and w >= 3:
+            n = int(rng.integers(1, 4))
+            mov = np.stack([random_frame(rng, h, w) for _ in range(n)])
+            lbp = vio.LoaderBadPixels(mov[0])
+            xy = sp.bad_pixels_list(lbp.handle)[0]
+            want = mov.copy()
+            for t in range(n):
+                want[t, :h - 3] = port.loader_remove_bad_pixels(mov[t, :h - 3], xy)
+            got = lbp.remove(mov.copy())
+            np.testing.assert_array_equal(got, want, err_msg=what + " loader medians")
+            np.testing.assert_array_equal(lbp.remove(to_dev(mov)).cpu().numpy().view(np.uint16), want, err_msg=what)
+            sx, sy = rng.uniform(-4, 4, n), rng.uniform(-4, 4, n)
+            moved = vio.remove_motion(mov, sx, sy)
+            for t in range(n):
+                wt = mov[t].copy()
+                wt[:h - 3] = port.loader_remove_motion(mov[t, :h - 3], sx[t], sy[t])
+                np.testing.assert_array_equal(moved[t], wt, err_msg=what + " motion")
+
+
+def test_fuzz_batches_equal_single_frames():
+    """Batched entries (one launch for a stack, host or device, per-frame shifts) against the per-frame entries."""
+    rng = np.random.default_rng(510 + SEED)
+    for case in range(12 * SCALE):
+        w = int(rng.choice(WIDTHS))
+        h = int(rng.integers(1, 100))
+        n = int(rng.integers(1, 7))
+        mov = np.stack([random_frame(rng, h, w) for _ in range(n)])
+        st = str(rng.choice(["nearest", "background", "wrap", ""]))
+        dx = rng.uniform(-5, 5, n).astype(np.float32)
+        dy = rng.uniform(-5, 5, n).astype(np.float32)
+        sigma = float(rng.choice([0.4, 1.0, 1.6, 2.3]))
+        what = f"case {case}: {n}x{h}x{w} {st!r} sigma {sigma}"
+        want_t = np.stack([sp.translate(mov[t], dx[t], dy[t], st, 77) for t in range(n)])
+        np.testing.assert_array_equal(sp.translate_batch(mov, dx, dy, st, 77), want_t, err_msg=what)
+        d = to_dev(mov)
+        got = sp.translate_batch(d, torch.from_numpy(dx).cuda(), torch.from_numpy(dy).cuda(), st, 77)
+        np.testing.assert_array_equal(got.cpu().numpy().view(np.uint16), want_t, err_msg=what + " (device)")
+        want_g = np.stack([sp.gaussian_filter(mov[t], sigma) for t in range(n)])
+        np.testing.assert_array_equal(sp.gaussian_filter_batch(mov, sigma), want_g, err_msg=what)
+        np.testing.assert_array_equal(sp.gaussian_filter_batch(d, sigma).cpu().numpy(), want_g, err_msg=what + " (device)")
+        f32 = mov.astype(np.float32)
+        np.testing.assert_array_equal(sp.gaussian_filter_batch(f32, sigma), np.stack([sp.gaussian_filter(f, sigma) for f in f32]),
+                                      err_msg=what + " (float32)")
