@@ -471,13 +471,12 @@ struct EccState {
     void* pinned[2] = {nullptr, nullptr};  // host frames: pinned staging ...
     void* stage2[2] = {nullptr, nullptr};  // ... and their device copies (double-buffered)
     size_t pin_cap[2] = {0, 0};
-    void* stage = nullptr;        // (unused since the prefetch path)
     float* filtered = nullptr;    // one full frame, Gaussian-filtered / converted to float
-    size_t stage_cap = 0, filtered_cap = 0;
+    size_t filtered_cap = 0;
     std::recursive_mutex mu;
     ~EccState()
     {
-        void* ptrs[] = {ref, cur, T, I, gx, gy, mask, qmask, q16, hist, mm, qout, d, partials, stage, filtered};
+        void* ptrs[] = {ref, cur, T, I, gx, gy, mask, qmask, q16, hist, mm, qout, d, partials, filtered};
         for (void* p : ptrs)
             if (p) cudaFree(p);
         for (int i = 0; i < 2; ++i) {
