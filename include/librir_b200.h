@@ -82,7 +82,10 @@ RIRB_API const char* rirb_version(void);
  * "loader_fused" (default 0): rirb_loader_read_movie as one fused pass instead of merge pass + motion pass.
  * "ecc_fused" (default 1): rirb_ecc_compute as ONE cooperative launch (grid barriers between the phases and the
  *   iterations) instead of one launch per iteration.
- * Initial values can also come from RIRB_TRANSLATE_TMA / RIRB_GAUSS_TMA / RIRB_LOADER_FUSED.  -1: unknown key. */
+ * "lossy_run" (default 1): rirb_lossy_add_images walks a run of frames in ONE cooperative launch (two grid barriers
+ *   per frame) instead of three launches per frame.
+ * Initial values can also come from RIRB_TRANSLATE_TMA / RIRB_GAUSS_TMA / RIRB_LOADER_FUSED / RIRB_ECC_FUSED /
+ * RIRB_LOSSY_RUN.  -1: unknown key. */
 RIRB_API int rirb_set_parameter(const char* key, const char* value);
 
 /* ---- batches of frames (nframes dense frames back to back) ---- */

@@ -139,7 +139,7 @@ def load() -> ct.CDLL:
 
 
 def set_parameter(key: str, value) -> None:
-    """``rirb_set_parameter``: process-wide kernel-variant switches ("translate_tma", "gauss_tma", "loader_fused", "ecc_fused")."""
+    """``rirb_set_parameter``: process-wide kernel-variant switches ("translate_tma", "gauss_tma", "loader_fused", "ecc_fused", "lossy_run")."""
     check(load().rirb_set_parameter(key.encode(), str(int(value)).encode()), "set_parameter")
 
 

@@ -46,9 +46,9 @@ void set_error(const char* fmt, ...)
 cudaStream_t current_stream() { return tls.stream; }
 
 // ---- run-time switches ---------------------------------------------------------------------------
-static const char* const k_opt_names[OPT_COUNT] = {"translate_tma", "gauss_tma", "loader_fused", "ecc_fused"};
-static const char* const k_opt_env[OPT_COUNT] = {"RIRB_TRANSLATE_TMA", "RIRB_GAUSS_TMA", "RIRB_LOADER_FUSED", "RIRB_ECC_FUSED"};
-static const int k_opt_default[OPT_COUNT] = {1, 1, 0, 1};
+static const char* const k_opt_names[OPT_COUNT] = {"translate_tma", "gauss_tma", "loader_fused", "ecc_fused", "lossy_run"};
+static const char* const k_opt_env[OPT_COUNT] = {"RIRB_TRANSLATE_TMA", "RIRB_GAUSS_TMA", "RIRB_LOADER_FUSED", "RIRB_ECC_FUSED", "RIRB_LOSSY_RUN"};
+static const int k_opt_default[OPT_COUNT] = {1, 1, 0, 1, 1};
 static std::atomic<int> g_opts[OPT_COUNT];
 static std::once_flag g_opts_once;
 static void init_options()
@@ -1132,6 +1132,7 @@ int rirb_key_frames(long long nframes, int gop, unsigned char* key)
 namespace {
 struct LossyState {
     int w = 0, h = 0, stop_h = 0, low = 6, high = 2, ra = 32, subtract_min = 0, bp_enabled = 0, device = 0;
+    bool use_run = true;  // several frames per cooperative launch; cleared if the device cannot do it (or by "lossy_run" = 0)
     double std_factor = 5.0;
     long long frames = 0;
     int bp_handle = 0;
@@ -1139,8 +1140,11 @@ struct LossyState {
     size_t o_lastDL = 0, o_refT = 0, o_prevT = 0, o_tmp = 0, o_tmpT = 0, o_sums = 0, o_cval = 0, o_ccnt = 0, o_ring = 0, o_scal = 0;
     int* errors_dev = nullptr;
     long long errors_cap = 0;
+    u16* cur_batch = nullptr;  // bad-pixel-corrected copies of a run of frames (lossy_run_kernel), when that is enabled
+    size_t cur_batch_frames = 0;
     ~LossyState()
     {
+        if (cur_batch) cudaFree(cur_batch);
         if (buf) cudaFree(buf);
         if (errors_dev) cudaFree(errors_dev);
         if (bp_handle) bad_pixels_destroy(bp_handle);
@@ -1243,9 +1247,44 @@ int rirb_lossy_add_images(int handle, const unsigned short* frames, long long nf
     unsigned* sums = (unsigned*)(b + s->o_sums);
     short* ccnt = (short*)(b + s->o_ccnt);
     void* scal = b + s->o_scal;
-    for (long long f = 0; f < nframes; ++f) {
+    long long f = 0;
+    while (f < nframes) {
         const u16* img = d_in + (size_t)f * n;
         u16* dst = (u16*)o.dev + (size_t)f * n;
+        if (s->frames >= 1 && s->use_run && option_enabled(OPT_LOSSY_RUN)) {
+            // a run of non-initial frames in one cooperative launch (lossy_run_kernel)
+            const long long m = std::min<long long>(nframes - f, 64);
+            const u16* cur = img;
+            if (s->bp_enabled && ns > 0) {
+                if (s->cur_batch_frames < (size_t)m) {
+                    if (s->cur_batch) cudaFree(s->cur_batch);
+                    s->cur_batch = nullptr;
+                    s->cur_batch_frames = 0;
+                    RIRB_CUDA_OK(cudaMalloc((void**)&s->cur_batch, (size_t)64 * n * 2));
+                    s->cur_batch_frames = 64;
+                }
+                auto bp = find_handle(s->bp_handle);
+                if (!bp) {
+                    set_error("lossy_add_images: the bad-pixel handle of the first frame is gone");
+                    return -1;
+                }
+                if (launch_bp_correct(img, s->cur_batch, bp->xy_dev, bp->span_off_dev, w, s->stop_h, bp->clamp_value, m, (size_t)n, st) != 0)
+                    return -1;
+                if (n > ns)
+                    RIRB_CUDA_OK(cudaMemcpy2DAsync(s->cur_batch + ns, (size_t)n * 2, img + ns, (size_t)n * 2, (size_t)(n - ns) * 2, (size_t)m,
+                                                   cudaMemcpyDeviceToDevice, st));
+                cur = s->cur_batch;
+            }
+            const int rc = launch_lossy_run(img, cur, tmpT, dst, lastDL, refT, prevT, sums, cval, ccnt, ring, n, ns, s->ra, s->subtract_min,
+                                            s->frames, (int)m, s->low, s->high, s->std_factor, scal, s->errors_dev + 2 * f, st);
+            if (rc < 0) return -1;
+            if (rc == 0) {
+                s->frames += m;
+                f += m;
+                continue;
+            }
+            s->use_run = false;  // no cooperative launch on this device: frame by frame from here on
+        }
         const u16* cur = img;  // "tmp" of the reference
         if (s->bp_enabled && ns > 0) {  // bp.init on the first image's lossy rows, bp.correct on every image (:2259-2266)
             if (s->frames == 0 && s->bp_handle == 0) {
@@ -1265,6 +1304,7 @@ int rirb_lossy_add_images(int handle, const unsigned short* frames, long long nf
                                     s->frames, s->low, s->high, s->std_factor, scal, s->errors_dev + 2 * f, st);
         if (rc != 0) return -1;
         ++s->frames;
+        ++f;
     }
     if (errors) RIRB_CUDA_OK(cudaMemcpyAsync(errors, s->errors_dev, sizeof(int) * 2 * (size_t)nframes, cudaMemcpyDefault, st));
     if (o.host) RIRB_CUDA_OK(copy_d2h(o.host, o.dev, o.bytes, st));

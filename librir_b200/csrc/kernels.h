@@ -73,6 +73,10 @@ int launch_decode_movie(const u8* lo, const u8* hi, long long nframes, int w, in
 size_t lossy_scalars_bytes();
 int launch_lossy_first(const u16* tmp, u16* out, u16* lastDL, u16* refT, u16* prevT, int n, int ns, int subtract_min, void* scalars,
                        int* errors_out_dev, int low0, int high0, cudaStream_t st);
+// several consecutive non-initial frames in ONE cooperative launch (lossy.cu, lossy_run_kernel); 1: not available
+int launch_lossy_run(const u16* img, const u16* cur, u16* tmpT, u16* out, u16* lastDL, u16* refT, u16* prevT, unsigned* sums, u16* cvalue,
+                     short* ccount, u16* ring, int n, int ns, int ra, int subtract_min, long long frame_index, int m, int low0,
+                     int high0, double std_factor, void* scalars, int* errors_out_dev, cudaStream_t st);
 int launch_lossy_frame(const u16* img, const u16* tmp, u16* tmpT, u16* out, u16* lastDL, u16* refT, u16* prevT, unsigned* sums,
                        u16* cvalue, short* ccount, u16* ring, int n, int ns, int ra, int subtract_min, long long frame_index,
                        int low0, int high0, double std_factor, void* scalars, int* errors_out_dev, cudaStream_t st);

@@ -17,6 +17,8 @@
 // non-contracted fp64 by one thread, so the outputs are bit-identical to the restated reference.
 // State per pixel: sums u32, const (value u16, count i16), refT, prevT, lastDL u16 and a ring of
 // `running_average` frames -- 12 + 2 * running_average bytes.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -32,6 +34,11 @@ struct LossyScalars {
     double stds[40][2];             // stdDevs window, circular: the oldest entry is stds[head] once 40 are in
     alignas(16) unsigned hist[16384];
     unsigned ticket[2];             // "last CTA done" counters of the two reduction kernels
+    // lossy_run_kernel (several frames per launch): two histograms and two sets of sums, used alternately by frame
+    // parity -- the set a frame does not use is cleared while it runs, so no extra grid barrier is spent on zeroing
+    alignas(16) unsigned hist2[2][16384];
+    unsigned long long rsum[2][4];
+    unsigned rcnt[2][2];
 };
 
 __global__ void lossy_min_kernel(const u16* __restrict__ tmp, int ns, LossyScalars* sc)
@@ -312,6 +319,269 @@ __global__ void lossy_update_kernel(const u16* __restrict__ tmp, const u16* __re
         prevT[i] = (u16)o;
         lastDL[i] = (u16)v;
     }
+}
+
+// ---- several frames per launch ------------------------------------------------------------------
+// The three launches per frame above cost more in launch latency than in work (0.65 MB per frame).  This kernel walks
+// through a run of frames by itself: one cooperative launch, one 1024-thread CTA per SM, TWO grid barriers per frame --
+//   histogram of the frame (+ tmpT)            | barrier |  every CTA finds the mode itself; stdDev sums
+//   | barrier |  every CTA evaluates the error bounds itself (CTA 0 also records them); per-pixel update
+// and straight on to the next frame: a pixel is always handled by the same thread (same grid-stride mapping in every
+// phase), so the per-pixel state needs no barrier between frames.  All reductions are integer sums: any order gives the
+// same bits.  The histogram / sum set of the other parity is cleared while a frame runs.
+struct LossyRun {
+    const u16* img;      // [m][n] frames as given (the "> background" test reads them)
+    const u16* cur;      // [m][n] the reference's tmp: the same frames, bad-pixel-corrected when that is enabled
+    u16* out;            // [m][n]
+    u16 *tmpT, *lastDL, *refT, *prevT, *cvalue, *ring;
+    unsigned* sums;
+    short* ccount;
+    LossyScalars* sc;
+    int* errors_out;     // [m][2]
+    int n, ns, ra, subtract_min, low0, high0, m;
+    long long frame_index;  // of the first frame of the run (>= 1)
+    double std_factor;
+};
+
+__global__ void __launch_bounds__(1024) lossy_run_kernel(const __grid_constant__ LossyRun p)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ unsigned sh[];  // 16,384 bins
+    __shared__ unsigned bv[1024];
+    __shared__ int bi[1024];
+    __shared__ unsigned long long part[32][4];
+    __shared__ unsigned pcnt[32][2];
+    __shared__ double win[40][2];
+    __shared__ int decided[2];
+    LossyScalars* sc = p.sc;
+    const int t = threadIdx.x, gt = blockIdx.x * 1024 + t, gstride = gridDim.x * 1024;
+    const int n = p.n, ns = p.ns, ra = p.ra;
+    const unsigned mn = p.subtract_min ? sc->minv : 0u;
+    for (int f = 0; f < p.m; ++f) {
+        const long long prior = p.frame_index + f - 1;  // non-initial frames before this one
+        const int par = (int)((p.frame_index + f) & 1);
+        const int nstds = (int)min(prior, 40LL), head = (int)(prior % 40), first = prior == 0;
+        const int len_before = (int)min(prior, (long long)ra), slot = ra > 0 ? (int)(prior % ra) : 0;
+        const u16* img = p.img + (size_t)f * n;
+        const u16* tmp = p.cur + (size_t)f * n;
+        u16* out = p.out + (size_t)f * n;
+        // ---- histogram of tmp >> 2, tmpT = tmp - min ----
+        for (int i = t; i < 16384; i += 1024) sh[i] = 0;
+        __syncthreads();
+        for (int i = gt; i < ns; i += gstride) {
+            const unsigned v = tmp[i];
+            p.tmpT[i] = (u16)(v < mn ? 0u : v - mn);
+            atomicAdd(&sh[v >> 2], 1u);
+        }
+        __syncthreads();
+        for (int i = t; i < 16384; i += 1024) {
+            const unsigned c = sh[i];
+            if (c) atomicAdd(&sc->hist2[par][i], c);
+        }
+        grid.sync();
+        // ---- background = (first maximum bin << 2) + 1, found by every CTA; the other parity's sets are cleared ----
+        for (int i = gt; i < 16384; i += gstride) sc->hist2[par ^ 1][i] = 0;
+        if (blockIdx.x == 0 && t < 4) sc->rsum[par ^ 1][t] = 0ull;
+        if (blockIdx.x == 0 && t >= 4 && t < 6) sc->rcnt[par ^ 1][t - 4] = 0u;
+        {
+            const uint4* hv = reinterpret_cast<const uint4*>(&sc->hist2[par][t * 16]);
+            uint4 q[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[k] = __ldcg(hv + k);
+            const unsigned c16[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w,
+                                      q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
+            unsigned best = c16[0];
+            int idx = t * 16;
+#pragma unroll
+            for (int k = 1; k < 16; ++k)
+                if (c16[k] > best) {
+                    best = c16[k];
+                    idx = t * 16 + k;
+                }
+            bv[t] = best;
+            bi[t] = idx;
+            __syncthreads();
+            for (int s2 = 512; s2 > 0; s2 >>= 1) {
+                if (t < s2 && (bv[t + s2] > bv[t] || (bv[t + s2] == bv[t] && bi[t + s2] < bi[t]))) {
+                    bv[t] = bv[t + s2];
+                    bi[t] = bi[t + s2];
+                }
+                __syncthreads();
+            }
+        }
+        const unsigned back = ((unsigned)bi[0] << 2) + 1u;
+        // ---- stdDev's sums, split by img > background ----
+        {
+            unsigned long long sd = 0, sd2 = 0, bd = 0, bd2 = 0;
+            unsigned nf = 0, nb = 0;
+            for (int i = gt; i < ns; i += gstride) {
+                const int d = abs((int)p.tmpT[i] - (int)p.prevT[i]);
+                const unsigned long long d2 = (unsigned long long)d * (unsigned long long)d;
+                if ((unsigned)img[i] > back) {
+                    sd += d; sd2 += d2; ++nf;
+                } else {
+                    bd += d; bd2 += d2; ++nb;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sd += __shfl_xor_sync(0xFFFFFFFFu, sd, o);
+                sd2 += __shfl_xor_sync(0xFFFFFFFFu, sd2, o);
+                bd += __shfl_xor_sync(0xFFFFFFFFu, bd, o);
+                bd2 += __shfl_xor_sync(0xFFFFFFFFu, bd2, o);
+                nf += __shfl_xor_sync(0xFFFFFFFFu, nf, o);
+                nb += __shfl_xor_sync(0xFFFFFFFFu, nb, o);
+            }
+            const int warp = t >> 5, lane = t & 31;
+            if (lane == 0) {
+                part[warp][0] = sd; part[warp][1] = sd2; part[warp][2] = bd; part[warp][3] = bd2;
+                pcnt[warp][0] = nf; pcnt[warp][1] = nb;
+            }
+            __syncthreads();
+            if (t < 4) {
+                unsigned long long a = 0;
+                for (int k = 0; k < 32; ++k) a += part[k][t];
+                atomicAdd(&sc->rsum[par][t], a);
+            } else if (t < 6) {
+                unsigned a = 0;
+                for (int k = 0; k < 32; ++k) a += pcnt[k][t - 4];
+                atomicAdd(&sc->rcnt[par][t - 4], a);
+            }
+        }
+        grid.sync();
+        // ---- error bounds of this frame (:2337-2376): the reference's fp64 operation order, one thread per CTA ----
+        if (t < 40) {  // window in time order: oldest first
+            const int s2 = nstds < 40 ? t : (head + t) % 40;
+            win[t][0] = sc->stds[s2][0];
+            win[t][1] = sc->stds[s2][1];
+        }
+        __syncthreads();
+        if (t == 0) {
+            unsigned long long su[4];
+            unsigned cn[2];
+            for (int k = 0; k < 4; ++k) su[k] = __ldcg(&sc->rsum[par][k]);
+            for (int k = 0; k < 2; ++k) cn[k] = __ldcg(&sc->rcnt[par][k]);
+            double sd0, sd1;
+            if (nstds < 40) {
+                const double s1 = (double)(su[0] + su[2]), s2 = (double)(su[1] + su[3]);
+                sd0 = sd1 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(s1, s1), s2)), (double)ns);
+            } else {
+                const double s1 = (double)su[0], s2 = (double)su[1], b1 = (double)su[2], b2 = (double)su[3];
+                sd0 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(b1, b1), b2)), (double)(int)cn[1]);
+                sd1 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(s1, s1), s2)), (double)(int)cn[0]);
+            }
+            const double f0 = first ? sd0 : sc->first[0], f1 = first ? sd1 : sc->first[1];
+            const int cnt = nstds < 40 ? nstds + 1 : 40, from = nstds < 40 ? 0 : 1;
+            double m0 = f0, m1 = f1;
+            for (int i = from; i < (nstds < 40 ? nstds : 40); ++i) {
+                m0 = __dadd_rn(m0, win[i][0]);
+                m1 = __dadd_rn(m1, win[i][1]);
+            }
+            m0 = __ddiv_rn(__dadd_rn(m0, sd0), (double)(cnt + 1));
+            m1 = __ddiv_rn(__dadd_rn(m1, sd1), (double)(cnt + 1));
+            int high = p.high0 - (int)round(__dmul_rn(fabs(__dsub_rn(sd1, m1)), p.std_factor));
+            int low = p.low0 - (int)round(__dmul_rn(fabs(__dsub_rn(sd0, m0)), p.std_factor));
+            if (high < 0) high = 0;
+            if (low < high) low = high;
+            decided[0] = low;
+            decided[1] = high;
+            if (blockIdx.x == 0) {  // the state that outlives the frame is written once
+                if (first) {
+                    sc->first[0] = sd0;
+                    sc->first[1] = sd1;
+                }
+                const int dst = nstds < 40 ? nstds : head;  // push, or the oldest slot becomes the newest
+                sc->stds[dst][0] = sd0;
+                sc->stds[dst][1] = sd1;
+                sc->background = back;
+                sc->low_error = low;
+                sc->high_error = high;
+                p.errors_out[2 * f] = low;
+                p.errors_out[2 * f + 1] = high;
+            }
+        }
+        __syncthreads();
+        const int low = decided[0], high = decided[1];
+        // ---- per-pixel update (:2392-2421) ----
+        const unsigned len_after = (unsigned)(len_before < ra ? len_before + 1 : ra);
+        for (int i = gt; i < n; i += gstride) {
+            const unsigned v = tmp[i];
+            if (i >= ns) {
+                out[i] = (u16)v;
+                p.lastDL[i] = (u16)v;
+                continue;
+            }
+            const unsigned tv = p.tmpT[i];
+            unsigned s = 0;
+            short cc = 0;
+            if (ra > 0) {
+                s = p.sums[i] + tv;
+                cc = p.ccount[i];
+                if (len_before == ra) {
+                    if (cc) {
+                        --cc;
+                        s -= p.cvalue[i];
+                    } else {
+                        s -= p.ring[(size_t)slot * ns + i];
+                    }
+                }
+                p.ring[(size_t)slot * ns + i] = (u16)tv;
+            }
+            const unsigned r = p.refT[i];
+            const int diff = abs((int)tv - (int)r);
+            const int max_error = v > back ? high : low;
+            unsigned o;
+            if (diff <= max_error && ((unsigned)p.lastDL[i] >> 13) == (v >> 13)) {
+                o = ra > 0 ? ((s / len_after) & 0xFFFFu) : r;
+            } else {
+                o = tv;
+                p.refT[i] = (u16)tv;
+                if (ra > 0) {
+                    p.cvalue[i] = (u16)tv;
+                    cc = (short)len_after;
+                    s = tv * len_after;
+                }
+            }
+            if (ra > 0) {
+                p.sums[i] = s;
+                p.ccount[i] = cc;
+            }
+            out[i] = (u16)o;
+            p.prevT[i] = (u16)o;
+            p.lastDL[i] = (u16)v;
+        }
+        // the window entry CTA 0 wrote is read by every CTA in the NEXT frame's decide step, two grid barriers away
+    }
+}
+
+// frames [0, m) of img / cur / out are consecutive non-initial frames, the first of them frame number frame_index.
+// Returns 1 when the device cannot launch cooperatively (the caller then goes frame by frame).
+int launch_lossy_run(const u16* img, const u16* cur, u16* tmpT, u16* out, u16* lastDL, u16* refT, u16* prevT, unsigned* sums, u16* cvalue,
+                     short* ccount, u16* ring, int n, int ns, int ra, int subtract_min, long long frame_index, int m, int low0,
+                     int high0, double std_factor, void* scalars, int* errors_out_dev, cudaStream_t st)
+{
+    if (m <= 0) return 0;
+    int dev = 0, coop = 0, per_sm = 0;
+    RIRB_CUDA_OK(cudaGetDevice(&dev));
+    RIRB_SMEM_ATTR(lossy_run_kernel, 16384 * 4);
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lossy_run_kernel, 1024, 16384 * 4) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return 1;
+    }
+    LossyRun p;
+    p.img = img; p.cur = cur; p.out = out; p.tmpT = tmpT; p.lastDL = lastDL; p.refT = refT; p.prevT = prevT; p.cvalue = cvalue;
+    p.ring = ring; p.sums = sums; p.ccount = ccount; p.sc = (LossyScalars*)scalars; p.errors_out = errors_out_dev;
+    p.n = n; p.ns = ns; p.ra = ra; p.subtract_min = subtract_min; p.low0 = low0; p.high0 = high0; p.m = m;
+    p.frame_index = frame_index; p.std_factor = std_factor;
+    const int grid = (int)max(1LL, min((long long)ceil_div(n, 1024 * 2), (long long)sm_count()));
+    // both parity sets start clean whatever ran before (a handle may alternate between this path and the per-frame one)
+    RIRB_CUDA_OK(cudaMemsetAsync(p.sc->hist2, 0, sizeof(p.sc->hist2) + sizeof(p.sc->rsum) + sizeof(p.sc->rcnt), st));
+    void* args[] = {&p};
+    RIRB_CUDA_OK(cudaLaunchCooperativeKernel((const void*)lossy_run_kernel, dim3((unsigned)grid), dim3(1024), args, 16384 * 4, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
 }
 
 // ---- launchers ----------------------------------------------------------------------------------

@@ -145,7 +145,7 @@ def test_fuzz_quantiles(port):
 
 def test_fuzz_lossy_preconditioner(port):
     rng = np.random.default_rng(505 + SEED)
-    for case in range(3 * SCALE):
+    for case in range(4 * SCALE):
         w = int(rng.choice([16, 40, 64, 96, 136]))
         h = int(rng.integers(8, 60))
         n = int(rng.integers(5, 70))
@@ -166,8 +166,13 @@ def test_fuzz_lossy_preconditioner(port):
                                       stdFactor=cfg["std_factor"], runningAverage=cfg["running_average"], subtractMin=cfg["subtract_min"],
                                       removeBadPixels=cfg["bp_enabled"])
         k = int(rng.integers(1, n))
+        from librir_b200 import _lib
+
+        _lib.set_parameter("lossy_run", int(rng.integers(0, 2)))  # the two drivers may alternate on one handle
         out_a, err_a = pre.add_images(mov[:k])
+        _lib.set_parameter("lossy_run", int(rng.integers(0, 2)))
         out_b, err_b = pre.add_images(mov[k:])
+        _lib.set_parameter("lossy_run", 1)
         np.testing.assert_array_equal(np.concatenate([out_a, out_b]), np.stack(want), err_msg=f"case {case}: {n}x{h}x{w} {cfg} stop {stop}")
         np.testing.assert_array_equal(np.concatenate([err_a, err_b]), np.array(werr))
 

@@ -732,10 +732,17 @@ def lossy_movie(n, h, w, seed=0):
     return np.clip(mov, 0, 65535).astype(np.uint16)
 
 
+@pytest.fixture(params=["one launch per run of frames", "three launches per frame"])
+def lossy_driver(request):
+    _lib.set_parameter("lossy_run", request.param == "one launch per run of frames")
+    yield request.param
+    _lib.set_parameter("lossy_run", 1)
+
+
 @pytest.mark.parametrize("cfg", [dict(), dict(runningAverage=0), dict(runningAverage=5, subtractMin=True),
                                  dict(removeBadPixels=True, lowValueError=12, highValueError=5),
                                  dict(runningAverage=64, subtractMin=True, removeBadPixels=True, stdFactor=2.0)])
-def test_lossy_preconditioner_matches_restated_reference(port, cfg):
+def test_lossy_preconditioner_matches_restated_reference(port, cfg, lossy_driver):
     """rirb_lossy_* against the line-by-line restatement of addImageLossyNoCamera, frame by frame and with the
     state carried across calls: the frozen / restarted pixels, the running average ring wrapping, the switch to
     background-split spreads after 40 frames, the per-frame error attributes."""
