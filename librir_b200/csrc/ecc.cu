@@ -350,9 +350,9 @@ ecc_iter_kernel(const float* __restrict__ T, const float* __restrict__ I, const 
 // arithmetic, identical result), so no second barrier is needed to publish the new shift.  The slots are double-buffered
 // by iteration parity: a fast CTA writes iteration it + 1's sums into the other buffer while a slow one still reads it's.
 __global__ void __launch_bounds__(ECC_THREADS)
-ecc_solve_kernel(const float* __restrict__ ref, const float* __restrict__ cur, const u8* __restrict__ mask, int w, int h, float thresh,
-                 float* __restrict__ T, float* __restrict__ I, float* __restrict__ gx, float* __restrict__ gy, EccDev* d, double* partials,
-                 float tx0, float ty0, int max_it, double eps)
+ecc_solve_kernel(const float* __restrict__ ref, float* cur, const float* cur_src, int cur_stride, const u8* __restrict__ mask, int w, int h,
+                 float thresh, float* __restrict__ T, float* __restrict__ I, float* __restrict__ gx, float* __restrict__ gy, EccDev* d,
+                 double* partials, float tx0, float ty0, int max_it, double eps)
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -364,11 +364,14 @@ ecc_solve_kernel(const float* __restrict__ ref, const float* __restrict__ cur, c
     const int gtid = blockIdx.x * ECC_THREADS + threadIdx.x, gthreads = gridDim.x * ECC_THREADS;
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
 
-    // ---- min / max of the clamped windows (d->mm was initialised by the host before the launch) ----
+    // ---- min / max of the clamped windows (d->mm is in its initial state: rirb_ecc_open, then the end of every solve);
+    //      the current window is picked out of the filtered frame on the way (cur_src, rows cur_stride floats apart) ----
     {
         unsigned k[4] = {0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u};
         for (int i = gtid; i < npx; i += gthreads) {
-            const float r = ref[i], c = cur[i];
+            const int yy = i / w, xx = i - yy * w;
+            const float r = ref[i], c = cur_src[(size_t)yy * cur_stride + xx];
+            cur[i] = c;
             const unsigned kr = fkey(clamp_pair(r, c, thresh)), kc = fkey(clamp_pair(c, r, thresh));
             k[0] = min(k[0], kr);
             k[1] = max(k[1], kr);
@@ -441,6 +444,8 @@ ecc_solve_kernel(const float* __restrict__ ref, const float* __restrict__ cur, c
         d->it = s.it;
         d->status = s.status;
         d->done = 1;
+        d->mm[0] = d->mm[2] = 0xFFFFFFFFu;  // ready for the next solve: every CTA read them two barriers ago
+        d->mm[1] = d->mm[3] = 0u;
     }
 }
 
@@ -450,6 +455,7 @@ struct EccState {
     float *ref = nullptr, *cur = nullptr, *T = nullptr, *I = nullptr, *gx = nullptr, *gy = nullptr;
     u8 *mask = nullptr, *qmask = nullptr;  // ECC mask; mask of the quantile thresholds (see rirb_ecc_set_mask)
     bool have_mask = false, have_qmask = false, have_ref = false, have_cur = false;
+    bool mm_clean = false;  // the min/max words of `d` are in their initial state (the one-launch solver leaves them so)
     u16* q16 = nullptr;               // quantile scratch: the crop cast to uint16
     unsigned long long* hist = nullptr;
     unsigned* mm = nullptr;
@@ -541,26 +547,35 @@ static int ecc_load_window(EccState& s, float* dst, const float* src, int stride
 // The solve in two halves, so that a caller can do host work (fetching the next frame) while the GPU is busy.
 // enqueue: everything up to and including the copy of the result towards the host; collect: wait, and for the
 // launch-per-iteration driver keep launching until the problem reports done.
-static int ecc_enqueue(EccState& s, float thresh, int use_mask, int max_iterations, double eps, const float* shift)
+static int ecc_enqueue(EccState& s, float thresh, int use_mask, int max_iterations, double eps, const float* shift,
+                       const float* cur_src = nullptr, int cur_stride = 0)
 {
     cudaStream_t st = current_stream();
     const int n = s.w * s.h;
     const float th = isnan(thresh) ? INFINITY : thresh;
     const u8* mask = (use_mask && s.have_mask) ? s.mask : nullptr;
     if (!s.result) RIRB_CUDA_OK(cudaMallocHost((void**)&s.result, sizeof(EccDev)));  // pinned: the copy back does not stall the host
-    RIRB_LAUNCH(ecc_begin_kernel, 1, 1, 0, st, s.d, shift[0], shift[1], max_iterations, eps);
     s.launched = 0;
     if (s.coop_grid > 0 && option_enabled(OPT_ECC_FUSED)) {
-        // the whole solve in one cooperative launch ("ecc_fused" = 0 selects the launch-per-iteration driver)
+        // the whole solve in one cooperative launch ("ecc_fused" = 0 selects the launch-per-iteration driver); it leaves
+        // the min/max words in their initial state, so no preparing launch is needed unless the other driver ran last
+        if (!s.mm_clean) RIRB_LAUNCH(ecc_begin_kernel, 1, 1, 0, st, s.d, shift[0], shift[1], max_iterations, eps);
+        s.mm_clean = true;
         const float* ref = s.ref;
-        const float* cur = s.cur;
+        float* cur = s.cur;
+        const float* src = cur_src ? cur_src : s.cur;
+        int stride = cur_src ? cur_stride : s.w;
         int w = s.w, h = s.h;
         float th_arg = th, tx0 = shift[0], ty0 = shift[1];
-        void* args[] = {&ref, &cur, &mask, &w, &h, &th_arg, &s.T, &s.I, &s.gx, &s.gy, &s.d, &s.partials, &tx0, &ty0, &max_iterations, &eps};
+        void* args[] = {&ref, &cur, &src, &stride, &mask, &w, &h, &th_arg, &s.T, &s.I, &s.gx, &s.gy, &s.d, &s.partials, &tx0, &ty0,
+                        &max_iterations, &eps};
         RIRB_CUDA_OK(cudaLaunchCooperativeKernel((const void*)ecc_solve_kernel, dim3((unsigned)s.coop_grid), dim3(ECC_THREADS), args, 0, st));
         g_launches.fetch_add(1);
         s.launched = max_iterations;
     } else {
+        if (cur_src && ecc_load_window(s, s.cur, cur_src, cur_stride, st) != 0) return -1;
+        RIRB_LAUNCH(ecc_begin_kernel, 1, 1, 0, st, s.d, shift[0], shift[1], max_iterations, eps);
+        s.mm_clean = false;
         const int blocks = (int)min((long long)ceil_div(n, ECC_THREADS), (long long)s.max_grid);
         RIRB_LAUNCH(ecc_minmax_kernel, (unsigned)blocks, ECC_THREADS, 0, st, s.ref, s.cur, n, th, s.d);
         RIRB_LAUNCH(ecc_normalise_kernel, dim3((unsigned)ceil_div(s.w, ECC_THREADS), (unsigned)s.h), ECC_THREADS, 0, st, s.ref, s.cur, mask,
@@ -887,7 +902,13 @@ int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, 
             RIRB_CUDA_OK(cudaStreamSynchronize(st));  // the staged frame is free again
             continue;
         }
-        if (ecc_load_window(*s, s->cur, window, full_w, st) != 0) return -1;
+        // the one-launch solver picks the window out of the filtered frame itself; the quantile thresholds (median < 1)
+        // read the compact copy first, so they get an explicit one
+        bool window_loaded = false;
+        if (s->median < 1.0) {
+            if (ecc_load_window(*s, s->cur, window, full_w, st) != 0) return -1;
+            window_loaded = true;
+        }
         s->have_cur = true;
         int tries = 0, status = 0, its = 0;
         double rho = 0.0;
@@ -902,7 +923,8 @@ int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, 
             }
             shift[0] = s->start[0];
             shift[1] = s->start[1];
-            if (ecc_enqueue(*s, thresh, use_mask, 500, 1e-3, shift) != 0) return -1;
+            if (ecc_enqueue(*s, thresh, use_mask, 500, 1e-3, shift, window_loaded ? nullptr : window, full_w) != 0) return -1;
+            window_loaded = true;  // a retry works on the compact copy
             if (fetch_next() != 0) return -1;  // host memcpy + upload of frame t + 1 while the GPU solves frame t
             status = ecc_collect(*s, use_mask, 500, shift, &rho, &its);
             if (status < 0) return -1;
