@@ -11,8 +11,9 @@
 //                         interleaved with PRMT, min_T is added per halfword where the row asks for
 //                         it, 256-bit store; then one thread per flagged pixel of the span takes the
 //                         median of the un-flagged cells of its shifted 3x3 window straight from the
-//                         two byte planes (rows the CTA is streaming anyway: L2 hits) and overwrites
-//                         the pixel.  4 B/px: 2 read + 2 written.
+//                         two byte planes (rows the CTA has just streamed: L1 hits, because spans with
+//                         flagged pixels load with default caching) and overwrites the pixel.
+//                         4 B/px: 2 read + 2 written.
 //   translate_u16_tma_kernel<MOTION>  (translate.cu) for the motion step, 4 B/px.
 #include "common.cuh"
 #include "kernels.h"
@@ -58,12 +59,17 @@ loader_merge_kernel(const u8* __restrict__ lo, const u8* __restrict__ hi, u16* _
         for (int k = 0; k < LD_UNROLL; ++k) {
             const int j = threadIdx.x + k * LD_THREADS;
             if (j < nvec) {
-                rl[k] = ld_stream(gl + j);
-                rh[k] = ld_stream(gh + j);
+                if (a != b) {  // spans with flagged pixels: default caching, their medians re-read these rows
+                    rl[k] = __ldg(gl + j);
+                    rh[k] = __ldg(gh + j);
+                } else {
+                    rl[k] = ld_stream(gl + j);
+                    rh[k] = ld_stream(gh + j);
+                }
             }
         }
     }
-    // first fix-up of this thread, gathered while the stream loads are in flight (as in bp_correct_kernel)
+    // first fix-up of this thread (evaluated after the streaming stores, see below)
     const int i0 = a + (int)threadIdx.x;
     int2 p0 = make_int2(0, 0);
     unsigned med0 = 0;
@@ -90,10 +96,6 @@ loader_merge_kernel(const u8* __restrict__ lo, const u8* __restrict__ hi, u16* _
         med = pick_mid(v, c);
         return true;
     };
-    if (i0 < b) {
-        p0 = reinterpret_cast<const int2*>(xy)[i0];
-        have0 = fix(p0, nbr[i0], med0);
-    }
     int done = s0;
     if (VEC) {
         const unsigned t2 = min_t | (min_t << 16);
@@ -118,6 +120,14 @@ loader_merge_kernel(const u8* __restrict__ lo, const u8* __restrict__ hi, u16* _
     }
     for (int i = done + threadIdx.x; i < s1; i += LD_THREADS) oframe[i] = (u16)merged_px(flo, fhi, i, i < t_limit_px ? min_t : 0u);
     if (a == b) return;  // CTA-uniform
+    // The medians re-read, byte by byte, rows this CTA has just streamed.  With the streaming (L1 no-allocate) loads
+    // every one of those 18 sectors per flagged pixel came from DRAM a second time (ncu: 1.73 GB read for 1.31 GB of
+    // planes) and the pass ran at 0.78 of peak; spans that hold flagged pixels therefore load through L1 (above), and
+    // the gather runs after the stores, when those lines have arrived: 1.03 of peak, the same as without medians.
+    if (i0 < b) {
+        p0 = reinterpret_cast<const int2*>(xy)[i0];
+        have0 = fix(p0, nbr[i0], med0);
+    }
     __syncthreads();
     if (have0) oframe[(size_t)p0.y * w + p0.x] = (u16)med0;
     for (int i = i0 + LD_THREADS; i < b; i += LD_THREADS) {

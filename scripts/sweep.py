@@ -26,9 +26,9 @@ BYTES_PER_PX = {"bp_correct": 4, "bp_correct_gaussian_fused": 8, "gaussian_u16_f
 
 
 def main():
-    # the reader chain is ONE pass over HBM (2 B/px in, 2 B/px out) when the fused kernel takes it,
-    # merge pass + motion pass (8 B/px) with RIRB_LOADER_FUSED=0
-    BYTES_PER_PX["loader_read_chain"] = 8 if os.environ.get("RIRB_LOADER_FUSED", "1").startswith("0") else 4
+    # the reader chain is merge pass + motion pass (8 B/px) by default, ONE pass over HBM (2 B/px in, 2 B/px out)
+    # with RIRB_LOADER_FUSED=1
+    BYTES_PER_PX["loader_read_chain"] = 4 if os.environ.get("RIRB_LOADER_FUSED", "0").startswith("1") else 8  # library default: two passes
     import torch
     import torch.distributed as dist
 
