@@ -68,11 +68,8 @@ movie_stats_kernel(const u16* __restrict__ p, size_t n, const u8* __restrict__ m
                 for (int k = 0; k < 4; ++k) {
                     lo2 = __vminu2(lo2, w[k]);
                     hi2 = __vmaxu2(hi2, w[k]);
-                    if (HIST) {
-                        count_px(w[k] & 0xFFFFu, sh, hist);
-                        count_px(w[k] >> 16, sh, hist);
-                    }
                 }
+                if (HIST) count_words(w, sh, hist);
             }
         }
         lo = min(lo2 & 0xFFFFu, lo2 >> 16);
