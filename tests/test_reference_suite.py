@@ -126,7 +126,7 @@ def _polygon_image(shape, polygon, value):
 
 
 @pytest.mark.gpu
-def test_mask_registrator():
+def test_mask_registrator(tmp_path):
     """100 frames of a polygon moving one pixel per frame along the diagonal over a brightening background, with noise:
     start() / compute() run through, and -- the part the reference left commented out -- the shifts come out as 0 .. 99."""
     from librir_b200.registration import MaskedRegistratorECC, manage_computation_and_tries
@@ -166,3 +166,11 @@ def test_mask_registrator():
     assert np.array_equal(np.array(reg2.x), np.array(reg.x[:20]))
     data = reg.stabilisation_data
     assert list(data.columns) == ["x-axis translations", "y-axis translations", "Confidence level"] and len(data) == 100
+    # test_set_registration_file_to_IRMovie: the .regfile it writes is the one the reader's motion correction loads
+    from librir_b200 import video_io as vio
+
+    reg.to_reg_file(tmp_path / "movie.regfile")
+    sx, sy = vio.load_translation_file(tmp_path / "movie.regfile", nframes=100)
+    assert np.allclose(sx, np.array(reg.x, dtype=np.float64), atol=1e-4) and np.allclose(sy, np.array(reg.y, dtype=np.float64), atol=1e-4)
+    steady = vio.remove_motion(np.stack(images[:4]), sx[:4], sy[:4], meta_rows=0)
+    assert steady.shape == (4, 512, 640)
