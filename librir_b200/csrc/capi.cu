@@ -575,7 +575,7 @@ int bad_pixels_create(unsigned short* first_image, int width, int height)
     }
     // Sum of int squares (the reference adds int products into a double, which stays exact below 2^53).  For
     // |d| >= 46341 -- a saturated 65535 pixel over an 8000-count background -- the reference's int product overflows:
-    // undefined in C++, a wrap modulo 2^32 in every x86-64 build of it (oracle/_ref agrees on 300 extreme frames).
+    // undefined in C++, a wrap modulo 2^32 in every x86-64 build of it (checked against the compiled reference by the tests, 300 extreme frames).
     // Real movies contain such pixels, so the wrap is reproduced, as are the x86 float->integer conversions below.
     long long ssum = 0;
     for (int v = 0; v < 65536; ++v) {
