@@ -45,4 +45,36 @@ if [ ! "$OUT/libs/libref_zfile.so" -nt "$HERE/zfile_shim.cpp" ] || [ ! "$OUT/lib
   $CXX $FLAGS -DBUILD_IO_LIB $INC -I$R/src/cpp/video_io "$R/src/cpp/video_io/ZFile.cpp" "$HERE/zfile_shim.cpp" \
       -L"$OUT/libs" -ltools -Wl,-rpath,'$ORIGIN' -o "$OUT/libs/libref_zfile.so"
 fi
+# video_io: the reference's writer / reader sources against its own ffmpeg 7.1 headers, with the 46 libav entry points
+# they call provided by oracle/libav_stub.c (identity codec + trivial container; ffmpeg / x264 / kvazaar themselves are
+# fetched from the network by the reference's build and are not available here).  Objects are built in parallel.
+VIO_SRC="BaseCalibration IRFileLoader h264 IRVideoLoader HCCLoader video_io ZFile"
+FF="$R/extra/ffmpeg/ffmpeg-7.1-msvc/include"
+if [ ! "$OUT/libs/libvideo_io.so" -nt "$HERE/libav_stub.c" ] || [ ! "$OUT/libs/libvideo_io.so" -nt "$0" ] || [ -n "${FORCE:-}" ]; then
+  echo "build_ref: libvideo_io.so (stub libav)"
+  mkdir -p "$OUT/obj"
+  pids=""
+  for f in $VIO_SRC; do
+    $CXX -std=c++14 -O3 -DNDEBUG -fPIC -w -DBUILD_IO_LIB -DUSE_ZFILE $INC -I$R/src/cpp/video_io -I"$FF" \
+        -c "$R/src/cpp/video_io/$f.cpp" -o "$OUT/obj/$f.o" & pids="$pids $!"
+  done
+  ${ORACLE_CC:-/usr/bin/gcc} -std=gnu11 -O2 -fPIC -w -I"$FF" -c "$HERE/libav_stub.c" -o "$OUT/obj/libav_stub.o" & pids="$pids $!"
+  for p in $pids; do wait $p; done
+  objs=""; for f in $VIO_SRC libav_stub; do objs="$objs $OUT/obj/$f.o"; done
+  $CXX -shared -o "$OUT/libs/libvideo_io.so" $objs -L"$OUT/libs" -lsignal_processing -lgeometry -ltools \
+      -Wl,-rpath,'$ORIGIN' -Wl,--no-undefined
+  rm -rf "$OUT/obj"
+fi
+# the reference's own Python package, laid out the way its wheel is (librir/ + librir/libs/*.so), so that the GPU box
+# (where /root/reference does not exist) can run the UNMODIFIED wrappers: once on the compiled reference
+# (oracle/_ref/pkg/librir) and once with this repo's libraries swapped in (tests/test_dropin_*.py copy the tree and
+# replace libs/).  oracle/_ref is git-ignored: nothing of the reference enters the history.
+if [ ! -f "$OUT/pkg/librir/__init__.py" ] || [ "$OUT/libs/libvideo_io.so" -nt "$OUT/pkg/librir/libs/libvideo_io.so" ] || [ -n "${FORCE:-}" ]; then
+  echo "build_ref: python package -> $OUT/pkg/librir"
+  rm -rf "$OUT/pkg"
+  mkdir -p "$OUT/pkg"
+  cp -r "$R/src/python/librir" "$OUT/pkg/librir"
+  mkdir -p "$OUT/pkg/librir/libs"
+  for l in tools geometry signal_processing video_io; do cp "$OUT/libs/lib$l.so" "$OUT/pkg/librir/libs/"; done
+fi
 echo "build_ref: done -> $OUT/libs"

@@ -616,8 +616,10 @@ ORC_API int orc_quantile_from_hist(const unsigned long long *hist65536, unsigned
 /* f-2  lossy "bounded-error" pre-conditioner of the H.264 saver                         */
 /*      H264_Saver::addImageLossyNoCamera  h264.cpp:2253-2424                           */
 /*      RunningAverage2 h264.cpp:1526-1615, get_background :1955-1991, stdDev :1993-2036 */
-/*      PARITY UNPINNED BY EXECUTION: video_io cannot be compiled here (ffmpeg/x264), and */
-/*      the reference has no test of these values; this is a line-by-line restatement.   */
+/*      and H264_Saver::addLoss :2426-2607 (variant 1).                                   */
+/*      PINNED BY EXECUTION (round 2): oracle/build_ref.sh builds the reference's video_io */
+/*      against oracle/libav_stub.c; tests/test_oracle_vs_refvio.py and the goldens made   */
+/*      by tests/golden/make_vio_golden.py compare frame by frame.                         */
 /* ------------------------------------------------------------------------------------ */
 typedef struct {
     int w, h, stop_h;           /* stop_h = stop_lossy_height: rows [0, stop_h) are lossy */
@@ -626,6 +628,8 @@ typedef struct {
     int running_average;        /* 32; 0 = off */
     int subtract_min;
     int bp_enabled;
+    int variant;                /* 0 = addImageLossyNoCamera (h264.cpp:2253-2424), 1 = addLoss (:2426-2607) */
+    int memcpy_quirk;           /* 1 (default) = the compiled reference's overlapping-memcpy outcome, see orc_lossy_add_image */
     /* state */
     long frames;                /* m_data->attributes.size() */
     unsigned short minv;
@@ -652,7 +656,14 @@ ORC_API orc_lossy *orc_lossy_open(int w, int h, int stop_h, int low_error, int h
     s->ring = (u16 *)calloc(ns * (size_t)(running_average > 0 ? running_average : 1), 2);
     s->sums = (unsigned *)calloc(ns ? ns : 1, 4); s->cvalue = (u16 *)calloc(ns ? ns : 1, 2); s->ccount = (short *)calloc(ns ? ns : 1, 2);
     s->bp_xy = (int *)malloc(sizeof(int) * 2 * (ns ? ns : 1));
+    s->memcpy_quirk = 1;
     return s;
+}
+/* variant: 0 = h264_add_image_lossy's path, 1 = h264_add_loss's; memcpy_quirk: see orc_lossy_add_image */
+ORC_API void orc_lossy_configure(orc_lossy *s, int variant, int memcpy_quirk)
+{
+    s->variant = variant;
+    s->memcpy_quirk = memcpy_quirk;
 }
 ORC_API void orc_lossy_close(orc_lossy *s)
 {
@@ -729,12 +740,29 @@ ORC_API void orc_lossy_add_image(orc_lossy *s, const u16 *img, u16 *out, int *er
     else lossy_std_dev(s->prevT, s->tmpT, ns, img, &background, sd);
     if (!s->have_first) { s->first_std[0] = sd[0]; s->first_std[1] = sd[1]; s->have_first = 1; }
     if (s->nstds < running_average_frames) { s->stds[s->nstds][0] = sd[0]; s->stds[s->nstds][1] = sd[1]; s->nstds++; }
-    else { memmove(&s->stds[0], &s->stds[1], sizeof(double) * 2 * (running_average_frames - 1)); s->stds[39][0] = sd[0]; s->stds[39][1] = sd[1]; }
+    else {
+        /* :2347 shifts the window with memcpy(data, data + 1, 39 pairs) -- OVERLAPPING, i.e. undefined behaviour.  What the
+         * reference does as compiled with its stock flags (g++ 13 -O3, x86-64; oracle/_ref, pinned by execution): the
+         * expansion copies the LAST 8 bytes first (pair 39's .second over pair 38's) and then the rest front to back, so
+         * after the shift pairs 37 and 38 both carry old pair 39's .second and old pair 38's .second is lost; every
+         * .first is shifted correctly.  memcpy_quirk == 0 gives the intended memmove. */
+        double last_second = s->stds[39][1];
+        memmove(&s->stds[0], &s->stds[1], sizeof(double) * 2 * (running_average_frames - 1));
+        if (s->memcpy_quirk) s->stds[37][1] = last_second;
+        s->stds[39][0] = sd[0]; s->stds[39][1] = sd[1];
+    }
     double mean0 = s->first_std[0], mean1 = s->first_std[1]; /* :2353-2365 */
     for (int i = 0; i < s->nstds; ++i) { mean0 += s->stds[i][0]; mean1 += s->stds[i][1]; }
     mean0 /= (s->nstds + 1); mean1 /= (s->nstds + 1);
-    highError -= (int)round(fabs(sd[1] - mean1) * s->std_factor);
-    lowError -= (int)round(fabs(sd[0] - mean0) * s->std_factor);
+    if (s->variant == 0) { /* :2367-2368 */
+        highError -= (int)round(fabs(sd[1] - mean1) * s->std_factor);
+        lowError -= (int)round(fabs(sd[0] - mean0) * s->std_factor);
+    } else { /* addLoss :2559-2563: only a spread ABOVE the running mean tightens the bound */
+        double diff_high = sd[1] < mean1 ? 0 : sd[1] - mean1;
+        double diff_low = sd[0] < mean0 ? 0 : sd[0] - mean0;
+        highError -= (int)round(diff_high * s->std_factor);
+        lowError -= (int)round(diff_low * s->std_factor);
+    }
     if (highError < 0) highError = 0;
     if (lowError < highError) lowError = highError;
     errors[0] = lowError; errors[1] = highError;
@@ -754,7 +782,8 @@ ORC_API void orc_lossy_add_image(orc_lossy *s, const u16 *img, u16 *out, int *er
     for (int i = 0; i < ns; ++i) { /* :2397-2413 */
         int diff = abs((int)s->tmpT[i] - (int)s->refT[i]);
         int max_error = s->tmp[i] > background ? highError : lowError;
-        if (diff <= max_error && (s->lastDL[i] >> 13) == (s->tmp[i] >> 13)) {
+        /* addLoss (:2584) has no integration-time test */
+        if (diff <= max_error && (s->variant == 1 || (s->lastDL[i] >> 13) == (s->tmp[i] >> 13))) {
             s->tmpT[i] = ra > 0 ? (u16)(s->sums[i] / (unsigned long)s->ring_len) : s->refT[i];
         } else {
             s->refT[i] = s->tmpT[i];

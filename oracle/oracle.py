@@ -217,12 +217,18 @@ class Port(_Base):
         return img
 
     def lossy_open(self, w, h, stop_h, low_error=6, high_error=2, std_factor=5.0, running_average=32, subtract_min=False,
-                   bp_enabled=False):
-        """H264_Saver::addImageLossyNoCamera state (h264.cpp:2253-2424); returns an opaque state for lossy_add."""
+                   bp_enabled=False, variant=0, memcpy_quirk=True):
+        """H264_Saver::addImageLossyNoCamera state (h264.cpp:2253-2424; variant=1: addLoss, :2426-2607); returns an
+        opaque state for lossy_add.  memcpy_quirk: reproduce the compiled reference's overlapping memcpy (oracle.c)."""
         f = self.lib.orc_lossy_open
         f.restype = ct.c_void_p
         f.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_double, ct.c_int, ct.c_int, ct.c_int]
-        return ct.c_void_p(f(w, h, stop_h, low_error, high_error, std_factor, running_average, int(subtract_min), int(bp_enabled)))
+        st = ct.c_void_p(f(w, h, stop_h, low_error, high_error, std_factor, running_average, int(subtract_min), int(bp_enabled)))
+        g = self.lib.orc_lossy_configure
+        g.restype = None
+        g.argtypes = [ct.c_void_p, ct.c_int, ct.c_int]
+        g(st, int(variant), int(memcpy_quirk))
+        return st
 
     def lossy_add(self, state, image):
         """One frame through the pre-conditioner: returns (frame handed to the lossless encoder, (lowError, highError))."""
