@@ -125,7 +125,8 @@ RIRB_API int rirb_loader_remove_motion(const unsigned short* in, unsigned short*
 /* IRFileLoader::readImage's post-decode chain for a run of frames (IRFileLoader.cpp:1168-1247, the
  * calibration == 0 branch), from the decoder's byte planes to corrected, registered uint16 frames:
  *   v = lo | hi << 8                          VideoGrabber::toArray, h264.cpp:3016-3051
- *   v += min_T on rows [0, min_T_height)      IRFileLoader.cpp:1174-1179 (min_T == 0: skipped)
+ *   v += min_T on rows [0, min_T_height)      IRFileLoader.cpp:1174-1179 (min_T == 0: skipped; min_T_height == 0:
+ *                                             h - meta_rows, the default the reference applies at open, :918-921)
  *   removeBadPixels on rows [0, h-meta_rows)  IRFileLoader.cpp:722-802 (handle == 0: skipped; else a handle
  *                                             created on the first frame cropped to h-meta_rows rows)
  *   removeMotion on rows [0, h-meta_rows)     IRFileLoader.cpp:617-627 (shift_x/shift_y NULL: skipped)
@@ -166,7 +167,8 @@ RIRB_API int rirb_decode_movie(const unsigned char* lo, const unsigned char* hi,
 RIRB_API int rirb_key_frames(long long nframes, int gop, unsigned char* key);
 
 /* ---- lossy "bounded-error" pre-conditioner of the H.264 saver (H264_Saver::addImageLossyNoCamera,
- *      h264.cpp:2253-2424; the frames it produces are what addImageLossLess then encodes) ----
+ *      h264.cpp:2253-2424; the frames it produces are what addImageLossLess then encodes; and H264_Saver::addLoss,
+ *      :2426-2607, see rirb_lossy_set_parameter) ----
  * open: image size, stop_lossy_height (rows [0, stop) are lossy, the rest is copied), lowValueError /
  * highValueError (reference defaults 6 / 2), stdFactor (5), runningAverage (32, <= 64, 0 = off), subtractMin,
  * removeBadPixels -- the saver's string parameters (h264.cpp:1709-1781).  Returns a handle > 0, 0 on failure.
@@ -177,6 +179,14 @@ RIRB_API int rirb_key_frames(long long nframes, int gop, unsigned char* key);
 RIRB_API int rirb_lossy_open(int w, int h, int stop_lossy_height, int low_error, int high_error, double std_factor,
                              int running_average, int subtract_min, int remove_bad_pixels);
 RIRB_API int rirb_lossy_add_images(int handle, const unsigned short* frames, long long nframes, unsigned short* out, int* errors);
+/* string switches of a handle, before the first frame:
+ *   "variant" = "add_image_lossy" (default; addImageLossyNoCamera, behind h264_add_image_lossy) | "add_loss"
+ *               (H264_Saver::addLoss, h264.cpp:2426-2607, behind h264_add_loss: the bounds only tighten when the
+ *               spread is above its running mean, no integration-time test);
+ *   "memcpyQuirk" = "1" (default) | "0": the reference shifts its window of 40 spreads with an overlapping memcpy
+ *               (h264.cpp:2347, undefined behaviour); 1 reproduces what the reference does as compiled with its
+ *               stock flags (g++ -O3, x86-64: one .second value is smeared, oracle/oracle.c), 0 the intended memmove. */
+RIRB_API int rirb_lossy_set_parameter(int handle, const char* key, const char* value);
 RIRB_API void rirb_lossy_close(int handle);
 
 /* ---- the whole per-frame path on HOST buffers, one call (the end-to-end drop-in) ----

@@ -864,6 +864,8 @@ int rirb_loader_read_movie(int handle, const unsigned char* lo, const unsigned c
     }
     if (nframes == 0) return 0;
     const int hb = h - meta_rows;
+    // an absent / zero MIN_T_HEIGHT means "every row but the metadata rows" (IRFileLoader::open, IRFileLoader.cpp:918-921)
+    if (min_T_height == 0) min_T_height = hb;
     std::shared_ptr<BadPixelState> s;
     if (handle != 0) {
         s = find_handle_here(handle, "loader_read_movie");
@@ -1132,6 +1134,9 @@ int rirb_key_frames(long long nframes, int gop, unsigned char* key)
 namespace {
 struct LossyState {
     int w = 0, h = 0, stop_h = 0, low = 6, high = 2, ra = 32, subtract_min = 0, bp_enabled = 0, device = 0;
+    int variant = 0;      // 0 = addImageLossyNoCamera (h264_add_image_lossy), 1 = addLoss (h264_add_loss)
+    int quirk = 1;        // the compiled reference's overlapping memcpy of the spread window (lossy.cu, lossy_window_quirk)
+    unsigned* hist_scratch = nullptr;  // lossy_back_kernel's per-frame histograms
     bool use_run = true;  // several frames per cooperative launch; cleared if the device cannot do it (or by "lossy_run" = 0)
     double std_factor = 5.0;
     long long frames = 0;
@@ -1145,6 +1150,7 @@ struct LossyState {
     ~LossyState()
     {
         if (cur_batch) cudaFree(cur_batch);
+        if (hist_scratch) cudaFree(hist_scratch);
         if (buf) cudaFree(buf);
         if (errors_dev) cudaFree(errors_dev);
         if (bp_handle) bad_pixels_destroy(bp_handle);
@@ -1201,6 +1207,40 @@ void rirb_lossy_close(int handle)
     g_lossy.erase(handle);
 }
 
+int rirb_lossy_set_parameter(int handle, const char* key, const char* value)
+{
+    std::shared_ptr<LossyState> s;
+    {
+        std::lock_guard<std::mutex> lock(g_lossy_mutex);
+        auto it = g_lossy.find(handle);
+        if (it != g_lossy.end()) s = it->second;
+    }
+    if (!s || !key || !value) {
+        set_error("lossy_set_parameter: unknown handle %d or NULL argument", handle);
+        return -1;
+    }
+    const std::string k(key), v(value);
+    if (k == "variant") {
+        if (s->frames != 0) {
+            set_error("lossy_set_parameter: the variant cannot change once frames were added");
+            return -1;
+        }
+        if (v == "add_image_lossy" || v == "0") s->variant = 0;
+        else if (v == "add_loss" || v == "1") s->variant = 1;
+        else {
+            set_error("lossy_set_parameter: variant must be add_image_lossy or add_loss");
+            return -1;
+        }
+        return 0;
+    }
+    if (k == "memcpyQuirk") {
+        s->quirk = atoi(value) != 0;
+        return 0;
+    }
+    set_error("lossy_set_parameter: unknown key %s", key);
+    return -1;
+}
+
 int rirb_lossy_add_images(int handle, const unsigned short* frames, long long nframes, unsigned short* out, int* errors)
 {
     std::shared_ptr<LossyState> s;
@@ -1253,15 +1293,19 @@ int rirb_lossy_add_images(int handle, const unsigned short* frames, long long nf
         u16* dst = (u16*)o.dev + (size_t)f * n;
         if (s->frames >= 1 && s->use_run && option_enabled(OPT_LOSSY_RUN)) {
             // a run of non-initial frames in one cooperative launch (lossy_run_kernel)
-            const long long m = std::min<long long>(nframes - f, 64);
+            const long long m = std::min<long long>(nframes - f, lossy_max_run());
+            if (!s->hist_scratch) {
+                RIRB_CUDA_OK(cudaMalloc((void**)&s->hist_scratch, lossy_hist_scratch_bytes()));
+                RIRB_CUDA_OK(cudaMemsetAsync(s->hist_scratch, 0, lossy_hist_scratch_bytes(), st));
+            }
             const u16* cur = img;
             if (s->bp_enabled && ns > 0) {
                 if (s->cur_batch_frames < (size_t)m) {
                     if (s->cur_batch) cudaFree(s->cur_batch);
                     s->cur_batch = nullptr;
                     s->cur_batch_frames = 0;
-                    RIRB_CUDA_OK(cudaMalloc((void**)&s->cur_batch, (size_t)64 * n * 2));
-                    s->cur_batch_frames = 64;
+                    RIRB_CUDA_OK(cudaMalloc((void**)&s->cur_batch, (size_t)lossy_max_run() * n * 2));
+                    s->cur_batch_frames = (size_t)lossy_max_run();
                 }
                 auto bp = find_handle(s->bp_handle);
                 if (!bp) {
@@ -1275,8 +1319,9 @@ int rirb_lossy_add_images(int handle, const unsigned short* frames, long long nf
                                                    cudaMemcpyDeviceToDevice, st));
                 cur = s->cur_batch;
             }
-            const int rc = launch_lossy_run(img, cur, tmpT, dst, lastDL, refT, prevT, sums, cval, ccnt, ring, n, ns, s->ra, s->subtract_min,
-                                            s->frames, (int)m, s->low, s->high, s->std_factor, scal, s->errors_dev + 2 * f, st);
+            const int rc = launch_lossy_run(img, cur, dst, lastDL, refT, prevT, sums, cval, ccnt, ring, n, ns, s->ra, s->subtract_min,
+                                            s->frames, (int)m, s->low, s->high, s->std_factor, s->variant, s->quirk, scal,
+                                            s->hist_scratch, s->errors_dev + 2 * f, st);
             if (rc < 0) return -1;
             if (rc == 0) {
                 s->frames += m;
@@ -1301,7 +1346,7 @@ int rirb_lossy_add_images(int handle, const unsigned short* frames, long long nf
             rc = launch_lossy_first(cur, dst, lastDL, refT, prevT, n, ns, s->subtract_min, scal, s->errors_dev + 2 * f, s->low, s->high, st);
         else
             rc = launch_lossy_frame(img, cur, tmpT, dst, lastDL, refT, prevT, sums, cval, ccnt, ring, n, ns, s->ra, s->subtract_min,
-                                    s->frames, s->low, s->high, s->std_factor, scal, s->errors_dev + 2 * f, st);
+                                    s->frames, s->low, s->high, s->std_factor, s->variant, s->quirk, scal, s->errors_dev + 2 * f, st);
         if (rc != 0) return -1;
         ++s->frames;
         ++f;

@@ -73,13 +73,19 @@ int launch_decode_movie(const u8* lo, const u8* hi, long long nframes, int w, in
 size_t lossy_scalars_bytes();
 int launch_lossy_first(const u16* tmp, u16* out, u16* lastDL, u16* refT, u16* prevT, int n, int ns, int subtract_min, void* scalars,
                        int* errors_out_dev, int low0, int high0, cudaStream_t st);
-// several consecutive non-initial frames in ONE cooperative launch (lossy.cu, lossy_run_kernel); 1: not available
-int launch_lossy_run(const u16* img, const u16* cur, u16* tmpT, u16* out, u16* lastDL, u16* refT, u16* prevT, unsigned* sums, u16* cvalue,
+// a run of consecutive non-initial frames: backgrounds of all of them in one launch, then ONE cooperative launch with one
+// grid barrier per frame (lossy.cu, lossy_run_kernel); 1: not available.  variant 0 = addImageLossyNoCamera, 1 = addLoss;
+// quirk: the compiled reference's overlapping memcpy (lossy_window_quirk)
+int launch_lossy_run(const u16* img, const u16* cur, u16* out, u16* lastDL, u16* refT, u16* prevT, unsigned* sums, u16* cvalue,
                      short* ccount, u16* ring, int n, int ns, int ra, int subtract_min, long long frame_index, int m, int low0,
-                     int high0, double std_factor, void* scalars, int* errors_out_dev, cudaStream_t st);
+                     int high0, double std_factor, int variant, int quirk, void* scalars, unsigned* hist_scratch, int* errors_out_dev,
+                     cudaStream_t st);
+size_t lossy_hist_scratch_bytes();
+int lossy_max_run();
 int launch_lossy_frame(const u16* img, const u16* tmp, u16* tmpT, u16* out, u16* lastDL, u16* refT, u16* prevT, unsigned* sums,
                        u16* cvalue, short* ccount, u16* ring, int n, int ns, int ra, int subtract_min, long long frame_index,
-                       int low0, int high0, double std_factor, void* scalars, int* errors_out_dev, cudaStream_t st);
+                       int low0, int high0, double std_factor, int variant, int quirk, void* scalars, int* errors_out_dev,
+                       cudaStream_t st);
 
 // stats.cu
 // minmax[0] = min, minmax[1] = max (unsigned, device); hist = 65536 x u64 (device) or nullptr.

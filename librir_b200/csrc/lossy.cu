@@ -1,6 +1,8 @@
 // librir_b200/csrc/lossy.cu -- the lossy "bounded-error" pre-conditioner of the H.264 saver.
 //
-// Reference: H264_Saver::addImageLossyNoCamera, h264.cpp:2253-2424 (input already in temperature),
+// Reference: H264_Saver::addImageLossyNoCamera, h264.cpp:2253-2424 (input already in temperature; behind
+// h264_add_image_lossy) and H264_Saver::addLoss, :2426-2607 (behind h264_add_loss; `variant` 1: the bounds only
+// tighten when the spread is ABOVE its running mean, and there is no integration-time test),
 // with RunningAverage2 (:1526-1615), get_background (:1955-1991) and stdDev (:1993-2036).  Per frame:
 //   tmp  = bad-pixel-corrected input (optional)                                   :2259-2271
 //   tmpT = tmp - min (saturating, lossy rows only, optional)                      :2314-2328
@@ -14,7 +16,9 @@
 // own), pixels are parallel: three small launches per frame on one stream (the two scalar steps run in the
 // last CTA of the reduction that feeds them).  All sums are exact integers
 // (the reference adds int products into doubles, exact below 2^53), the scalar decision is evaluated in
-// non-contracted fp64 by one thread, so the outputs are bit-identical to the restated reference.
+// non-contracted fp64 by one thread, so the outputs are bit-identical to the COMPILED reference (oracle/_ref/libs/
+// libvideo_io.so; tests/golden/vio_golden.npz) -- including what its overlapping memcpy at :2347 does to the window of
+// spreads (see lossy_window_quirk below).
 // State per pixel: sums u32, const (value u16, count i16), refT, prevT, lastDL u16 and a ring of
 // `running_average` frames -- 12 + 2 * running_average bytes.
 #include <cooperative_groups.h>
@@ -23,6 +27,9 @@
 #include "kernels.h"
 
 namespace rirb {
+
+constexpr int LOSSY_MAX_CTAS = 256;  // CTAs of lossy_run_kernel (one per SM)
+constexpr int LOSSY_MAX_RUN = 64;    // frames per launch of it
 
 struct LossyScalars {
     unsigned minv;                  // m_data->min
@@ -34,12 +41,26 @@ struct LossyScalars {
     double stds[40][2];             // stdDevs window, circular: the oldest entry is stds[head] once 40 are in
     alignas(16) unsigned hist[16384];
     unsigned ticket[2];             // "last CTA done" counters of the two reduction kernels
-    // lossy_run_kernel (several frames per launch): two histograms and two sets of sums, used alternately by frame
-    // parity -- the set a frame does not use is cleared while it runs, so no extra grid barrier is spent on zeroing
-    alignas(16) unsigned hist2[2][16384];
-    unsigned long long rsum[2][4];
-    unsigned rcnt[2][2];
+    // lossy_run_kernel (several frames per launch): per-CTA partial sums of stdDev, two sets used alternately by frame
+    // parity (written while the previous frame is updated, read after the grid barrier: nothing to clear, no atomics),
+    // the grid barrier's counter, the backgrounds of the run's frames and the tickets of the pass that finds them
+    alignas(16) unsigned long long psum[2][LOSSY_MAX_CTAS][4];
+    unsigned pcnt[2][LOSSY_MAX_CTAS][2];
+    unsigned barrier;
+    unsigned back_run[LOSSY_MAX_RUN];
+    unsigned back_ticket[LOSSY_MAX_RUN];
 };
+
+// h264.cpp:2347 (and :2538 in addLoss) shifts the full window of 40 (background, foreground) spreads with
+// memcpy(data, data + 1, 39 pairs): overlapping, i.e. undefined behaviour.  As compiled with the reference's stock flags
+// (g++ -O3, x86-64) the copy moves the LAST 8 bytes first and the rest front to back, so after every shift the pair that
+// is now third from the end carries the old last pair's .second (its own is lost); every .first is right.  win[] is the
+// window in time order BEFORE the shift: the shifted window is win[1..39] + the new pair, so the smear lands on win[38].
+// quirk == 0 gives the memmove the author meant.
+__device__ __forceinline__ void lossy_window_quirk(double (*win)[2], int nstds, int quirk)
+{
+    if (quirk && nstds == 40) win[38][1] = win[39][1];
+}
 
 __global__ void lossy_min_kernel(const u16* __restrict__ tmp, int ns, LossyScalars* sc)
 {
@@ -151,8 +172,27 @@ __global__ void __launch_bounds__(1024) lossy_prep_kernel(const u16* __restrict_
 // memory pays a full round trip per entry: 40 us per frame in the first version of this kernel).
 // nstds: size of the stdDevs window BEFORE this frame (0..40); head: slot of its oldest entry when full;
 // first: this is the first non-initial frame.
+__device__ __forceinline__ void lossy_bounds(double sd0, double sd1, double m0, double m1, double std_factor, int variant, int low0,
+                                             int high0, int* low_out, int* high_out)
+{
+    double dh, dl;
+    if (variant == 0) {  // addImageLossyNoCamera :2367-2368
+        dh = fabs(__dsub_rn(sd1, m1));
+        dl = fabs(__dsub_rn(sd0, m0));
+    } else {  // addLoss :2559-2563
+        dh = sd1 < m1 ? 0.0 : __dsub_rn(sd1, m1);
+        dl = sd0 < m0 ? 0.0 : __dsub_rn(sd0, m0);
+    }
+    int high = high0 - (int)round(__dmul_rn(dh, std_factor));
+    int low = low0 - (int)round(__dmul_rn(dl, std_factor));
+    if (high < 0) high = 0;
+    if (low < high) low = high;
+    *low_out = low;
+    *high_out = high;
+}
+
 __device__ __forceinline__ void lossy_decide_body(LossyScalars* sc, int ns, int nstds, int head, int first, int low0, int high0,
-                                                  double std_factor, int* __restrict__ errors_out)
+                                                  double std_factor, int variant, int quirk, int* __restrict__ errors_out)
 {
     __shared__ double win[40][2];
     __shared__ unsigned long long sums[4];
@@ -169,6 +209,8 @@ __device__ __forceinline__ void lossy_decide_body(LossyScalars* sc, int ns, int 
     }
     __syncthreads();
     if (t != 0) return;
+    lossy_window_quirk(win, nstds, quirk);
+    if (quirk && nstds == 40) sc->stds[(head + 38) % 40][1] = win[38][1];
     double sd0, sd1;
     if (nstds < 40) {
         const double s = (double)(sums[0] + sums[2]), s2 = (double)(sums[1] + sums[3]);
@@ -205,10 +247,8 @@ __device__ __forceinline__ void lossy_decide_body(LossyScalars* sc, int ns, int 
     m1 = __dadd_rn(m1, sd1);
     m0 = __ddiv_rn(m0, (double)(n + 1));
     m1 = __ddiv_rn(m1, (double)(n + 1));
-    int high = high0 - (int)round(__dmul_rn(fabs(__dsub_rn(sd1, m1)), std_factor));
-    int low = low0 - (int)round(__dmul_rn(fabs(__dsub_rn(sd0, m0)), std_factor));
-    if (high < 0) high = 0;
-    if (low < high) low = high;
+    int high, low;
+    lossy_bounds(sd0, sd1, m0, m1, std_factor, variant, low0, high0, &low, &high);
     sc->low_error = low;
     sc->high_error = high;
     errors_out[0] = low;
@@ -218,7 +258,8 @@ __device__ __forceinline__ void lossy_decide_body(LossyScalars* sc, int ns, int 
 // stdDev's sums (:1993-2036), always split by img > background (the un-split case is the sum of both halves)
 __global__ void __launch_bounds__(1024)
 lossy_sums_kernel(const u16* __restrict__ prevT, const u16* __restrict__ tmpT, const u16* __restrict__ img, int ns, LossyScalars* sc,
-                  int nstds, int head, int first, int low0, int high0, double std_factor, int* __restrict__ errors_out)
+                  int nstds, int head, int first, int low0, int high0, double std_factor, int variant, int quirk,
+                  int* __restrict__ errors_out)
 {
     const unsigned back = sc->background;
     unsigned long long sd = 0, sd2 = 0, bd = 0, bd2 = 0;
@@ -259,7 +300,7 @@ lossy_sums_kernel(const u16* __restrict__ prevT, const u16* __restrict__ tmpT, c
         for (int k = 0; k < nwarps; ++k) a += pcnt[k][threadIdx.x - 4];
         atomicAdd(&sc->cnt[threadIdx.x - 4], a);
     }
-    if (lossy_last_cta(&sc->ticket[1])) lossy_decide_body(sc, ns, nstds, head, first, low0, high0, std_factor, errors_out);
+    if (lossy_last_cta(&sc->ticket[1])) lossy_decide_body(sc, ns, nstds, head, first, low0, high0, std_factor, variant, quirk, errors_out);
 }
 
 // Per-pixel update (:2392-2421) with RunningAverage2::addImage / pixel / resetPixel folded in.
@@ -268,7 +309,7 @@ lossy_sums_kernel(const u16* __restrict__ prevT, const u16* __restrict__ tmpT, c
 __global__ void lossy_update_kernel(const u16* __restrict__ tmp, const u16* __restrict__ tmpT, u16* __restrict__ out,
                                     u16* __restrict__ lastDL, u16* __restrict__ refT, u16* __restrict__ prevT, unsigned* __restrict__ sums,
                                     u16* __restrict__ cvalue, short* __restrict__ ccount, u16* __restrict__ ring, int n, int ns, int ra,
-                                    int len_before, int slot_new, int slot_old, const LossyScalars* __restrict__ sc)
+                                    int len_before, int slot_new, int slot_old, int variant, const LossyScalars* __restrict__ sc)
 {
     const unsigned back = sc->background;
     const int low = sc->low_error, high = sc->high_error;
@@ -300,7 +341,7 @@ __global__ void lossy_update_kernel(const u16* __restrict__ tmp, const u16* __re
         const int diff = abs((int)t - (int)r);
         const int max_error = v > back ? high : low;
         unsigned o;
-        if (diff <= max_error && ((unsigned)lastDL[i] >> 13) == (v >> 13)) {
+        if (diff <= max_error && (variant == 1 || ((unsigned)lastDL[i] >> 13) == (v >> 13))) {
             o = ra > 0 ? ((s / len_after) & 0xFFFFu) : r;
         } else {
             o = t;
@@ -322,188 +363,314 @@ __global__ void lossy_update_kernel(const u16* __restrict__ tmp, const u16* __re
 }
 
 // ---- several frames per launch ------------------------------------------------------------------
-// The three launches per frame above cost more in launch latency than in work (0.65 MB per frame).  This kernel walks
-// through a run of frames by itself: one cooperative launch, one 1024-thread CTA per SM, TWO grid barriers per frame --
-//   histogram of the frame (+ tmpT)            | barrier |  every CTA finds the mode itself; stdDev sums
-//   | barrier |  every CTA evaluates the error bounds itself (CTA 0 also records them); per-pixel update
-// and straight on to the next frame: a pixel is always handled by the same thread (same grid-stride mapping in every
-// phase), so the per-pixel state needs no barrier between frames.  All reductions are integer sums: any order gives the
-// same bits.  The histogram / sum set of the other parity is cleared while a frame runs.
+// The three launches per frame above cost more in launch latency than in work (0.65 MB per frame).  A run of frames
+// goes through two launches instead:
+//   1. lossy_back_kernel: get_background of EVERY frame of the run at once -- it depends on the input frame only
+//      (h264.cpp:2331), so it does not belong in the sequential loop;
+//   2. lossy_run_kernel: one cooperative launch, one 1024-thread CTA per SM, ONE grid barrier per frame.  The spread of
+//      frame f+1 is |tmpT[f+1] - prevT| with prevT = the OUTPUT of frame f, so a thread adds its pixels' share of frame
+//      f+1's sums right after it has produced them in frame f's update pass (each CTA stores its partial sums in its own
+//      slot: no atomics, nothing to clear).  After the barrier every CTA adds the slots in the same order and evaluates
+//      the error bounds itself (CTA 0 also records them), then updates its pixels of frame f+1, and so on.
+// A pixel is always handled by the same thread (same grid-stride mapping in every frame), so the per-pixel state needs
+// no barrier at all.  All reductions are integer sums: any order gives the same bits.
 struct LossyRun {
     const u16* img;      // [m][n] frames as given (the "> background" test reads them)
     const u16* cur;      // [m][n] the reference's tmp: the same frames, bad-pixel-corrected when that is enabled
     u16* out;            // [m][n]
-    u16 *tmpT, *lastDL, *refT, *prevT, *cvalue, *ring;
+    u16 *lastDL, *refT, *prevT, *cvalue, *ring;
     unsigned* sums;
     short* ccount;
     LossyScalars* sc;
     int* errors_out;     // [m][2]
-    int n, ns, ra, subtract_min, low0, high0, m;
+    int n, ns, ra, subtract_min, low0, high0, m, variant, quirk;
     long long frame_index;  // of the first frame of the run (>= 1)
     double std_factor;
 };
 
+// first-maximum bin of a 16,384-bin histogram (:1974-1990), by the 1024 threads of a CTA; bins in shared or global memory
+__device__ __forceinline__ unsigned lossy_mode_of(const unsigned* hist, bool global, unsigned* bv, int* bi)
+{
+    const int t = threadIdx.x;
+    const uint4* hv = reinterpret_cast<const uint4*>(hist + t * 16);
+    uint4 q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = global ? __ldcg(hv + k) : hv[k];
+    const unsigned c16[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w,
+                              q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
+    unsigned best = c16[0];
+    int idx = t * 16;
+#pragma unroll
+    for (int k = 1; k < 16; ++k)
+        if (c16[k] > best) {  // strict: the first maximum wins
+            best = c16[k];
+            idx = t * 16 + k;
+        }
+    // warp level first, then one value per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        const int oi = __shfl_xor_sync(0xFFFFFFFFu, idx, o);
+        if (ob > best || (ob == best && oi < idx)) {
+            best = ob;
+            idx = oi;
+        }
+    }
+    __syncthreads();  // bv / bi may still be read from a previous call
+    if ((t & 31) == 0) {
+        bv[t >> 5] = best;
+        bi[t >> 5] = idx;
+    }
+    __syncthreads();
+    if (t < 32) {
+        best = bv[t];
+        idx = bi[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+            const int oi = __shfl_xor_sync(0xFFFFFFFFu, idx, o);
+            if (ob > best || (ob == best && oi < idx)) {
+                best = ob;
+                idx = oi;
+            }
+        }
+        if (t == 0) bi[32] = idx;
+    }
+    __syncthreads();
+    return ((unsigned)bi[32] << 2) + 1u;
+}
+
+// get_background of frames [0, m) of `cur` (lossy rows): grid = (parts, m).  parts == 1: the CTA's shared histogram is
+// the frame's; otherwise the parts meet in hist_scratch[f] and the last one to arrive takes the mode (and clears it).
+__global__ void __launch_bounds__(1024)
+lossy_back_kernel(const u16* __restrict__ cur, int n, int ns, unsigned* __restrict__ hist_scratch, LossyScalars* sc)
+{
+    extern __shared__ unsigned sh[];  // 16,384 bins
+    __shared__ unsigned bv[32];
+    __shared__ int bi[33];
+    __shared__ bool last;
+    const int t = threadIdx.x, f = blockIdx.y, parts = gridDim.x;
+    const u16* tmp = cur + (size_t)f * n;
+    for (int i = t; i < 16384; i += 1024) sh[i] = 0;
+    __syncthreads();
+    if ((ns & 7) == 0) {  // 8 pixels per 128-bit load
+        const uint4* v4 = reinterpret_cast<const uint4*>(tmp);
+        for (int i = blockIdx.x * 1024 + t; i < ns / 8; i += parts * 1024) {
+            const uint4 q = __ldg(v4 + i);
+            const unsigned wds[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                atomicAdd(&sh[(wds[k] & 0xFFFFu) >> 2], 1u);
+                atomicAdd(&sh[wds[k] >> 18], 1u);
+            }
+        }
+    } else {
+        for (int i = blockIdx.x * 1024 + t; i < ns; i += parts * 1024) atomicAdd(&sh[tmp[i] >> 2], 1u);
+    }
+    __syncthreads();
+    if (parts == 1) {
+        const unsigned b = lossy_mode_of(sh, false, bv, bi);
+        if (t == 0) sc->back_run[f] = b;
+        return;
+    }
+    unsigned* gh = hist_scratch + (size_t)f * 16384;
+    for (int i = t; i < 16384; i += 1024) {
+        const unsigned c = sh[i];
+        if (c) atomicAdd(&gh[i], c);
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+        const unsigned k = atomicAdd(&sc->back_ticket[f], 1u);
+        last = (k == (unsigned)parts - 1);
+        if (last) sc->back_ticket[f] = 0;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const unsigned b = lossy_mode_of(gh, true, bv, bi);
+    for (int i = t; i < 16384; i += 1024) gh[i] = 0;  // ready for the next run
+    if (t == 0) sc->back_run[f] = b;
+}
+
+// all CTAs of a cooperative launch meet here; `target` counts arrivals since the launch (the counter starts at 0)
+__device__ __forceinline__ void lossy_grid_barrier(unsigned* counter, unsigned& target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024) lossy_run_kernel(const __grid_constant__ LossyRun p)
 {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    extern __shared__ unsigned sh[];  // 16,384 bins
-    __shared__ unsigned bv[1024];
-    __shared__ int bi[1024];
     __shared__ unsigned long long part[32][4];
     __shared__ unsigned pcnt[32][2];
     __shared__ double win[40][2];
     __shared__ int decided[2];
     LossyScalars* sc = p.sc;
     const int t = threadIdx.x, gt = blockIdx.x * 1024 + t, gstride = gridDim.x * 1024;
-    const int n = p.n, ns = p.ns, ra = p.ra;
+    const int warp = t >> 5, lane = t & 31;
+    const int n = p.n, ns = p.ns, ra = p.ra, G = gridDim.x;
     const unsigned mn = p.subtract_min ? sc->minv : 0u;
+    unsigned bar_target = 0;
+
+    // this CTA's share of stdDev's sums for frame `f`, given the pixel value `prev` it is compared with; stored in the
+    // CTA's slot of set `par`
+    unsigned long long sd = 0, sd2 = 0, bd = 0, bd2 = 0;
+    unsigned nf = 0, nb = 0;
+    auto add_pixel = [&](unsigned tv1, unsigned prev, bool fore) {
+        const int d = abs((int)tv1 - (int)prev);
+        const unsigned long long d2 = (unsigned long long)d * (unsigned long long)d;
+        if (fore) {
+            sd += d; sd2 += d2; ++nf;
+        } else {
+            bd += d; bd2 += d2; ++nb;
+        }
+    };
+    auto store_partials = [&](int par) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sd += __shfl_xor_sync(0xFFFFFFFFu, sd, o);
+            sd2 += __shfl_xor_sync(0xFFFFFFFFu, sd2, o);
+            bd += __shfl_xor_sync(0xFFFFFFFFu, bd, o);
+            bd2 += __shfl_xor_sync(0xFFFFFFFFu, bd2, o);
+            nf += __shfl_xor_sync(0xFFFFFFFFu, nf, o);
+            nb += __shfl_xor_sync(0xFFFFFFFFu, nb, o);
+        }
+        if (lane == 0) {
+            part[warp][0] = sd; part[warp][1] = sd2; part[warp][2] = bd; part[warp][3] = bd2;
+            pcnt[warp][0] = nf; pcnt[warp][1] = nb;
+        }
+        __syncthreads();
+        if (t < 4) {
+            unsigned long long a = 0;
+            for (int k = 0; k < 32; ++k) a += part[k][t];
+            sc->psum[par][blockIdx.x][t] = a;
+        } else if (t < 6) {
+            unsigned a = 0;
+            for (int k = 0; k < 32; ++k) a += pcnt[k][t - 4];
+            sc->pcnt[par][blockIdx.x][t - 4] = a;
+        }
+        sd = sd2 = bd = bd2 = 0;
+        nf = nb = 0;
+    };
+
+    // ---- sums of the run's first frame against the state's prevT ----
+    {
+        const unsigned back0 = __ldcg(&sc->back_run[0]);
+        for (int i = gt; i < ns; i += gstride) {
+            const unsigned v = p.cur[i];
+            add_pixel(v < mn ? 0u : v - mn, p.prevT[i], (unsigned)p.img[i] > back0);
+        }
+        store_partials((int)(p.frame_index & 1));
+    }
     for (int f = 0; f < p.m; ++f) {
+        lossy_grid_barrier(&sc->barrier, bar_target);
         const long long prior = p.frame_index + f - 1;  // non-initial frames before this one
         const int par = (int)((p.frame_index + f) & 1);
         const int nstds = (int)min(prior, 40LL), head = (int)(prior % 40), first = prior == 0;
         const int len_before = (int)min(prior, (long long)ra), slot = ra > 0 ? (int)(prior % ra) : 0;
-        const u16* img = p.img + (size_t)f * n;
         const u16* tmp = p.cur + (size_t)f * n;
         u16* out = p.out + (size_t)f * n;
-        // ---- histogram of tmp >> 2, tmpT = tmp - min ----
-        for (int i = t; i < 16384; i += 1024) sh[i] = 0;
-        __syncthreads();
-        for (int i = gt; i < ns; i += gstride) {
-            const unsigned v = tmp[i];
-            p.tmpT[i] = (u16)(v < mn ? 0u : v - mn);
-            atomicAdd(&sh[v >> 2], 1u);
-        }
-        __syncthreads();
-        for (int i = t; i < 16384; i += 1024) {
-            const unsigned c = sh[i];
-            if (c) atomicAdd(&sc->hist2[par][i], c);
-        }
-        grid.sync();
-        // ---- background = (first maximum bin << 2) + 1, found by every CTA; the other parity's sets are cleared ----
-        for (int i = gt; i < 16384; i += gstride) sc->hist2[par ^ 1][i] = 0;
-        if (blockIdx.x == 0 && t < 4) sc->rsum[par ^ 1][t] = 0ull;
-        if (blockIdx.x == 0 && t >= 4 && t < 6) sc->rcnt[par ^ 1][t - 4] = 0u;
+        const unsigned back = __ldcg(&sc->back_run[f]);
+        // ---- error bounds of this frame (:2337-2376): every CTA adds the slots and runs the reference's fp64 operation
+        //      order in one thread ----
         {
-            const uint4* hv = reinterpret_cast<const uint4*>(&sc->hist2[par][t * 16]);
-            uint4 q[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) q[k] = __ldcg(hv + k);
-            const unsigned c16[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w,
-                                      q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
-            unsigned best = c16[0];
-            int idx = t * 16;
-#pragma unroll
-            for (int k = 1; k < 16; ++k)
-                if (c16[k] > best) {
-                    best = c16[k];
-                    idx = t * 16 + k;
-                }
-            bv[t] = best;
-            bi[t] = idx;
-            __syncthreads();
-            for (int s2 = 512; s2 > 0; s2 >>= 1) {
-                if (t < s2 && (bv[t + s2] > bv[t] || (bv[t + s2] == bv[t] && bi[t + s2] < bi[t]))) {
-                    bv[t] = bv[t + s2];
-                    bi[t] = bi[t + s2];
-                }
-                __syncthreads();
+            unsigned long long su[4] = {0, 0, 0, 0};
+            unsigned cn[2] = {0, 0};
+            if (t < G) {
+                const ulonglong2* ps = reinterpret_cast<const ulonglong2*>(&sc->psum[par][t][0]);
+                const ulonglong2 a = __ldcg(ps), b = __ldcg(ps + 1);
+                const uint2 c = __ldcg(reinterpret_cast<const uint2*>(&sc->pcnt[par][t][0]));
+                su[0] = a.x; su[1] = a.y; su[2] = b.x; su[3] = b.y;
+                cn[0] = c.x; cn[1] = c.y;
             }
-        }
-        const unsigned back = ((unsigned)bi[0] << 2) + 1u;
-        // ---- stdDev's sums, split by img > background ----
-        {
-            unsigned long long sd = 0, sd2 = 0, bd = 0, bd2 = 0;
-            unsigned nf = 0, nb = 0;
-            for (int i = gt; i < ns; i += gstride) {
-                const int d = abs((int)p.tmpT[i] - (int)p.prevT[i]);
-                const unsigned long long d2 = (unsigned long long)d * (unsigned long long)d;
-                if ((unsigned)img[i] > back) {
-                    sd += d; sd2 += d2; ++nf;
+            if (t < 256) {  // LOSSY_MAX_CTAS slots: the first eight warps
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) su[k] += __shfl_xor_sync(0xFFFFFFFFu, su[k], o);
+                    cn[0] += __shfl_xor_sync(0xFFFFFFFFu, cn[0], o);
+                    cn[1] += __shfl_xor_sync(0xFFFFFFFFu, cn[1], o);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) part[warp][k] = su[k];
+                    pcnt[warp][0] = cn[0];
+                    pcnt[warp][1] = cn[1];
+                }
+            } else if (t >= 512 && t < 552) {  // window in time order: oldest first
+                const int e = t - 512;
+                const int s2 = nstds < 40 ? e : (head + e) % 40;
+                win[e][0] = __ldcg(&sc->stds[s2][0]);
+                win[e][1] = __ldcg(&sc->stds[s2][1]);
+            }
+            __syncthreads();
+            if (t == 0) {
+                for (int k = 0; k < 4; ++k) su[k] = 0;
+                cn[0] = cn[1] = 0;
+                for (int wv = 0; wv < 8; ++wv) {
+                    for (int k = 0; k < 4; ++k) su[k] += part[wv][k];
+                    cn[0] += pcnt[wv][0];
+                    cn[1] += pcnt[wv][1];
+                }
+                lossy_window_quirk(win, nstds, p.quirk);
+                double sd0, sd1;
+                if (nstds < 40) {
+                    const double s1 = (double)(su[0] + su[2]), s2 = (double)(su[1] + su[3]);
+                    sd0 = sd1 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(s1, s1), s2)), (double)ns);
                 } else {
-                    bd += d; bd2 += d2; ++nb;
+                    const double s1 = (double)su[0], s2 = (double)su[1], b1 = (double)su[2], b2 = (double)su[3];
+                    sd0 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(b1, b1), b2)), (double)(int)cn[1]);
+                    sd1 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(s1, s1), s2)), (double)(int)cn[0]);
                 }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                sd += __shfl_xor_sync(0xFFFFFFFFu, sd, o);
-                sd2 += __shfl_xor_sync(0xFFFFFFFFu, sd2, o);
-                bd += __shfl_xor_sync(0xFFFFFFFFu, bd, o);
-                bd2 += __shfl_xor_sync(0xFFFFFFFFu, bd2, o);
-                nf += __shfl_xor_sync(0xFFFFFFFFu, nf, o);
-                nb += __shfl_xor_sync(0xFFFFFFFFu, nb, o);
-            }
-            const int warp = t >> 5, lane = t & 31;
-            if (lane == 0) {
-                part[warp][0] = sd; part[warp][1] = sd2; part[warp][2] = bd; part[warp][3] = bd2;
-                pcnt[warp][0] = nf; pcnt[warp][1] = nb;
+                const double f0 = first ? sd0 : __ldcg(&sc->first[0]), f1 = first ? sd1 : __ldcg(&sc->first[1]);
+                const int cnt = nstds < 40 ? nstds + 1 : 40, from = nstds < 40 ? 0 : 1;
+                double m0 = f0, m1 = f1;
+                for (int i = from; i < (nstds < 40 ? nstds : 40); ++i) {
+                    m0 = __dadd_rn(m0, win[i][0]);
+                    m1 = __dadd_rn(m1, win[i][1]);
+                }
+                m0 = __ddiv_rn(__dadd_rn(m0, sd0), (double)(cnt + 1));
+                m1 = __ddiv_rn(__dadd_rn(m1, sd1), (double)(cnt + 1));
+                int low, high;
+                lossy_bounds(sd0, sd1, m0, m1, p.std_factor, p.variant, p.low0, p.high0, &low, &high);
+                decided[0] = low;
+                decided[1] = high;
+                if (blockIdx.x == 0) {  // the state that outlives the frame is written once
+                    if (first) {
+                        sc->first[0] = sd0;
+                        sc->first[1] = sd1;
+                    }
+                    // the other CTAs read the window in this same interval: the smeared value is what they compute for
+                    // themselves, and the slot of the new entry is the one nobody uses (the oldest, or beyond the end)
+                    if (p.quirk && nstds == 40) sc->stds[(head + 38) % 40][1] = win[38][1];
+                    const int dst = nstds < 40 ? nstds : head;  // push, or the oldest slot becomes the newest
+                    sc->stds[dst][0] = sd0;
+                    sc->stds[dst][1] = sd1;
+                    sc->background = back;
+                    sc->low_error = low;
+                    sc->high_error = high;
+                    p.errors_out[2 * f] = low;
+                    p.errors_out[2 * f + 1] = high;
+                }
             }
             __syncthreads();
-            if (t < 4) {
-                unsigned long long a = 0;
-                for (int k = 0; k < 32; ++k) a += part[k][t];
-                atomicAdd(&sc->rsum[par][t], a);
-            } else if (t < 6) {
-                unsigned a = 0;
-                for (int k = 0; k < 32; ++k) a += pcnt[k][t - 4];
-                atomicAdd(&sc->rcnt[par][t - 4], a);
-            }
         }
-        grid.sync();
-        // ---- error bounds of this frame (:2337-2376): the reference's fp64 operation order, one thread per CTA ----
-        if (t < 40) {  // window in time order: oldest first
-            const int s2 = nstds < 40 ? t : (head + t) % 40;
-            win[t][0] = sc->stds[s2][0];
-            win[t][1] = sc->stds[s2][1];
-        }
-        __syncthreads();
-        if (t == 0) {
-            unsigned long long su[4];
-            unsigned cn[2];
-            for (int k = 0; k < 4; ++k) su[k] = __ldcg(&sc->rsum[par][k]);
-            for (int k = 0; k < 2; ++k) cn[k] = __ldcg(&sc->rcnt[par][k]);
-            double sd0, sd1;
-            if (nstds < 40) {
-                const double s1 = (double)(su[0] + su[2]), s2 = (double)(su[1] + su[3]);
-                sd0 = sd1 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(s1, s1), s2)), (double)ns);
-            } else {
-                const double s1 = (double)su[0], s2 = (double)su[1], b1 = (double)su[2], b2 = (double)su[3];
-                sd0 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(b1, b1), b2)), (double)(int)cn[1]);
-                sd1 = __ddiv_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(s1, s1), s2)), (double)(int)cn[0]);
-            }
-            const double f0 = first ? sd0 : sc->first[0], f1 = first ? sd1 : sc->first[1];
-            const int cnt = nstds < 40 ? nstds + 1 : 40, from = nstds < 40 ? 0 : 1;
-            double m0 = f0, m1 = f1;
-            for (int i = from; i < (nstds < 40 ? nstds : 40); ++i) {
-                m0 = __dadd_rn(m0, win[i][0]);
-                m1 = __dadd_rn(m1, win[i][1]);
-            }
-            m0 = __ddiv_rn(__dadd_rn(m0, sd0), (double)(cnt + 1));
-            m1 = __ddiv_rn(__dadd_rn(m1, sd1), (double)(cnt + 1));
-            int high = p.high0 - (int)round(__dmul_rn(fabs(__dsub_rn(sd1, m1)), p.std_factor));
-            int low = p.low0 - (int)round(__dmul_rn(fabs(__dsub_rn(sd0, m0)), p.std_factor));
-            if (high < 0) high = 0;
-            if (low < high) low = high;
-            decided[0] = low;
-            decided[1] = high;
-            if (blockIdx.x == 0) {  // the state that outlives the frame is written once
-                if (first) {
-                    sc->first[0] = sd0;
-                    sc->first[1] = sd1;
-                }
-                const int dst = nstds < 40 ? nstds : head;  // push, or the oldest slot becomes the newest
-                sc->stds[dst][0] = sd0;
-                sc->stds[dst][1] = sd1;
-                sc->background = back;
-                sc->low_error = low;
-                sc->high_error = high;
-                p.errors_out[2 * f] = low;
-                p.errors_out[2 * f + 1] = high;
-            }
-        }
-        __syncthreads();
         const int low = decided[0], high = decided[1];
-        // ---- per-pixel update (:2392-2421) ----
+        // ---- per-pixel update (:2392-2421), and this CTA's share of the next frame's spread ----
+        const bool more = f + 1 < p.m;
+        const u16* tmp1 = tmp + n;
+        const u16* img1 = p.img + (size_t)(f + 1) * n;
+        const unsigned back1 = more ? __ldcg(&sc->back_run[f + 1]) : 0u;
         const unsigned len_after = (unsigned)(len_before < ra ? len_before + 1 : ra);
         for (int i = gt; i < n; i += gstride) {
             const unsigned v = tmp[i];
@@ -512,7 +679,7 @@ __global__ void __launch_bounds__(1024) lossy_run_kernel(const __grid_constant__
                 p.lastDL[i] = (u16)v;
                 continue;
             }
-            const unsigned tv = p.tmpT[i];
+            const unsigned tv = v < mn ? 0u : v - mn;
             unsigned s = 0;
             short cc = 0;
             if (ra > 0) {
@@ -532,7 +699,7 @@ __global__ void __launch_bounds__(1024) lossy_run_kernel(const __grid_constant__
             const int diff = abs((int)tv - (int)r);
             const int max_error = v > back ? high : low;
             unsigned o;
-            if (diff <= max_error && ((unsigned)p.lastDL[i] >> 13) == (v >> 13)) {
+            if (diff <= max_error && (p.variant == 1 || ((unsigned)p.lastDL[i] >> 13) == (v >> 13))) {
                 o = ra > 0 ? ((s / len_after) & 0xFFFFu) : r;
             } else {
                 o = tv;
@@ -548,41 +715,58 @@ __global__ void __launch_bounds__(1024) lossy_run_kernel(const __grid_constant__
                 p.ccount[i] = cc;
             }
             out[i] = (u16)o;
-            p.prevT[i] = (u16)o;
             p.lastDL[i] = (u16)v;
+            if (more) {
+                const unsigned v1 = tmp1[i];
+                add_pixel(v1 < mn ? 0u : v1 - mn, o, (unsigned)img1[i] > back1);
+            } else {
+                p.prevT[i] = (u16)o;  // the state the next call starts from
+            }
         }
-        // the window entry CTA 0 wrote is read by every CTA in the NEXT frame's decide step, two grid barriers away
+        if (more) store_partials(par ^ 1);
     }
 }
 
 // frames [0, m) of img / cur / out are consecutive non-initial frames, the first of them frame number frame_index.
-// Returns 1 when the device cannot launch cooperatively (the caller then goes frame by frame).
-int launch_lossy_run(const u16* img, const u16* cur, u16* tmpT, u16* out, u16* lastDL, u16* refT, u16* prevT, unsigned* sums, u16* cvalue,
+// hist_scratch: LOSSY_MAX_RUN x 16,384 zeroed counters.  Returns 1 when the device cannot launch cooperatively (the caller
+// then goes frame by frame).
+int launch_lossy_run(const u16* img, const u16* cur, u16* out, u16* lastDL, u16* refT, u16* prevT, unsigned* sums, u16* cvalue,
                      short* ccount, u16* ring, int n, int ns, int ra, int subtract_min, long long frame_index, int m, int low0,
-                     int high0, double std_factor, void* scalars, int* errors_out_dev, cudaStream_t st)
+                     int high0, double std_factor, int variant, int quirk, void* scalars, unsigned* hist_scratch, int* errors_out_dev,
+                     cudaStream_t st)
 {
     if (m <= 0) return 0;
+    if (m > LOSSY_MAX_RUN) {
+        set_error("lossy_run: at most %d frames per launch", LOSSY_MAX_RUN);
+        return -1;
+    }
     int dev = 0, coop = 0, per_sm = 0;
     RIRB_CUDA_OK(cudaGetDevice(&dev));
-    RIRB_SMEM_ATTR(lossy_run_kernel, 16384 * 4);
     if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lossy_run_kernel, 1024, 16384 * 4) != cudaSuccess || per_sm < 1) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lossy_run_kernel, 1024, 0) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         return 1;
     }
     LossyRun p;
-    p.img = img; p.cur = cur; p.out = out; p.tmpT = tmpT; p.lastDL = lastDL; p.refT = refT; p.prevT = prevT; p.cvalue = cvalue;
+    p.img = img; p.cur = cur; p.out = out; p.lastDL = lastDL; p.refT = refT; p.prevT = prevT; p.cvalue = cvalue;
     p.ring = ring; p.sums = sums; p.ccount = ccount; p.sc = (LossyScalars*)scalars; p.errors_out = errors_out_dev;
     p.n = n; p.ns = ns; p.ra = ra; p.subtract_min = subtract_min; p.low0 = low0; p.high0 = high0; p.m = m;
+    p.variant = variant; p.quirk = quirk;
     p.frame_index = frame_index; p.std_factor = std_factor;
-    const int grid = (int)max(1LL, min((long long)ceil_div(n, 1024 * 2), (long long)sm_count()));
-    // both parity sets start clean whatever ran before (a handle may alternate between this path and the per-frame one)
-    RIRB_CUDA_OK(cudaMemsetAsync(p.sc->hist2, 0, sizeof(p.sc->hist2) + sizeof(p.sc->rsum) + sizeof(p.sc->rcnt), st));
+    // backgrounds of the whole run: enough CTAs per frame to fill the machine once
+    RIRB_SMEM_ATTR(lossy_back_kernel, 16384 * 4);
+    int parts = (int)max(1LL, min((long long)ceil_div(ns, 1024 * 8 * 4), (long long)(2 * sm_count() / m)));
+    RIRB_LAUNCH(lossy_back_kernel, dim3((unsigned)parts, (unsigned)m), 1024, 16384 * 4, st, cur, n, ns, hist_scratch, p.sc);
+    const int grid = (int)max(1LL, min(min((long long)ceil_div(n, 1024 * 2), (long long)sm_count()), (long long)LOSSY_MAX_CTAS));
+    RIRB_CUDA_OK(cudaMemsetAsync(&p.sc->barrier, 0, sizeof(unsigned), st));
     void* args[] = {&p};
-    RIRB_CUDA_OK(cudaLaunchCooperativeKernel((const void*)lossy_run_kernel, dim3((unsigned)grid), dim3(1024), args, 16384 * 4, st));
+    RIRB_CUDA_OK(cudaLaunchCooperativeKernel((const void*)lossy_run_kernel, dim3((unsigned)grid), dim3(1024), args, 0, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
+
+size_t lossy_hist_scratch_bytes() { return (size_t)LOSSY_MAX_RUN * 16384 * sizeof(unsigned); }
+int lossy_max_run() { return LOSSY_MAX_RUN; }
 
 // ---- launchers ----------------------------------------------------------------------------------
 size_t lossy_scalars_bytes() { return sizeof(LossyScalars); }
@@ -606,7 +790,7 @@ int launch_lossy_first(const u16* tmp, u16* out, u16* lastDL, u16* refT, u16* pr
 
 int launch_lossy_frame(const u16* img, const u16* tmp, u16* tmpT, u16* out, u16* lastDL, u16* refT, u16* prevT, unsigned* sums,
                        u16* cvalue, short* ccount, u16* ring, int n, int ns, int ra, int subtract_min, long long frame_index,
-                       int low0, int high0, double std_factor, void* scalars, int* errors_out_dev, cudaStream_t st)
+                       int low0, int high0, double std_factor, int variant, int quirk, void* scalars, int* errors_out_dev, cudaStream_t st)
 {
     LossyScalars* sc = (LossyScalars*)scalars;
     const int grid_s = (int)max(1LL, min((long long)ceil_div(ns, 256), (long long)sm_count() * 8));
@@ -623,9 +807,9 @@ int launch_lossy_frame(const u16* img, const u16* tmp, u16* tmpT, u16* out, u16*
     // three launches per frame: the two scalar steps run in the last CTA of the reduction before them
     RIRB_LAUNCH(lossy_prep_kernel, grid_r, 1024, 16384 * 4, st, tmp, tmpT, ns, subtract_min, sc);
     RIRB_LAUNCH(lossy_sums_kernel, grid_r, 1024, 0, st, prevT, tmpT, img, ns, sc, nstds, head, prior == 0 ? 1 : 0, low0, high0, std_factor,
-                errors_out_dev);
+                variant, quirk, errors_out_dev);
     RIRB_LAUNCH(lossy_update_kernel, grid_n, 256, 0, st, tmp, tmpT, out, lastDL, refT, prevT, sums, cvalue, ccount, ring, n, ns, ra,
-                len_before, slot_new, slot_old, sc);
+                len_before, slot_new, slot_old, variant, sc);
     return 0;
 }
 

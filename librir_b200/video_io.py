@@ -258,10 +258,12 @@ class LossyPreconditioner:
     """``H264_Saver``'s lossy "bounded-error" pre-conditioner (``addImageLossyNoCamera``, h264.cpp:2253-2424):
     frames in temperature, IN TIME ORDER -> the frames the lossless encoder then receives, pixels that stay
     within the per-frame error bounds being frozen to a reference / running-average value.  Parameters are the
-    saver's string parameters (h264.cpp:1709-1781) with their defaults (PrivateData(), :1663-1665)."""
+    saver's string parameters (h264.cpp:1709-1781) with their defaults (PrivateData(), :1663-1665).
+    ``variant="add_loss"`` selects ``H264_Saver::addLoss`` (h264.cpp:2426-2607, what ``h264_add_loss`` runs) instead;
+    ``memcpyQuirk=False`` replaces the compiled reference's overlapping memcpy of its spread window by a memmove."""
 
     def __init__(self, width, height, lossy_height=None, lowValueError=6, highValueError=2, stdFactor=5.0, runningAverage=32,
-                 subtractMin=False, removeBadPixels=False):
+                 subtractMin=False, removeBadPixels=False, variant="add_image_lossy", memcpyQuirk=True):
         lib = _lib.load()
         self.width, self.height = int(width), int(height)
         self.lossy_height = self.height if lossy_height is None else int(lossy_height)
@@ -269,6 +271,9 @@ class LossyPreconditioner:
                                           float(stdFactor), int(runningAverage), int(bool(subtractMin)), int(bool(removeBadPixels)))
         if self.handle <= 0:
             raise RuntimeError(f"An error occured while calling 'lossy_open': {_lib.last_error()}")
+        self.variant = str(variant)
+        _lib.check(lib.rirb_lossy_set_parameter(self.handle, b"variant", self.variant.encode()), "lossy_set_parameter")
+        _lib.check(lib.rirb_lossy_set_parameter(self.handle, b"memcpyQuirk", b"1" if memcpyQuirk else b"0"), "lossy_set_parameter")
 
     def __del__(self):
         try:

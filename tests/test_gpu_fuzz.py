@@ -100,7 +100,8 @@ def test_fuzz_reader_chain(port):
         finally:
             _lib.set_parameter("loader_fused", 0)
         for t in range(n):
-            want = port.loader_read_image(lo[t], hi[t], xy, min_T, rows, (sx[t], sy[t]) if use_motion else None)
+            # MIN_T_HEIGHT == 0 is "absent": the loader makes it height - 3 when it opens the file (IRFileLoader.cpp:918-921)
+            want = port.loader_read_image(lo[t], hi[t], xy, min_T, rows if rows else h - 3, (sx[t], sy[t]) if use_motion else None)
             np.testing.assert_array_equal(got[t], want, err_msg=f"case {case}: {n}x{h}x{w} bp={use_bp} motion={use_motion} "
                                           f"min_T={min_T} rows={rows} shift=({sx[t]!r},{sy[t]!r})")
 

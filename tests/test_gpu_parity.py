@@ -458,14 +458,15 @@ def test_loader_read_movie_chain(port, best, shape, loader_mode):
     xy = sp.bad_pixels_list(bp.handle)[0] if bp is not None else None
     cases = [dict(bad=False, min_T=0, rows=0, motion=False), dict(bad=True, min_T=0, rows=0, motion=False),
              dict(bad=True, min_T=273, rows=h - 3, motion=True), dict(bad=False, min_T=60000, rows=h // 2, motion=True),
-             dict(bad=True, min_T=-5, rows=h, motion=False)]
+             dict(bad=True, min_T=-5, rows=h, motion=False),
+             dict(bad=False, min_T=300, rows=0, motion=False)]  # MIN_T_HEIGHT absent: height - 3 (IRFileLoader.cpp:918-921)
     for c in cases:
         if c["bad"] and bp is None:
             continue
         got = vio.read_movie(lo, hi, bp if c["bad"] else None, c["min_T"], c["rows"], sx if c["motion"] else None,
                              sy if c["motion"] else None)
         for t in range(n):
-            want = port.loader_read_image(lo[t], hi[t], xy if c["bad"] else None, c["min_T"], c["rows"],
+            want = port.loader_read_image(lo[t], hi[t], xy if c["bad"] else None, c["min_T"], c["rows"] if c["rows"] else max(h - 3, 0),
                                           (sx[t], sy[t]) if c["motion"] else None)
             np.testing.assert_array_equal(got[t], want, err_msg=f"{shape} {c} frame {t}")
     # device-resident planes give the same frames
@@ -742,15 +743,18 @@ def lossy_driver(request):
 @pytest.mark.parametrize("cfg", [dict(), dict(runningAverage=0), dict(runningAverage=5, subtractMin=True),
                                  dict(removeBadPixels=True, lowValueError=12, highValueError=5),
                                  dict(runningAverage=64, subtractMin=True, removeBadPixels=True, stdFactor=2.0)])
-def test_lossy_preconditioner_matches_restated_reference(port, cfg, lossy_driver):
-    """rirb_lossy_* against the line-by-line restatement of addImageLossyNoCamera, frame by frame and with the
-    state carried across calls: the frozen / restarted pixels, the running average ring wrapping, the switch to
-    background-split spreads after 40 frames, the per-frame error attributes."""
+@pytest.mark.parametrize("variant", ["add_image_lossy", "add_loss"])
+def test_lossy_preconditioner_matches_restated_reference(port, cfg, lossy_driver, variant):
+    """rirb_lossy_* against the restatement of addImageLossyNoCamera / addLoss (itself bit-equal to the compiled
+    reference, tests/test_oracle_vs_refvio.py), frame by frame and with the state carried across calls: the frozen /
+    restarted pixels, the running average ring wrapping, the switch to background-split spreads after 40 frames, the
+    smeared window entry, the per-frame error attributes."""
     n, h, w = 90, 43, 64
     mov = lossy_movie(n, h, w)
     stop = h - 3
     st = port.lossy_open(w, h, stop, cfg.get("lowValueError", 6), cfg.get("highValueError", 2), cfg.get("stdFactor", 5.0),
-                         cfg.get("runningAverage", 32), cfg.get("subtractMin", False), cfg.get("removeBadPixels", False))
+                         cfg.get("runningAverage", 32), cfg.get("subtractMin", False), cfg.get("removeBadPixels", False),
+                         variant=int(variant == "add_loss"))
     want, werr = [], []
     for t in range(n):
         o, e = port.lossy_add(st, mov[t])
@@ -758,7 +762,7 @@ def test_lossy_preconditioner_matches_restated_reference(port, cfg, lossy_driver
         werr.append(e)
     port.lossy_close(st)
     want, werr = np.stack(want), np.array(werr)
-    pre = vio.LossyPreconditioner(w, h, stop, **cfg)
+    pre = vio.LossyPreconditioner(w, h, stop, variant=variant, **cfg)
     got_a, err_a = pre.add_images(mov[:37])            # host frames, several calls
     got_b, err_b = pre.add_images(to_dev(mov[37:]))    # device frames
     got = np.concatenate([got_a, to_host(got_b)])
