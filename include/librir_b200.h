@@ -75,6 +75,9 @@ RIRB_API int rirb_set_device(int device);             /* cudaSetDevice for the c
 RIRB_API int rirb_set_stream(void* cuda_stream);      /* stream for the calling thread (NULL = default) */
 RIRB_API int rirb_synchronize(void);                  /* wait for the calling thread's stream */
 RIRB_API const char* rirb_last_error(void);           /* calling thread's last error text */
+/* The calling thread's staging buffers (device scratch, pinned ring, the three streams + buffers of
+ * rirb_process_movie_host) are grow-only while the thread lives and are freed when it exits; this frees them now. */
+RIRB_API void rirb_release_thread_resources(void);
 RIRB_API long long rirb_kernel_launch_count(void);    /* kernels launched by this library so far */
 RIRB_API const char* rirb_version(void);
 /* string key/value switches, the reference's *_set_parameter convention (h264.cpp:1709-1781); process-wide.

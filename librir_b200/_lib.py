@@ -74,6 +74,7 @@ SIGNATURES = {
     "rirb_lossy_open": (_i, [_i, _i, _i, _i, _i, ct.c_double, _i, _i, _i]),
     "rirb_lossy_add_images": (_i, [_i, _vp, _ll, _vp, _vp]),
     "rirb_lossy_close": (None, [_i]),
+    "rirb_release_thread_resources": (None, []),
     "rirb_lossy_set_parameter": (_i, [_i, ct.c_char_p, ct.c_char_p]),
     "rirb_process_movie_host": (_i, [_i, _vp, _ll, _i, _i, _f, _vp, _vp, ct.c_char_p, ct.c_uint, _i, _i, _ll, _vp, _vp, _vp]),
     "rirb_movie_stats": (_i, [_vp, _sz, _vp, _vp, _i]),

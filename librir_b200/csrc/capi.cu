@@ -28,9 +28,28 @@ struct ThreadState {
     cudaStream_t stream = 0;
     // grow-only device scratch slots for host-pointer callers (never shared between threads)
     // slots 0-5: operands of the entry that is running; 6-7: bad_pixels_create, which other entries call
-    void* dev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int dev_of[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    // 8-11: launchers' own work space (kernels.h: scratch_buffer)
+    static constexpr int SLOTS = 12;
+    void* dev[SLOTS] = {};
+    size_t cap[SLOTS] = {};
+    int dev_of[SLOTS] = {};
+    ThreadState()
+    {
+        for (int i = 0; i < SLOTS; ++i) dev_of[i] = -1;
+    }
+    // a thread that exits gives its device memory back (cudaFree of a UVA pointer works from any current device; at process
+    // exit the runtime may already be gone: cudaErrorCudartUnloading is expected and ignored)
+    ~ThreadState() { release(); }
+    void release()
+    {
+        for (int i = 0; i < SLOTS; ++i) {
+            if (dev[i]) (void)cudaFree(dev[i]);
+            dev[i] = nullptr;
+            cap[i] = 0;
+            dev_of[i] = -1;
+        }
+        (void)cudaGetLastError();
+    }
 };
 static thread_local ThreadState tls;
 
@@ -46,9 +65,9 @@ void set_error(const char* fmt, ...)
 cudaStream_t current_stream() { return tls.stream; }
 
 // ---- run-time switches ---------------------------------------------------------------------------
-static const char* const k_opt_names[OPT_COUNT] = {"translate_tma", "gauss_tma", "loader_fused", "ecc_fused", "lossy_run"};
-static const char* const k_opt_env[OPT_COUNT] = {"RIRB_TRANSLATE_TMA", "RIRB_GAUSS_TMA", "RIRB_LOADER_FUSED", "RIRB_ECC_FUSED", "RIRB_LOSSY_RUN"};
-static const int k_opt_default[OPT_COUNT] = {1, 1, 0, 1, 1};
+static const char* const k_opt_names[OPT_COUNT] = {"translate_tma", "gauss_tma", "loader_fused", "ecc_fused", "lossy_run", "translate_rows"};
+static const char* const k_opt_env[OPT_COUNT] = {"RIRB_TRANSLATE_TMA", "RIRB_GAUSS_TMA", "RIRB_LOADER_FUSED", "RIRB_ECC_FUSED", "RIRB_LOSSY_RUN", "RIRB_TRANSLATE_ROWS"};
+static const int k_opt_default[OPT_COUNT] = {1, 1, 0, 1, 1, 1};
 static std::atomic<int> g_opts[OPT_COUNT];
 static std::once_flag g_opts_once;
 static void init_options()
@@ -112,7 +131,7 @@ static void* scratch(int slot, size_t bytes)
     int dev = 0;
     cudaGetDevice(&dev);
     if (tls.cap[slot] < bytes || tls.dev_of[slot] != dev) {
-        if (tls.dev[slot] && tls.dev_of[slot] == dev) cudaFree(tls.dev[slot]);
+        if (tls.dev[slot]) cudaFree(tls.dev[slot]);  // also when the thread moved to another device: UVA pointers free from anywhere
         tls.dev[slot] = nullptr;
         tls.cap[slot] = 0;
         size_t want = bytes < (1u << 20) ? (1u << 20) : bytes + bytes / 4;
@@ -127,6 +146,8 @@ static void* scratch(int slot, size_t bytes)
     return tls.dev[slot];
 }
 
+void* scratch_buffer(int slot, size_t bytes) { return (slot >= 8 && slot < ThreadState::SLOTS) ? scratch(slot, bytes) : nullptr; }
+
 // ---- pageable host buffers --------------------------------------------------------------------
 // A device->host cudaMemcpyAsync into pageable memory is staged by the driver at ~5 GB/s for one
 // 640x512 frame (measured: profiles/r1_percall.md).  Host-pointer callers are the reference's own
@@ -140,6 +161,18 @@ struct PinRing {
     char* buf[PIN_NB] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev[PIN_NB] = {nullptr, nullptr, nullptr, nullptr};
     int state = 0;  // 0 not tried, 1 ready, -1 unavailable (fall back to plain copies)
+    ~PinRing() { release(); }
+    void release()
+    {
+        for (int i = 0; i < PIN_NB; ++i) {
+            if (buf[i]) (void)cudaFreeHost(buf[i]);
+            if (ev[i]) (void)cudaEventDestroy(ev[i]);
+            buf[i] = nullptr;
+            ev[i] = nullptr;
+        }
+        (void)cudaGetLastError();
+        state = 0;
+    }
 };
 // Events belong to the device that was current when they were created, so a thread that moves between devices
 // (rirb_set_device) gets one ring per device.
@@ -1370,6 +1403,17 @@ struct HostPipeSlot {
 struct HostPipe {
     HostPipeSlot slot[HP_SLOTS];
     int device = -1;
+    ~HostPipe() { release(); }
+    void release()
+    {
+        for (int k = 0; k < HP_SLOTS; ++k) {
+            if (slot[k].buf) (void)cudaFree(slot[k].buf);
+            if (slot[k].stream) (void)cudaStreamDestroy(slot[k].stream);
+            slot[k] = HostPipeSlot();
+        }
+        (void)cudaGetLastError();
+        device = -1;
+    }
 };
 thread_local HostPipe g_host_pipe;
 }  // namespace
@@ -1446,9 +1490,19 @@ int rirb_process_movie_host(int handle, const unsigned short* frames, long long 
         u16 *d_in = (u16*)(base + o_in), *d_cor = (u16*)(base + o_cor), *d_reg = (u16*)(base + o_reg);
         u8 *d_lo = (u8*)(base + o_lo), *d_hi = (u8*)(base + o_hi);
         float *d_sm = (float*)(base + o_sm), *d_dx = (float*)(base + o_dx), *d_dy = (float*)(base + o_dy);
-        RIRB_CUDA_OK(cudaMemcpyAsync(d_in, frames + a * fpx, fpx * 2 * m, cudaMemcpyHostToDevice, st));
-        RIRB_CUDA_OK(cudaMemcpyAsync(d_dx, dx + a, 4 * m, cudaMemcpyHostToDevice, st));
-        RIRB_CUDA_OK(cudaMemcpyAsync(d_dy, dy + a, 4 * m, cudaMemcpyHostToDevice, st));
+        // no early return in here: copies already queued on the other slots' streams write into the caller's buffers, so the
+        // streams are drained below whatever happens
+        auto ok = [&](cudaError_t e, const char* what) {
+            if (e == cudaSuccess) return true;
+            set_error("process_movie_host: %s failed: %s", what, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            rc = -1;
+            return false;
+        };
+        if (!ok(cudaMemcpyAsync(d_in, frames + a * fpx, fpx * 2 * m, cudaMemcpyHostToDevice, st), "upload of the frames") ||
+            !ok(cudaMemcpyAsync(d_dx, dx + a, 4 * m, cudaMemcpyHostToDevice, st), "upload of the shifts") ||
+            !ok(cudaMemcpyAsync(d_dy, dy + a, 4 * m, cudaMemcpyHostToDevice, st), "upload of the shifts"))
+            break;
         if (launch_bp_correct(d_in, d_cor, s->xy_dev, s->span_off_dev, w, h, s->clamp_value, m, fpx, st) != 0 ||
             launch_gaussian_u16(d_cor, d_sm, w, h, m, taps, st) != 0 ||
             launch_translate_u16(d_cor, d_reg, w, h, m, fpx, fpx, d_dx, d_dy, 0.f, 0.f, strat, background & 0xFFFFu, false, st) != 0 ||
@@ -1456,9 +1510,10 @@ int rirb_process_movie_host(int handle, const unsigned short* frames, long long 
             rc = -1;
             break;
         }
-        RIRB_CUDA_OK(cudaMemcpyAsync(lo + a * fpx, d_lo, fpx * m, cudaMemcpyDeviceToHost, st));
-        RIRB_CUDA_OK(cudaMemcpyAsync(hi + a * fpx, d_hi, fpx * m, cudaMemcpyDeviceToHost, st));
-        if (smoothed) RIRB_CUDA_OK(cudaMemcpyAsync(smoothed + a * fpx, d_sm, fpx * 4 * m, cudaMemcpyDeviceToHost, st));
+        if (!ok(cudaMemcpyAsync(lo + a * fpx, d_lo, fpx * m, cudaMemcpyDeviceToHost, st), "download of the low-byte planes") ||
+            !ok(cudaMemcpyAsync(hi + a * fpx, d_hi, fpx * m, cudaMemcpyDeviceToHost, st), "download of the high-byte planes") ||
+            (smoothed && !ok(cudaMemcpyAsync(smoothed + a * fpx, d_sm, fpx * 4 * m, cudaMemcpyDeviceToHost, st), "download of the smoothed frames")))
+            break;
     }
     for (int q = 0; q < HP_SLOTS; ++q) {
         cudaError_t e = cudaStreamSynchronize(hp.slot[q].stream);
@@ -1468,6 +1523,14 @@ int rirb_process_movie_host(int handle, const unsigned short* frames, long long 
         }
     }
     return rc;
+}
+
+void rirb_release_thread_resources(void)
+{
+    if (tls.stream) (void)cudaStreamSynchronize(tls.stream);
+    g_host_pipe.release();
+    for (int d = 0; d < PIN_MAX_DEVICES; ++d) pin_rings[d].release();
+    tls.release();
 }
 
 // =================================================================================================

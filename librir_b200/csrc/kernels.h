@@ -57,6 +57,9 @@ int launch_gaussian_u16(const u16* src, float* dst, int w, int h, long long nfra
 int launch_gaussian_bp_u16(const u16* raw, u16* corrected, float* dst, int w, int h, long long nframes, const GaussTaps& taps,
                            const int* xy_dev, const int* row_off_dev, int clamp_value, cudaStream_t st);
 
+// capi.cu: grow-only per-thread device work space for launchers, slots 8..11 (nullptr + set_error when out of memory)
+void* scratch_buffer(int slot, size_t bytes);
+
 // precode.cu
 int launch_split_planes(const u16* img, const u8* it, int w, int h, u8* y_plane, u8* u_plane, u8* v_plane, int ls_y, int ls_u,
                         int ls_v, cudaStream_t st);

@@ -75,6 +75,12 @@ __device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, 
                  "l"(map), "r"(smem_addr(bar)), "r"(x), "r"(y), "r"(frame)
                  : "memory");
 }
+// the same box, only as far as L2 (no shared-memory destination, no completion): covers the DRAM part of the latency for
+// tiles that have no free stage yet
+__device__ __forceinline__ void tma_prefetch_box(const CUtensorMap* map, int x, int y, int frame)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(frame) : "memory");
+}
 #endif  // __CUDACC__
 
 }  // namespace rirb
