@@ -74,13 +74,19 @@ static void init_options()
 {
     for (int i = 0; i < OPT_COUNT; ++i) {
         const char* e = getenv(k_opt_env[i]);
-        g_opts[i].store(e && *e ? (e[0] != '0') : k_opt_default[i]);
+        g_opts[i].store(e && *e ? atoi(e) : k_opt_default[i]);
     }
 }
 bool option_enabled(int which)
 {
     std::call_once(g_opts_once, init_options);
     return which >= 0 && which < OPT_COUNT && g_opts[which].load() != 0;
+}
+
+int option_value(int which)
+{
+    std::call_once(g_opts_once, init_options);
+    return which >= 0 && which < OPT_COUNT ? g_opts[which].load() : 0;
 }
 
 int sm_count()
@@ -451,7 +457,7 @@ int rirb_set_parameter(const char* key, const char* value)
     if (key && value)
         for (int i = 0; i < OPT_COUNT; ++i)
             if (strcmp(key, k_opt_names[i]) == 0) {
-                g_opts[i].store(value[0] != '0' && value[0] != 0);
+                g_opts[i].store(atoi(value));  // 0 = off; switches with more than two settings take 1, 2, ...
                 return 0;
             }
     set_error("set_parameter: unknown key '%s'", key ? key : "(null)");

@@ -782,16 +782,17 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     }
 }
 
+
 // ------------------------------------------------------------------------------------------------
-// uint16 hot path, second generation: warps that never wait for each other
+// uint16 hot path, second generation: warps that do not wait for each other
 // ------------------------------------------------------------------------------------------------
 // The kernel above spends its time waiting, not computing (ncu, profiles/r1_v11_ncu_summary.md: 58 % of the issue slots,
 // two CTA-wide barriers per tile, a CTA-wide queue for the edge groups, every source row unpacked twice).  Same staging
 // (one TMA box per 128 x 64 destination tile, two stages), same exact arithmetic (blend_group's), different schedule:
 //   * a CTA is FOUR warps and there is no __syncthreads in the tile loop.  A warp waits for a stage's box on its mbarrier,
-//     does ITS rows of the tile -- fast groups, edge pixels and border rows alike -- and signs off on a per-stage counter;
-//     the warp that signs off LAST prepares the next row table for that stage and issues the box of tile ty + 2 into it
-//     (its lanes' shared-memory writes are published by the mbarrier arrive of its lane 0).
+//     does ITS 16 rows of the tile -- fast groups, edge pixels and border rows alike -- and signs off on a per-stage
+//     counter; the warp that signs off LAST prepares the next row table for that stage and issues the box of tile ty + 2
+//     into it (its lanes' shared-memory writes are published by the mbarrier arrive of its lane 0).
 //   * lanes 0-15 of a warp own the 16 column groups of rows [16w, 16w+8), lanes 16-31 those of rows [16w+8, 16w+16): a thread
 //     walks down 8 CONSECUTIVE destination rows, so the source row that is the bottom of row y is carried in registers as
 //     the top of row y + 1 -- 9 staged rows are read and unpacked for 8 destination rows instead of 16.  Each octet of
@@ -799,18 +800,15 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 //   * what is not a fast group is done by the warp that owns the rows, one pixel per lane: pixels of the image's first /
 //     last group with the tabulated per-pixel weights (EdgeTable), pixels of border rows and everything else with the
 //     literal per-pixel routine reading the staged box.
+// Measured on the B200 (profiles/r2_translate_notes.md): 0.848 of the copy bandwidth in bench.py (first generation 0.733),
+// 14.8 instructions per pixel instead of 17.9.  What was tried on top of it and NOT kept, each measured: a 256-pixel-wide
+// footprint per CTA (staging alone 0.865 -> 0.889, but the arithmetic hides worse: 0.81), full-width 16-row bands (0.71), a
+// per-warp cp.async ring instead of TMA boxes (0.52-0.61: the copy loop's registers spill into the blend), a leaner edge
+// path (no change), an L2 prefetch of the boxes two tiles ahead (no change), a suspend-time hint on the mbarrier wait (no
+// change).  The eight row-routine instances must not be unrolled further: fully unrolled they fall out of the 32 KB
+// instruction cache (1.5x slower).
 constexpr int TW_WARPS = 4, TW_THREADS = 32 * TW_WARPS;
-constexpr int TW_ROWS = 8;                     // consecutive destination rows per thread
-constexpr int TW_BW = TT_W + 16;               // box width: thread c reads columns [8c, 8c+16)
-constexpr int TW_H1 = 2 * TW_ROWS * TW_WARPS;  // tile rows when a CTA owns ONE 128-pixel column (the two halves of a warp: rows)
-constexpr int TW_H2 = TW_ROWS * TW_WARPS;      // tile rows when it owns TWO adjacent columns (the two halves of a warp: columns)
-constexpr int TW_BH1 = TW_H1 + 2, TW_BH2 = TW_H2 + 2;  // one row below for the bottom tap, one spare (rounded-up rows read it)
-constexpr int TW_STAGES = 2;
-constexpr unsigned TW_BOX2_BYTES = TW_BH2 * TW_BW * 2;                   // what one box of the paired mode brings
-constexpr unsigned TW_BOX2_STRIDE = (TW_BOX2_BYTES + 127u) & ~127u;       // TMA destinations are 128-byte aligned
-constexpr unsigned TW_STAGE_BYTES = ((TW_BH1 * TW_BW * 2 > 2 * TW_BOX2_STRIDE ? TW_BH1 * TW_BW * 2 : 2 * TW_BOX2_STRIDE) + 127u) & ~127u;
-static_assert(TT_W / 8 == 16 && TW_STAGES <= TW_WARPS && TW_H1 <= 64, "lane mapping");
-
+constexpr int TW_ROWS = 8;  // consecutive destination rows per thread
 struct RowAB {       // vertical weights of a destination row on the 2^-23 grid: N = p_bottom * A + p_top * B
     unsigned A, B;   // B == ROW_SLOW: not a regular row (border rows, rows whose source rows are not y+sy / y+sy+1, fine fractions)
 };
@@ -857,7 +855,7 @@ __device__ __forceinline__ void blend_rows(const unsigned (&pb)[9], const unsign
     unsigned o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const HWeights& c = (XOFF != 0 && j >= 8 - XOFF) ? cb : ca;  // static choice
+        const HWeights& c = (XOFF != 0 && j >= 8 - XOFF) ? cb : ca;
         const double val = __dadd_rn(__fma_rn(m[j], c.omu, c.k_l), __fma_rn(m[j + 1], c.u, c.k_r));
         if (MOTION)
             o[j] = (unsigned)(u16)(float)val;
@@ -874,27 +872,18 @@ __device__ __forceinline__ void blend_rows(const unsigned (&pb)[9], const unsign
 
 // a thread's 8 rows of one tile.  srow: shared address of the thread's 16 staged pixels in the box row of its first
 // destination row; rab: shared address of that row's RowAB
-template <int XOFF, bool MOTION, int PROBE = 0>
+template <int XOFF, bool MOTION>
 __device__ __forceinline__ void fast_column(uint32_t srow, uint32_t rab, bool clamp_rt, const HWeights& ca, const HWeights& cb,
                                             u16* orow, size_t w)
 {
-    if (PROBE == 1) {  // measurement only: the staging pipeline without the arithmetic (one LDS + one STG per row)
-#pragma unroll 2
-        for (int k = 0; k < TW_ROWS; ++k) {
-            srow += TW_BW * 2;
-            st_stream(reinterpret_cast<uint4*>(orow), lds128(srow));
-            orow += w;
-        }
-        return;
-    }
     unsigned long long magic = 0x41C0000000000000ULL;
     asm volatile("" : "+l"(magic));
     unsigned pt[9], pb[9];
     unpack9<XOFF>(lds128(srow), lds128(srow + 16), pt);
     if (clamp_rt) pt[8] = pt[7];
-#pragma unroll 2  // eight instances of the full body do not fit the instruction cache (measured: 1.5x slower fully unrolled)
+#pragma unroll 2  // not more: see the instruction-cache note above
     for (int k = 0; k < TW_ROWS; ++k) {
-        srow += TW_BW * 2;
+        srow += TT_BW * 2;
         unpack9<XOFF>(lds128(srow), lds128(srow + 16), pb);
         if (clamp_rt) pb[8] = pb[7];  // rt of the last pixel clamps to its l (Filters.h:309)
         unsigned A, B;
@@ -906,92 +895,44 @@ __device__ __forceinline__ void fast_column(uint32_t srow, uint32_t rab, bool cl
     }
 }
 
-// staged box first (bh rows of TW_BW pixels, origin (xs, ys)), global memory for the few source pixels outside it
-struct BoxSrc {
-    const u16* tile;
-    const u16* __restrict__ frame;
-    int xs, ys, w, h, bh;
-    __device__ __forceinline__ u16 operator()(long long row, long long col) const
-    {
-        const long long r = row - ys, c = col - xs;
-        if (col < w && row < h && r >= 0 && r < bh && c >= 0 && c < TW_BW) return tile[r * TW_BW + c];
-        const long long i = row * w + col, npx = (long long)w * h;
-        return frame[i < npx ? i : npx - 1];
-    }
-};
-
-// The literal per-pixel routine for the second-generation kernel, OUT OF LINE: it is rare, and three inlined copies of it pushed
-// the kernel over the instruction cache (ncu: 31 % of the warps' time in stall_no_inst, 1.35 ms instead of 1.0).
 template <bool MOTION>
-__device__ __noinline__ void generic_pixel(const u16* tile, const u16* frame, int xs, int ys, int w, int h, int bh, int gx, int gy, float dx,
-                                           float dy, int strategy, unsigned background, u16* o)
-{
-    const BoxSrc ts{tile, frame, xs, ys, w, h, bh};
-    if (MOTION) {
-        float r;
-        if (translate_pixel<u16, float>(ts, w, h, gx, gy, dx, dy, strategy, (float)background, r)) *o = (u16)r;
-    } else {
-        u16 r;
-        if (translate_pixel<u16, u16>(ts, w, h, gx, gy, dx, dy, strategy, (u16)background, r)) *o = r;
-    }
-}
-
-// A CTA owns the 128-pixel tile columns 2*blockIdx.x and 2*blockIdx.x + 1 of one frame and walks down them.
-//   paired (both columns exist): tiles of 256 x 32 pixels, two boxes per stage; lanes 0-15 of a warp take the left column,
-//     lanes 16-31 the right one, both on rows [8w, 8w+8) -- a warp's store covers 512 contiguous bytes of a row and the
-//     CTA's footprint in DRAM is twice as wide (frames are row-major: what the memory system sees as one stream);
-//   single (the image's last, odd column): tiles of 128 x 64 pixels, one box per stage; lanes 16-31 take rows [16w+8, 16w+16).
-// tmap1 / tmap2 describe the same movie with boxes of TW_BH1 / TW_BH2 rows.
-template <bool MOTION, int PROBE = 0>
 __global__ void __launch_bounds__(TW_THREADS, 5)
-translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2, const u16* __restrict__ src,
-                          u16* __restrict__ dst, int w, int h, size_t src_stride, size_t dst_stride, const float* __restrict__ dxs,
-                          const float* __restrict__ dys, float dx0, float dy0, int strategy, unsigned background,
-                          const int* __restrict__ order)
+translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* __restrict__ src, u16* __restrict__ dst, int w, int h,
+                          size_t src_stride, size_t dst_stride, const float* __restrict__ dxs, const float* __restrict__ dys,
+                          float dx0, float dy0, int strategy, unsigned background, int tiles_y, const int* __restrict__ order)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bar[TW_STAGES];
-    __shared__ __align__(8) RowAB rowab[TW_STAGES][TW_H1];
-    __shared__ unsigned done[TW_STAGES];  // warps that are through with the stage's current tile
+    __shared__ __align__(8) unsigned long long bar[TT_STAGES];
+    __shared__ __align__(8) RowAB rowab[TT_STAGES][TT_H];
+    __shared__ unsigned done[TT_STAGES];  // warps that are through with the stage's current tile
     __shared__ EdgeTable edge_tab[2];     // [0]: the image's first group of a row, [1]: its last
     const int f = order ? order[blockIdx.y] : (int)blockIdx.y;  // frames grouped by column offset (translate_order_kernel)
-    const int x0c = blockIdx.x * (2 * TT_W);       // first pixel column of the CTA
-    const bool paired = x0c + TT_W < w;             // the second tile column exists
-    const int th = paired ? TW_H2 : TW_H1;          // tile rows
-    const int bh = paired ? TW_BH2 : TW_BH1;        // box rows
-    const int wrows = paired ? TW_ROWS : 2 * TW_ROWS;  // rows of a tile that belong to one warp
-    const int fwid = paired ? 2 * TT_W : TT_W;      // footprint width
-    const int tiles_y = (h + th - 1) / th;
+    const int x0t = blockIdx.x * TT_W;
     const float dx = dxs ? dxs[f] : dx0;
     const float dy = dys ? dys[f] : dy0;
     const float fw = (float)w;
     const float fh = (float)h;
     const int sx = (int)fminf(fmaxf(floorf(-dx), -fw - 16.f), fw + 16.f);
     const int sy = (int)fminf(fmaxf(floorf(-dy), -fh - 16.f), fh + 16.f);
-    const int xs0 = (x0c + sx) & ~7;       // box origin of the left column; the right one starts TT_W further
-    const int xoff = (x0c + sx) - xs0;     // 0..7, the same for both columns
+    const int xs = (x0t + sx) & ~7;
+    const int xoff = (x0t + sx) - xs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // rows of tile `tile_row` into stage s, by one whole warp: the row table first, then lane 0 publishes it and asks for the box(es)
+    // rows of tile `tile_row` into stage s, by one whole warp: the row table first, then lane 0 publishes it and asks for the box
     auto prepare_stage = [&](int s, int tile_row) {
-        const int y0 = tile_row * th;
-        for (int k = lane; k < th; k += 32) rowab[s][k] = make_row_ab(y0 + k, h, dy, y0 + k + sy);
+        const int y0 = tile_row * TT_H;
+#pragma unroll
+        for (int k = 0; k < TT_H / 32; ++k) rowab[s][lane + 32 * k] = make_row_ab(y0 + lane + 32 * k, h, dy, y0 + lane + 32 * k + sy);
         __syncwarp();
         if (lane == 0) {
             done[s] = 0;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (paired) {
-                mbar_expect_tx(&bar[s], 2 * TW_BOX2_BYTES);
-                tma_load_box(smem_raw + s * TW_STAGE_BYTES, &tmap2, &bar[s], xs0, y0 + sy, f);
-                tma_load_box(smem_raw + s * TW_STAGE_BYTES + TW_BOX2_STRIDE, &tmap2, &bar[s], xs0 + TT_W, y0 + sy, f);
-            } else {
-                mbar_expect_tx(&bar[s], TW_BH1 * TW_BW * 2);
-                tma_load_box(smem_raw + s * TW_STAGE_BYTES, &tmap1, &bar[s], xs0, y0 + sy, f);
-            }
+            mbar_expect_tx(&bar[s], TT_BH * TT_BW * 2);
+            tma_load_box(smem_raw + s * TT_STAGE_BYTES, &tmap, &bar[s], xs, y0 + sy, f);
         }
     };
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < TW_STAGES; ++s) mbar_init(&bar[s], 1);
+        for (int s = 0; s < TT_STAGES; ++s) mbar_init(&bar[s], 1);
         mbar_fence_init();
     }
     if (warp == TW_WARPS - 1 && lane < 16) {  // 2 tables x 8 pixels
@@ -999,7 +940,7 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap1, const __gri
         const int xe0 = e ? w - 8 : 0;
         const int x = xe0 + i;
         const float px = (float)x - dx;
-        bool ok = (xe0 >= x0c) && (xe0 < x0c + fwid) && !(px < 0) && (px < fw);
+        bool ok = (xe0 >= x0t) && (xe0 < x0t + TT_W) && !(px < 0) && (px < fw);
         const int l = (int)px;
         const int rt = (int)(px + 1.0f);
         const bool cl = ok && (rt == w) && (l == w - 1);
@@ -1012,13 +953,12 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap1, const __gri
         }
     }
     __syncthreads();  // barriers initialised, edge tables written: the only CTA-wide barrier of the kernel
-    if (warp < TW_STAGES && warp < tiles_y) prepare_stage(warp, warp);
+    if (warp < TT_STAGES && warp < tiles_y) prepare_stage(warp, warp);
 
     // ---- per-thread column constants (while the first boxes are in flight) -----------------------
     const int cx = lane & 15, half = lane >> 4;
-    const int colsel = paired ? half : 0;                          // which of the CTA's tile columns
-    const int r0 = wrows * warp + (paired ? 0 : TW_ROWS * half);   // the thread's first row inside a tile
-    const int x0 = x0c + TT_W * colsel + 8 * cx;
+    const int r0 = 2 * TW_ROWS * warp + TW_ROWS * half;  // the thread's first row inside a tile
+    const int x0 = x0t + 8 * cx;
     const int isplit = (8 - xoff) & 7;
     const float pxf = (float)x0 - dx, pxl = (float)(x0 + 7) - dx;
     const int l0 = (int)pxf, l7 = (int)pxl;
@@ -1033,106 +973,70 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap1, const __gri
     }
     const bool clamp_rt = (l0 + 8 == w);
     const HWeights ca = make_hweights(u0), cb = make_hweights(u7);
-    // column groups of the CTA's footprint that exist but are not fast: bit = group index (in single mode both halves agree)
-    const unsigned slowcols = __ballot_sync(0xFFFFFFFFu, !xfast && x0 < w) & (paired ? 0xFFFFFFFFu : 0xFFFFu);
+    // column groups of this tile column that exist but are not fast: bit cx (the same in both halves of the warp)
+    const unsigned slowcols = __ballot_sync(0xFFFFFFFFu, !xfast && x0 < w) & 0xFFFFu;
     const u16* frame = src + (size_t)f * src_stride;
     u16* oframe = dst + (size_t)f * dst_stride;
-    const unsigned box_off = (unsigned)colsel * TW_BOX2_STRIDE;  // the thread's box inside a stage
 
 #pragma unroll 1
     for (int ty = 0; ty < tiles_y; ++ty) {
-        const int stage = ty % TW_STAGES;
-        const unsigned parity = (unsigned)(ty / TW_STAGES) & 1u;
-        const int y0t = ty * th, ys = y0t + sy;
+        const int stage = ty % TT_STAGES;
+        const unsigned parity = (unsigned)(ty / TT_STAGES) & 1u;
+        const int y0t = ty * TT_H, ys = y0t + sy;
         mbar_wait(&bar[stage], parity);
-        const unsigned char* stage_base = smem_raw + stage * TW_STAGE_BYTES;
+        const u16* tile = reinterpret_cast<const u16*>(smem_raw + stage * TT_STAGE_BYTES);
         if (xfast) {
-            const uint32_t srow = smem_addr(stage_base + box_off) + (uint32_t)(r0 * TW_BW + 8 * cx) * 2u;
+            const uint32_t srow = smem_addr(tile + r0 * TT_BW + 8 * cx);
             const uint32_t rab = smem_addr(&rowab[stage][r0]);
             u16* orow = oframe + (size_t)(y0t + r0) * w + x0;
             switch (xoff) {  // CTA-uniform
-            case 0: fast_column<0, MOTION, PROBE>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
-            case 1: fast_column<1, MOTION, PROBE>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
-            case 2: fast_column<2, MOTION, PROBE>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
-            case 3: fast_column<3, MOTION, PROBE>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
-            case 4: fast_column<4, MOTION, PROBE>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
-            case 5: fast_column<5, MOTION, PROBE>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
-            case 6: fast_column<6, MOTION, PROBE>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
-            default: fast_column<7, MOTION, PROBE>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
+            case 0: fast_column<0, MOTION>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
+            case 1: fast_column<1, MOTION>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
+            case 2: fast_column<2, MOTION>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
+            case 3: fast_column<3, MOTION>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
+            case 4: fast_column<4, MOTION>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
+            case 5: fast_column<5, MOTION>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
+            case 6: fast_column<6, MOTION>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
+            default: fast_column<7, MOTION>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
             }
         }
         __syncwarp();
-        // ---- the rest of the warp's rows, one pixel per lane ----
-        const int wr0 = wrows * warp;  // the warp's first row inside the tile
-        const unsigned slowrows = __ballot_sync(0xFFFFFFFFu, lane < wrows && rowab[stage][wr0 + (lane < wrows ? lane : 0)].B == ROW_SLOW);
-        // one pixel by the literal routine, with a short cut for destination pixels that have no source (the bulk of what
-        // comes here): col = pixel inside the CTA's footprint, row = inside the tile
-        auto slow_pixel = [&](int col, int row) {
-            const int gx = x0c + col, gy = y0t + row;
+        // ---- the rest of the warp's 16 rows, one pixel per lane ----
+        const int wr0 = 2 * TW_ROWS * warp;  // the warp's first row inside the tile
+        const unsigned slowrows = __ballot_sync(0xFFFFFFFFu, lane < 16 && rowab[stage][wr0 + (lane & 15)].B == ROW_SLOW) & 0xFFFFu;
+        const TileSrc ts{tile, frame, xs, ys, w, h};
+        auto slow_pixel = [&](int col, int row) {  // col: pixel inside the tile column, row: inside the tile
+            const int gx = x0t + col, gy = y0t + row;
             if (gx >= w || gy >= h) return;
             u16* o = oframe + (size_t)gy * w + gx;
-            const int csel = col >> 7;  // tile column of the pixel (0 in single mode)
-            const BoxSrc ts{reinterpret_cast<const u16*>(stage_base + (unsigned)csel * TW_BOX2_STRIDE), frame, xs0 + TT_W * csel, ys, w, h, bh};
-            const float px = (float)gx - dx, py = (float)gy - dy;
-            if ((px < 0 || px >= fw || py < 0 || py >= fh) && strategy != STRAT_WRAP) {
-                if (strategy == STRAT_BACKGROUND) *o = (u16)background;  // (u16)(float)b == b in the motion variant
-                if (strategy == STRAT_NEAREST) {                         // a copy: no arithmetic, and u16 -> float -> u16 is exact
-                    const long long nx = px < 0 ? 0 : (px >= fw ? w - 1 : (long long)px);
-                    const long long ny = py < 0 ? 0 : (py >= fh ? h - 1 : (long long)py);
-                    *o = ts(ny, nx);
-                }
+            const int gx0 = gx & ~7, gi = gx & 7;
+            const int e = (gx0 == 0) ? 0 : ((gx0 == w - 8) ? 1 : -1);
+            const RowAB ra = rowab[stage][row];
+            if (e >= 0 && ra.B != ROW_SLOW && ((edge_tab[e].valid >> gi) & 1u)) {
+                const unsigned rows = (unsigned)(row * (TT_BW * 2)) | ((unsigned)((row + 1) * (TT_BW * 2)) << 16);
+                *o = blend_edge_pixel<MOTION>(tile, rows, ra.A, ra.B, col + xoff, (edge_tab[e].clamped >> gi) & 1u, edge_tab[e].wt[gi]);
                 return;
             }
-            generic_pixel<MOTION>(ts.tile, frame, ts.xs, ys, w, h, bh, gx, gy, dx, dy, strategy, background, o);
+            if (MOTION) {
+                float r;
+                if (translate_pixel<u16, float>(ts, w, h, gx, gy, dx, dy, strategy, (float)background, r)) *o = (u16)r;
+            } else {
+                u16 r;
+                if (translate_pixel<u16, u16>(ts, w, h, gx, gy, dx, dy, strategy, (u16)background, r)) *o = r;
+            }
         };
-        if (slowcols) {  // CTA-uniform.  Per slow column group: lane = (pixel of the group, block of the warp's rows)
-            const int gi = lane & 7, rb = lane >> 3, nrb = wrows >> 2;  // rows per block: 4 (single) or 2 (paired)
+        if (slowcols) {  // CTA-uniform: 16 rows x 8 pixels per slow column group, 4 rows per pass
             for (unsigned m = slowcols; m; m &= m - 1) {
-                const int col = 8 * (__ffs(m) - 1) + gi, gx = x0c + col;
-                const int gx0 = gx & ~7;
-                const int e = (gx0 == 0) ? 0 : ((gx0 == w - 8) ? 1 : -1);
-                const int rbeg = wr0 + rb * nrb;
-                if (gx >= w) continue;
-                if (e >= 0 && ((edge_tab[e].valid >> gi) & 1u)) {
-                    // a pixel of the image's first / last group with tabulated weights: the fast path's arithmetic, walking
-                    // down the block's rows with the top taps carried
-                    const HWeights c = edge_tab[e].wt[gi];
-                    const int rstep = ((edge_tab[e].clamped >> gi) & 1u) ? 0 : 1;
-                    const u16* p = reinterpret_cast<const u16*>(stage_base + (unsigned)(col >> 7) * TW_BOX2_STRIDE) + rbeg * TW_BW +
-                                   (col & (TT_W - 1)) + xoff;
-                    u16* o = oframe + (size_t)(y0t + rbeg) * w + gx;
-                    unsigned tl = p[0], tr = p[rstep];
+                const int g = __ffs(m) - 1;
 #pragma unroll 1
-                    for (int k = 0; k < nrb; ++k) {
-                        p += TW_BW;
-                        const unsigned bl = p[0], br = p[rstep];
-                        const RowAB ra = rowab[stage][rbeg + k];
-                        if (y0t + rbeg + k < h) {
-                            if (ra.B != ROW_SLOW) {
-                                const unsigned long long nl = (unsigned long long)bl * ra.A + (unsigned long long)tl * ra.B + 0x41C0000000000000ULL;
-                                const unsigned long long nr = (unsigned long long)br * ra.A + (unsigned long long)tr * ra.B + 0x41C0000000000000ULL;
-                                const double val = __dadd_rn(__fma_rn(__longlong_as_double((long long)nl), c.omu, c.k_l),
-                                                             __fma_rn(__longlong_as_double((long long)nr), c.u, c.k_r));
-                                *o = MOTION ? (u16)(float)val : (u16)__double2loint(__dadd_rd(val, 4503599627370496.0));
-                            } else {
-                                slow_pixel(col, rbeg + k);
-                            }
-                        }
-                        o += w;
-                        tl = bl;
-                        tr = br;
-                    }
-                } else {
-#pragma unroll 1
-                    for (int k = 0; k < nrb; ++k) slow_pixel(col, rbeg + k);
-                }
+                for (int rr = lane >> 3; rr < 2 * TW_ROWS; rr += 4) slow_pixel(8 * g + (lane & 7), wr0 + rr);
             }
         }
         if (slowrows) {  // warp-uniform: the pixels of border rows that are not in a slow column group
             for (unsigned m = slowrows; m; m &= m - 1) {
                 const int rr = __ffs(m) - 1;
 #pragma unroll 1
-                for (int c = lane; c < fwid; c += 32)
+                for (int c = lane; c < TT_W; c += 32)
                     if (!((slowcols >> (c >> 3)) & 1u)) slow_pixel(c, wr0 + rr);
             }
         }
@@ -1145,14 +1049,14 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap1, const __gri
             last = (old == TW_WARPS - 1);
         }
         last = __shfl_sync(0xFFFFFFFFu, last, 0);
-        if (last && ty + TW_STAGES < tiles_y) prepare_stage(stage, ty + TW_STAGES);
+        if (last && ty + TT_STAGES < tiles_y) prepare_stage(stage, ty + TT_STAGES);
     }
 }
 
 // The eight instances of the row routine (one per residual column offset) are ~3 KB of code each, and the offset follows the
-// frame's shift: with per-frame shifts the CTAs resident on an SM ran up to five different instances and fell out of the 32 KB
-// instruction cache (ncu: stall_no_inst 31 %).  Frames are therefore handed out grouped by offset: order[i] = i-th frame of a
-// counting sort by (floor(-dx) & 7).  One CTA; n <= 65535.
+// frame's shift: with per-frame shifts the CTAs resident on an SM run up to five different instances.  For the motion variant
+// (more code per instance) handing the frames out grouped by offset is worth 4 %: order[i] = i-th frame of a counting sort by
+// (floor(-dx) & 7).  (The plain variant loses 1.5 % to the indirection and is launched without it.)  One CTA; n <= 65535.
 __global__ void __launch_bounds__(1024) translate_order_kernel(const float* __restrict__ dxs, int n, int w, int* __restrict__ order)
 {
     __shared__ int count[8], start[8];
@@ -1181,13 +1085,11 @@ int launch_translate_u16(const u16* src, u16* dst, int w, int h, long long nfram
     const bool tma_enabled = option_enabled(OPT_TRANSLATE_TMA);  // "translate_tma" = 0 selects the plain kernel (A/B measurements)
     const int tiles_x = (int)ceil_div(w, TT_W), tiles_y = (int)ceil_div(h, TT_H);
     if (tma_enabled && (w % 8 == 0) && aligned16(dst) && (dst_stride % 8 == 0) && tma_compatible(src, (size_t)w * 2, src_stride * 2)) {
-        const bool rows_kernel = option_enabled(OPT_TRANSLATE_ROWS);  // "translate_rows" = 0: the first-generation tiled kernel (A/B)
-        const size_t smem = rows_kernel ? (size_t)TW_STAGES * TW_STAGE_BYTES : (size_t)TT_STAGES * TT_STAGE_BYTES;
+        const size_t smem = (size_t)TT_STAGES * TT_STAGE_BYTES;
         RIRB_SMEM_ATTR((translate_u16_tma_kernel<true, false>), smem);
         RIRB_SMEM_ATTR((translate_u16_tma_kernel<false, false>), smem);
         RIRB_SMEM_ATTR((translate_u16_rows_kernel<true>), smem);
         RIRB_SMEM_ATTR((translate_u16_rows_kernel<false>), smem);
-        RIRB_SMEM_ATTR((translate_u16_rows_kernel<false, 1>), smem);
         // grid = (tile column, frame); gridDim.y <= 65535, so long movies go in several launches
         for (long long f0 = 0; f0 < nframes; f0 += 65535) {
             const long long n = min(nframes - f0, 65535LL);
@@ -1195,33 +1097,25 @@ int launch_translate_u16(const u16* src, u16* dst, int w, int h, long long nfram
             u16* d0 = dst + f0 * dst_stride;
             const float* dx_p = dxs ? dxs + f0 : nullptr;
             const float* dy_p = dys ? dys + f0 : nullptr;
-            if (rows_kernel) {
-                CUtensorMap tmap1, tmap2;
-                if (make_movie_tensor_map(&tmap1, s0, 2, w, h, n, (size_t)w * 2, src_stride * 2, TW_BW, TW_BH1) != 0 ||
-                    make_movie_tensor_map(&tmap2, s0, 2, w, h, n, (size_t)w * 2, src_stride * 2, TW_BW, TW_BH2) != 0)
-                    return -1;
-                const dim3 rgrid((unsigned)ceil_div(tiles_x, 2), (unsigned)n);
+            CUtensorMap tmap;
+            if (make_movie_tensor_map(&tmap, s0, 2, w, h, n, (size_t)w * 2, src_stride * 2, TT_BW, TT_BH) != 0) return -1;
+            const dim3 tgrid((unsigned)tiles_x, (unsigned)n);
+            const PlaneSrc none{};
+            if (option_enabled(OPT_TRANSLATE_ROWS)) {  // "translate_rows" = 0: the first-generation tiled kernel (A/B)
                 int* order = nullptr;
-                if (dx_p && n > 1) {  // per-frame shifts: hand the frames out grouped by their column offset
+                if (motion && dx_p && n > 1) {  // per-frame shifts: hand the frames out grouped by their column offset
                     order = (int*)scratch_buffer(8, sizeof(int) * 65536);
                     if (!order) return -1;
                     RIRB_LAUNCH(translate_order_kernel, 1, 1024, 0, st, dx_p, (int)n, w, order);
                 }
                 if (motion)
-                    RIRB_LAUNCH((translate_u16_rows_kernel<true>), rgrid, TW_THREADS, smem, st, tmap1, tmap2, s0, d0, w, h, src_stride,
-                                dst_stride, dx_p, dy_p, dx0, dy0, strategy, background, order);
-                else if (getenv("RIRB_TRANSLATE_PROBE"))
-                    RIRB_LAUNCH((translate_u16_rows_kernel<false, 1>), rgrid, TW_THREADS, smem, st, tmap1, tmap2, s0, d0, w, h, src_stride,
-                                dst_stride, dx_p, dy_p, dx0, dy0, strategy, background, order);
+                    RIRB_LAUNCH((translate_u16_rows_kernel<true>), tgrid, TW_THREADS, smem, st, tmap, s0, d0, w, h, src_stride, dst_stride,
+                                dx_p, dy_p, dx0, dy0, strategy, background, tiles_y, order);
                 else
-                    RIRB_LAUNCH((translate_u16_rows_kernel<false>), rgrid, TW_THREADS, smem, st, tmap1, tmap2, s0, d0, w, h, src_stride,
-                                dst_stride, dx_p, dy_p, dx0, dy0, strategy, background, order);
+                    RIRB_LAUNCH((translate_u16_rows_kernel<false>), tgrid, TW_THREADS, smem, st, tmap, s0, d0, w, h, src_stride, dst_stride,
+                                dx_p, dy_p, dx0, dy0, strategy, background, tiles_y, order);
                 continue;
             }
-            CUtensorMap tmap;
-            if (make_movie_tensor_map(&tmap, s0, 2, w, h, n, (size_t)w * 2, src_stride * 2, TT_BW, TT_BH) != 0) return -1;
-            const dim3 tgrid((unsigned)tiles_x, (unsigned)n);
-            const PlaneSrc none{};
             if (motion)
                 RIRB_LAUNCH((translate_u16_tma_kernel<true, false>), tgrid, TT_THREADS, smem, st, tmap, tmap, s0, d0, w, h, src_stride,
                             dst_stride, dx_p, dy_p, dx0, dy0, strategy, background, tiles_y, none);
