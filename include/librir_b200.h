@@ -139,6 +139,12 @@ RIRB_API int rirb_loader_read_movie(int handle, const unsigned char* lo, const u
                                     int min_T, int min_T_height, const double* shift_x, const double* shift_y, int meta_rows,
                                     unsigned short* out);
 
+/* readImage's chain for frames that are uint16 already (e.g. decoded from the zstd movie file, rirb_z_read_images):
+ * += min_T on rows [0, min_T_height) -> removeBadPixels -> removeMotion, IN PLACE on frames[nframes][h][w] (host or device);
+ * handle / shifts / meta_rows as in rirb_loader_read_movie. */
+RIRB_API int rirb_loader_finish_frames(int handle, unsigned short* frames, long long nframes, int w, int h, int min_T, int min_T_height,
+                                       const double* shift_x, const double* shift_y, int meta_rows);
+
 /* ---- lossless-writer pre-coder (H264Capture::AddFrame, h264.cpp:1066-1103; inverse
  *      VideoGrabber::toArray, h264.cpp:3016-3051) ---- */
 
@@ -191,6 +197,8 @@ RIRB_API int rirb_lossy_add_images(int handle, const unsigned short* frames, lon
  *               stock flags (g++ -O3, x86-64: one .second value is smeared, oracle/oracle.c), 0 the intended memmove. */
 RIRB_API int rirb_lossy_set_parameter(int handle, const char* key, const char* value);
 RIRB_API void rirb_lossy_close(int handle);
+/* the minimum the first image fixed (the saver's MIN_T global attribute, h264.cpp:2277-2296); 0 without subtractMin */
+RIRB_API int rirb_lossy_get_min(int handle, int* min_value);
 
 /* ---- the whole per-frame path on HOST buffers, one call (the end-to-end drop-in) ----
  * frames[nframes][h][w] (host) -> bad_pixels_correct (handle) -> gaussian_filter (sigma; result kept on
@@ -251,10 +259,16 @@ RIRB_API int rirb_attrs_set_global_attributes(int handle, const char* keys, cons
 /* ---- zstd movie file: replaces z_open_file_write / z_write_image / z_close_file / z_open_file_read /
  *      z_image_count / z_image_size / z_read_image / z_get_timestamps, ZFile.h:16-52 / ZFile.cpp (the
  *      BIN_FILE_Z_COMPRESSED branch of IRFileLoader, IRFileLoader.cpp:331-370,540-541).  Files are
- *      byte-compatible both ways with the reference's.  Handles are ints (the reference hands out pointers);
- *      method must be 1 (zstd of the raw image: the only one ZFile.cpp implements).  The *_images entries take
+ *      byte-compatible both ways with the reference's.  Handles are ints (the reference hands out pointers).
+ *      method 1 = zstd of the raw image (the only one ZFile.cpp implements; byte-identical files).  Methods 2 and 3,
+ *      which the reference documents (video_io.h:298-305) but never implemented, are defined here as the path's
+ *      pre-coder in front of the same zstd stage: record payload = zstd([low-byte plane | high-byte plane]) of the image
+ *      (2) or of its temporal residual with a key frame every GOP frames (3); split / delta and their inverses run on
+ *      the GPU in whole GOPs (frames that do not fill a GOP wait for the next call or the close).  The *_images entries take
  *      frames[n][h][w] as host or device pointers and use `threads` host threads (0 = all cores). */
 RIRB_API int rirb_z_open_file_write(const char* filename, int width, int height, int rate, int method, int clevel);
+/* the same with the GOP length of method 3 (rirb_z_open_file_write uses 50, the saver's default) */
+RIRB_API int rirb_z_open_file_write_gop(const char* filename, int width, int height, int rate, int method, int clevel, int gop);
 RIRB_API int rirb_z_write_image(int handle, const unsigned short* img, long long timestamp);
 RIRB_API int rirb_z_write_images(int handle, const unsigned short* frames, long long nframes, const long long* timestamps,
                                  int threads);

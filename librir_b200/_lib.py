@@ -63,6 +63,7 @@ SIGNATURES = {
     "rirb_loader_remove_bad_pixels": (_i, [_i, _vp, _ll, _sz]),
     "rirb_loader_remove_motion": (_i, [_vp, _vp, _i, _i, _ll, _sz, _vp, _vp]),
     "rirb_loader_read_movie": (_i, [_i, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "rirb_loader_finish_frames": (_i, [_i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i]),
     "rirb_split_yuv444": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i]),
     "rirb_merge_yuv444": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rirb_split_yuv420": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i]),
@@ -74,6 +75,7 @@ SIGNATURES = {
     "rirb_lossy_open": (_i, [_i, _i, _i, _i, _i, ct.c_double, _i, _i, _i]),
     "rirb_lossy_add_images": (_i, [_i, _vp, _ll, _vp, _vp]),
     "rirb_lossy_close": (None, [_i]),
+    "rirb_lossy_get_min": (_i, [_i, _vp]),
     "rirb_release_thread_resources": (None, []),
     "rirb_lossy_set_parameter": (_i, [_i, ct.c_char_p, ct.c_char_p]),
     "rirb_process_movie_host": (_i, [_i, _vp, _ll, _i, _i, _f, _vp, _vp, ct.c_char_p, ct.c_uint, _i, _i, _ll, _vp, _vp, _vp]),
@@ -101,6 +103,7 @@ SIGNATURES = {
     "rirb_attrs_set_frame_attributes": (_i, [_i, _i, _vp, _vp, _vp, _vp, _i]),
     "rirb_attrs_set_global_attributes": (_i, [_i, _vp, _vp, _vp, _vp, _i]),
     "rirb_z_open_file_write": (_i, [ct.c_char_p, _i, _i, _i, _i, _i]),
+    "rirb_z_open_file_write_gop": (_i, [ct.c_char_p, _i, _i, _i, _i, _i, _i]),
     "rirb_z_write_image": (_i, [_i, _vp, _ll]),
     "rirb_z_write_images": (_i, [_i, _vp, _ll, _vp, _i]),
     "rirb_z_close_file": (_ll, [_i]),

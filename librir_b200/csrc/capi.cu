@@ -980,6 +980,47 @@ int rirb_loader_read_movie(int handle, const unsigned char* lo, const unsigned c
     return 0;
 }
 
+// The same chain for frames that are uint16 already (decoded from the zstd movie file): += min_T -> removeBadPixels ->
+// removeMotion, in place.
+int rirb_loader_finish_frames(int handle, unsigned short* frames, long long nframes, int w, int h, int min_T, int min_T_height,
+                              const double* shift_x, const double* shift_y, int meta_rows)
+{
+    if (!frames || w <= 0 || h <= 0 || nframes < 0 || meta_rows < 0 || meta_rows >= h || (!shift_x) != (!shift_y)) {
+        set_error("loader_finish_frames: bad arguments");
+        return -1;
+    }
+    if (nframes == 0) return 0;
+    const int hb = h - meta_rows;
+    if (min_T_height == 0) min_T_height = hb;  // IRFileLoader.cpp:918-921
+    std::shared_ptr<BadPixelState> s;
+    if (handle != 0) {
+        s = find_handle_here(handle, "loader_finish_frames");
+        if (!s) return -1;
+        if (s->w != w || s->h != hb) {
+            set_error("loader_finish_frames: the handle was created on a %dx%d image, expected %dx%d", s->w, s->h, w, hb);
+            return -1;
+        }
+    }
+    RIRB_REQUIRE_DEVICE();
+    cudaStream_t st = tls.stream;
+    const size_t fpx = (size_t)w * h;
+    StagedOut io;
+    if (!stage_out(io, frames, fpx * 2 * (size_t)nframes, 0, true, st)) return -1;
+    u16* d = (u16*)io.dev;
+    const int rows_t = (min_T == 0 || min_T_height < 0) ? 0 : (min_T_height > h ? h : min_T_height);
+    if (launch_loader_add_min(d, w, rows_t, nframes, fpx, min_T, st) != 0) return -1;
+    if (s && !s->xy.empty())
+        if (launch_loader_bp(d, s->xy_dev, s->mask_dev, (int)(s->xy.size() / 2), w, hb, nframes, fpx, st) != 0) return -1;
+    if (shift_x) {
+        // the motion step is out of place: through a scratch copy, on device pointers (no further staging)
+        u16* tmp = (u16*)scratch(3, fpx * 2 * (size_t)nframes);
+        if (!tmp) return -1;
+        RIRB_CUDA_OK(cudaMemcpyAsync(tmp, d, fpx * 2 * (size_t)nframes, cudaMemcpyDeviceToDevice, st));
+        if (rirb_loader_remove_motion(tmp, d, w, hb, nframes, fpx, shift_x, shift_y) != 0) return -1;
+    }
+    return finish_out(&io, 1, st);
+}
+
 // =================================================================================================
 // pre-coder
 // =================================================================================================
@@ -1278,6 +1319,27 @@ int rirb_lossy_set_parameter(int handle, const char* key, const char* value)
     }
     set_error("lossy_set_parameter: unknown key %s", key);
     return -1;
+}
+
+int rirb_lossy_get_min(int handle, int* min_value)
+{
+    std::shared_ptr<LossyState> s;
+    {
+        std::lock_guard<std::mutex> lock(g_lossy_mutex);
+        auto it = g_lossy.find(handle);
+        if (it != g_lossy.end()) s = it->second;
+    }
+    if (!s || !min_value) {
+        set_error("lossy_get_min: unknown handle %d", handle);
+        return -1;
+    }
+    *min_value = 0;
+    if (!s->subtract_min || s->frames == 0) return 0;
+    unsigned m = 0;  // LossyScalars starts with m_data->min
+    RIRB_CUDA_OK(cudaMemcpyAsync(&m, s->buf + s->o_scal, sizeof(unsigned), cudaMemcpyDeviceToHost, tls.stream));
+    RIRB_CUDA_OK(cudaStreamSynchronize(tls.stream));
+    *min_value = (int)m;
+    return 0;
 }
 
 int rirb_lossy_add_images(int handle, const unsigned short* frames, long long nframes, unsigned short* out, int* errors)

@@ -19,6 +19,12 @@
 //   map    = u64 count, then count x (string key, string value) in key order
 //   string = u64 n, n bytes; values of >= 1000 bytes that zstd shrinks are stored as
 //            u64 (8 + csize) | 1<<63, u64 raw size, zstd bytes
+// Methods 2 and 3 -- which the reference documents ("blosc + ZSTD", video_io.h:298-305, ZFile.cpp:77) but never
+// implemented (ZFile.cpp:492-499 compresses only when compression == 1) -- are defined HERE as the north star's
+// pre-coder in front of the same zstd stage: the payload of a record is the ZSTD frame of [low-byte plane | high-byte
+// plane] (w*h bytes each) of the image (method 2) or of its temporal residual (method 3: key frame every GOP frames,
+// otherwise (frame[t] - frame[t-1]) mod 2^16; the GOP is stored in trigger word 12 and as the global attribute "GOP").
+// The split / delta and their inverses run on the GPU (rirb_precode_movie / rirb_decode_movie), whole GOPs per launch.
 // The entropy stage stays on the host (the north star's choice).  What this file adds over the
 // reference is that a run of frames is compressed / decompressed by a pool of host threads while the
 // records keep their order, and that frames may be handed over as device pointers (downloaded /
@@ -354,7 +360,7 @@ struct ZHeader {  // BIN_HEADER + BIN_TRIGGER, ZFile.cpp:18-46
     uint64_t trig[16];
 };
 static_assert(sizeof(ZHeader) == 256, "two 128-byte blocks");
-enum { T_DATE, T_RATE, T_SAMPLES, T_PRE, T_TYPE, T_CHANNELS, T_DTYPE, T_FORMAT, T_REPETITION, T_SIZE_X, T_SIZE_Y };
+enum { T_DATE, T_RATE, T_SAMPLES, T_PRE, T_TYPE, T_CHANNELS, T_DTYPE, T_FORMAT, T_REPETITION, T_SIZE_X, T_SIZE_Y, T_SPARE, T_GOP };
 
 static int pool_size(int threads, long long jobs)
 {
@@ -420,11 +426,59 @@ struct ZMovie {
     std::unique_ptr<Contexts> ctx;
     std::unique_ptr<char[]> raw;  // reading: the record bytes of the batch in flight
     size_t raw_cap = 0;
+    // methods 2 / 3 (byte planes, + temporal delta): the pre-coder runs on the GPU in whole GOPs
+    int gop = 50;
+    std::vector<u16> pending;            // writing: frames that do not fill a GOP yet (host)
+    std::vector<int64_t> pending_times;
+    char* host_planes = nullptr;         // pinned: [frame][lo plane | hi plane]
+    size_t host_planes_frames = 0;
+    char* dev_buf = nullptr;             // device: frames | lo planes | hi planes for dev_frames frames
+    size_t dev_frames = 0;
+    int dev_device = -1;
+    long long cache_first = -1, cache_count = 0;  // reading: decoded frames [cache_first, +cache_count) still in dev_buf
     std::mutex mu;
     ~ZMovie()
     {
         if (f) fclose(f);
+        if (host_planes) (void)cudaFreeHost(host_planes);
+        if (dev_buf) (void)cudaFree(dev_buf);
+        (void)cudaGetLastError();
     }
+    // grow-only work space for m frames; false + set_error when memory runs out
+    bool reserve(size_t m)
+    {
+        const size_t npx = (size_t)w * h;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (m > dev_frames || dev != dev_device) {
+            if (dev_buf) cudaFree(dev_buf);
+            dev_buf = nullptr;
+            dev_frames = 0;
+            cache_first = -1;
+            if (cudaMalloc((void**)&dev_buf, m * npx * 4) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("zstd movie file: out of device memory for %zu frames", m);
+                return false;
+            }
+            dev_frames = m;
+            dev_device = dev;
+        }
+        if (m > host_planes_frames) {
+            if (host_planes) cudaFreeHost(host_planes);
+            host_planes = nullptr;
+            host_planes_frames = 0;
+            if (cudaMallocHost((void**)&host_planes, m * npx * 2) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("zstd movie file: out of pinned host memory for %zu frames", m);
+                return false;
+            }
+            host_planes_frames = m;
+        }
+        return true;
+    }
+    u16* dev_movie() const { return (u16*)dev_buf; }
+    u8* dev_lo() const { return (u8*)dev_buf + dev_frames * (size_t)w * h * 2; }
+    u8* dev_hi() const { return dev_lo() + dev_frames * (size_t)w * h; }
 };
 static Table<ZMovie> g_zfiles;
 
@@ -642,15 +696,24 @@ int rirb_attrs_set_global_attributes(int handle, const char* keys, const int* ke
 // ================================================================================================
 int rirb_z_open_file_write(const char* filename, int width, int height, int rate, int method, int clevel)
 {
-    if (!filename || width <= 0 || height <= 0) {
+    return rirb_z_open_file_write_gop(filename, width, height, rate, method, clevel, 50);
+}
+
+int rirb_z_open_file_write_gop(const char* filename, int width, int height, int rate, int method, int clevel, int gop)
+{
+    if (!filename || width <= 0 || height <= 0 || gop < 1 || gop > 65535) {
         set_error("z_open_file_write: bad arguments");
         return 0;
     }
-    if (method != 1) {  // the reference writes empty records for 2 and 3 (ZFile.cpp:493-499): refuse instead
-        set_error("z_open_file_write: only method 1 (zstd of the raw image) is defined");
+    if (method < 1 || method > 3) {
+        set_error("z_open_file_write: method must be 1 (zstd), 2 (byte planes + zstd) or 3 (temporal delta + byte planes + zstd)");
         return 0;
     }
     if (!need_zstd()) return 0;
+    if (method != 1 && rirb_device_count() <= 0) {  // the pre-coder is a CUDA kernel and there is no CPU fallback
+        set_error("z_open_file_write: methods 2 and 3 need a CUDA device (no CPU implementation)");
+        return 0;
+    }
     auto z = std::make_shared<ZMovie>();
     z->f = fopen(filename, "wb");
     if (!z->f) {
@@ -674,6 +737,8 @@ int rirb_z_open_file_write(const char* filename, int width, int height, int rate
     z->hdr.trig[T_REPETITION] = 1;
     z->hdr.trig[T_SIZE_X] = (uint64_t)width;
     z->hdr.trig[T_SIZE_Y] = (uint64_t)height;
+    z->gop = gop;
+    if (method == 3) z->hdr.trig[T_GOP] = (uint64_t)gop;
     if (fwrite(&z->hdr, 1, sizeof(z->hdr), z->f) != sizeof(z->hdr) || fflush(z->f) != 0) {  // records go through pwrite
         set_error("z_open_file_write: write failed");
         return 0;
@@ -681,6 +746,11 @@ int rirb_z_open_file_write(const char* filename, int width, int height, int rate
     z->pos = sizeof(z->hdr);
     return g_zfiles.add(z);
 }
+
+static int z_write_records(ZMovie* z, const void* frames, long long nframes, const long long* timestamps, int threads);
+static int z_read_records(ZMovie* z, int pos, int count, void* out, long long* timestamps, int threads, bool to_pinned_planes);
+static int z_read_precoded(ZMovie* z, int pos, int count, unsigned short* out, int threads);
+static int z_write_precoded(ZMovie* z, const unsigned short* frames, long long nframes, const long long* timestamps, int threads);
 
 // frames[nframes][h][w] host or device; timestamps host.  Records are appended in order; the frames
 // are compressed `threads` at a time (0: all host cores).
@@ -693,6 +763,13 @@ int rirb_z_write_images(int handle, const unsigned short* frames, long long nfra
     }
     if (nframes == 0) return 0;
     std::lock_guard<std::mutex> lock(z->mu);
+    return z->method == 1 ? z_write_records(z.get(), frames, nframes, timestamps, threads)
+                          : z_write_precoded(z.get(), frames, nframes, timestamps, threads);
+}
+
+// `nframes` payloads of w*h*2 bytes each, back to back at `frames` (host or device) -> zstd -> records
+static int z_write_records(ZMovie* z, const void* frames, long long nframes, const long long* timestamps, int threads)
+{
     const size_t fbytes = (size_t)z->w * z->h * 2;
     const size_t bound = zstd().compressBound(fbytes);
     const int workers = pool_size(threads, nframes);
@@ -775,6 +852,88 @@ int rirb_z_write_images(int handle, const unsigned short* frames, long long nfra
     return 0;
 }
 
+// m frames on the DEVICE, the first of them a key frame (frame number `first`): pre-coder -> pinned planes -> zstd -> records
+static int z_flush_gops(ZMovie* z, const u16* dev_frames, long long m, long long first, const long long* timestamps, int threads)
+{
+    const size_t npx = (size_t)z->w * z->h;
+    cudaStream_t st = current_stream();
+    if (rirb_precode_movie(dev_frames, m, z->w, z->h, z->gop, z->method == 3, first, z->dev_lo(), z->dev_hi()) != 0) return -1;
+    // per frame [lo | hi], so that a record's payload is one contiguous run for zstd
+    RIRB_CUDA_OK(cudaMemcpy2DAsync(z->host_planes, 2 * npx, z->dev_lo(), npx, npx, (size_t)m, cudaMemcpyDeviceToHost, st));
+    RIRB_CUDA_OK(cudaMemcpy2DAsync(z->host_planes + npx, 2 * npx, z->dev_hi(), npx, npx, (size_t)m, cudaMemcpyDeviceToHost, st));
+    RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    return z_write_records(z, z->host_planes, m, timestamps, threads);
+}
+
+// methods 2 / 3.  Whole GOPs go through the GPU pre-coder as they come; what does not fill a GOP waits in z->pending
+// (host) for the next call or for the close.
+static int z_write_precoded(ZMovie* z, const unsigned short* frames, long long nframes, const long long* timestamps, int threads)
+{
+    const size_t npx = (size_t)z->w * z->h;
+    const long long gop = z->method == 3 ? z->gop : 1;
+    // how many frames one pass takes: whole GOPs, about 64 MB of pixels
+    long long chunk = std::max<long long>(1, (64ll << 20) / (long long)(npx * 2));
+    chunk = std::max(gop, chunk / gop * gop);
+    const bool on_device = device_pointer(frames);
+    cudaStream_t st = current_stream();
+    long long done = 0;
+    // 1. top up a GOP that is already waiting
+    while (!z->pending_times.empty() && done < nframes) {
+        const size_t have = z->pending_times.size();
+        z->pending.resize((have + 1) * npx);
+        if (on_device)
+            RIRB_CUDA_OK(cudaMemcpy(z->pending.data() + have * npx, frames + (size_t)done * npx, npx * 2, cudaMemcpyDeviceToHost));
+        else
+            memcpy(z->pending.data() + have * npx, frames + (size_t)done * npx, npx * 2);
+        z->pending_times.push_back(timestamps[done]);
+        ++done;
+        if ((long long)z->pending_times.size() == gop) {
+            if (!z->reserve((size_t)chunk)) return -1;
+            RIRB_CUDA_OK(cudaMemcpyAsync(z->dev_movie(), z->pending.data(), (size_t)gop * npx * 2, cudaMemcpyHostToDevice, st));
+            if (z_flush_gops(z, z->dev_movie(), gop, (long long)z->times.size(), (const long long*)z->pending_times.data(), threads) != 0) return -1;
+            z->pending.clear();
+            z->pending_times.clear();
+        }
+    }
+    // 2. whole GOPs straight from the caller's buffer
+    while (nframes - done >= gop) {
+        const long long m = std::min(chunk, (nframes - done) / gop * gop);
+        if (!z->reserve((size_t)chunk)) return -1;
+        const u16* src = frames + (size_t)done * npx;
+        if (!on_device) {
+            RIRB_CUDA_OK(cudaMemcpyAsync(z->dev_movie(), src, (size_t)m * npx * 2, cudaMemcpyHostToDevice, st));
+            src = z->dev_movie();
+        }
+        if (z_flush_gops(z, src, m, (long long)z->times.size(), timestamps + done, threads) != 0) return -1;
+        done += m;
+    }
+    // 3. the rest waits
+    for (; done < nframes; ++done) {
+        const size_t have = z->pending_times.size();
+        z->pending.resize((have + 1) * npx);
+        if (on_device)
+            RIRB_CUDA_OK(cudaMemcpy(z->pending.data() + have * npx, frames + (size_t)done * npx, npx * 2, cudaMemcpyDeviceToHost));
+        else
+            memcpy(z->pending.data() + have * npx, frames + (size_t)done * npx, npx * 2);
+        z->pending_times.push_back(timestamps[done]);
+    }
+    return 0;
+}
+
+// the frames of an unfinished GOP (it starts on a key frame, so it stands on its own)
+static int z_flush_pending(ZMovie* z)
+{
+    const long long m = (long long)z->pending_times.size();
+    if (m == 0) return 0;
+    const size_t npx = (size_t)z->w * z->h;
+    if (!z->reserve((size_t)std::max<long long>(m, 1))) return -1;
+    RIRB_CUDA_OK(cudaMemcpyAsync(z->dev_movie(), z->pending.data(), (size_t)m * npx * 2, cudaMemcpyHostToDevice, current_stream()));
+    const int rc = z_flush_gops(z, z->dev_movie(), m, (long long)z->times.size(), (const long long*)z->pending_times.data(), 0);
+    z->pending.clear();
+    z->pending_times.clear();
+    return rc;
+}
+
 int rirb_z_write_image(int handle, const unsigned short* img, long long timestamp)
 {
     return rirb_z_write_images(handle, img, 1, &timestamp, 1);
@@ -788,6 +947,7 @@ long long rirb_z_close_file(int handle)
     long long res = 0;
     if (z->writing) {
         std::lock_guard<std::mutex> lock(z->mu);
+        if (z->method != 1 && z_flush_pending(z.get()) != 0) set_error("z_close_file: the last frames could not be written");
         z->hdr.trig[T_SAMPLES] = (uint64_t)z->times.size();
         if (pwrite(fileno(z->f), z->hdr.trig, 128, 128) != 128) set_error("z_close_file: cannot update the sample count");
         fclose(z->f);
@@ -799,6 +959,7 @@ long long rirb_z_close_file(int handle)
         a.t.times = z->times;
         a.t.frames.assign(z->times.size(), AttrMap());
         a.t.global["positions"] = std::string((const char*)z->positions.data(), z->positions.size() * 8);
+        if (z->method == 3) a.t.global["GOP"] = std::to_string(z->gop);
         attrs_write_if_dirty(a);
     }
     g_zfiles.remove(handle);
@@ -828,13 +989,18 @@ int rirb_z_open_file_read(const char* filename)
         set_error("z_open_file_read: '%s' is not a zstd movie file", filename);
         return 0;
     }
-    if (comp != 1) {
-        set_error("z_open_file_read: compression method %u has no decoder (the reference returns undefined pixels for it)", comp);
+    if (comp != 1 && rirb_device_count() <= 0) {
+        set_error("z_open_file_read: compression methods 2 and 3 are decoded on the GPU, and there is no CUDA device");
         return 0;
     }
     z->w = (int)sx;
     z->h = (int)sy;
     z->method = (int)comp;
+    z->gop = comp == 3 ? (int)z->hdr.trig[T_GOP] : 1;
+    if (comp == 3 && (z->gop < 1 || z->gop > 65535)) {
+        set_error("z_open_file_read: '%s' claims method 3 without a GOP length", filename);
+        return 0;
+    }
     // The trailer, when present, bounds the record area and carries the record positions and timestamps
     // (ZFile.cpp:163-190); without it, or if it does not add up, the records are walked (:192-249).
     long long end = fsize;
@@ -921,10 +1087,23 @@ int rirb_z_read_images(int handle, int pos, int count, unsigned short* out, long
     }
     if (count == 0) return 0;
     std::lock_guard<std::mutex> lock(z->mu);
+    if (z->method != 1) {
+        const int rc = z_read_precoded(z.get(), pos, count, out, threads);
+        if (rc == 0 && timestamps)
+            for (int i = 0; i < count; ++i) timestamps[i] = z->times[pos + i];
+        return rc;
+    }
+    return z_read_records(z.get(), pos, count, out, timestamps, threads, false);
+}
+
+// records [pos, pos + count) -> decompressed payloads (w*h*2 bytes each) back to back at `out`; to_pinned_planes: `out` is
+// z->host_planes (host memory, whatever cudaPointerGetAttributes says about pinned buffers)
+static int z_read_records(ZMovie* z, int pos, int count, void* out, long long* timestamps, int threads, bool to_pinned_planes)
+{
     const size_t fbytes = (size_t)z->w * z->h * 2;
     const int workers = pool_size(threads, count);
     const int batch = std::min(count, std::max(2 * workers, 8));
-    const bool to_device = device_pointer(out);
+    const bool to_device = !to_pinned_planes && device_pointer(out);
     PinnedPair pin;
     cudaStream_t st = current_stream();
     if (to_device && !pin.init(fbytes * batch)) {
@@ -981,6 +1160,40 @@ int rirb_z_read_images(int handle, int pos, int count, unsigned short* out, long
     if (timestamps)
         for (int i = 0; i < count; ++i) timestamps[i] = z->times[pos + i];
     if (to_device) RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// methods 2 / 3: records -> planes (host) -> device -> merge (+ undo the temporal delta from the GOP's key frame on).
+// The decoded frames of the last pass stay in z->dev_buf: a reader that asks for one frame at a time decodes a GOP once.
+static int z_read_precoded(ZMovie* z, int pos, int count, unsigned short* out, int threads)
+{
+    const size_t npx = (size_t)z->w * z->h;
+    const long long gop = z->method == 3 ? z->gop : 1;
+    long long chunk = std::max<long long>(1, (64ll << 20) / (long long)(npx * 2));
+    chunk = std::max(gop, chunk / gop * gop);
+    cudaStream_t st = current_stream();
+    const bool to_device = device_pointer(out);
+    long long p = pos;
+    const long long end = (long long)pos + count;
+    while (p < end) {
+        if (!(z->cache_first >= 0 && p >= z->cache_first && p < z->cache_first + z->cache_count)) {
+            const long long k0 = p - p % gop;                                            // the GOP's key frame
+            const long long m = std::min<long long>(chunk, (long long)z->times.size() - k0);
+            if (!z->reserve((size_t)chunk)) return -1;
+            z->cache_first = -1;
+            if (z_read_records(z, (int)k0, (int)m, z->host_planes, nullptr, threads, true) != 0) return -1;
+            RIRB_CUDA_OK(cudaMemcpy2DAsync(z->dev_lo(), npx, z->host_planes, 2 * npx, npx, (size_t)m, cudaMemcpyHostToDevice, st));
+            RIRB_CUDA_OK(cudaMemcpy2DAsync(z->dev_hi(), npx, z->host_planes + npx, 2 * npx, npx, (size_t)m, cudaMemcpyHostToDevice, st));
+            if (rirb_decode_movie(z->dev_lo(), z->dev_hi(), m, z->w, z->h, z->gop, z->method == 3, k0, z->dev_movie()) != 0) return -1;
+            z->cache_first = k0;
+            z->cache_count = m;
+        }
+        const long long n = std::min(end, z->cache_first + z->cache_count) - p;
+        RIRB_CUDA_OK(cudaMemcpyAsync(out + (size_t)(p - pos) * npx, z->dev_movie() + (size_t)(p - z->cache_first) * npx, (size_t)n * npx * 2,
+                                     to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        p += n;
+    }
+    RIRB_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }
 

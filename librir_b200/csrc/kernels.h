@@ -31,6 +31,7 @@ int launch_loader_merge(const u8* lo, const u8* hi, u16* out, int w, int h, int 
                         cudaStream_t st);
 
 // translate.cu: the reader's chain fused into the motion translate; returns 1 if the layout cannot take it
+int launch_loader_add_min(u16* frames, int w, int t_rows, long long nframes, size_t frame_stride, int min_t, cudaStream_t st);
 int launch_loader_fused(const u8* lo, const u8* hi, u16* out, int w, int h_full, int hb, long long nframes, int min_t, int t_rows,
                         const int* xy_dev, const int* nbr_dev, const int* row_off_dev, const u8* mask_dev, const float* dxs,
                         const float* dys, cudaStream_t st);

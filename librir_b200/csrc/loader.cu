@@ -165,4 +165,24 @@ int launch_loader_merge(const u8* lo, const u8* hi, u16* out, int w, int h, int 
     return 0;
 }
 
+// pixels[i] += min_T on the first t_rows rows of every frame, modulo 2^16 (IRFileLoader.cpp:1174-1179), in place: for frames
+// that reach the chain as uint16 already (the zstd movie file), where there is no merge pass to fold it into
+__global__ void loader_add_min_kernel(u16* __restrict__ frames, int t_px, unsigned min_t, size_t frame_stride)
+{
+    u16* fr = frames + (size_t)blockIdx.y * frame_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t_px; i += gridDim.x * blockDim.x) fr[i] = (u16)(fr[i] + min_t);
+}
+
+int launch_loader_add_min(u16* frames, int w, int t_rows, long long nframes, size_t frame_stride, int min_t, cudaStream_t st)
+{
+    if (nframes <= 0 || t_rows <= 0 || min_t == 0) return 0;
+    const int t_px = w * t_rows;
+    for (long long f0 = 0; f0 < nframes; f0 += 65535) {
+        const long long n = min(nframes - f0, 65535LL);
+        const dim3 grid((unsigned)min((long long)ceil_div(t_px, 256), 64LL), (unsigned)n);
+        RIRB_LAUNCH(loader_add_min_kernel, grid, 256, 0, st, frames + f0 * frame_stride, t_px, (unsigned)min_t & 0xFFFFu, frame_stride);
+    }
+    return 0;
+}
+
 }  // namespace rirb

@@ -141,3 +141,54 @@ def test_forwarded_entries_fail_cleanly_without_forward_lib():
     n = ct.c_int(4)
     assert lib.extract_times(None, 0, None, 0, out.ctypes.data_as(ct.c_void_p), ct.byref(n)) == -1
     assert "LIBRIR_B200_FORWARD_LIB" in _lib.last_error()
+
+
+# ---- the video_io side of the boundary (include/librir_b200_video_io.h, libvideo_io_b200.so) ----
+VIDEO_IO_REFERENCE_EXPORTS = [  # video_io.h:30-314 of the reference, the entries the path touches
+    "open_camera_file", "video_file_format", "close_camera", "get_image_count", "get_image_time", "get_image_size", "get_filename",
+    "supported_calibrations", "calibration_name", "load_image", "enable_bad_pixels", "bad_pixels_enabled",
+    "load_motion_correction_file", "enable_motion_correction", "motion_correction_enabled", "get_attribute_count", "get_attribute",
+    "get_global_attribute_count", "get_global_attribute", "set_ffmpeg_log_enabled", "h264_open_file", "h264_close_file",
+    "h264_set_parameter", "h264_set_global_attributes", "h264_add_image_lossless", "h264_add_image_lossy", "h264_add_loss",
+    "h264_get_low_errors", "h264_get_high_errors", "open_video_write", "image_write", "close_video",
+]
+
+
+def video_io_lib_path():
+    return os.path.join(os.path.dirname(_lib.lib_path()), "libvideo_io_b200.so")
+
+
+def test_video_io_library_exports_every_declared_symbol():
+    text = open(os.path.join(ROOT, "include", "librir_b200_video_io.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"RIRB_VIO_API\s+[\w\s\*]+?\b(\w+)\s*\(", text)
+    assert len(names) == len(set(names))
+    for n in VIDEO_IO_REFERENCE_EXPORTS:
+        assert n in names, n
+    assert "video_io" in os.path.basename(video_io_lib_path())  # librir/low_level/misc.py:117 globs "*video_io*.so"
+    lib = ct.CDLL(video_io_lib_path())
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/librir_b200_video_io.h but not exported"
+
+
+@pytest.mark.skipif(_lib.device_available(), reason="checks behaviour WITHOUT a CUDA device")
+def test_video_io_without_gpu_fails_loudly(tmp_path):
+    lib = ct.CDLL(video_io_lib_path())
+    lib.rirb_video_io_last_error.restype = ct.c_char_p
+    assert lib.h264_open_file(str(tmp_path / "x.bin").encode(), 64, 48, 48) == 0
+    assert b"no CUDA device" in lib.rirb_video_io_last_error()
+    assert lib.open_video_write(str(tmp_path / "y.bin").encode(), 64, 48, 50, 3, 3) == 0
+    img = np.zeros((48, 64), dtype=np.uint16)
+    assert lib.h264_add_loss(0, img.ctypes.data_as(ct.c_void_p)) == -1
+    # method 1 is host code (zstd of the raw image, byte-identical to the reference): it works without a GPU
+    w = lib.open_video_write(str(tmp_path / "z.bin").encode(), 64, 48, 50, 1, 3)
+    assert w > 0
+    assert lib.image_write(w, img.ctypes.data_as(ct.c_void_p), ct.c_int64(5)) == 0
+    lib.close_video.restype = ct.c_int64
+    assert lib.close_video(w) > 256
+    fmt = ct.c_int(0)
+    cam = lib.open_camera_file(str(tmp_path / "z.bin").encode(), ct.byref(fmt))
+    assert cam > 0 and fmt.value == 4 and lib.get_image_count(cam) == 1
+    out = np.ones((48, 64), dtype=np.uint16)
+    assert lib.load_image(cam, 0, 0, out.ctypes.data_as(ct.c_void_p)) == 0 and not out.any()
+    assert lib.close_camera(cam) == 0
