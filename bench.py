@@ -251,6 +251,138 @@ def run_reference(args, out):
     out.emit(line)
 
 
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE.json configs, each kernel alone (device-resident inputs far larger than L2)
+# ------------------------------------------------------------------------------------------------
+def synth_frames_torch(n, h, w, device, seed):
+    """IR-like frames of any size (same recipe as synth_movie_torch, without the drifting spot)."""
+    import torch
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    y = torch.arange(h, device=device, dtype=torch.float32).view(1, h, 1)
+    x = torch.arange(w, device=device, dtype=torch.float32).view(1, 1, w)
+    bg = 8000 + 2000 * torch.exp(-(((x - w / 2) / (0.23 * w)) ** 2) - ((y - h / 2) / (0.23 * h)) ** 2)
+    out = torch.empty((n, h, w), dtype=torch.uint16, device=device)
+    step = max(1, (64 << 20) // (h * w * 4))
+    for a in range(0, n, step):
+        b = min(n, a + step)
+        f = (bg + 3.0 * torch.randn((b - a, h, w), generator=g, device=device)).clamp_(0, 16383).to(torch.int16)
+        out.view(torch.int16)[a:b] = f
+    npx = h * w
+    bad = torch.randperm(npx, generator=torch.Generator(device="cpu").manual_seed(4321))[: max(2, round(1e-3 * npx))].to(device)
+    fv = out.view(torch.int16).view(n, -1)
+    fv[:, bad[: len(bad) // 2]] = 0
+    fv[:, bad[len(bad) // 2:]] = 16000
+    return out
+
+
+def measure_configs(dev, rank, world, dist, peak, reps=3):
+    """BASELINE.json configs[0], [1], [3], [4] (C1, C2, C4, C5; C3 is the headline): every kernel of the path alone on
+    device-resident movies of ~1.3 GB, CUDA events, one warm-up + median of `reps`, max over ranks.  Returns the `configs`
+    object of the JSON line: {config: {case: {ms, gbs, frac, frames, frame}}}."""
+    import statistics
+
+    import torch
+
+    from librir_b200 import movie, signal_processing as sp, video_io as vio
+
+    def timed(fn):
+        fn()
+        times = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        t = torch.tensor([statistics.median(times)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def cell(ms, bytes_per_px, n, h, w, **extra):
+        gbs = bytes_per_px * n * h * w / (ms * 1e-3) / 1e9
+        d = {"ms": round(ms, 4), "gbs": round(gbs, 1), "frac": round(gbs / peak, 3), "frames": n, "frame": [w, h],
+             "frames_per_s_per_gpu": round(n / (ms * 1e-3))}
+        d.update(extra)
+        return d
+
+    out = {}
+    # ---- C1 / C2: 640x512 x 1000 ------------------------------------------------------------------
+    n, h, w = 1000, H, W
+    frames = synth_frames_torch(n, h, w, dev, 1234 + rank)
+    bp = sp.BadPixels(frames[0])
+    o16 = torch.empty_like(frames)
+    o32 = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+    lo = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+    hi = torch.empty_like(lo)
+    c1 = {"what": "640x512 x 1000 frames, each kernel alone (bad-pixel correct, Gaussian at the three named sigmas, translate (1.3, -2.7) nearest)"}
+    c1["bp_correct"] = cell(timed(lambda: bp.correct_batch(frames, out=o16)), 4, n, h, w)
+    for sg in (0.5, 1.0, 2.0):
+        c1[f"gaussian_u16_f32_sigma{sg}"] = cell(timed(lambda: sp.gaussian_filter_batch(frames, sg, out=o32)), 6, n, h, w, sigma=sg)
+    c1["translate_u16"] = cell(timed(lambda: sp.translate_batch(frames, 1.3, -2.7, "nearest", background=0, out=o16)), 4, n, h, w)
+    out["C1"] = c1
+    c2 = {"what": "640x512 x 1000 frames through the pre-coder and back (GOP 50)"}
+    c2["precode_split"] = cell(timed(lambda: vio.precode_movie(frames, GOP, False, 0, out=(lo, hi))), 4, n, h, w)
+    c2["precode_delta_split"] = cell(timed(lambda: vio.precode_movie(frames, GOP, True, 0, out=(lo, hi))), 4, n, h, w)
+    c2["decode_delta_merge"] = cell(timed(lambda: vio.decode_movie(lo, hi, GOP, True, 0, out=o16)), 4, n, h, w)
+    c2["round_trip_is_identity"] = bool(torch.equal(o16.view(torch.int16), frames.view(torch.int16)))
+    out["C2"] = c2
+    del frames, o16, o32, lo, hi, bp
+    torch.cuda.empty_cache()
+    # ---- C4: 1024x1024, per-frame shifts, statistics and their all-reduce INSIDE the step ---------
+    n, h, w = 600, 1024, 1024
+    frames = synth_frames_torch(n, h, w, dev, 777 + rank)
+    o16 = torch.empty_like(frames)
+    g = torch.Generator(device=dev).manual_seed(777 + rank)
+    dx = torch.rand(n, generator=g, device=dev) * 6 - 3
+    dy = torch.rand(n, generator=g, device=dev) * 6 - 3
+    stats = movie.MovieStats(dev)
+
+    def c4_step():
+        sp.translate_batch(frames, dx, dy, "nearest", background=0, out=o16)
+        stats.reset()
+        stats.update(o16)
+        stats.all_reduce()
+
+    c4_step()  # NCCL set-up of the shapes
+    ms = timed(c4_step)
+    out["C4"] = {"what": "1024x1024 x 600 frames per GPU per step: translate with per-frame shifts U(-3,3) + min/max/histogram + their "
+                         "all-reduce (NCCL) inside the step",
+                 "step": cell(ms, 6, n, h, w, frames_per_s_all_gpus=round(n * world / (ms * 1e-3))),
+                 "translate_u16": cell(timed(lambda: sp.translate_batch(frames, dx, dy, "nearest", background=0, out=o16)), 4, n, h, w),
+                 "stats_minmax_hist": cell(timed(lambda: stats.update(o16)), 2, n, h, w)}
+    del frames, o16
+    torch.cuda.empty_cache()
+    # ---- C5: frame-size sweep ---------------------------------------------------------------------
+    c5 = {"what": "each kernel alone per frame size, ~1.3 GB of input per launch; fractions of the measured copy bandwidth"}
+    for w, h in [(320, 256), (640, 512), (1024, 1024), (1280, 1024), (2048, 2048)]:
+        n = max(50, int(1.3e9 / (w * h * 2)) // 50 * 50)
+        frames = synth_frames_torch(n, h, w, dev, 99 + rank)
+        bp = sp.BadPixels(frames[0])
+        o16 = torch.empty_like(frames)
+        o32 = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+        lo = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+        hi = torch.empty_like(lo)
+        g = torch.Generator(device=dev).manual_seed(5 + rank)
+        dx = torch.rand(n, generator=g, device=dev) * 6 - 3
+        dy = torch.rand(n, generator=g, device=dev) * 6 - 3
+        stats = movie.MovieStats(dev)
+        c5[f"{w}x{h}"] = {
+            "bp_correct": cell(timed(lambda: bp.correct_batch(frames, out=o16)), 4, n, h, w),
+            "gaussian_u16_f32": cell(timed(lambda: sp.gaussian_filter_batch(frames, SIGMA, out=o32)), 6, n, h, w),
+            "translate_u16": cell(timed(lambda: sp.translate_batch(frames, dx, dy, "nearest", background=0, out=o16)), 4, n, h, w),
+            "precode_delta_split": cell(timed(lambda: vio.precode_movie(frames, GOP, True, 0, out=(lo, hi))), 4, n, h, w),
+            "stats_minmax_hist": cell(timed(lambda: stats.update(frames)), 2, n, h, w),
+        }
+        del frames, o16, o32, lo, hi, bp
+        torch.cuda.empty_cache()
+    out["C5"] = c5
+    return out
+
+
 def workload_config(chunk, n_gpus):
     return {
         "workload": "C3 (BASELINE.json configs[2]): WEST-style 640x512 uint16 movie, full per-frame pipeline, "
@@ -370,14 +502,59 @@ def run_ours(args, out):
     ok = bool(torch.equal(host_lo[:64], pipe.process_chunk(frames[:e2e_n], dx[:e2e_n], dy[:e2e_n], shard.start,
                                                            with_stats=False)[3][:64].cpu()))
 
+    # ---- e2e with EVERY output returned (the smoothed float32 frames as well: 4 more bytes per pixel down) ----
+    e2e_all = None
+    if not args.no_e2e_all:
+        host_sm = torch.empty((e2e_n, H, W), dtype=torch.float32).pin_memory()
+
+        def e2e_all_call():
+            movie.process_movie_host(pipe.bad_pixels, host_in, host_dx, host_dy, SIGMA, "nearest", 0, GOP, True, shard.start,
+                                     host_lo, host_hi, host_sm)
+        e2e_all_call()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(e2e_steps):
+            e2e_all_call()
+        a1.record()
+        barrier()
+        e2e_all = a0.elapsed_time(a1)
+        del host_sm
+
+    # ---- C3 as named: 100,000 DISTINCT frames streamed through the chunk ring (device-resident, generated on the device) ----
+    stream = None
+    if args.stream_frames > 0:
+        try:
+            per_rank = max(chunk, (args.stream_frames // world) // chunk * chunk)
+            nchunks = per_rank // chunk
+            chunks = [frames] + [synth_movie_torch(chunk, shard.start + k * chunk, dev) for k in range(1, nchunks)]
+            pipe.stats.reset()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for k, ch in enumerate(chunks):
+                pipe.process_chunk(ch, dx, dy, shard.start + k * chunk)
+            s1.record()
+            barrier()
+            stream = (s0.elapsed_time(s1), per_rank)
+            del chunks
+            torch.cuda.empty_cache()
+        except Exception as e:  # e.g. not enough free HBM next to another tenant: reported, not fatal
+            stream = (None, str(e)[:200])
+
+    configs = None
+    if not args.no_configs:
+        peak_all, _src = hbm_peak()
+        configs = measure_configs(dev, rank, world, dist, peak_all)
+
     # ---- reduce over ranks ------------------------------------------------------------------------
-    vals = torch.tensor([ms, e2e_ms] + per_stage, dtype=torch.float64, device=dev)
+    vals = torch.tensor([ms, e2e_ms, e2e_all or 0.0, (stream[0] if stream and stream[0] else 0.0)] + per_stage, dtype=torch.float64, device=dev)
     cnt = torch.tensor([launches], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms, e2e_ms = float(vals[0]), float(vals[1])
-    per_stage = [float(v) for v in vals[2:]]
+    ms, e2e_ms, e2e_all_ms, stream_ms = float(vals[0]), float(vals[1]), float(vals[2]), float(vals[3])
+    per_stage = [float(v) for v in vals[4:]]
     if rank == 0:
         peak, peak_src = hbm_peak()
         npx = W * H
@@ -405,9 +582,23 @@ def run_ours(args, out):
                     "h2d_bytes_per_step": e2e_n * (npx * 2 + 8), "d2h_bytes_per_step": e2e_n * npx * 2,
                     "frames_per_step_per_gpu": e2e_n, "steps": e2e_steps, "matches_device_path": ok,
                     "wall_ms_rank0": e2e_wall_ms,
-                    "api": args.e2e_api, "what": e2e_what},
+                    "api": args.e2e_api, "what": e2e_what,
+                    "note": "the Gaussian output stays on the device in this figure; `e2e_all_outputs` returns it as well"},
             "gpu_launches": int(cnt[0]), "clocks": clocks, "stats_allreduce_ms": allreduce_ms,
         }
+        if e2e_all:
+            line["e2e_all_outputs"] = {"value": e2e_n * world * e2e_steps / (e2e_all_ms * 1e-3), "unit": "frames/s",
+                                       "h2d_bytes_per_step": e2e_n * (npx * 2 + 8), "d2h_bytes_per_step": e2e_n * npx * 6,
+                                       "what": "the same call with the smoothed float32 frames downloaded too (lo, hi, smoothed)"}
+        if stream:
+            if stream[0]:
+                line["c3_stream"] = {"value": stream[1] * world / (stream_ms * 1e-3), "unit": "frames/s", "distinct_frames": stream[1] * world,
+                                     "frames_per_gpu": stream[1], "ms": stream_ms,
+                                     "what": "config 3 as named: that many DISTINCT device-resident frames through the reused chunk buffers, one pass"}
+            else:
+                line["c3_stream"] = {"unavailable": stream[1]}
+        if configs is not None:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu:
             ncpu = args.cpu_frames
             mov = frames[:ncpu].cpu().view(torch.int16).numpy().view(np.uint16)
@@ -455,6 +646,10 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--unfused-stats", action="store_true", help="statistics as their own kernel instead of inside the pre-coder's pass")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-kernel figures of the other BASELINE configs (C1, C2, C4, C5)")
+    ap.add_argument("--no-e2e-all", action="store_true", help="skip the host-path figure that also downloads the smoothed frames")
+    ap.add_argument("--stream-frames", type=int, default=100000,
+                    help="distinct frames (all GPUs together) streamed once through the chunk ring: config 3 as named; 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     with JsonOnlyStdout() as out:

@@ -79,6 +79,10 @@ class MovieStats:
     def count(self, v: int) -> None:
         self._sums[65536] = int(v)
 
+    def reset(self) -> None:
+        """Start a new movie: the next ``update`` initialises the statistics instead of folding into them."""
+        self._fresh = True
+
     def update(self, frames) -> None:
         """Fold a chunk of uint16 frames (torch CUDA tensor) into the statistics."""
         lib = _lib.load()
