@@ -502,6 +502,30 @@ def run_ours(args, out):
     ok = bool(torch.equal(host_lo[:64], pipe.process_chunk(frames[:e2e_n], dx[:e2e_n], dy[:e2e_n], shard.start,
                                                            with_stats=False)[3][:64].cpu()))
 
+    # ---- what the host links carry with every rank copying at once, both directions (the e2e path's own roofline) ----
+    link_gbs = None
+    try:
+        nb = 256 << 20
+        lh_in = torch.empty(nb, dtype=torch.uint8).pin_memory()
+        lh_out = torch.empty(nb, dtype=torch.uint8).pin_memory()
+        ld_in = torch.empty(nb, dtype=torch.uint8, device=dev)
+        ld_out = torch.empty(nb, dtype=torch.uint8, device=dev)
+        ls1, ls2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        for timed_pass in (False, True):
+            barrier()
+            t_l = time.perf_counter()
+            for _ in range(3):
+                with torch.cuda.stream(ls1):
+                    ld_in.copy_(lh_in, non_blocking=True)
+                with torch.cuda.stream(ls2):
+                    lh_out.copy_(ld_out, non_blocking=True)
+            torch.cuda.synchronize()
+            if timed_pass:
+                link_gbs = 3 * nb / (time.perf_counter() - t_l) / 1e9  # per direction, this rank
+        del lh_in, lh_out, ld_in, ld_out
+    except Exception:
+        link_gbs = None
+
     # ---- e2e with EVERY output returned (the smoothed float32 frames as well: 4 more bytes per pixel down) ----
     e2e_all = None
     if not args.no_e2e_all:
@@ -550,9 +574,11 @@ def run_ours(args, out):
     # ---- reduce over ranks ------------------------------------------------------------------------
     vals = torch.tensor([ms, e2e_ms, e2e_all or 0.0, (stream[0] if stream and stream[0] else 0.0)] + per_stage, dtype=torch.float64, device=dev)
     cnt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    link = torch.tensor([link_gbs or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(link, op=dist.ReduceOp.SUM)
     ms, e2e_ms, e2e_all_ms, stream_ms = float(vals[0]), float(vals[1]), float(vals[2]), float(vals[3])
     per_stage = [float(v) for v in vals[4:]]
     if rank == 0:
@@ -586,6 +612,13 @@ def run_ours(args, out):
                     "note": "the Gaussian output stays on the device in this figure; `e2e_all_outputs` returns it as well"},
             "gpu_launches": int(cnt[0]), "clocks": clocks, "stats_allreduce_ms": allreduce_ms,
         }
+        if float(link[0]) > 0:
+            cap = float(link[0]) * 1e9 / (npx * 2)  # frames/s the links carry: 2 B/px up and 2 B/px down, both directions busy
+            line["e2e"]["host_link"] = {"both_directions_gbs_per_direction_all_ranks": float(link[0]), "cap_frames_per_s": cap,
+                                        "frac_of_cap": line["e2e"]["value"] / cap,
+                                        "what": "pinned H2D + D2H copies of 256 MB by every rank at the same time, measured in this run: the "
+                                                "end-to-end path's own roofline (profiles/r2_hostlink.md: this box's host side carries 47 / "
+                                                "52 / 51 / 77 GB/s per direction at 1 / 2 / 4 / 8 GPUs, so the e2e figure cannot scale with N)"}
         if e2e_all:
             line["e2e_all_outputs"] = {"value": e2e_n * world * e2e_steps / (e2e_all_ms * 1e-3), "unit": "frames/s",
                                        "h2d_bytes_per_step": e2e_n * (npx * 2 + 8), "d2h_bytes_per_step": e2e_n * npx * 6,
