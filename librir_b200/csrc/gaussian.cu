@@ -435,6 +435,169 @@ gauss_tile_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA-tiled path for the wide kernels (R = 3, 4: sigma 1.5 .. 2.49, a named configuration of BASELINE.json)
+// ------------------------------------------------------------------------------------------------
+// gauss_tile_kernel is FMA-bound there (0.80 / 0.61 of the copy bandwidth in round 1): 2R+1 scalar FFMA per pixel in the
+// horizontal pass, run over 16 + 2R source rows for 16 output rows, in a fully unrolled body of 24 rows that no longer
+// fits the 32 KB instruction cache.  Same tile staging, different inner loop:
+//   * source rows are taken TWO AT A TIME and the horizontal pass is packed across the two rows: (win_r[i], win_r+1[i])
+//     sit in one register pair because the unpack writes them there, so one FFMA2 does a tap of both rows -- half the
+//     instructions of the pass, no repacking of its inputs;
+//   * a warp owns 32 output rows instead of 16: the 2R halo rows cost 2R/32 instead of 2R/16 of the horizontal work;
+//   * the ring of horizontally filtered rows has 2R+2 slots addressed modulo at compile time and the loop is unrolled by
+//     exactly one turn of the ring, so the body is 2R+2 rows long whatever the strip height.
+// 4 consecutive elements of two staged rows -> (row 0, row 1) pairs as float: for uint16 two PRMT build the bits of
+// 2^23 + p in an aligned register pair and ONE packed add (sm_100 add.f32x2) removes the bias of both
+__device__ __forceinline__ void load4x2(const u16* p0, const u16* p1, float2 (&a)[4])
+{
+    const uint2 v = *reinterpret_cast<const uint2*>(p0);
+    const uint2 u = *reinterpret_cast<const uint2*>(p1);
+    const float2 bias = make_float2(-8388608.0f, -8388608.0f);
+    a[0] = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(u.x, 0x4B000000u, 0x7610))), bias);
+    a[1] = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7632)), __uint_as_float(__byte_perm(u.x, 0x4B000000u, 0x7632))), bias);
+    a[2] = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(u.y, 0x4B000000u, 0x7610))), bias);
+    a[3] = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7632)), __uint_as_float(__byte_perm(u.y, 0x4B000000u, 0x7632))), bias);
+}
+__device__ __forceinline__ void load4x2(const float* p0, const float* p1, float2 (&a)[4])
+{
+    const float4 v = *reinterpret_cast<const float4*>(p0);
+    const float4 u = *reinterpret_cast<const float4*>(p1);
+    a[0] = make_float2(v.x, u.x);
+    a[1] = make_float2(v.y, u.y);
+    a[2] = make_float2(v.z, u.z);
+    a[3] = make_float2(v.w, u.w);
+}
+
+constexpr int GW_RG = 32;                    // output rows per warp
+constexpr int GW_H = GT_WARPS * GW_RG;       // 128 output rows per CTA
+
+template <int R, typename TIN>
+__global__ void __launch_bounds__(GT_WARPS * 32, sizeof(TIN) == 2 ? 4 : 3)
+gauss_tile_wide_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ dst, int w, int h, int tiles_x, int tiles_y,
+                       GaussTaps taps)
+{
+    constexpr int BH = GW_H + 2 * R;
+    constexpr int BW = GtBox<TIN>::BW;
+    constexpr int HALO = GtBox<TIN>::HALO;
+    constexpr int RS = 2 * R + 2;        // ring slots (even: rows come in pairs)
+    constexpr int S = GW_RG + 2 * R;     // source rows of a warp's strip (even)
+    static_assert(R >= 1 && R <= 4 && (S % 2) == 0, "window: 4 pixels either side of the lane's own 4; rows in pairs");
+    extern __shared__ __align__(128) unsigned char gw_smem[];
+    TIN(*tile)[BW] = reinterpret_cast<TIN(*)[BW]>(gw_smem);
+    __shared__ __align__(8) unsigned long long bar;
+    const int tiles = tiles_x * tiles_y;
+    const long long f = blockIdx.x / tiles;
+    const int tile_id = (int)(blockIdx.x - f * tiles);
+    const int ty = tile_id / tiles_x, tx = tile_id - ty * tiles_x;
+    const int x0t = tx * GT_W, y0t = ty * GW_H;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (unsigned)(BH * BW * sizeof(TIN)));
+        tma_load_box(&tile[0][0], &tmap, &bar, x0t - HALO, y0t - R, (int)f);
+    }
+    // ---- per-thread constants (while the box is in flight) ----
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int x = x0t + 4 * lane;
+    float k[2 * R + 1];
+    float2 kk[2 * R + 1];
+    float kfull = 0.f;
+#pragma unroll
+    for (int d = 0; d <= 2 * R; ++d) {
+        k[d] = taps.k[d];
+        kk[d] = make_float2(k[d], k[d]);
+        kfull += k[d];
+    }
+    float nx[4], rx[4];  // see gauss_tile_kernel: horizontal normaliser of each owned column
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d <= 2 * R; ++d) {
+            const int xx = x + j + d - R;
+            if (xx >= 0 && xx < w) s += k[d];
+        }
+        const bool xb = (x + j < R) || (x + j >= w - R);
+        nx[j] = xb ? s : kfull;
+        rx[j] = xb ? 1.0f / (kfull * s) : 1.0f;
+    }
+    float* oframe = dst + (size_t)f * w * h;
+    float2 ring[RS][2];
+#pragma unroll
+    for (int i = 0; i < RS; ++i) ring[i][0] = ring[i][1] = make_float2(0.f, 0.f);
+    mbar_wait(&bar, 0);
+
+#pragma unroll 1
+    for (int b = 0; b < S; b += RS) {
+#pragma unroll
+        for (int i = 0; i < RS; i += 2) {
+            const int rr = b + i;  // source rows rr and rr + 1 of the warp's strip
+            if (rr >= S) break;    // warp-uniform (the last turn of the ring may be partial)
+            // ---- unpack both rows, interleaved: wp[c] = (row rr, row rr + 1) at source column x - R + c ----
+            const TIN* s0 = &tile[wi * GW_RG + rr][HALO + 4 * lane];
+            const TIN* s1 = s0 + BW;
+            float2 av[4];
+            float2 wp[4 + 2 * R];
+            load4x2(s0 - 4, s1 - 4, av);
+#pragma unroll
+            for (int j = 0; j < R; ++j) wp[j] = av[4 - R + j];
+            load4x2(s0, s1, av);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wp[R + j] = av[j];
+            load4x2(s0 + 4, s1 + 4, av);
+#pragma unroll
+            for (int j = 0; j < R; ++j) wp[R + 4 + j] = av[j];
+            // ---- horizontal pass of both rows: one FFMA2 per tap and column ----
+            float2 P[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 acc = __fmul2_rn(kk[0], wp[j]);
+#pragma unroll
+                for (int d = 1; d <= 2 * R; ++d) acc = __ffma2_rn(kk[d], wp[j + d], acc);
+                P[j] = acc;
+            }
+            ring[i][0] = make_float2(P[0].x, P[1].x);
+            ring[i][1] = make_float2(P[2].x, P[3].x);
+            ring[i + 1][0] = make_float2(P[0].y, P[1].y);
+            ring[i + 1][1] = make_float2(P[2].y, P[3].y);
+            // ---- vertical pass: output rows rr - 2R and rr + 1 - 2R of the strip ----
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int ro = rr + q - 2 * R;
+                if (ro < 0) continue;  // warp-uniform: the first 2R source rows only fill the ring
+                const int yo = y0t + wi * GW_RG + ro;
+                // taps d = 0..2R sit in slots (i + q - 2R + d) mod RS = (i + q + 2 + d) mod RS
+                float2 o0 = __fmul2_rn(kk[0], ring[(i + q + 2) % RS][0]);
+                float2 o1 = __fmul2_rn(kk[0], ring[(i + q + 2) % RS][1]);
+#pragma unroll
+                for (int d = 1; d <= 2 * R; ++d) {
+                    o0 = __ffma2_rn(kk[d], ring[(i + q + 2 + d) % RS][0], o0);
+                    o1 = __ffma2_rn(kk[d], ring[(i + q + 2 + d) % RS][1], o1);
+                }
+                const bool yborder = (yo < R) || (yo >= h - R);
+                if (yborder) {  // warp-uniform; partial-kernel renormalisation (signal_processing.cpp:130-144)
+                    float ny = 0.f;
+#pragma unroll
+                    for (int d = 0; d <= 2 * R; ++d) {
+                        const int yyy = yo + d - R;
+                        if (yyy >= 0 && yyy < h) ny += k[d];
+                    }
+                    o0 = make_float2(o0.x / (ny * nx[0]), o0.y / (ny * nx[1]));
+                    o1 = make_float2(o1.x / (ny * nx[2]), o1.y / (ny * nx[3]));
+                } else {
+                    o0 = __fmul2_rn(o0, make_float2(rx[0], rx[1]));
+                    o1 = __fmul2_rn(o1, make_float2(rx[2], rx[3]));
+                }
+                if (x < w && yo < h) st_stream(reinterpret_cast<float4*>(oframe + (size_t)yo * w + x), make_float4(o0.x, o0.y, o1.x, o1.y));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic path: any width, any radius up to GAUSS_MAX_RADIUS -- one thread per output pixel
 // ------------------------------------------------------------------------------------------------
 template <typename TIN>
@@ -533,6 +696,25 @@ static int launch_gaussian(const TIN* src, float* dst, int w, int h, long long n
             return -1;                                                                                                       \
         RIRB_LAUNCH((gauss_tile_kernel<RR, TIN, false>), (unsigned)tgrid, GT_WARPS * 32, 0, st, tmap, dst, w, h, tiles_x, tiles_y, taps, BpFuse{}); \
     } while (0)
+        // R >= 3: the row-pair kernel with 32-row strips (gauss_tile_wide_kernel); "gauss_tma" = 2 keeps the first-generation one
+        const bool wide = r >= 3 && option_value(OPT_GAUSS_TMA) != 2;
+        const int wtiles_y = (int)ceil_div(h, GW_H);
+        const long long wgrid = nframes * tiles_x * wtiles_y;
+#define RIRB_GW(RR)                                                                                                          \
+    do {                                                                                                                     \
+        const size_t smem = (size_t)(GW_H + 2 * RR) * GtBox<TIN>::BW * esz;                                                  \
+        RIRB_SMEM_ATTR((gauss_tile_wide_kernel<RR, TIN>), smem);                                                             \
+        if (make_movie_tensor_map(&tmap, src, (int)esz, w, h, nframes, (size_t)w * esz, (size_t)w * h * esz, GtBox<TIN>::BW, \
+                                  GW_H + 2 * RR) != 0)                                                                       \
+            return -1;                                                                                                       \
+        RIRB_LAUNCH((gauss_tile_wide_kernel<RR, TIN>), (unsigned)wgrid, GT_WARPS * 32, smem, st, tmap, dst, w, h, tiles_x, wtiles_y, taps); \
+    } while (0)
+        if (wide && wgrid <= 0x7FFFFFFFLL) {
+            if (r == 3) RIRB_GW(3);
+            else RIRB_GW(4);
+            return 0;
+        }
+#undef RIRB_GW
         switch (r) {
         case 1: RIRB_GT(1); break;
         case 2: RIRB_GT(2); break;
