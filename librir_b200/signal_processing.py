@@ -90,14 +90,11 @@ def _prepare_device_call(x):
 # translate
 # ----------------------------------------------------------------------------------------
 def translate(image, dx, dy, strategy=str(), background=None):
-    """
-    Translate input image by a floating point offset (dx,dy).
+    """Sub-pixel shift of one 2-D image by ``(dx, dy)`` with bilinear weights (rir_signal_processing.py:23-82).
 
-    strategy controls the way border pixels are managed.
-    If strategy is empty, border pixels are set to the original image ones.
-    If strategy is "constant", border pixels are set to the given background value.
-    If strategy is "nearest", border pixels are set to closest valid pixels.
-    If strategy is "wrap", border pixels are extended by wrapping around to the opposite edge.
+    ``strategy`` decides what the pixels without a source get: ``""`` / ``"noborder"`` keep the input's value,
+    ``"constant"`` (alias of ``"background"``) writes ``background``, ``"nearest"`` repeats the closest valid
+    row / column, ``"wrap"`` continues from the opposite edge.  Result: same shape and dtype as ``image``.
     """
     lib = _lib.load()
     if len(image.shape) != 2:
@@ -161,10 +158,8 @@ def translate_batch(frames, dx, dy, strategy=str(), background=None, out=None):
 # gaussian
 # ----------------------------------------------------------------------------------------
 def gaussian_filter(image, sigma=1.0):
-    """
-    Apply a gaussian filter on input image with given sigma value.
-    The result image is always of type np.float32.
-    """
+    """Gaussian smoothing of one 2-D image, radius ``max(1, int(2 * sigma))``, taps outside the image dropped and the
+    rest renormalised (rir_signal_processing.py:85-113).  The output is float32 whatever the input dtype."""
     lib = _lib.load()
     if len(image.shape) != 2:
         raise RuntimeError("gaussian_filter: wrong input image dimension")
@@ -205,9 +200,8 @@ def gaussian_filter_batch(frames, sigma=1.0, out=None):
 # statistics
 # ----------------------------------------------------------------------------------------
 def find_median_pixel(image, percent=0.5, mask=None):
-    """
-    Find the pixel value from which at least percent*image.size pixels are included
-    """
+    """Quantile of a uint16 image through its histogram: the smallest level whose cumulated count reaches
+    ``percent * size`` (optionally over the pixels where ``mask`` is non-zero); rir_signal_processing.py:116-147."""
     lib = _lib.load()
     if len(image.shape) != 2:
         raise RuntimeError("find_median_pixel: wrong input image dimension")
@@ -224,11 +218,8 @@ def find_median_pixel(image, percent=0.5, mask=None):
 # bad pixels
 # ----------------------------------------------------------------------------------------
 def bad_pixels_create(first_image):
-    """
-    Create an object meant to correct bad pixels inside IR videos.
-    The list of bad pixels is constructed from the first image.
-    Returns the object handle.
-    """
+    """Run the bad-pixel detection on ``first_image`` and keep the flagged set (and the clamp level) behind a new
+    handle, which is what the call returns (rir_signal_processing.py:273-289)."""
     lib = _lib.load()
     if _is_torch(first_image):
         _prepare_device_call(first_image)
@@ -258,16 +249,12 @@ def bad_pixels_correct_gaussian_batch(handle, frames, sigma=1.0, out=None, smoot
 
 
 def bad_pixels_destroy(handle):
-    """
-    Destroy bad pixel object
-    """
+    """Release a handle obtained from ``bad_pixels_create``."""
     _lib.load().bad_pixels_destroy(handle)
 
 
 def bad_pixels_correct(handle, img):
-    """
-    Corrects input image from bad pixels and returns the result.
-    """
+    """Median-replace the handle's flagged pixels in ``img`` and clamp the rest; returns a new uint16 image."""
     lib = _lib.load()
     img = np.ascontiguousarray(img, dtype=np.uint16)
     out = np.empty(img.shape, dtype=np.uint16)
@@ -301,9 +288,8 @@ def bad_pixels_list(handle):
 
 
 class BadPixels:
-    """
-    Class used to correct bad pixels inside an IR handle
-    """
+    """Owner of a bad-pixel handle: detection at construction, ``correct`` per image, release on deletion
+    (BadPixels.py:16-29)."""
 
     def __init__(self, first_image):
         self.handle = bad_pixels_create(first_image)

@@ -274,8 +274,11 @@ def _is_torch(x) -> bool:
 class ZFileWriter:
     """``z_open_file_write`` / ``z_write_image`` / ``z_close_file`` (ZFile.cpp:255-296, 483-542, 410-452)."""
 
-    def __init__(self, filename, width, height, rate=50, method=1, clevel=2, threads=0):
-        self.handle = _lib.load().rirb_z_open_file_write(str(filename).encode(), int(width), int(height), int(rate), int(method), int(clevel))
+    def __init__(self, filename, width, height, rate=50, method=1, clevel=2, threads=0, gop=50):
+        """``method`` 1 = zstd of the raw image (the reference's files), 2 = byte planes + zstd, 3 = temporal delta with
+        key frames every ``gop`` images + byte planes + zstd (video_io.h:298-305); 2 and 3 pre-code on the GPU."""
+        self.handle = _lib.load().rirb_z_open_file_write_gop(str(filename).encode(), int(width), int(height), int(rate), int(method),
+                                                             int(clevel), int(gop))
         if self.handle <= 0:
             raise RuntimeError(f"cannot open '{filename}' for writing: {_lib.last_error()}")
         self.width, self.height, self.threads = int(width), int(height), int(threads)

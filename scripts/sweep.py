@@ -116,13 +116,18 @@ def main():
                 torch.cuda.synchronize()
                 times.append(e0.elapsed_time(e1))
             ms = statistics.median(times)
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            t = torch.tensor([ms, min(times), max(times)], dtype=torch.float64, device=dev)
+            per_rank = None
             if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t[0])
+                allt = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(allt, t)
+                per_rank = [[round(float(v), 4) for v in a] for a in allt]  # [median, min, max] of every rank
+                ms = max(a[0] for a in per_rank)
             gbs = BYTES_PER_PX[name] * npx * n / (ms * 1e-3) / 1e9
             row = {"frame": [w, h], "frames_per_launch": n, "kernel": name, "ms": ms, "achieved_gbs": gbs, "peak_gbs": peak,
                    "frac": gbs / peak, "frames_per_s_per_gpu": n / (ms * 1e-3), "n_gpus": world, "peak_source": peak_src}
+            if per_rank is not None:
+                row["per_rank_ms_median_min_max"] = per_rank
             rows.append(row)
             if rank == 0:
                 print(json.dumps(row), flush=True)

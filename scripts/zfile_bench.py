@@ -83,6 +83,28 @@ def main():
             torch.cuda.synchronize()
             rec("read", "product, frames to HBM", cores, time.perf_counter() - t0)
             assert torch.equal(out.view(torch.int16), d.view(torch.int16))
+            # methods 2 / 3 (video_io.h:298-305): the GPU pre-coder in front of zstd; host frames and frames in HBM
+            for method in (1, 2, 3):
+                for where, src in (("host", mov), ("HBM", d)):
+                    p = os.path.join(tmp, f"m{method}{where}.bin")
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    with tools.ZFileWriter(p, w, h, method=method, clevel=args.clevel, threads=0, gop=50) as wr:
+                        wr.add_images(src, ts)
+                    rec("write", f"product, method {method}, frames in {where}", cores, time.perf_counter() - t0,
+                        {"file_MB": round(os.path.getsize(p) / 1e6, 1)})
+                    t0 = time.perf_counter()
+                    with tools.ZFileReader(p, threads=0) as rd:
+                        if where == "host":
+                            back = rd.read_images()
+                        else:
+                            rd.read_images(0, n, out=out)
+                    torch.cuda.synchronize()
+                    rec("read", f"product, method {method}, frames to {where}", cores, time.perf_counter() - t0)
+                    if where == "host":
+                        assert np.array_equal(back, mov)
+                    else:
+                        assert torch.equal(out.view(torch.int16), d.view(torch.int16))
     except ImportError:
         pass
     for f in os.listdir(tmp):
