@@ -828,6 +828,15 @@ __device__ __forceinline__ RowAB make_row_ab(int y, int h, float dy, int t_expec
     if (clamped) b = t;
     const float vf = (float)b - py;
     const float vs = vf * 8388608.0f;
+    if (y < h && !(py < 0) && (py < fh) && t == t_expected + 1 && py == (float)t) {
+        // -dy within half a float ulp below an integer: py has rounded UP to the integer t_expected + 1 and the reference
+        // blends row t with weight 1 (or, clamped, with itself).  Seen from the regular taps (top t_expected, bottom
+        // t_expected + 1) that is the bottom row alone -- the same value, and the row stays on the fast path.  Without
+        // this, every row of the upper float binades of such a frame is a border row (one CTA column ran 50x longer).
+        r.A = 8388608u;
+        r.B = 0;
+        return r;
+    }
     if (y < h && !(py < 0) && (py < fh) && (vs == truncf(vs)) && (fabsf(vf) <= 1.0f) && t == t_expected && (clamped || b == t + 1)) {
         if (clamped) {  // both taps are the top pixel: N = p * 2^23 (see make_row_info)
             r.A = 0;
@@ -917,6 +926,15 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
     const int xs = (x0t + sx) & ~7;
     const int xoff = (x0t + sx) - xs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // Weight of the RIGHT tap of destination pixel xp when its left tap is source column xp + sx: px - l in the regular case.
+    // When -dx lies within half a float ulp below an integer, px rounds UP to the integer xp + sx + 1 in the upper float
+    // binades of the row; the reference then takes l = px, u = 0, i.e. the value of column xp + sx + 1 alone -- which is the
+    // regular taps with u = 1.  -1: neither (the pixel goes to the literal routine).
+    auto tap_u = [&](float px, int xp) -> float {
+        const int l = (int)px;
+        const float u = px - (float)l;
+        return (l == xp + sx) ? u : ((l == xp + sx + 1 && u == 0.f) ? 1.0f : -1.0f);
+    };
     // rows of tile `tile_row` into stage s, by one whole warp: the row table first, then lane 0 publishes it and asks for the box
     auto prepare_stage = [&](int s, int tile_row) {
         const int y0 = tile_row * TT_H;
@@ -943,9 +961,10 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
         bool ok = (xe0 >= x0t) && (xe0 < x0t + TT_W) && !(px < 0) && (px < fw);
         const int l = (int)px;
         const int rt = (int)(px + 1.0f);
-        const bool cl = ok && (rt == w) && (l == w - 1);
-        ok = ok && (l == x + sx) && (cl || rt == l + 1);
-        edge_tab[e].wt[i] = make_hweights(ok ? px - (float)l : 0.f);
+        const float un = tap_u(px, x);
+        const bool cl = ok && (rt == w) && (l == w - 1) && (l == x + sx);
+        ok = ok && (un >= 0.f) && (cl || rt == l + 1);
+        edge_tab[e].wt[i] = make_hweights(ok ? un : 0.f);
         const unsigned vb = __ballot_sync(0x0000FFFFu, ok), cb2 = __ballot_sync(0x0000FFFFu, cl);
         if (i == 0) {
             edge_tab[e].valid = (vb >> (8 * e)) & 0xFFu;
@@ -961,17 +980,15 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
     const int x0 = x0t + 8 * cx;
     const int isplit = (8 - xoff) & 7;
     const float pxf = (float)x0 - dx, pxl = (float)(x0 + 7) - dx;
-    const int l0 = (int)pxf, l7 = (int)pxl;
-    const float u0 = pxf - (float)l0, u7 = pxl - (float)l7;
-    bool xfast = (x0 + 8 <= w) && !(pxf < 0) && (pxl < fw) && (l0 == x0 + sx) && (l7 == l0 + 7) && ((int)(pxl + 1.0f) == l7 + 1);
+    const float u0 = tap_u(pxf, x0), u7 = tap_u(pxl, x0 + 7);
+    bool xfast = (x0 + 8 <= w) && !(pxf < 0) && (pxl < fw) && (u0 >= 0.f) && (u7 >= 0.f) && ((int)(pxl + 1.0f) == (int)pxl + 1);
     if (isplit == 0) {
         xfast = xfast && (u0 == u7);
     } else {
         const float pxa = (float)(x0 + isplit - 1) - dx, pxb = (float)(x0 + isplit) - dx;
-        const int la = l0 + isplit - 1;
-        xfast = xfast && (pxa - (float)la == u0) && (pxb - (float)(la + 1) == u7) && ((int)(pxa + 1.0f) == la + 1);
+        xfast = xfast && (tap_u(pxa, x0 + isplit - 1) == u0) && (tap_u(pxb, x0 + isplit) == u7) && ((int)(pxa + 1.0f) == (int)pxa + 1);
     }
-    const bool clamp_rt = (l0 + 8 == w);
+    const bool clamp_rt = (x0 + sx + 8 == w);
     const HWeights ca = make_hweights(u0), cb = make_hweights(u7);
     // column groups of this tile column that exist but are not fast: bit cx (the same in both halves of the warp)
     const unsigned slowcols = __ballot_sync(0xFFFFFFFFu, !xfast && x0 < w) & 0xFFFFu;

@@ -40,7 +40,7 @@ WANT = [
 ]
 
 
-SHORT = [("bp_correct_kernel", "bp_correct"), ("gauss_tile_kernel", "gaussian_u16_f32"), ("translate_u16_tma_kernel", "translate_u16"),
+SHORT = [("bp_correct_kernel", "bp_correct"), ("gauss_tile_kernel", "gaussian_u16_f32"), ("translate_u16_rows_kernel", "translate_u16"), ("translate_u16_tma_kernel", "translate_u16"),
          ("split_stats_kernel", "precode_delta_split_stats"), ("delta_split_kernel", "precode_delta_split"),
          ("movie_stats_kernel", "stats_minmax_hist")]
 

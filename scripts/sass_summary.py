@@ -17,8 +17,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "librir_b200", "libs", "libsignal_processing_b200.so")
-KEYS = ["UTMALDG", "UTMAPF", "SYNCS", "BAR.SYNC", "DFMA", "DADD", "DMUL", "FFMA2", "FADD2", "FMUL2", "FFMA", "IMAD.WIDE", "LDS.128", "LDS.64", "LDG.E.128", "LDG.E.ENL2.256",
-        "STG.E.128", "STG.E.ENL2.256", "ATOMS", "ATOMG", "RED", "I2F", "F2I", "F2F", "LDGSTS", "STL", "LDL"]
+KEYS = ["UTMALDG", "UTMAPF", "SYNCS", "BAR.SYNC", "DFMA", "DADD", "DMUL", "FFMA2", "FADD2", "FMUL2", "FFMA", "IMAD.WIDE", "LDS.128", "LDS.64", "LDG 256", "LDG 128",
+        "STG 256", "STG 128", "ATOMS", "ATOMG", "RED", "I2F", "F2I", "F2F", "LDGSTS", "STL", "LDL"]
 
 
 def kernels():
@@ -58,6 +58,9 @@ def main():
         for _, t in ins:
             t = re.sub(r"^@!?U?P\d+\s+", "", t)
             op = t.split()[0] if t else ""
+            if op.startswith(("LDG.", "STG.")) and (".256" in op or ".128" in op):  # width whatever the cache / scope modifiers
+                c[op[:3] + (" 256" if ".256" in op else " 128")] += 1
+                continue
             for k in KEYS:
                 if op == k or op.startswith(k + "."):
                     c[k] += 1

@@ -225,6 +225,33 @@ def test_translate_source_index_one_past_the_clamp(best, port, h, w, st, dx, dy)
         np.testing.assert_array_equal(moved[k][~undefined], want_k[~undefined])
 
 
+@pytest.mark.parametrize("w,h", [(640, 136), (2048, 72), (1288, 200)])
+def test_translate_shifts_half_an_ulp_from_an_integer(best, port, w, h):
+    """-dx (-dy) within half a float ulp below an integer: in the upper float binades of a row (column) px rounds up to
+    the next integer and the reference blends that column with weight 1 -- a different (l, u) than in the lower binades
+    of the same row.  The tiled kernel keeps such pixels on its fast path as `regular taps, u = 1` (they used to go
+    through the per-pixel routine: one such frame in 200 made a 2048 x 2048 launch 2.3x slower,
+    profiles/r2_translate_seed_probe.md); values must not move."""
+    rng = np.random.default_rng(w + h)
+    shifts = [(-0.99997, 0.4), (3e-05, -1.25), (2.00002, 2.00002), (-1.999985, -0.99997), (0.75, 3e-05), (-0.99997, -1.999985),
+              (1.0000001, -2.0000002), (-3.0, 2.0), (0.0, 0.0), (-0.9999999, 0.9999999)]
+    mov = rng.integers(0, 65536, (len(shifts), h, w), dtype=np.uint16)
+    dx = np.array([s[0] for s in shifts], np.float32)
+    dy = np.array([s[1] for s in shifts], np.float32)
+    for st in ("nearest", "background"):
+        got = to_host(sp.translate_batch(to_dev(mov), to_dev(dx), to_dev(dy), st, 77))
+        for k in range(len(shifts)):
+            undefined = reference_reads_past_the_buffer(h, w, float(dx[k]), float(dy[k]))
+            want = best.translate(mov[k], dx[k], dy[k], st, 77)
+            np.testing.assert_array_equal(got[k][~undefined], want[~undefined], err_msg=f"{st} shift {shifts[k]}")
+    moved = vio.remove_motion(mov, (-dx).astype(np.float64), (-dy).astype(np.float64), meta_rows=3)
+    for k in range(len(shifts)):
+        want_k = port.loader_remove_motion(mov[k][: h - 3], -float(dx[k]), -float(dy[k]))
+        undefined = reference_reads_past_the_buffer(h - 3, w, float(dx[k]), float(dy[k]))
+        np.testing.assert_array_equal(moved[k][: h - 3][~undefined], want_k[~undefined], err_msg=f"motion, shift {shifts[k]}")
+        np.testing.assert_array_equal(moved[k][h - 3:], mov[k][h - 3:])
+
+
 def test_translate_batch_per_frame_shifts_device(best):
     mov = ir_movie(9, 96, 128)
     rng = np.random.default_rng(777)
