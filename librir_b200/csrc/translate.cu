@@ -849,6 +849,19 @@ __device__ __forceinline__ RowAB make_row_ab(int y, int h, float dy, int t_expec
     return r;
 }
 
+// (u16)(float)val for 0 <= val < 65536 without the two conversions (F2F.F32.F64 runs at 16 lanes per clock and SM: at
+// the copy rate the motion variant needs 11 pixels per clock and SM, so that one instruction was 70 % of the budget).
+// Rounding val to float and truncating is floor(val + h), h = half a float ulp of val's binade = 2^(e-24): the two differ
+// only when val is a tie that rounds DOWN onto an odd float just below an integer, and an integer below 2^16 always has an
+// even float mantissa.  h comes from val's exponent field; both additions round down, so the sum never creeps up onto an
+// integer it has not reached; the second one (2^52) leaves floor() in the low word.
+__device__ __forceinline__ unsigned trunc_of_float_of(double val)
+{
+    const int e24 = max((__double2hiint(val) & 0x7FF00000) - (24 << 20), 0);
+    const double h = __hiloint2double(e24, 0);
+    return (unsigned)__double2loint(__dadd_rd(__dadd_rd(val, h), 4503599627370496.0));
+}
+
 // 8 destination pixels from two unpacked source rows (pt: top, pb: bottom); the arithmetic of blend_group
 template <int XOFF, bool MOTION>
 __device__ __forceinline__ void blend_rows(const unsigned (&pb)[9], const unsigned (&pt)[9], unsigned A, unsigned B, const HWeights& ca,
@@ -867,7 +880,7 @@ __device__ __forceinline__ void blend_rows(const unsigned (&pb)[9], const unsign
         const HWeights& c = (XOFF != 0 && j >= 8 - XOFF) ? cb : ca;
         const double val = __dadd_rn(__fma_rn(m[j], c.omu, c.k_l), __fma_rn(m[j + 1], c.u, c.k_r));
         if (MOTION)
-            o[j] = (unsigned)(u16)(float)val;
+            o[j] = trunc_of_float_of(val);
         else
             o[j] = (unsigned)__double2loint(__dadd_rd(val, 4503599627370496.0));
     }
