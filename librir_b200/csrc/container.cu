@@ -32,12 +32,14 @@
 #include <dlfcn.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -412,6 +414,44 @@ static size_t z_decompress(void* dctx, void* dst, size_t cap, const void* src, s
     return dctx ? zstd().decompressDCtx(dctx, dst, cap, src, n) : zstd().decompress(dst, cap, src, n);
 }
 
+// Work space of the pre-coded methods (a pinned plane buffer + a device buffer, ~64 MB of frames each way).  Pinning and
+// unpinning cost 10-800 ms a time on the measured host (a VM), more than reading a 400-frame file, so a closed file PARKS
+// its pair here and the next file of the process takes it over; one pair is kept, a second one is freed.
+static std::mutex g_park_mu;
+static char* g_park_host = nullptr;
+static char* g_park_dev = nullptr;
+static size_t g_park_host_bytes = 0, g_park_dev_bytes = 0;
+static int g_park_device = -1;
+static void z_park_buffers(char* host, size_t host_bytes, char* dev, size_t dev_bytes, int device)
+{
+    if (!host && !dev) return;
+    {
+        std::lock_guard<std::mutex> lock(g_park_mu);
+        if (host && dev && host_bytes + dev_bytes > g_park_host_bytes + g_park_dev_bytes) {
+            std::swap(host, g_park_host);
+            std::swap(dev, g_park_dev);
+            g_park_host_bytes = host_bytes;
+            g_park_dev_bytes = dev_bytes;
+            g_park_device = device;
+        }
+    }
+    if (host) (void)cudaFreeHost(host);
+    if (dev) (void)cudaFree(dev);
+    (void)cudaGetLastError();
+}
+static bool z_unpark_buffers(size_t host_bytes, size_t dev_bytes, int device, char** host, size_t* host_has, char** dev, size_t* dev_has)
+{
+    std::lock_guard<std::mutex> lock(g_park_mu);
+    if (!g_park_host || g_park_device != device || g_park_host_bytes < host_bytes || g_park_dev_bytes < dev_bytes) return false;
+    *host = g_park_host;
+    *dev = g_park_dev;
+    *host_has = g_park_host_bytes;
+    *dev_has = g_park_dev_bytes;
+    g_park_host = g_park_dev = nullptr;
+    g_park_host_bytes = g_park_dev_bytes = 0;
+    return true;
+}
+
 struct ZMovie {
     bool writing = false;
     std::string filename;
@@ -437,12 +477,11 @@ struct ZMovie {
     int dev_device = -1;
     long long cache_first = -1, cache_count = 0;  // reading: decoded frames [cache_first, +cache_count) still in dev_buf
     std::mutex mu;
+    size_t host_bytes = 0, dev_bytes = 0;  // what the two buffers really hold (a pair taken over may be larger than asked)
     ~ZMovie()
     {
         if (f) fclose(f);
-        if (host_planes) (void)cudaFreeHost(host_planes);
-        if (dev_buf) (void)cudaFree(dev_buf);
-        (void)cudaGetLastError();
+        z_park_buffers(host_planes, host_bytes, dev_buf, dev_bytes, dev_device);
     }
     // grow-only work space for m frames; false + set_error when memory runs out
     bool reserve(size_t m)
@@ -450,30 +489,33 @@ struct ZMovie {
         const size_t npx = (size_t)w * h;
         int dev = 0;
         cudaGetDevice(&dev);
-        if (m > dev_frames || dev != dev_device) {
-            if (dev_buf) cudaFree(dev_buf);
-            dev_buf = nullptr;
-            dev_frames = 0;
-            cache_first = -1;
+        if (m <= dev_frames && m <= host_planes_frames && dev == dev_device) return true;
+        // both at once, so that the pair a closed file parked can be taken over as it is
+        m = std::max(m, std::max(dev_frames, host_planes_frames));
+        z_park_buffers(host_planes, host_bytes, dev_buf, dev_bytes, dev_device);
+        host_planes = dev_buf = nullptr;
+        host_planes_frames = dev_frames = 0;
+        host_bytes = dev_bytes = 0;
+        cache_first = -1;
+        if (!z_unpark_buffers(m * npx * 2, m * npx * 4, dev, &host_planes, &host_bytes, &dev_buf, &dev_bytes)) {
             if (cudaMalloc((void**)&dev_buf, m * npx * 4) != cudaSuccess) {
                 cudaGetLastError();
+                dev_buf = nullptr;
                 set_error("zstd movie file: out of device memory for %zu frames", m);
                 return false;
             }
-            dev_frames = m;
-            dev_device = dev;
-        }
-        if (m > host_planes_frames) {
-            if (host_planes) cudaFreeHost(host_planes);
-            host_planes = nullptr;
-            host_planes_frames = 0;
             if (cudaMallocHost((void**)&host_planes, m * npx * 2) != cudaSuccess) {
                 cudaGetLastError();
+                cudaFree(dev_buf);
+                host_planes = dev_buf = nullptr;
                 set_error("zstd movie file: out of pinned host memory for %zu frames", m);
                 return false;
             }
-            host_planes_frames = m;
+            host_bytes = m * npx * 2;
+            dev_bytes = m * npx * 4;
         }
+        dev_frames = host_planes_frames = m;
+        dev_device = dev;
         return true;
     }
     u16* dev_movie() const { return (u16*)dev_buf; }
@@ -852,17 +894,38 @@ static int z_write_records(ZMovie* z, const void* frames, long long nframes, con
     return 0;
 }
 
+// RIRB_Z_TRACE=1: wall-clock milliseconds of the phases of a methods-2/3 pass on stderr (diagnostics; off by default)
+static bool z_trace()
+{
+    static const bool on = [] { const char* e = getenv("RIRB_Z_TRACE"); return e && *e == '1'; }();
+    return on;
+}
+struct ZPhase {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char* what, long long frames)
+    {
+        if (!z_trace()) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rirb z] %-28s %6lld frames %9.3f ms\n", what, frames, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 // m frames on the DEVICE, the first of them a key frame (frame number `first`): pre-coder -> pinned planes -> zstd -> records
 static int z_flush_gops(ZMovie* z, const u16* dev_frames, long long m, long long first, const long long* timestamps, int threads)
 {
     const size_t npx = (size_t)z->w * z->h;
     cudaStream_t st = current_stream();
+    ZPhase ph;
     if (rirb_precode_movie(dev_frames, m, z->w, z->h, z->gop, z->method == 3, first, z->dev_lo(), z->dev_hi()) != 0) return -1;
     // per frame [lo | hi], so that a record's payload is one contiguous run for zstd
     RIRB_CUDA_OK(cudaMemcpy2DAsync(z->host_planes, 2 * npx, z->dev_lo(), npx, npx, (size_t)m, cudaMemcpyDeviceToHost, st));
     RIRB_CUDA_OK(cudaMemcpy2DAsync(z->host_planes + npx, 2 * npx, z->dev_hi(), npx, npx, (size_t)m, cudaMemcpyDeviceToHost, st));
     RIRB_CUDA_OK(cudaStreamSynchronize(st));
-    return z_write_records(z, z->host_planes, m, timestamps, threads);
+    ph.mark("write: pre-code + download", m);
+    const int rc = z_write_records(z, z->host_planes, m, timestamps, threads);
+    ph.mark("write: zstd + records", m);
+    return rc;
 }
 
 // methods 2 / 3.  Whole GOPs go through the GPU pre-coder as they come; what does not fill a GOP waits in z->pending
@@ -1175,13 +1238,20 @@ static int z_read_precoded(ZMovie* z, int pos, int count, unsigned short* out, i
     const bool to_device = device_pointer(out);
     long long p = pos;
     const long long end = (long long)pos + count;
+    bool in_flight = false;  // the stream may still be reading host_planes / dev_buf for the previous chunk
     while (p < end) {
         if (!(z->cache_first >= 0 && p >= z->cache_first && p < z->cache_first + z->cache_count)) {
             const long long k0 = p - p % gop;                                            // the GOP's key frame
             const long long m = std::min<long long>(chunk, (long long)z->times.size() - k0);
+            ZPhase ph;
+            if (in_flight) RIRB_CUDA_OK(cudaStreamSynchronize(st));  // before the host threads overwrite the pinned planes
+            in_flight = false;
+            ph.mark("read: wait for previous pass", m);
             if (!z->reserve((size_t)chunk)) return -1;
+            ph.mark("read: reserve", m);
             z->cache_first = -1;
             if (z_read_records(z, (int)k0, (int)m, z->host_planes, nullptr, threads, true) != 0) return -1;
+            ph.mark("read: records + zstd", m);
             RIRB_CUDA_OK(cudaMemcpy2DAsync(z->dev_lo(), npx, z->host_planes, 2 * npx, npx, (size_t)m, cudaMemcpyHostToDevice, st));
             RIRB_CUDA_OK(cudaMemcpy2DAsync(z->dev_hi(), npx, z->host_planes + npx, 2 * npx, npx, (size_t)m, cudaMemcpyHostToDevice, st));
             if (rirb_decode_movie(z->dev_lo(), z->dev_hi(), m, z->w, z->h, z->gop, z->method == 3, k0, z->dev_movie()) != 0) return -1;
@@ -1189,8 +1259,23 @@ static int z_read_precoded(ZMovie* z, int pos, int count, unsigned short* out, i
             z->cache_count = m;
         }
         const long long n = std::min(end, z->cache_first + z->cache_count) - p;
-        RIRB_CUDA_OK(cudaMemcpyAsync(out + (size_t)(p - pos) * npx, z->dev_movie() + (size_t)(p - z->cache_first) * npx, (size_t)n * npx * 2,
-                                     to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        const u16* from = z->dev_movie() + (size_t)(p - z->cache_first) * npx;
+        u16* to = out + (size_t)(p - pos) * npx;
+        if (to_device) {
+            RIRB_CUDA_OK(cudaMemcpyAsync(to, from, (size_t)n * npx * 2, cudaMemcpyDeviceToDevice, st));
+            in_flight = true;
+        } else if (n >= 4) {
+            // a run of frames for a host caller: down into the pinned buffer (the planes in it are consumed by now, it holds
+            // exactly a chunk of frames), then into the caller's pageable memory by the host pool -- the driver's own pageable
+            // download is one thread faulting the destination in page by page (0.3 GB/s measured on a fresh numpy array)
+            RIRB_CUDA_OK(cudaMemcpyAsync(z->host_planes, from, (size_t)n * npx * 2, cudaMemcpyDeviceToHost, st));
+            RIRB_CUDA_OK(cudaStreamSynchronize(st));
+            const char* hp = z->host_planes;
+            parallel_for(n, pool_size(threads, (int)n), [&](long long i, int) { memcpy(to + (size_t)i * npx, hp + (size_t)i * npx * 2, npx * 2); });
+        } else {
+            RIRB_CUDA_OK(cudaMemcpyAsync(to, from, (size_t)n * npx * 2, cudaMemcpyDeviceToHost, st));
+            RIRB_CUDA_OK(cudaStreamSynchronize(st));
+        }
         p += n;
     }
     RIRB_CUDA_OK(cudaStreamSynchronize(st));

@@ -849,19 +849,6 @@ __device__ __forceinline__ RowAB make_row_ab(int y, int h, float dy, int t_expec
     return r;
 }
 
-// (u16)(float)val for 0 <= val < 65536 without the two conversions (F2F.F32.F64 runs at 16 lanes per clock and SM: at
-// the copy rate the motion variant needs 11 pixels per clock and SM, so that one instruction was 70 % of the budget).
-// Rounding val to float and truncating is floor(val + h), h = half a float ulp of val's binade = 2^(e-24): the two differ
-// only when val is a tie that rounds DOWN onto an odd float just below an integer, and an integer below 2^16 always has an
-// even float mantissa.  h comes from val's exponent field; both additions round down, so the sum never creeps up onto an
-// integer it has not reached; the second one (2^52) leaves floor() in the low word.
-__device__ __forceinline__ unsigned trunc_of_float_of(double val)
-{
-    const int e24 = max((__double2hiint(val) & 0x7FF00000) - (24 << 20), 0);
-    const double h = __hiloint2double(e24, 0);
-    return (unsigned)__double2loint(__dadd_rd(__dadd_rd(val, h), 4503599627370496.0));
-}
-
 // 8 destination pixels from two unpacked source rows (pt: top, pb: bottom); the arithmetic of blend_group
 template <int XOFF, bool MOTION>
 __device__ __forceinline__ void blend_rows(const unsigned (&pb)[9], const unsigned (&pt)[9], unsigned A, unsigned B, const HWeights& ca,
@@ -879,8 +866,12 @@ __device__ __forceinline__ void blend_rows(const unsigned (&pb)[9], const unsign
     for (int j = 0; j < 8; ++j) {
         const HWeights& c = (XOFF != 0 && j >= 8 - XOFF) ? cb : ca;
         const double val = __dadd_rn(__fma_rn(m[j], c.omu, c.k_l), __fma_rn(m[j + 1], c.u, c.k_r));
+        // MOTION: the reference's translate<u16, float> result narrowed to u16.  Emulating the two conversions on the
+        // integer / fp64 side (floor(val + half a float ulp of val's binade)) was built and measured: +4.8 instructions per
+        // pixel instead of +2 and 2 % slower; with one half-ulp per 8-pixel group, faster on smooth images but 20 % slower
+        // on noise (profiles/r2_translate_notes.md).  The kernel's time follows its instruction count, not the conversion pipe.
         if (MOTION)
-            o[j] = trunc_of_float_of(val);
+            o[j] = (unsigned)(u16)(float)val;
         else
             o[j] = (unsigned)__double2loint(__dadd_rd(val, 4503599627370496.0));
     }

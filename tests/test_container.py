@@ -185,8 +185,9 @@ def test_zfile_without_trailer_and_truncated(tmp_path):
     p.write_bytes(b"not a movie" * 40)
     with pytest.raises(RuntimeError):
         tools.ZFileReader(p)
-    with pytest.raises(RuntimeError):
-        tools.ZFileWriter(tmp_path / "m2.bin", 32, 24, method=2)
+    if not _lib.device_available():  # methods 2 / 3 pre-code on the GPU; there is no CPU pre-coder in the product
+        with pytest.raises(RuntimeError):
+            tools.ZFileWriter(tmp_path / "m2.bin", 32, 24, method=2)
 
 
 @pytest.mark.parametrize("shape,n", [((64, 80), 31), ((512, 640), 12)])

@@ -51,6 +51,28 @@ def test_round_trip_in_pieces(tmp_path, method, gop, shape):
     r.close()
 
 
+@pytest.mark.parametrize("method", [2, 3])
+def test_reads_longer_than_one_pass(tmp_path, method):
+    """A read that spans several passes of the reader (a pass is ~64 MB of frames) into DEVICE memory: the next pass's zstd
+    threads must not overwrite the pinned planes the previous pass is still uploading (scripts/zfile_bench.py caught it)."""
+    t, h, w = 230, 512, 640
+    rng = np.random.default_rng(method)
+    base = C.movie(10, h, w, seed=method)
+    mov = base[rng.integers(0, 10, t)] + rng.integers(0, 4, (t, 1, 1)).astype(np.uint16)
+    ts = np.arange(t, dtype=np.int64)
+    fn = str(tmp_path / "long.bin")
+    with tools.ZFileWriter(fn, w, h, method=method, clevel=1, gop=50) as wr:
+        wr.add_images(mov, ts)
+    d = torch.empty((t, h, w), dtype=torch.uint16, device="cuda")
+    with tools.ZFileReader(fn) as r:
+        for _ in range(2):
+            d.zero_()
+            r.read_images(0, t, out=d)
+            assert np.array_equal(d.cpu().view(torch.int16).numpy().view(np.uint16), mov)
+        assert np.array_equal(r.read_images(3, t - 7), mov[3:t - 4])  # host destination, not aligned to a pass
+    os.remove(fn)
+
+
 def test_precoder_shrinks_the_file(tmp_path):
     mov = C.movie(200, 128, 160, seed=4)
     sizes = {}
