@@ -441,6 +441,8 @@ struct EdgeTable {
     HWeights wt[8];
     unsigned valid;     // bit i: pixel i is in range, its source column is l0 + i and rt is l + 1 (or clamped)
     unsigned clamped;   // bit i: rt of pixel i clamps onto l (l == w - 1)
+    unsigned outside;   // bit i: px of pixel i is < 0 or >= w: the border strategy decides (second-generation kernel only)
+    unsigned below;     // bit i: px of pixel i is < 0 (an 8-pixel-wide image has both kinds in its one group)
 };
 
 // One pixel of an edge group in a regular row: the fast path's arithmetic with the pixel's own
@@ -927,7 +929,9 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
     const float fh = (float)h;
     const int sx = (int)fminf(fmaxf(floorf(-dx), -fw - 16.f), fw + 16.f);
     const int sy = (int)fminf(fmaxf(floorf(-dy), -fh - 16.f), fh + 16.f);
-    const int xs = (x0t + sx) & ~7;
+    // the box starts on a 32-byte sector (16 pixels): its 288-byte rows are then 9 sectors, never 10.  xoff = 0..15; the
+    // row routines are instantiated for xoff & 7 and read 16 bytes further into the staged row when xoff >= 8
+    const int xs = (x0t + sx) & ~15;
     const int xoff = (x0t + sx) - xs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // Weight of the RIGHT tap of destination pixel xp when its left tap is source column xp + sx: px - l in the regular case.
@@ -970,9 +974,12 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
         ok = ok && (un >= 0.f) && (cl || rt == l + 1);
         edge_tab[e].wt[i] = make_hweights(ok ? un : 0.f);
         const unsigned vb = __ballot_sync(0x0000FFFFu, ok), cb2 = __ballot_sync(0x0000FFFFu, cl);
+        const unsigned ob = __ballot_sync(0x0000FFFFu, (px < 0) || !(px < fw)), lb = __ballot_sync(0x0000FFFFu, px < 0);
         if (i == 0) {
             edge_tab[e].valid = (vb >> (8 * e)) & 0xFFu;
             edge_tab[e].clamped = (cb2 >> (8 * e)) & 0xFFu;
+            edge_tab[e].outside = (ob >> (8 * e)) & 0xFFu;
+            edge_tab[e].below = (lb >> (8 * e)) & 0xFFu;
         }
     }
     __syncthreads();  // barriers initialised, edge tables written: the only CTA-wide barrier of the kernel
@@ -1007,10 +1014,10 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
         mbar_wait(&bar[stage], parity);
         const u16* tile = reinterpret_cast<const u16*>(smem_raw + stage * TT_STAGE_BYTES);
         if (xfast) {
-            const uint32_t srow = smem_addr(tile + r0 * TT_BW + 8 * cx);
+            const uint32_t srow = smem_addr(tile + r0 * TT_BW + 8 * cx + (xoff & 8));
             const uint32_t rab = smem_addr(&rowab[stage][r0]);
             u16* orow = oframe + (size_t)(y0t + r0) * w + x0;
-            switch (xoff) {  // CTA-uniform
+            switch (xoff & 7) {  // CTA-uniform
             case 0: fast_column<0, MOTION>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
             case 1: fast_column<1, MOTION>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
             case 2: fast_column<2, MOTION>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
@@ -1046,19 +1053,71 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
                 if (translate_pixel<u16, u16>(ts, w, h, gx, gy, dx, dy, strategy, (u16)background, r)) *o = r;
             }
         };
-        if (slowcols) {  // CTA-uniform: 16 rows x 8 pixels per slow column group, 4 rows per pass
+        // The image's first and last group of a row are slow column groups for nearly every shift (pixels left of / beyond
+        // the image, a different weight per pixel where px < 8), i.e. in two of a 640-wide frame's five CTAs; one pixel per
+        // lane through slow_pixel they cost those CTAs as much again as their fast groups (the divergent border / blend
+        // branches, everything recomputed per pixel).  Here a lane takes 4 pixels of one regular row: 5 + 5 staged pixels,
+        // the row's integer blend once per column, the tabulated weights (a broadcast read per pixel), the border
+        // strategy decided from the table's `outside` bits without the literal routine.  Rows that are not regular are left
+        // to the border-row pass below.
+        auto edge_rows = [&](int g, int e) {
+            const EdgeTable& et = edge_tab[e];
+            const int row = wr0 + (lane & 15), j0 = 4 * (lane >> 4);
+            const int gy = y0t + row;
+            if (gy >= h) return;
+            const RowAB ra = rowab[stage][row];
+            if (ra.B == ROW_SLOW) return;
+            const u16* top = tile + row * TT_BW + 8 * g + xoff + j0;  // left tap of pixel j0, top source row
+            const u16* bot = top + TT_BW;
+            u16* o = oframe + (size_t)gy * w + x0t + 8 * g + j0;
+            unsigned long long nn[5];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) nn[c] = (unsigned long long)bot[c] * ra.A + (unsigned long long)top[c] * ra.B + 0x41C0000000000000ULL;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned bit = 1u << (j0 + q);
+                if (et.valid & bit) {
+                    const HWeights c = et.wt[j0 + q];
+                    const unsigned long long nr = (et.clamped & bit) ? nn[q] : nn[q + 1];
+                    const double val = __dadd_rn(__fma_rn(__longlong_as_double((long long)nn[q]), c.omu, c.k_l),
+                                                 __fma_rn(__longlong_as_double((long long)nr), c.u, c.k_r));
+                    o[q] = MOTION ? (u16)(float)val : (u16)__double2loint(__dadd_rd(val, 4503599627370496.0));
+                } else {  // outside the image (the caller has checked that the table knows every pixel of the group)
+                    // translate_pixel's border branch: src((long long)py, column 0 or w - 1).  (long long)py is the row of the
+                    // top tap -- or, when py has rounded up to an integer (make_row_ab's B == 0 case), the one below it
+                    if (strategy == STRAT_NEAREST)
+                        o[q] = tile[(row + (ra.B == 0 ? 1 : 0)) * TT_BW + (((et.below & bit) ? 0 : w - 1) - xs)];
+                    else if (strategy == STRAT_BACKGROUND)
+                        o[q] = (u16)background;
+                }
+            }
+        };
+        unsigned generic_cols = 0;  // slow column groups done pixel by pixel, all 16 rows of the warp
+        if (slowcols) {  // CTA-uniform
             for (unsigned m = slowcols; m; m &= m - 1) {
                 const int g = __ffs(m) - 1;
+                const int xg = x0t + 8 * g;
+                const int e = (xg == 0) ? 0 : ((xg == w - 8) ? 1 : -1);
+                if (e >= 0 && strategy != STRAT_WRAP) {
+                    // every pixel either tabulated or outside the image, and the border column staged: else pixel by pixel
+                    const unsigned below = edge_tab[e].below, above = edge_tab[e].outside & ~below;
+                    const bool staged = (below == 0 || (-xs >= 0 && -xs < TT_BW)) && (above == 0 || (w - 1 - xs >= 0 && w - 1 - xs < TT_BW));
+                    if (((edge_tab[e].valid | edge_tab[e].outside) & 0xFFu) == 0xFFu && staged) {
+                        edge_rows(g, e);
+                        continue;
+                    }
+                }
+                generic_cols |= 1u << g;
 #pragma unroll 1
-                for (int rr = lane >> 3; rr < 2 * TW_ROWS; rr += 4) slow_pixel(8 * g + (lane & 7), wr0 + rr);
+                for (int rr = lane >> 3; rr < 2 * TW_ROWS; rr += 4) slow_pixel(8 * g + (lane & 7), wr0 + rr);  // 4 rows per pass
             }
         }
-        if (slowrows) {  // warp-uniform: the pixels of border rows that are not in a slow column group
+        if (slowrows) {  // warp-uniform: the pixels of border rows that the passes above have not done
             for (unsigned m = slowrows; m; m &= m - 1) {
                 const int rr = __ffs(m) - 1;
 #pragma unroll 1
                 for (int c = lane; c < TT_W; c += 32)
-                    if (!((slowcols >> (c >> 3)) & 1u)) slow_pixel(c, wr0 + rr);
+                    if (!((generic_cols >> (c >> 3)) & 1u)) slow_pixel(c, wr0 + rr);
             }
         }
         // ---- sign off; the last warp through refills the stage ----
