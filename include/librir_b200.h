@@ -85,10 +85,14 @@ RIRB_API const char* rirb_version(void);
  * "loader_fused" (default 0): rirb_loader_read_movie as one fused pass instead of merge pass + motion pass.
  * "ecc_fused" (default 1): rirb_ecc_compute as ONE cooperative launch (grid barriers between the phases and the
  *   iterations) instead of one launch per iteration.
- * "lossy_run" (default 1): rirb_lossy_add_images walks a run of frames in ONE cooperative launch (two grid barriers
+ * "lossy_run" (default 1): rirb_lossy_add_images walks a run of frames in ONE cooperative launch (one grid barrier
  *   per frame) instead of three launches per frame.
+ * "translate_rows" (default 1): the second-generation tiled translate kernel (0: the first one, for A/B runs).
+ * "ecc_queue" (default 1): rirb_ecc_track solves runs of up to 16 device-resident frames in ONE cooperative launch (the
+ *   warm start stays on the device, a frame that fails or triggers the replacement of the reference image ends the
+ *   run) instead of one launch + copy back + synchronisation per frame.
  * Initial values can also come from RIRB_TRANSLATE_TMA / RIRB_GAUSS_TMA / RIRB_LOADER_FUSED / RIRB_ECC_FUSED /
- * RIRB_LOSSY_RUN.  -1: unknown key. */
+ * RIRB_LOSSY_RUN / RIRB_TRANSLATE_ROWS / RIRB_ECC_QUEUE.  -1: unknown key. */
 RIRB_API int rirb_set_parameter(const char* key, const char* value);
 
 /* ---- batches of frames (nframes dense frames back to back) ---- */

@@ -45,6 +45,10 @@ struct EccDev {
     unsigned mm[4];  // order-preserving keys: template min, max, image min, max
     float tx, ty;
     int it, max_it, done, status;  // status: 0 ok, 1 NaN (cv2: "NaN encountered."), 2 correlation about to be minimised
+    // a run of solves queued back to back (rirb_ecc_track): the solve after this one must not run -- this one failed, or its
+    // correlation fell under the confidence threshold and the host will replace the reference image; skipped = this slot's
+    // solve did not run for that reason
+    int stop, skipped;
 };
 
 struct EccResult {  // what the host reads back
@@ -80,6 +84,7 @@ __global__ void ecc_begin_kernel(EccDev* d, float tx, float ty, int max_it, doub
     d->max_it = max_it;
     d->done = (max_it <= 0) || !(fabs(-1.0 + eps) >= eps);
     d->status = 0;
+    d->stop = d->skipped = 0;
 }
 
 constexpr int ECC_THREADS = 256;
@@ -237,14 +242,34 @@ __device__ __forceinline__ void ecc_block_partial(double (&a)[NACC], double (*re
 }
 
 // Sum of all CTAs' slots, 8 threads per value (strided, then a fixed shuffle tree); result in sums[NACC] (shared).
-__device__ __forceinline__ void ecc_sum_partials(const double* partials, int nblk, double* sums)
+// The slots come down first, every thread of the CTA fetching its share in ONE round trip to L2 (the strided loop used to
+// be ~19 dependent round trips for the 120 adding threads: a third of an iteration); the order of the additions is the
+// old one, so the sums are the same bits.
+constexpr int ECC_MAX_SLOTS = 320;  // >= the largest grid either driver launches (2 CTAs per SM)
+__device__ __forceinline__ void ecc_sum_partials(const double* partials, int nblk, double* sums, double* stage)
 {
     static_assert(NACC * 8 <= ECC_THREADS, "8 threads per accumulated value");
+    const int total = nblk * NACC;
+    constexpr int PER = 10;
+    for (int base = 0; base < total; base += PER * ECC_THREADS) {
+        double v[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int i = base + q * ECC_THREADS + (int)threadIdx.x;
+            v[q] = i < total ? __ldcg(&partials[i]) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int i = base + q * ECC_THREADS + (int)threadIdx.x;
+            if (i < total) stage[i] = v[q];
+        }
+    }
+    __syncthreads();
     const bool active = threadIdx.x < NACC * 8;
     const int k = threadIdx.x >> 3, j = threadIdx.x & 7;
     double v = 0.0;
     if (active)
-        for (int b = j; b < nblk; b += 8) v += __ldcg(&partials[(size_t)b * NACC + k]);
+        for (int b = j; b < nblk; b += 8) v += stage[b * NACC + k];
     v += __shfl_down_sync(0xFFFFFFFFu, v, 4, 8);
     v += __shfl_down_sync(0xFFFFFFFFu, v, 2, 8);
     v += __shfl_down_sync(0xFFFFFFFFu, v, 1, 8);
@@ -316,6 +341,7 @@ ecc_iter_kernel(const float* __restrict__ T, const float* __restrict__ I, const 
     if (d->done) return;  // written by the previous launch's last CTA only
     __shared__ double red[ECC_THREADS / 32][NACC];
     __shared__ double sums[NACC];
+    __shared__ double stage[ECC_MAX_SLOTS * NACC];
     __shared__ bool last;
     const EccShift sh(d->tx, d->ty);
     double a[NACC];
@@ -329,7 +355,7 @@ ecc_iter_kernel(const float* __restrict__ T, const float* __restrict__ I, const 
     __syncthreads();
     if (!last) return;
     __threadfence();
-    ecc_sum_partials(partials, (int)gridDim.x, sums);
+    ecc_sum_partials(partials, (int)gridDim.x, sums, stage);
     if (threadIdx.x != 0) return;
     EccIterate s{d->tx, d->ty, d->rho, d->last_rho, d->it, 0, 0};
     ecc_update(sums, s, d->max_it, d->eps);
@@ -350,34 +376,32 @@ ecc_iter_kernel(const float* __restrict__ T, const float* __restrict__ I, const 
 // arithmetic, identical result), so no second barrier is needed to publish the new shift.  The slots are double-buffered
 // by iteration parity: a fast CTA writes iteration it + 1's sums into the other buffer while a slow one still reads it's.
 __global__ void __launch_bounds__(ECC_THREADS)
-ecc_solve_kernel(const float* __restrict__ ref, float* cur, const float* cur_src, int cur_stride, const u8* __restrict__ mask, int w, int h,
-                 float thresh, float* __restrict__ T, float* __restrict__ I, float* __restrict__ gx, float* __restrict__ gy, EccDev* d,
-                 double* partials, float tx0, float ty0, int max_it, double eps)
+ecc_solve_kernel(const float* __restrict__ ref, float* cur, const float* cur_src0, int cur_stride, const u8* __restrict__ mask, int w, int h,
+                 float thresh, float* __restrict__ T, float* __restrict__ I, float* __restrict__ gx, float* __restrict__ gy, EccDev* d0,
+                 double* partials, float tx0, float ty0, int max_it, double eps, int nrun, size_t frame_stride, double conf_thresh,
+                 int have_thresh)
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[ECC_THREADS / 32][NACC];
     __shared__ double sums[NACC];
+    __shared__ double stage[ECC_MAX_SLOTS * NACC];
     __shared__ unsigned kred[ECC_THREADS / 32][4];
     __shared__ EccIterate shared_state;
     const int npx = w * h;
     const int gtid = blockIdx.x * ECC_THREADS + threadIdx.x, gthreads = gridDim.x * ECC_THREADS;
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
 
-    // ---- min / max of the clamped windows (d->mm is in its initial state: rirb_ecc_open, then the end of every solve);
-    //      the current window is picked out of the filtered frame on the way (cur_src, rows cur_stride floats apart) ----
-    {
-        unsigned k[4] = {0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u};
-        for (int i = gtid; i < npx; i += gthreads) {
-            const int yy = i / w, xx = i - yy * w;
-            const float r = ref[i], c = cur_src[(size_t)yy * cur_stride + xx];
-            cur[i] = c;
-            const unsigned kr = fkey(clamp_pair(r, c, thresh)), kc = fkey(clamp_pair(c, r, thresh));
-            k[0] = min(k[0], kr);
-            k[1] = max(k[1], kr);
-            k[2] = min(k[2], kc);
-            k[3] = max(k[3], kc);
-        }
+    // nrun > 1: a RUN of frames (rirb_ecc_track, frames in device memory) without the host in between.  Frame r's window is
+    // cur_src0 + r * frame_stride, its state d0[r]; its warm start is frame r - 1's shift, and the run ends behind a frame
+    // that failed or whose correlation fell under the confidence threshold (the host then replaces the reference image):
+    // the slots behind it keep `skipped`.  Every CTA holds the same scalar state, so all of them leave together.  No barrier
+    // is needed between two frames: the first thing a frame writes that another phase reads (cur, then d0[r + 1].mm) is read
+    // again only behind the frame's own first barrier.
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int r = 0; r < nrun; ++r) d0[r].skipped = 1;
+    // CTA-wide min / max of four keys, then one atomic per word into dst->mm
+    auto publish_minmax = [&](unsigned (&k)[4], EccDev* dst) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             k[0] = min(k[0], __shfl_down_sync(0xFFFFFFFFu, k[0], o));
@@ -385,6 +409,7 @@ ecc_solve_kernel(const float* __restrict__ ref, float* cur, const float* cur_src
             k[2] = min(k[2], __shfl_down_sync(0xFFFFFFFFu, k[2], o));
             k[3] = max(k[3], __shfl_down_sync(0xFFFFFFFFu, k[3], o));
         }
+        __syncthreads();  // kred may still be read from the previous use
         if (lane == 0)
 #pragma unroll
             for (int q = 0; q < 4; ++q) kred[wi][q] = k[q];
@@ -392,28 +417,61 @@ ecc_solve_kernel(const float* __restrict__ ref, float* cur, const float* cur_src
         if (threadIdx.x < 4) {
             unsigned v = kred[0][threadIdx.x];
             for (int q = 1; q < ECC_THREADS / 32; ++q) v = (threadIdx.x & 1) ? max(v, kred[q][threadIdx.x]) : min(v, kred[q][threadIdx.x]);
-            if (threadIdx.x & 1) atomicMax(&d->mm[threadIdx.x], v); else atomicMin(&d->mm[threadIdx.x], v);
+            if (threadIdx.x & 1) atomicMax(&dst->mm[threadIdx.x], v); else atomicMin(&dst->mm[threadIdx.x], v);
         }
+    };
+    for (int r = 0; r < nrun; ++r) {
+    EccDev* d = d0 + r;
+    const float* cur_src = cur_src0 + (size_t)r * frame_stride;
+    // ---- min / max of the clamped windows (d->mm is in its initial state: rirb_ecc_open, then the end of every solve).
+    //      Only the first frame of a run pays a phase of its own for it: frame r + 1's are taken while frame r is
+    //      normalised (they do not depend on frame r's solution), which saves a pass and a grid barrier per frame ----
+    if (r == 0) {
+        unsigned k[4] = {0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u};
+        for (int i = gtid; i < npx; i += gthreads) {
+            const int yy = i / w, xx = i - yy * w;
+            const float rv = ref[i], c = cur_src[(size_t)yy * cur_stride + xx];
+            const unsigned kr = fkey(clamp_pair(rv, c, thresh)), kc = fkey(clamp_pair(c, rv, thresh));
+            k[0] = min(k[0], kr);
+            k[1] = max(k[1], kr);
+            k[2] = min(k[2], kc);
+            k[3] = max(k[3], kc);
+        }
+        publish_minmax(k, d);
+        grid.sync();
     }
-    grid.sync();
-    // ---- normalisation + gradients ----
+    // ---- normalisation + gradients; the window is picked out of the filtered frame (cur_src, rows cur_stride floats
+    //      apart) and its compact copy left in `cur` for the host (rirb_ecc_reset_reference, quantiles) ----
     {
         const float mi_t = fkey_inv(d->mm[0]), span_t = __fsub_rn(fkey_inv(d->mm[1]), mi_t);
         const float mi_i = fkey_inv(d->mm[2]), span_i = __fsub_rn(fkey_inv(d->mm[3]), mi_i);
+        const bool more = r + 1 < nrun;
+        const float* next_src = cur_src + frame_stride;
+        unsigned k[4] = {0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u};
         auto img = [&](int xx, int yy) {
-            const int i = yy * w + xx;
-            return normalise(clamp_pair(cur[i], ref[i], thresh), mi_i, span_i);
+            return normalise(clamp_pair(cur_src[(size_t)yy * cur_stride + xx], ref[yy * w + xx], thresh), mi_i, span_i);
         };
         for (int i = gtid; i < npx; i += gthreads) {
             const int y = i / w, x = i - y * w;
-            T[i] = normalise(clamp_pair(ref[i], cur[i], thresh), mi_t, span_t);
-            I[i] = img(x, y);
+            const float rv = ref[i], c = cur_src[(size_t)y * cur_stride + x];
+            if (cur != cur_src) cur[i] = c;
+            T[i] = normalise(clamp_pair(rv, c, thresh), mi_t, span_t);
+            I[i] = normalise(clamp_pair(c, rv, thresh), mi_i, span_i);
             const int xm = x == 0 ? 1 : x - 1, xp = x == w - 1 ? w - 2 : x + 1;  // w, h >= 2 (rirb_ecc_open)
             const int ym = y == 0 ? 1 : y - 1, yp = y == h - 1 ? h - 2 : y + 1;
             const float m = (mask == nullptr || mask[i] != 0) ? 1.0f : 0.0f;
             gx[i] = __fmul_rn(__fsub_rn(__fmul_rn(0.5f, img(xp, y)), __fmul_rn(0.5f, img(xm, y))), m);
             gy[i] = __fmul_rn(__fsub_rn(__fmul_rn(0.5f, img(x, yp)), __fmul_rn(0.5f, img(x, ym))), m);
+            if (more) {
+                const float cn = next_src[(size_t)y * cur_stride + x];
+                const unsigned kr = fkey(clamp_pair(rv, cn, thresh)), kc = fkey(clamp_pair(cn, rv, thresh));
+                k[0] = min(k[0], kr);
+                k[1] = max(k[1], kr);
+                k[2] = min(k[2], kc);
+                k[3] = max(k[3], kc);
+            }
         }
+        if (more) publish_minmax(k, d + 1);
     }
     grid.sync();
     // ---- iterations ----
@@ -428,7 +486,7 @@ ecc_solve_kernel(const float* __restrict__ ref, float* cur, const float* cur_src
         ecc_accumulate(T, I, gx, gy, mask, w, h, sh, gtid, gthreads, a);
         ecc_block_partial(a, red, slots);
         grid.sync();
-        ecc_sum_partials(slots, (int)gridDim.x, sums);
+        ecc_sum_partials(slots, (int)gridDim.x, sums, stage);
         if (threadIdx.x == 0) {
             ecc_update(sums, s, max_it, eps);
             shared_state = s;
@@ -436,6 +494,7 @@ ecc_solve_kernel(const float* __restrict__ ref, float* cur, const float* cur_src
         __syncthreads();
         s = shared_state;
     }
+    const bool stop = (s.status != 0) || (have_thresh && s.rho < conf_thresh);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         d->tx = s.tx;
         d->ty = s.ty;
@@ -444,8 +503,18 @@ ecc_solve_kernel(const float* __restrict__ ref, float* cur, const float* cur_src
         d->it = s.it;
         d->status = s.status;
         d->done = 1;
+        d->skipped = 0;
+        d->stop = stop ? 1 : 0;
         d->mm[0] = d->mm[2] = 0xFFFFFFFFu;  // ready for the next solve: every CTA read them two barriers ago
         d->mm[1] = d->mm[3] = 0u;
+        if (stop && r + 1 < nrun) {  // the next frame's min / max were taken on the way and will not be used
+            d[1].mm[0] = d[1].mm[2] = 0xFFFFFFFFu;
+            d[1].mm[1] = d[1].mm[3] = 0u;
+        }
+    }
+    if (stop) break;
+    tx0 = s.tx;
+    ty0 = s.ty;
     }
 }
 
@@ -471,6 +540,10 @@ struct EccState {
     float start[2] = {0.f, 0.f};  // warp_matrix[0,2], warp_matrix[1,2]: the warm start of the next frame
     std::vector<double> confs;
     EccDev* result = nullptr;     // pinned host copy of the device state
+    EccDev* dq = nullptr;         // device states of a run of solves queued back to back (ECC_BATCH slots) ...
+    EccDev* resultq = nullptr;    // ... and their pinned host copies
+    const char* filt_src = nullptr;  // within one rirb_ecc_track call: s.filtered holds the filtered frames filt_src + i * frame bytes,
+    int filt_n = 0;                  // i < filt_n (a run that stopped early does not filter its tail again)
     int launched = 0;             // iteration launches enqueued for the solve in flight
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr};
@@ -491,6 +564,8 @@ struct EccState {
             if (copied[i]) cudaEventDestroy(copied[i]);
         }
         if (result) cudaFreeHost(result);
+        if (dq) cudaFree(dq);
+        if (resultq) cudaFreeHost(resultq);
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 };
@@ -567,8 +642,11 @@ static int ecc_enqueue(EccState& s, float thresh, int use_mask, int max_iteratio
         int stride = cur_src ? cur_stride : s.w;
         int w = s.w, h = s.h;
         float th_arg = th, tx0 = shift[0], ty0 = shift[1];
+        int nrun = 1, have_thresh = 0;
+        size_t frame_stride = 0;
+        double no_thresh = 0.0;
         void* args[] = {&ref, &cur, &src, &stride, &mask, &w, &h, &th_arg, &s.T, &s.I, &s.gx, &s.gy, &s.d, &s.partials, &tx0, &ty0,
-                        &max_iterations, &eps};
+                        &max_iterations, &eps, &nrun, &frame_stride, &no_thresh, &have_thresh};
         RIRB_CUDA_OK(cudaLaunchCooperativeKernel((const void*)ecc_solve_kernel, dim3((unsigned)s.coop_grid), dim3(ECC_THREADS), args, 0, st));
         g_launches.fetch_add(1);
         s.launched = max_iterations;
@@ -637,6 +715,117 @@ static int ecc_prefetch(EccState& s, const void* src, size_t bytes, int slot)
     return 0;
 }
 
+// ---- a run of frames that are already in device memory, solved without the host in between ----------------------
+// rirb_ecc_track's loop costs a launch, a copy back and a synchronisation per frame, about as long as the solve itself.
+// Nothing in frame t + 1's solve needs the host: its warm start is frame t's shift and the one thing the host decides
+// between two frames -- replace the reference image when the correlation falls under the confidence threshold
+// (masked_registration_ecc.py:176-186), or deal with a failed frame -- only ever ENDS a run.  So up to ECC_BATCH frames are
+// filtered in one Gaussian launch and ONE cooperative launch walks them (ecc_solve_kernel, nrun > 1), leaving behind the
+// frame that ends the run.  The host then walks the results in order and applies the class's rules as before; the frames
+// that were filtered but not reached stay in s.filtered for the next run.  Same arithmetic, same results as frame by frame.
+// (Queuing one cooperative launch per frame instead was measured first: 5,000 frames/s against 14,400 frame by frame --
+// a cooperative launch behind a running kernel is expensive.)
+constexpr int ECC_BATCH = 16;
+
+// frames [0, K) at src0 (device); *done = frames fully handled (>= 0; 0: frame 0 failed, the caller redoes it the slow way)
+static int ecc_track_run(EccState& s, int handle, int type, const char* src0, int K, size_t fpx, size_t esz, int full_w, int full_h,
+                         int x0, int y0, int use_mask, const GaussTaps& taps, double* x, double* y, double* conf, int* iters, int* done)
+{
+    cudaStream_t st = current_stream();
+    *done = 0;
+    if (!s.dq) {
+        RIRB_CUDA_OK(cudaMalloc((void**)&s.dq, sizeof(EccDev) * ECC_BATCH));
+        RIRB_CUDA_OK(cudaMallocHost((void**)&s.resultq, sizeof(EccDev) * ECC_BATCH));
+        for (int k = 0; k < ECC_BATCH; ++k) RIRB_LAUNCH(ecc_begin_kernel, 1, 1, 0, st, s.dq + k, 0.f, 0.f, 500, 1e-3);  // clean min / max words
+    }
+    if (s.filtered_cap < fpx * 4 * (size_t)K) {
+        if (s.filtered) cudaFree(s.filtered);
+        s.filtered = nullptr;
+        s.filtered_cap = 0;
+        RIRB_CUDA_OK(cudaMalloc((void**)&s.filtered, fpx * 4 * (size_t)ECC_BATCH));
+        s.filtered_cap = fpx * 4 * (size_t)ECC_BATCH;
+        s.filt_src = nullptr;
+    }
+    const float* full = s.filtered;
+    const size_t fbytes = fpx * esz;
+    if (s.filt_src && src0 >= s.filt_src && src0 < s.filt_src + (size_t)s.filt_n * fbytes && (size_t)(src0 - s.filt_src) % fbytes == 0) {
+        const int j = (int)((size_t)(src0 - s.filt_src) / fbytes);  // already filtered by the run that stopped before this frame
+        full = s.filtered + (size_t)j * fpx;
+        K = std::min(K, s.filt_n - j);
+    } else {
+        s.filt_src = nullptr;
+        if (s.sigma > 0.f) {
+            if ((type == 'H' ? launch_gaussian_u16((const u16*)src0, s.filtered, full_w, full_h, K, taps, st)
+                             : launch_gaussian_f32((const float*)src0, s.filtered, full_w, full_h, K, taps, st)) != 0)
+                return -1;
+        } else if (type == 'H') {
+            RIRB_LAUNCH(ecc_u16_to_f32_kernel, (unsigned)ceil_div((long long)(fpx * K), 256), 256, 0, st, (const u16*)src0, s.filtered, (int)(fpx * K));
+        }
+        if (s.sigma > 0.f || type == 'H') {
+            s.filt_src = src0;
+            s.filt_n = K;
+        }
+    }
+    if (!(s.sigma > 0.f) && type != 'H') full = (const float*)src0;
+    const int Kq = K;  // frames behind the one that ends the run cost nothing: the kernel leaves
+    const u8* mask = (use_mask && s.have_mask) ? s.mask : nullptr;
+    const bool may_reset = !s.fixed_ref;
+    {
+        const float* ref = s.ref;
+        float* cur = s.cur;
+        const float* src = full + (size_t)y0 * full_w + x0;
+        int stride = full_w, w = s.w, h = s.h, max_it = 500, have_thresh = (may_reset && s.have_thresh) ? 1 : 0, nrun = Kq;
+        float th = INFINITY, tx0 = s.start[0], ty0 = s.start[1];
+        double eps = 1e-3, conf_thresh = s.conf_thresh;
+        size_t frame_stride = fpx;
+        EccDev* d = s.dq;
+        void* args[] = {&ref, &cur, &src, &stride, &mask, &w, &h, &th, &s.T, &s.I, &s.gx, &s.gy, &d, &s.partials, &tx0, &ty0,
+                        &max_it, &eps, &nrun, &frame_stride, &conf_thresh, &have_thresh};
+        RIRB_CUDA_OK(cudaLaunchCooperativeKernel((const void*)ecc_solve_kernel, dim3((unsigned)s.coop_grid), dim3(ECC_THREADS), args, 0, st));
+        g_launches.fetch_add(1);
+    }
+    RIRB_CUDA_OK(cudaMemcpyAsync(s.resultq, s.dq, sizeof(EccDev) * (size_t)Kq, cudaMemcpyDeviceToHost, st));
+    RIRB_CUDA_OK(cudaStreamSynchronize(st));
+    s.have_cur = true;
+    bool ended = false;
+    for (int k = 0; k < Kq; ++k) {
+        const EccDev& r = s.resultq[k];
+        if (r.skipped || r.status != 0) {  // a failed frame is redone by the caller's frame-by-frame path (retries, error codes)
+            ended = true;
+            break;
+        }
+        s.start[0] = r.tx;
+        s.start[1] = r.ty;
+        x[k] = s.last_x = (double)r.tx;
+        y[k] = s.last_y = (double)r.ty;
+        conf[k] = s.last_conf = r.rho;
+        if (iters) iters[k] = r.it;
+        s.confs.push_back(r.rho);
+        *done = k + 1;
+        if (s.confs.size() > 20 && may_reset) {  // :176-186, as in rirb_ecc_track
+            if (!s.have_thresh) {
+                double mn = s.confs[0], mean = 0.0, var = 0.0;
+                for (double c : s.confs) {
+                    mn = c < mn ? c : mn;
+                    mean += c;
+                }
+                mean /= (double)s.confs.size();
+                for (double c : s.confs) var += (c - mean) * (c - mean);
+                s.conf_thresh = mn - 2.0 * sqrt(var / (double)s.confs.size());
+                s.have_thresh = true;
+            }
+            if (r.rho < s.conf_thresh) {  // s.cur holds this frame's window: the solves queued after it did not run
+                if (rirb_ecc_reset_reference(handle, -r.tx, -r.ty) != 0) return -1;
+                s.start[0] = s.start[1] = 0.f;
+                ended = true;
+                break;
+            }
+        }
+    }
+    (void)ended;
+    return 0;
+}
+
 }  // namespace rirb
 
 using namespace rirb;
@@ -662,7 +851,7 @@ int rirb_ecc_open(int width, int height)
          cudaMalloc((void**)&s->hist, 65536 * sizeof(unsigned long long)) == cudaSuccess &&
          cudaMalloc((void**)&s->mm, 2 * sizeof(unsigned)) == cudaSuccess && cudaMalloc((void**)&s->qout, sizeof(int)) == cudaSuccess &&
          cudaMalloc((void**)&s->d, sizeof(EccDev)) == cudaSuccess;
-    s->max_grid = sm_count() * 2;
+    s->max_grid = std::min(sm_count() * 2, ECC_MAX_SLOTS);
     ok = ok && cudaMalloc((void**)&s->partials, (size_t)2 * s->max_grid * NACC * sizeof(double)) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
@@ -866,8 +1055,27 @@ int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, 
     }
     GaussTaps taps;
     if (s->sigma > 0.f && gaussian_taps_host(s->sigma, &taps) != 0) return -1;
+    s->filt_src = nullptr;   // the caller's frames may have changed since the last call
+    s->filt_n = 0;
+    bool slow_once = false;  // the frame a queued run stopped at with a failure goes through the frame-by-frame path
     for (long long t = 0; t < nframes; ++t) {
         const char* src = (const char*)frames + (size_t)t * fpx * esz;
+        if (on_device && s->started && !slow_once && s->median >= 1.0 && s->coop_grid > 0 && option_enabled(OPT_ECC_FUSED) &&
+            option_enabled(OPT_ECC_QUEUE)) {
+            long long K = std::min<long long>(ECC_BATCH, nframes - t);
+            // the confidence threshold is fixed by the host when the 21st confidence arrives, and applies to that frame
+            if (!s->fixed_ref && !s->have_thresh) K = std::min<long long>(K, std::max<long long>(1, 21 - (long long)s->confs.size()));
+            int did = 0;
+            if (ecc_track_run(*s, handle, type, src, (int)K, fpx, esz, full_w, full_h, x0, y0, use_mask, taps, x + t, y + t, conf + t,
+                              iters ? iters + t : nullptr, &did) != 0)
+                return -1;
+            if (processed) *processed = t + did;
+            if (did == 0) slow_once = true;
+            t += did - 1;  // did == 0: the same frame again, frame by frame
+            continue;
+        }
+        slow_once = false;
+        s->filt_src = nullptr;  // this path filters into the first slot
         bool next_fetched = on_device || t + 1 >= nframes;
         auto fetch_next = [&]() -> int {  // called once per frame, as soon as the GPU has work queued
             if (next_fetched) return 0;

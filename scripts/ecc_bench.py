@@ -92,6 +92,28 @@ def main():
             extra["max_abs_diff_vs_reference_px_before_first_reset"] = float(np.max(dd[:, :first_reset + 1]))
         rec(name, el, extra)
 
+    # the other regime: a camera that only vibrates around its position (no drift), where the confidence stays above the
+    # threshold and the reference image is never replaced -- the queued runs then go their full 16 frames
+    tt = np.arange(40, dtype=np.float64)
+    vib = np.stack([ec.frame(int(t), 1.5 * np.sin(t / 3.0), 1.1 * np.cos(t / 4.0) - 1.1) for t in tt])
+    vmov = np.concatenate([vib, vib[::-1]] * ((n + 79) // 80))[:n]
+    dv = torch.from_numpy(vmov.view(np.int16)).cuda().view(torch.uint16)
+    for rep in range(2):
+        reg = rg.MaskedRegistratorECC()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reg.compute_movie(dv, max_try=5)
+        el = time.perf_counter() - t0
+    thr = reg.conf_thresh if reg.conf_thresh is not None else -1
+    rec("product, one call for the movie, frames in HBM, vibration-only movie", el,
+        {"mean_iterations": round(float(np.mean([i for i in reg.iterations if i > 0])), 2),
+         "reference_replacements": int(np.sum(np.array(reg.confidences[21:]) < thr))})
+    # replacements in the drifting movie above, for comparison
+    reg = rg.MaskedRegistratorECC()
+    reg.compute_movie(d, max_try=5)
+    thr = reg.conf_thresh if reg.conf_thresh is not None else -1
+    print(json.dumps({"note": "drifting movie", "reference_replacements": int(np.sum(np.array(reg.confidences[21:]) < thr)), "frames": n}), flush=True)
+
 
 if __name__ == "__main__":
     main()

@@ -222,6 +222,29 @@ def test_product_class_reset_rule_failures_and_device_input():
     _close(a, g, CHAIN_END_TOL, CHAIN_RHO_TOL)
     assert abs(reg.conf_thresh - float(GOLD["seq_reset_thresh"])) < 1e-6
     assert np.array_equal(a[2] < reg.conf_thresh, g[2] < float(GOLD["seq_reset_thresh"]))
+    # the whole movie in one call: solves queued back to back on the device ("ecc_queue", the default) give the same numbers
+    # as frame-by-frame calls and as the one-launch-per-frame loop, across the replacements of the reference image
+    from librir_b200 import _lib
+
+    runs = {}
+    for q in (1, 0):
+        _lib.set_parameter("ecc_queue", q)
+        whole = rg.MaskedRegistratorECC()
+        assert whole.compute_movie(d, max_try=0) == len(mov2)
+        runs[q] = np.array([whole.x, whole.y, whole.confidences], dtype=np.float64)
+        assert whole.iterations == reg.iterations and whole.conf_thresh == reg.conf_thresh
+    _lib.set_parameter("ecc_queue", 1)
+    assert np.array_equal(runs[1], a) and np.array_equal(runs[0], a)
+    # ... and a failing frame inside a queued run ends it, goes through the retries, and the run resumes behind it
+    bad = ec.failing_frames()[0]
+    mixed = np.concatenate([mov2[:9], bad[None], mov2[9:14]])
+    one = rg.MaskedRegistratorECC()
+    one.compute_movie(torch.from_numpy(mixed.view(np.int16)).cuda().view(torch.uint16), max_try=5)
+    two = rg.MaskedRegistratorECC()
+    two.start(mixed[0])
+    for t in range(1, len(mixed)):
+        rg.manage_computation_and_tries(mixed[t], two)
+    assert np.array_equal(np.array([one.x, one.y, one.confidences]), np.array([two.x, two.y, two.confidences])) and one.median == two.median
     for k, img in enumerate(ec.failing_frames()):
         reg = rg.MaskedRegistratorECC()
         reg.start(mov2[0])
