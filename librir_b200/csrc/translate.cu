@@ -918,7 +918,7 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar[TT_STAGES];
-    __shared__ __align__(8) RowAB rowab[TT_STAGES][TT_H];
+    __shared__ __align__(8) RowAB rowab[3][TT_H];  // row tables of three consecutive tiles (tile % 3): see make_table
     __shared__ unsigned done[TT_STAGES];  // warps that are through with the stage's current tile
     __shared__ EdgeTable edge_tab[2];     // [0]: the image's first group of a row, [1]: its last
     const int f = order ? order[blockIdx.y] : (int)blockIdx.y;  // frames grouped by column offset (translate_order_kernel)
@@ -943,17 +943,22 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
         const float u = px - (float)l;
         return (l == xp + sx) ? u : ((l == xp + sx + 1 && u == 0.f) ? 1.0f : -1.0f);
     };
-    // rows of tile `tile_row` into stage s, by one whole warp: the row table first, then lane 0 publishes it and asks for the box
-    auto prepare_stage = [&](int s, int tile_row) {
+    // The row table of a tile is made one tile EARLIER than its box is asked for, so that what stands between the last warp's
+    // sign-off and the next box is a fence and the TMA instruction, not ~130 instructions of float arithmetic: the tables
+    // of tiles 0, 1, 2 at the start, the table of tile t + 3 by the warp that signs tile t off last (slot t % 3 is free then).
+    auto make_table = [&](int tile_row) {  // by one whole warp
         const int y0 = tile_row * TT_H;
+        RowAB* tab = rowab[tile_row % 3];
 #pragma unroll
-        for (int k = 0; k < TT_H / 32; ++k) rowab[s][lane + 32 * k] = make_row_ab(y0 + lane + 32 * k, h, dy, y0 + lane + 32 * k + sy);
+        for (int k = 0; k < TT_H / 32; ++k) tab[lane + 32 * k] = make_row_ab(y0 + lane + 32 * k, h, dy, y0 + lane + 32 * k + sy);
         __syncwarp();
+    };
+    auto issue_box = [&](int s, int tile_row) {  // lane 0 of the calling warp; publishes the warp's earlier shared-memory writes too
         if (lane == 0) {
             done[s] = 0;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&bar[s], TT_BH * TT_BW * 2);
-            tma_load_box(smem_raw + s * TT_STAGE_BYTES, &tmap, &bar[s], xs, y0 + sy, f);
+            tma_load_box(smem_raw + s * TT_STAGE_BYTES, &tmap, &bar[s], xs, tile_row * TT_H + sy, f);
         }
     };
     if (threadIdx.x == 0) {
@@ -982,8 +987,9 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
             edge_tab[e].below = (lb >> (8 * e)) & 0xFFu;
         }
     }
-    __syncthreads();  // barriers initialised, edge tables written: the only CTA-wide barrier of the kernel
-    if (warp < TT_STAGES && warp < tiles_y) prepare_stage(warp, warp);
+    if (warp < 3 && warp < tiles_y) make_table(warp);
+    __syncthreads();  // barriers initialised, edge tables and the first three row tables written: the only CTA-wide barrier
+    if (warp < TT_STAGES && warp < tiles_y) issue_box(warp, warp);
 
     // ---- per-thread column constants (while the first boxes are in flight) -----------------------
     const int cx = lane & 15, half = lane >> 4;
@@ -1009,13 +1015,14 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
 #pragma unroll 1
     for (int ty = 0; ty < tiles_y; ++ty) {
         const int stage = ty % TT_STAGES;
+        const int tslot = ty % 3;
         const unsigned parity = (unsigned)(ty / TT_STAGES) & 1u;
         const int y0t = ty * TT_H, ys = y0t + sy;
         mbar_wait(&bar[stage], parity);
         const u16* tile = reinterpret_cast<const u16*>(smem_raw + stage * TT_STAGE_BYTES);
         if (xfast) {
             const uint32_t srow = smem_addr(tile + r0 * TT_BW + 8 * cx + (xoff & 8));
-            const uint32_t rab = smem_addr(&rowab[stage][r0]);
+            const uint32_t rab = smem_addr(&rowab[tslot][r0]);
             u16* orow = oframe + (size_t)(y0t + r0) * w + x0;
             switch (xoff & 7) {  // CTA-uniform
             case 0: fast_column<0, MOTION>(srow, rab, clamp_rt, ca, cb, orow, (size_t)w); break;
@@ -1031,7 +1038,7 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
         __syncwarp();
         // ---- the rest of the warp's 16 rows, one pixel per lane ----
         const int wr0 = 2 * TW_ROWS * warp;  // the warp's first row inside the tile
-        const unsigned slowrows = __ballot_sync(0xFFFFFFFFu, lane < 16 && rowab[stage][wr0 + (lane & 15)].B == ROW_SLOW) & 0xFFFFu;
+        const unsigned slowrows = __ballot_sync(0xFFFFFFFFu, lane < 16 && rowab[tslot][wr0 + (lane & 15)].B == ROW_SLOW) & 0xFFFFu;
         const TileSrc ts{tile, frame, xs, ys, w, h};
         auto slow_pixel = [&](int col, int row) {  // col: pixel inside the tile column, row: inside the tile
             const int gx = x0t + col, gy = y0t + row;
@@ -1039,7 +1046,7 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
             u16* o = oframe + (size_t)gy * w + gx;
             const int gx0 = gx & ~7, gi = gx & 7;
             const int e = (gx0 == 0) ? 0 : ((gx0 == w - 8) ? 1 : -1);
-            const RowAB ra = rowab[stage][row];
+            const RowAB ra = rowab[tslot][row];
             if (e >= 0 && ra.B != ROW_SLOW && ((edge_tab[e].valid >> gi) & 1u)) {
                 const unsigned rows = (unsigned)(row * (TT_BW * 2)) | ((unsigned)((row + 1) * (TT_BW * 2)) << 16);
                 *o = blend_edge_pixel<MOTION>(tile, rows, ra.A, ra.B, col + xoff, (edge_tab[e].clamped >> gi) & 1u, edge_tab[e].wt[gi]);
@@ -1065,7 +1072,7 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
             const int row = wr0 + (lane & 15), j0 = 4 * (lane >> 4);
             const int gy = y0t + row;
             if (gy >= h) return;
-            const RowAB ra = rowab[stage][row];
+            const RowAB ra = rowab[tslot][row];
             if (ra.B == ROW_SLOW) return;
             const u16* top = tile + row * TT_BW + 8 * g + xoff + j0;  // left tap of pixel j0, top source row
             const u16* bot = top + TT_BW;
@@ -1129,7 +1136,10 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
             last = (old == TW_WARPS - 1);
         }
         last = __shfl_sync(0xFFFFFFFFu, last, 0);
-        if (last && ty + TT_STAGES < tiles_y) prepare_stage(stage, ty + TT_STAGES);
+        if (last) {
+            if (ty + TT_STAGES < tiles_y) issue_box(stage, ty + TT_STAGES);
+            if (ty + 3 < tiles_y) make_table(ty + 3);
+        }
     }
 }
 
