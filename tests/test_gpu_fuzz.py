@@ -260,8 +260,13 @@ def test_fuzz_ecc_solver(port):
             # No convergence (tiny windows, shifts of several pixels): the iteration wanders between neighbouring 1/32-pixel
             # steps of OpenCV's warp until the cap or until the 1e-3 stopping test happens to fire; hundreds of chained
             # updates amplify rounding, so two correct implementations end in different places (cv2 and the restatement do
-            # too).  Nothing numeric can be compared there: the call must just come back without a device error.
+            # too).  No number can be compared there, but the regime can: the call comes back without a device error, and a
+            # solve that reports success wandered as well (not a two-iteration "convergence" on garbage) and ended on
+            # finite values with a correlation that is one.
             assert st in (0, 1, 2), what
+            if st == 0:
+                assert its.value > 25, what + f" -> converged in {its.value} iterations where the restatement needs {want[3]}"
+                assert np.isfinite(shift).all() and np.isfinite(rho.value) and abs(rho.value) <= 1.0 + 1e-6, what + f" -> rho {rho.value}, shift {shift}"
             wandering += 1
             continue
         assert st == 0 and its.value == want[3], what + f" -> {st}, {its.value} iterations vs {want[3]}"
