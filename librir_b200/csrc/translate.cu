@@ -1193,7 +1193,7 @@ int launch_translate_u16(const u16* src, u16* dst, int w, int h, long long nfram
             const PlaneSrc none{};
             if (option_enabled(OPT_TRANSLATE_ROWS)) {  // "translate_rows" = 0: the first-generation tiled kernel (A/B)
                 int* order = nullptr;
-                if (motion && dx_p && n > 1) {  // per-frame shifts: hand the frames out grouped by their column offset
+                if ((motion || option_value(OPT_TRANSLATE_ROWS) >= 2) && dx_p && n > 1) {  // per-frame shifts: hand the frames out grouped by their column offset
                     order = (int*)scratch_buffer(8, sizeof(int) * 65536);
                     if (!order) return -1;
                     RIRB_LAUNCH(translate_order_kernel, 1, 1024, 0, st, dx_p, (int)n, w, order);
