@@ -812,7 +812,8 @@ translate_u16_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 constexpr int TW_WARPS = 4, TW_THREADS = 32 * TW_WARPS;
 constexpr int TW_ROWS = 8;  // consecutive destination rows per thread
 struct RowAB {       // vertical weights of a destination row on the 2^-23 grid: N = p_bottom * A + p_top * B
-    unsigned A, B;   // B == ROW_SLOW: not a regular row (border rows, rows whose source rows are not y+sy / y+sy+1, fine fractions)
+    unsigned A, B;   // B == ROW_SLOW: not a regular row (border rows, rows whose source rows are not y+sy / y+sy+1, fine fractions);
+                     // A then says which: 1 = py < 0 (above the image), 2 = py >= h (below it), 0 = anything else
 };
 constexpr unsigned ROW_SLOW = 0xFFFFFFFFu;
 
@@ -830,6 +831,8 @@ __device__ __forceinline__ RowAB make_row_ab(int y, int h, float dy, int t_expec
     if (clamped) b = t;
     const float vf = (float)b - py;
     const float vs = vf * 8388608.0f;
+    if (y < h && py < 0) r.A = 1;
+    if (y < h && !(py < fh)) r.A = 2;
     if (y < h && !(py < 0) && (py < fh) && t == t_expected + 1 && py == (float)t) {
         // -dy within half a float ulp below an integer: py has rounded UP to the integer t_expected + 1 and the reference
         // blends row t with weight 1 (or, clamped, with itself).  Seen from the regular taps (top t_expected, bottom
@@ -1122,6 +1125,29 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
         if (slowrows) {  // warp-uniform: the pixels of border rows that the passes above have not done
             for (unsigned m = slowrows; m; m &= m - 1) {
                 const int rr = __ffs(m) - 1;
+                const RowAB ra = rowab[tslot][wr0 + rr];
+                // rows above / below the image (up to |dy| of them per frame, in every CTA of the frame): the border strategy
+                // alone decides -- for "nearest" a copy of the image's first / last row at the clamped source column,
+                // translate_pixel's border branch without the routine around it (a quarter of its instructions)
+                const int brow = (ra.A == 1 ? 0 : h - 1) - ys;  // that row in the staged box
+                auto clamped_col = [&](int gx) {  // (long long)px clamped into the image, as a box column
+                    const float px = (float)gx - dx;
+                    return (px < 0 ? 0 : (px >= fw ? w - 1 : (int)px)) - xs;
+                };
+                // the source column is monotonic in gx: staged for the tile's first and last pixel = staged for all of them
+                const int bc_a = clamped_col(x0t), bc_b = clamped_col(min(x0t + TT_W, w) - 1);
+                if (ra.A != 0 && strategy != STRAT_WRAP && brow >= 0 && brow < TT_BH && bc_a >= 0 && bc_b < TT_BW) {
+                    const int gy = y0t + wr0 + rr;
+                    if (strategy == STRAT_NOBORDER) continue;
+#pragma unroll 1
+                    for (int c = lane; c < TT_W; c += 32) {
+                        const int gx = x0t + c;
+                        if (gx >= w || ((generic_cols >> (c >> 3)) & 1u)) continue;
+                        const unsigned v = strategy == STRAT_NEAREST ? (unsigned)tile[brow * TT_BW + clamped_col(gx)] : background;
+                        oframe[(size_t)gy * w + gx] = (u16)v;
+                    }
+                    continue;
+                }
 #pragma unroll 1
                 for (int c = lane; c < TT_W; c += 32)
                     if (!((generic_cols >> (c >> 3)) & 1u)) slow_pixel(c, wr0 + rr);
