@@ -544,6 +544,8 @@ struct EccState {
     EccDev* resultq = nullptr;    // ... and their pinned host copies
     const char* filt_src = nullptr;  // within one rirb_ecc_track call: s.filtered holds the filtered frames filt_src + i * frame bytes,
     int filt_n = 0;                  // i < filt_n (a run that stopped early does not filter its tail again)
+    size_t filt_frame = 0, filt_off = 0;  // floats per filtered frame in s.filtered, offset of the window's first pixel in it
+    int filt_stride = 0;                  // floats per row of it
     int launched = 0;             // iteration launches enqueued for the solve in flight
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr};
@@ -725,6 +727,38 @@ static int ecc_prefetch(EccState& s, const void* src, size_t bytes, int slot)
 // that were filtered but not reached stay in s.filtered for the next run.  Same arithmetic, same results as frame by frame.
 // (Queuing one cooperative launch per frame instead was measured first: 5,000 frames/s against 14,400 frame by frame --
 // a cooperative launch behind a running kernel is expensive.)
+// Gaussian of K frames (device memory) into s.filtered -- of what the window needs of them: the window grown by the kernel
+// radius, clipped to the frame, its left / right edge moved out to whole 16-byte vectors.  Filtering the region as an image of
+// its own is exact inside the window (a region border that is not a frame border only spoils the `radius` pixels next to it),
+// and a 448 x 358 window of a 640 x 512 frame is half the work.  Sets s.filt_frame / filt_off / filt_stride.
+static int ecc_filter_frames(EccState& s, int type, const char* src0, int K, size_t fpx, int full_w, int full_h, int x0, int y0,
+                             const GaussTaps& taps, cudaStream_t st)
+{
+    const int r = taps.radius, al = type == 'H' ? 8 : 4;
+    const int rx0 = std::max(0, x0 - r) / al * al, ry0 = std::max(0, y0 - r);
+    const int rx1 = std::min(full_w, (x0 + s.w + r + al - 1) / al * al), ry1 = std::min(full_h, y0 + s.h + r);
+    const int wr = rx1 - rx0, hr = ry1 - ry0;
+    if ((long long)wr * hr * 10 < (long long)full_w * full_h * 9) {  // worth it
+        const size_t off = (size_t)ry0 * full_w + rx0;
+        const int rc = type == 'H' ? launch_gaussian_u16_region((const u16*)src0 + off, (size_t)full_w, fpx, s.filtered, wr, hr, K, taps, st)
+                                   : launch_gaussian_f32_region((const float*)src0 + off, (size_t)full_w, fpx, s.filtered, wr, hr, K, taps, st);
+        if (rc < 0) return -1;
+        if (rc == 0) {
+            s.filt_frame = (size_t)wr * hr;
+            s.filt_stride = wr;
+            s.filt_off = (size_t)(y0 - ry0) * wr + (x0 - rx0);
+            return 0;
+        }
+    }
+    if ((type == 'H' ? launch_gaussian_u16((const u16*)src0, s.filtered, full_w, full_h, K, taps, st)
+                     : launch_gaussian_f32((const float*)src0, s.filtered, full_w, full_h, K, taps, st)) != 0)
+        return -1;
+    s.filt_frame = fpx;
+    s.filt_stride = full_w;
+    s.filt_off = (size_t)y0 * full_w + x0;
+    return 0;
+}
+
 constexpr int ECC_BATCH = 16;
 
 // frames [0, K) at src0 (device); *done = frames fully handled (>= 0; 0: frame 0 failed, the caller redoes it the slow way)
@@ -746,38 +780,51 @@ static int ecc_track_run(EccState& s, int handle, int type, const char* src0, in
         s.filtered_cap = fpx * 4 * (size_t)ECC_BATCH;
         s.filt_src = nullptr;
     }
-    const float* full = s.filtered;
     const size_t fbytes = fpx * esz;
+    const float* win0;   // the window of the run's first frame, rows win_stride floats and frames win_frame floats apart
+    int win_stride;
+    size_t win_frame;
     if (s.filt_src && src0 >= s.filt_src && src0 < s.filt_src + (size_t)s.filt_n * fbytes && (size_t)(src0 - s.filt_src) % fbytes == 0) {
         const int j = (int)((size_t)(src0 - s.filt_src) / fbytes);  // already filtered by the run that stopped before this frame
-        full = s.filtered + (size_t)j * fpx;
+        win0 = s.filtered + (size_t)j * s.filt_frame + s.filt_off;
+        win_stride = s.filt_stride;
+        win_frame = s.filt_frame;
         K = std::min(K, s.filt_n - j);
+    } else if (s.sigma > 0.f) {
+        s.filt_src = nullptr;
+        if (ecc_filter_frames(s, type, src0, K, fpx, full_w, full_h, x0, y0, taps, st) != 0) return -1;
+        s.filt_src = src0;
+        s.filt_n = K;
+        win0 = s.filtered + s.filt_off;
+        win_stride = s.filt_stride;
+        win_frame = s.filt_frame;
     } else {
         s.filt_src = nullptr;
-        if (s.sigma > 0.f) {
-            if ((type == 'H' ? launch_gaussian_u16((const u16*)src0, s.filtered, full_w, full_h, K, taps, st)
-                             : launch_gaussian_f32((const float*)src0, s.filtered, full_w, full_h, K, taps, st)) != 0)
-                return -1;
-        } else if (type == 'H') {
+        const float* full = (const float*)src0;
+        if (type == 'H') {
             RIRB_LAUNCH(ecc_u16_to_f32_kernel, (unsigned)ceil_div((long long)(fpx * K), 256), 256, 0, st, (const u16*)src0, s.filtered, (int)(fpx * K));
-        }
-        if (s.sigma > 0.f || type == 'H') {
+            full = s.filtered;
             s.filt_src = src0;
             s.filt_n = K;
+            s.filt_frame = fpx;
+            s.filt_stride = full_w;
+            s.filt_off = (size_t)y0 * full_w + x0;
         }
+        win0 = full + (size_t)y0 * full_w + x0;
+        win_stride = full_w;
+        win_frame = fpx;
     }
-    if (!(s.sigma > 0.f) && type != 'H') full = (const float*)src0;
     const int Kq = K;  // frames behind the one that ends the run cost nothing: the kernel leaves
     const u8* mask = (use_mask && s.have_mask) ? s.mask : nullptr;
     const bool may_reset = !s.fixed_ref;
     {
         const float* ref = s.ref;
         float* cur = s.cur;
-        const float* src = full + (size_t)y0 * full_w + x0;
-        int stride = full_w, w = s.w, h = s.h, max_it = 500, have_thresh = (may_reset && s.have_thresh) ? 1 : 0, nrun = Kq;
+        const float* src = win0;
+        int stride = win_stride, w = s.w, h = s.h, max_it = 500, have_thresh = (may_reset && s.have_thresh) ? 1 : 0, nrun = Kq;
         float th = INFINITY, tx0 = s.start[0], ty0 = s.start[1];
         double eps = 1e-3, conf_thresh = s.conf_thresh;
-        size_t frame_stride = fpx;
+        size_t frame_stride = win_frame;
         EccDev* d = s.dq;
         void* args[] = {&ref, &cur, &src, &stride, &mask, &w, &h, &th, &s.T, &s.I, &s.gx, &s.gy, &d, &s.partials, &tx0, &ty0,
                         &max_it, &eps, &nrun, &frame_stride, &conf_thresh, &have_thresh};
@@ -1086,19 +1133,20 @@ int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, 
             RIRB_CUDA_OK(cudaStreamWaitEvent(st, s->copied[t & 1], 0));
             src = (const char*)s->stage2[t & 1];
         }
-        const float* full = s->filtered;
+        const float* window;  // the frame's window, rows wstride floats apart
+        int wstride = full_w;
         if (s->sigma > 0.f) {
-            if ((type == 'H' ? launch_gaussian_u16((const u16*)src, s->filtered, full_w, full_h, 1, taps, st)
-                             : launch_gaussian_f32((const float*)src, s->filtered, full_w, full_h, 1, taps, st)) != 0)
-                return -1;
+            if (ecc_filter_frames(*s, type, src, 1, fpx, full_w, full_h, x0, y0, taps, st) != 0) return -1;
+            window = s->filtered + s->filt_off;
+            wstride = s->filt_stride;
         } else if (type == 'H') {
             RIRB_LAUNCH(ecc_u16_to_f32_kernel, (unsigned)ceil_div((long long)fpx, 256), 256, 0, st, (const u16*)src, s->filtered, (int)fpx);
+            window = s->filtered + (size_t)y0 * full_w + x0;
         } else {
-            full = (const float*)src;
+            window = (const float*)src + (size_t)y0 * full_w + x0;
         }
-        const float* window = full + (size_t)y0 * full_w + x0;
         if (!s->started) {  // start(): the first window is the reference (unless one was given), shifts 0, confidence 1
-            if (ecc_load_window(*s, s->fixed_ref ? s->cur : s->ref, window, full_w, st) != 0) return -1;
+            if (ecc_load_window(*s, s->fixed_ref ? s->cur : s->ref, window, wstride, st) != 0) return -1;
             (s->fixed_ref ? s->have_cur : s->have_ref) = true;
             s->started = true;
             s->confs.push_back(1.0);
@@ -1114,7 +1162,7 @@ int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, 
         // read the compact copy first, so they get an explicit one
         bool window_loaded = false;
         if (s->median < 1.0) {
-            if (ecc_load_window(*s, s->cur, window, full_w, st) != 0) return -1;
+            if (ecc_load_window(*s, s->cur, window, wstride, st) != 0) return -1;
             window_loaded = true;
         }
         s->have_cur = true;
@@ -1131,7 +1179,7 @@ int rirb_ecc_track(int handle, int type, const void* frames, long long nframes, 
             }
             shift[0] = s->start[0];
             shift[1] = s->start[1];
-            if (ecc_enqueue(*s, thresh, use_mask, 500, 1e-3, shift, window_loaded ? nullptr : window, full_w) != 0) return -1;
+            if (ecc_enqueue(*s, thresh, use_mask, 500, 1e-3, shift, window_loaded ? nullptr : window, wstride) != 0) return -1;
             window_loaded = true;  // a retry works on the compact copy
             if (fetch_next() != 0) return -1;  // host memcpy + upload of frame t + 1 while the GPU solves frame t
             status = ecc_collect(*s, use_mask, 500, shift, &rho, &its);

@@ -672,12 +672,21 @@ int launch_gaussian_bp_u16(const u16* raw, u16* corrected, float* dst, int w, in
 }
 
 template <typename TIN>
-static int launch_gaussian(const TIN* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st)
+static int launch_gaussian(const TIN* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st,
+                           size_t src_row = 0, size_t src_frame = 0)
 {
+    // src_row / src_frame (pixels; 0 = dense): the source is a w x h REGION of larger frames.  Only the TMA-tiled kernels
+    // take that (the strides are the tensor map's); anything else answers 1 and the caller filters whole frames.
     if (nframes <= 0 || w <= 0 || h <= 0) return 0;
+    const bool region = src_row != 0;
+    if (!region) {
+        src_row = (size_t)w;
+        src_frame = (size_t)w * h;
+    }
     const int r = taps.radius;
     const bool fast = (r <= 4) && (w % 4 == 0) && aligned16(dst) && aligned16(src);
     if (!fast) {
+        if (region) return 1;
         dim3 block(32, 8);
         dim3 grid((unsigned)ceil_div(w, 32), (unsigned)ceil_div(h, 8), (unsigned)min(nframes, 32768LL));
         RIRB_LAUNCH(gauss_generic_kernel<TIN>, grid, block, 0, st, src, dst, w, h, nframes, taps);
@@ -687,11 +696,11 @@ static int launch_gaussian(const TIN* src, float* dst, int w, int h, long long n
     const size_t esz = sizeof(TIN);
     const int tiles_x = (int)ceil_div(w, GT_W), tiles_y = (int)ceil_div(h, GT_H);
     const long long tgrid = nframes * tiles_x * tiles_y;
-    if (tma_enabled && tma_compatible(src, (size_t)w * esz, (size_t)w * h * esz) && nframes <= 0x7FFFFFFFLL && tgrid <= 0x7FFFFFFFLL) {
+    if (tma_enabled && tma_compatible(src, src_row * esz, src_frame * esz) && nframes <= 0x7FFFFFFFLL && tgrid <= 0x7FFFFFFFLL) {
         CUtensorMap tmap;
 #define RIRB_GT(RR)                                                                                                          \
     do {                                                                                                                     \
-        if (make_movie_tensor_map(&tmap, src, (int)esz, w, h, nframes, (size_t)w * esz, (size_t)w * h * esz, GtBox<TIN>::BW, \
+        if (make_movie_tensor_map(&tmap, src, (int)esz, w, h, nframes, src_row * esz, src_frame * esz, GtBox<TIN>::BW,       \
                                   GT_H + 2 * RR) != 0)                                                                       \
             return -1;                                                                                                       \
         RIRB_LAUNCH((gauss_tile_kernel<RR, TIN, false>), (unsigned)tgrid, GT_WARPS * 32, 0, st, tmap, dst, w, h, tiles_x, tiles_y, taps, BpFuse{}); \
@@ -704,7 +713,7 @@ static int launch_gaussian(const TIN* src, float* dst, int w, int h, long long n
     do {                                                                                                                     \
         const size_t smem = (size_t)(GW_H + 2 * RR) * GtBox<TIN>::BW * esz;                                                  \
         RIRB_SMEM_ATTR((gauss_tile_wide_kernel<RR, TIN>), smem);                                                             \
-        if (make_movie_tensor_map(&tmap, src, (int)esz, w, h, nframes, (size_t)w * esz, (size_t)w * h * esz, GtBox<TIN>::BW, \
+        if (make_movie_tensor_map(&tmap, src, (int)esz, w, h, nframes, src_row * esz, src_frame * esz, GtBox<TIN>::BW,       \
                                   GW_H + 2 * RR) != 0)                                                                       \
             return -1;                                                                                                       \
         RIRB_LAUNCH((gauss_tile_wide_kernel<RR, TIN>), (unsigned)wgrid, GT_WARPS * 32, smem, st, tmap, dst, w, h, tiles_x, wtiles_y, taps); \
@@ -724,6 +733,7 @@ static int launch_gaussian(const TIN* src, float* dst, int w, int h, long long n
 #undef RIRB_GT
         return 0;
     }
+    if (region) return 1;
     const int xstrips = (int)ceil_div(w, GS_STRIP);
     // full-height strips when there are enough frames; otherwise cut rows to fill the GPU
     const long long target = (long long)sm_count() * 16;
@@ -760,6 +770,19 @@ int launch_gaussian_f32(const float* src, float* dst, int w, int h, long long nf
 int launch_gaussian_u16(const u16* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st)
 {
     return launch_gaussian<u16>(src, dst, w, h, nframes, taps, st);
+}
+// A w x h region (top-left pixel at src) of frames whose rows are src_row pixels and whose frames are src_frame pixels apart,
+// filtered as an image of its own into dense dst[n][h][w]: a border of the region that is not a border of the frame gets the
+// image-border renormalisation, so the caller leaves `radius` pixels of margin there.  1: this layout is not taken.
+int launch_gaussian_u16_region(const u16* src, size_t src_row, size_t src_frame, float* dst, int w, int h, long long nframes,
+                               const GaussTaps& taps, cudaStream_t st)
+{
+    return launch_gaussian<u16>(src, dst, w, h, nframes, taps, st, src_row, src_frame);
+}
+int launch_gaussian_f32_region(const float* src, size_t src_row, size_t src_frame, float* dst, int w, int h, long long nframes,
+                               const GaussTaps& taps, cudaStream_t st)
+{
+    return launch_gaussian<float>(src, dst, w, h, nframes, taps, st, src_row, src_frame);
 }
 
 }  // namespace rirb

@@ -54,6 +54,11 @@ struct GaussTaps {
 int gaussian_taps_host(float sigma, GaussTaps* taps);
 int launch_gaussian_f32(const float* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st);
 int launch_gaussian_u16(const u16* src, float* dst, int w, int h, long long nframes, const GaussTaps& taps, cudaStream_t st);
+// a w x h region of larger frames (strides in pixels) -> dense dst; 1 when the layout is not taken (see gaussian.cu)
+int launch_gaussian_u16_region(const u16* src, size_t src_row, size_t src_frame, float* dst, int w, int h, long long nframes,
+                               const GaussTaps& taps, cudaStream_t st);
+int launch_gaussian_f32_region(const float* src, size_t src_row, size_t src_frame, float* dst, int w, int h, long long nframes,
+                               const GaussTaps& taps, cudaStream_t st);
 // correction + filter in one pass (gaussian.cu, BpFuse); 1: layout not eligible, run the two kernels
 int launch_gaussian_bp_u16(const u16* raw, u16* corrected, float* dst, int w, int h, long long nframes, const GaussTaps& taps,
                            const int* xy_dev, const int* row_off_dev, int clamp_value, cudaStream_t st);
