@@ -174,7 +174,7 @@ def test_live_lossy_against_the_compiled_saver(tmp_path, seed):
         if door != "add_loss":
             d = rv.read_stub_file(tmp_path / "l.bin")
             ref = np.stack([r["planes"][1].astype(np.uint16) | (r["planes"][2].astype(np.uint16) << 8) for r in d["records"]])
-        outs, errs = gpu_lossy(mov, stop, cfg, door, [90, 60], device=bool(seed & 1))
+        outs, errs = gpu_lossy(mov, stop, cfg, door, [90, 1, 79, 60], device=bool(seed & 1))
         assert np.array_equal(errs[:, 0], lo_e) and np.array_equal(errs[:, 1], hi_e), (door, cfg)
         assert np.array_equal(outs, ref), (door, cfg)
 
