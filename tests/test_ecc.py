@@ -204,6 +204,29 @@ def test_product_class_matches_port_and_reference_golden(ecc_driver):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fh,fv,sigma,crop", [(0.7, 0.7, 0.5, None), (0.97, 0.99, 1.0, None), (1.0, 1.0, 0.5, None), (0.55, 0.8, 2.0, None),
+                                              (0.7, 0.7, 0.5, (510, 636))])
+def test_windows_and_the_region_the_gaussian_filters(fh, fv, sigma, crop):
+    """The Gaussian in front of the solver filters only the region the window needs (window + kernel radius, clipped to the
+    frame): windows that touch the frame's borders, wide kernels, and a frame width that is not a multiple of the vector
+    width (the layout falls back to whole frames) must all track like the restated class."""
+    from librir_b200 import registration as rg
+    import torch
+
+    mov, _, _ = ec.movie(12)
+    if crop:
+        mov = np.ascontiguousarray(mov[:, :crop[0], :crop[1]])
+    shape = mov.shape[1:]
+    a = _run(oe.MaskedRegistratorECC(O.Port(), window_factorh=fh, window_factorv=fv, sigma=sigma, shape=shape), mov)
+    reg = rg.MaskedRegistratorECC(window_factorh=fh, window_factorv=fv, sigma=sigma, shape=shape)
+    b = _run(reg, mov)
+    _close(b, a, 5e-5, 5e-7)
+    whole = rg.MaskedRegistratorECC(window_factorh=fh, window_factorv=fv, sigma=sigma, shape=shape)
+    whole.compute_movie(torch.from_numpy(mov.view(np.int16)).cuda().view(torch.uint16), max_try=0)
+    assert np.array_equal(np.array([whole.x, whole.y, whole.confidences], dtype=np.float64), b)
+
+
+@pytest.mark.gpu
 def test_product_class_reset_rule_failures_and_device_input():
     import torch
 
