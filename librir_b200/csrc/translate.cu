@@ -875,8 +875,10 @@ __device__ __forceinline__ void blend_rows(const unsigned (&pb)[9], const unsign
         // integer / fp64 side (floor(val + half a float ulp of val's binade)) was built and measured: +4.8 instructions per
         // pixel instead of +2 and 2 % slower; with one half-ulp per 8-pixel group, faster on smooth images but 20 % slower
         // on noise (profiles/r2_translate_notes.md).  The kernel's time follows its instruction count, not the conversion pipe.
+        // MOTION: (u16)(float)val with the float -> integer truncation as FADD.RZ with 2^23 (the low 16 bits of the sum's
+        // mantissa are trunc(f); the byte permutes below take exactly those): one conversion on the 16-lane pipe instead of two
         if (MOTION)
-            o[j] = (unsigned)(u16)(float)val;
+            o[j] = __float_as_uint(__fadd_rz((float)val, 8388608.0f));
         else
             o[j] = (unsigned)__double2loint(__dadd_rd(val, 4503599627370496.0));
     }
