@@ -1093,7 +1093,7 @@ translate_u16_rows_kernel(const __grid_constant__ CUtensorMap tmap, const u16* _
                     const unsigned long long nr = (et.clamped & bit) ? nn[q] : nn[q + 1];
                     const double val = __dadd_rn(__fma_rn(__longlong_as_double((long long)nn[q]), c.omu, c.k_l),
                                                  __fma_rn(__longlong_as_double((long long)nr), c.u, c.k_r));
-                    o[q] = MOTION ? (u16)(float)val : (u16)__double2loint(__dadd_rd(val, 4503599627370496.0));
+                    o[q] = MOTION ? (u16)__float_as_uint(__fadd_rz((float)val, 8388608.0f)) : (u16)__double2loint(__dadd_rd(val, 4503599627370496.0));
                 } else {  // outside the image (the caller has checked that the table knows every pixel of the group)
                     // translate_pixel's border branch: src((long long)py, column 0 or w - 1).  (long long)py is the row of the
                     // top tap -- or, when py has rounded up to an integer (make_row_ab's B == 0 case), the one below it
