@@ -306,19 +306,6 @@ lossy_sums_kernel(const u16* __restrict__ prevT, const u16* __restrict__ tmpT, c
 // Per-pixel update (:2392-2421) with RunningAverage2::addImage / pixel / resetPixel folded in.
 // len_before: frames in the ring before this one; slot_new: ring slot this frame is written to;
 // slot_old: slot of the oldest frame (read only when the ring is full).
-// sums / len without the hardware's ~20-instruction division (two of them on the conversion pipe): multiply by
-// floor(2^32 / len) + 1 -- the quotient or one more -- and step back when it is one more
-struct LenDiv {
-    unsigned len, magic;
-    __device__ __forceinline__ explicit LenDiv(unsigned l) : len(l), magic(l ? (unsigned)(0x100000000ull / l) + 1u : 0u) {}
-    __device__ __forceinline__ unsigned operator()(unsigned v) const
-    {
-        unsigned q = len == 1 ? v : __umulhi(v, magic);
-        if (q * len > v) --q;
-        return q;
-    }
-};
-
 __global__ void lossy_update_kernel(const u16* __restrict__ tmp, const u16* __restrict__ tmpT, u16* __restrict__ out,
                                     u16* __restrict__ lastDL, u16* __restrict__ refT, u16* __restrict__ prevT, unsigned* __restrict__ sums,
                                     u16* __restrict__ cvalue, short* __restrict__ ccount, u16* __restrict__ ring, int n, int ns, int ra,
@@ -327,7 +314,6 @@ __global__ void lossy_update_kernel(const u16* __restrict__ tmp, const u16* __re
     const unsigned back = sc->background;
     const int low = sc->low_error, high = sc->high_error;
     const unsigned len_after = (unsigned)(len_before < ra ? len_before + 1 : ra);
-    const LenDiv div_len(len_after);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned v = tmp[i];
         if (i >= ns) {  // metadata rows: copied (:2419)
@@ -356,7 +342,7 @@ __global__ void lossy_update_kernel(const u16* __restrict__ tmp, const u16* __re
         const int max_error = v > back ? high : low;
         unsigned o;
         if (diff <= max_error && (variant == 1 || ((unsigned)lastDL[i] >> 13) == (v >> 13))) {
-            o = ra > 0 ? (div_len(s) & 0xFFFFu) : r;
+            o = ra > 0 ? ((s / len_after) & 0xFFFFu) : r;
         } else {
             o = t;
             refT[i] = (u16)t;
@@ -686,7 +672,6 @@ __global__ void __launch_bounds__(1024) lossy_run_kernel(const __grid_constant__
         const u16* img1 = p.img + (size_t)(f + 1) * n;
         const unsigned back1 = more ? __ldcg(&sc->back_run[f + 1]) : 0u;
         const unsigned len_after = (unsigned)(len_before < ra ? len_before + 1 : ra);
-        const LenDiv div_len(len_after);
         // Three pixels of the thread at a time, ALL their loads first: the state arrays may alias each other as far as the
         // compiler knows, so a plain grid-stride loop waits for one pixel's stores before it issues the next pixel's loads --
         // three serial trips to L2 per frame at 640 x 512 (2.2 pixels per thread).
@@ -749,7 +734,7 @@ __global__ void __launch_bounds__(1024) lossy_run_kernel(const __grid_constant__
                 const int max_error = v[q] > back ? high : low;
                 unsigned o;
                 if (diff <= max_error && (p.variant == 1 || (ld[q] >> 13) == (v[q] >> 13))) {
-                    o = ra > 0 ? (div_len(sacc) & 0xFFFFu) : r;
+                    o = ra > 0 ? ((sacc / len_after) & 0xFFFFu) : r;
                 } else {
                     o = tv;
                     p.refT[i] = (u16)tv;
