@@ -87,7 +87,7 @@ __global__ void ecc_begin_kernel(EccDev* d, float tx, float ty, int max_it, doub
     d->stop = d->skipped = 0;
 }
 
-constexpr int ECC_THREADS = 256;
+constexpr int ECC_THREADS = 256;  // 512 and 1024 were measured: no consistent gain (profiles/r2_ecc_bench.jsonl), 1024 spills
 
 __global__ void __launch_bounds__(ECC_THREADS) ecc_minmax_kernel(const float* __restrict__ ref, const float* __restrict__ cur, int n,
                                                                   float thresh, EccDev* d)
