@@ -1013,7 +1013,7 @@ int rirb_loader_finish_frames(int handle, unsigned short* frames, long long nfra
         if (launch_loader_bp(d, s->xy_dev, s->mask_dev, (int)(s->xy.size() / 2), w, hb, nframes, fpx, st) != 0) return -1;
     if (shift_x) {
         // the motion step is out of place: through a scratch copy, on device pointers (no further staging)
-        u16* tmp = (u16*)scratch(3, fpx * 2 * (size_t)nframes);
+        u16* tmp = (u16*)scratch(4, fpx * 2 * (size_t)nframes);  // not 0-3: rirb_loader_remove_motion stages its shifts there
         if (!tmp) return -1;
         RIRB_CUDA_OK(cudaMemcpyAsync(tmp, d, fpx * 2 * (size_t)nframes, cudaMemcpyDeviceToDevice, st));
         if (rirb_loader_remove_motion(tmp, d, w, hb, nframes, fpx, shift_x, shift_y) != 0) return -1;

@@ -221,6 +221,27 @@ def remove_motion(frames, shifts_x, shifts_y, meta_rows=3, out=None):
     return out
 
 
+def finish_frames(frames, bad_pixels=None, min_T=0, min_T_height=0, shifts_x=None, shifts_y=None, meta_rows=3):
+    """The same chain as :func:`read_movie` for frames that are uint16 already (decoded from the zstd movie file):
+    ``+= min_T`` -> ``removeBadPixels`` -> ``removeMotion``, IN PLACE on ``frames`` ``[n, h, w]`` (numpy or torch CUDA).
+    What ``load_image`` of ``libvideo_io_b200.so`` runs after the decode."""
+    lib = _lib.load()
+    _prepare_device_call(frames)
+    single = len(frames.shape) == 2
+    n = 1 if single else frames.shape[0]
+    h, w = frames.shape[-2:]
+    sx = sy = None
+    if shifts_x is not None or shifts_y is not None:
+        sx = np.ascontiguousarray(np.atleast_1d(shifts_x), dtype=np.float64)
+        sy = np.ascontiguousarray(np.atleast_1d(shifts_y), dtype=np.float64)
+        if sx.size != n or sy.size != n:
+            raise RuntimeError("finish_frames: one shift per frame expected")
+    r = lib.rirb_loader_finish_frames(bad_pixels.handle if bad_pixels is not None else 0, _ptr(frames), n, w, h, int(min_T), int(min_T_height),
+                                      _ptr(sx) if sx is not None else None, _ptr(sy) if sy is not None else None, int(meta_rows))
+    _lib.check(r, "loader_finish_frames")
+    return frames
+
+
 def read_movie(lo, hi, bad_pixels=None, min_T=0, min_T_height=0, shifts_x=None, shifts_y=None, meta_rows=3, out=None):
     """``IRFileLoader::readImage``'s post-decode chain (IRFileLoader.cpp:1168-1247, calibration 0) on a
     run of decoded frames: byte planes ``lo``/``hi`` ``[n, h, w]`` (what ``VideoGrabber::toArray`` merges,
@@ -329,7 +350,7 @@ def save_translation_file(filename, x, y, confidence=None):
 
 __all__ = [
     "DEFAULT_GOP", "linesize", "key_frames", "split_yuv444", "merge_yuv444", "split_yuv420", "merge_yuv420",
-    "precode_movie", "decode_movie", "LosslessPrecoder", "LoaderBadPixels", "remove_motion", "read_movie", "LossyPreconditioner",
+    "precode_movie", "decode_movie", "LosslessPrecoder", "LoaderBadPixels", "remove_motion", "read_movie", "finish_frames", "LossyPreconditioner",
     "load_translation_file",
     "save_translation_file",
 ]

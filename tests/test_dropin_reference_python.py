@@ -166,6 +166,31 @@ def test_reference_saver_and_reader_wrappers_round_trip(tmp_path):
             assert all(np.array_equal(rv.load_image(cam, i, 0), mov[i]) for i in (0, 64, 129, 5))
             rv.close_camera(cam)
         assert sizes[3] < sizes[2] < sizes[1], sizes
+        # the reference's IRMovie class on top of the same file: indexing, slicing, timestamps, attributes, the loader's
+        # bad-pixel switch and its registration file
+        from librir.video_io.IRMovie import IRMovie
+        m = IRMovie.from_filename(fn)
+        assert len(m) == len(mov) and tuple(m.image_size) == mov.shape[1:] and m.calibrations == ["Digital Level"]
+        assert np.array_equal(m[5], mov[5]) and np.array_equal(m[-1], mov[-1]) and np.array_equal(m[10:60:7], mov[10:60:7])
+        assert np.allclose(m.timestamps[:4], [0.0, 0.02, 0.04, 0.06]) and m.attributes["Device"] == b"B200"
+        assert os.path.basename(m.filename) == "m.bin"
+        m.bad_pixels_correction = True
+        corrected = m[3]
+        assert corrected.shape == mov[3].shape and (corrected != mov[3]).sum() < corrected.size // 50   # a few flagged pixels replaced
+        m.bad_pixels_correction = False
+        reg = fn + ".regfile"
+        with open(reg, "w") as f:
+            f.write("\\tx-axis translations\\ty-axis translations\\tConfidence level\\n")
+            for i in range(len(mov)):
+                f.write(f"{{i}}\\t{{0.25 * (i % 5)}}\\t{{-0.5 * (i % 3)}}\\t1.0\\n")
+        m.registration_file = reg
+        m.registration = True
+        moved = m[7]                                # shifted by (0.5, -0.5): rows [0, h-3), the metadata rows pass through
+        assert not np.array_equal(moved, mov[7]) and np.array_equal(moved[-3:], mov[7][-3:])
+        assert np.array_equal(m[15], mov[15])       # frame 15: shift (0, 0)
+        m.registration = False
+        assert np.array_equal(m[7], mov[7])
+        m.close()
         print("DONE", sizes)
     """)
     assert "DONE" in res.stdout, res.stdout + res.stderr

@@ -503,6 +503,34 @@ def test_loader_read_movie_chain(port, best, shape, loader_mode):
         np.testing.assert_array_equal(got_d, vio.read_movie(lo, hi, bp, c["min_T"], c["rows"], sx, sy))
 
 
+@pytest.mark.parametrize("shape", [(5, 64, 80), (3, 35, 48), (4, 130, 264)])
+def test_loader_finish_frames_chain(port, shape):
+    """The chain behind load_image of libvideo_io_b200.so (frames already uint16): += min_T -> removeBadPixels -> removeMotion
+    in place, host and device frames, every stage on and off -- the same oracle as the plane-fed reader.  (The motion step
+    once staged its shifts into the scratch slot that held the frames' copy: the first pixels of frame 0 came back as the
+    bits of a float.)"""
+    n, h, w = shape
+    rng = np.random.default_rng(5)
+    mov = ir_movie(n, h, w, seed=11)
+    mov[:, -3:] = rng.integers(0, 65536, (n, 3, w), dtype=np.uint16)
+    lo, hi = (mov & 0xFF).astype(np.uint8), (mov >> 8).astype(np.uint8)
+    sx = rng.uniform(-3, 3, n)
+    sy = rng.uniform(-3, 3, n)
+    sx[0] = sy[0] = 0.0
+    bp = vio.LoaderBadPixels(mov[0])
+    xy = sp.bad_pixels_list(bp.handle)[0]
+    for c in [dict(bad=False, min_T=0, rows=0, motion=True), dict(bad=True, min_T=273, rows=h - 3, motion=True),
+              dict(bad=True, min_T=0, rows=0, motion=False), dict(bad=False, min_T=300, rows=0, motion=False)]:
+        want = np.stack([port.loader_read_image(lo[t], hi[t], xy if c["bad"] else None, c["min_T"], c["rows"] if c["rows"] else h - 3,
+                                                (sx[t], sy[t]) if c["motion"] else None) for t in range(n)])
+        args = (bp if c["bad"] else None, c["min_T"], c["rows"], sx if c["motion"] else None, sy if c["motion"] else None)
+        np.testing.assert_array_equal(vio.finish_frames(mov.copy(), *args), want, err_msg=f"{shape} {c} host")
+        np.testing.assert_array_equal(to_host(vio.finish_frames(to_dev(mov.copy()), *args)), want, err_msg=f"{shape} {c} device")
+        one = mov[1].copy()  # a single frame, as load_image calls it
+        args1 = (bp if c["bad"] else None, c["min_T"], c["rows"], sx[1:2] if c["motion"] else None, sy[1:2] if c["motion"] else None)
+        np.testing.assert_array_equal(vio.finish_frames(one[None], *args1)[0], want[1], err_msg=f"{shape} {c} one frame")
+
+
 def test_loader_read_movie_fused_large_shifts_and_edges(port, loader_mode):
     """Fused reader kernel (w % 16 == 0): shifts far beyond the staged box (clamped reads rebuilt from the
     planes, including flagged source pixels), integer shifts, image smaller than a tile, many flagged pixels."""
