@@ -11,7 +11,7 @@
  * reference's zstd movie file (ZFile.cpp) with compression method 3 = temporal delta + byte planes + zstd, the method
  * video_io.h:298-305 documents and the reference never implemented: GPU pre-coder -> host zstd -> records, plus the
  * reference's attribute trailer.  There is NO CPU implementation: without a CUDA device h264_open_file returns 0.
- * Entry points of video_io.h that are not listed here (calibration, emissivity, PCR / HCC tooling, memory readers) are not
+ * Entry points of video_io.h that are not listed here (HCC tooling, the file-reader callbacks, float-image loads) are not
  * exported.
  */
 #ifndef LIBRIR_B200_VIDEO_IO_H
@@ -81,6 +81,27 @@ RIRB_VIO_API int get_attribute_count(int camera);
 RIRB_VIO_API int get_attribute(int camera, int index, char* key, int* key_len, char* value, int* value_len);
 RIRB_VIO_API int get_global_attribute_count(int camera);
 RIRB_VIO_API int get_global_attribute(int camera, int index, char* key, int* key_len, char* value, int* value_len);
+
+/* ---- raw movies and the entries of the calibration objects.  open_camera_file also opens the reference's raw PCR files (a
+ *      1024-byte header, IRFileLoader.h:43-61, then frames; *file_format = 1, or 3 for the encapsulated form) -- what
+ *      IRMovie.from_numpy_array writes before it converts; open_camera_from_memory (video_io.cpp:110-145) goes through a
+ *      temporary file; correct_PCR_file as video_io.cpp:911-930.  The movies this library opens carry no camera calibration:
+ *      emissivities are loader state (IRVideoLoader.h:47-95), calibration_files / support_emissivity / calibrate_* /
+ *      get_table* answer -1 and flip_camera_calibration -2, the reference's answers for such a movie. ---- */
+RIRB_VIO_API int open_camera_from_memory(void* ptr, int64_t size, int* file_format);
+RIRB_VIO_API int correct_PCR_file(const char* filename, int width, int height, int freq);
+RIRB_VIO_API int flip_camera_calibration(int camera, int flip_rl, int flip_ud);
+RIRB_VIO_API int set_global_emissivity(int cam, float emi);
+RIRB_VIO_API int set_emissivity(int cam, float* emi, int size);
+RIRB_VIO_API int get_emissivity(int cam, float* emi, int size);
+RIRB_VIO_API int support_emissivity(int cam);
+RIRB_VIO_API int camera_saturate(int cam);
+RIRB_VIO_API int calibration_files(int cam, char* dst, int* dstSize);
+RIRB_VIO_API int calibrate_inplace(int cam, unsigned short* img, int size, int calibration);
+RIRB_VIO_API int calibrate_image(int cam, unsigned short* img, float* out, int size, int calib);
+RIRB_VIO_API int calibrate_image_inplace(int cam, unsigned short* img, int size, int calib);
+RIRB_VIO_API int get_table_names(int cam, char* dst, int* dst_size);
+RIRB_VIO_API int get_table(int cam, const char* name, float* dst, int* dst_size);
 
 /* additive: text of the calling thread's last failure in this library */
 RIRB_VIO_API const char* rirb_video_io_last_error(void);

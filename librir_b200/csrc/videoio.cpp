@@ -206,8 +206,21 @@ Table<Saver> g_savers;
 // ---------------------------------------------------------------------------------------------------------------------
 // reader
 // ---------------------------------------------------------------------------------------------------------------------
+// The raw movie files of the reference's reader (IRFileLoader.h:43-61): a 1024-byte PCR header (int32 Version, NbImages, X, Y,
+// Band, Bits, Interlaced, Frequency, ImagesPerBuffer, TransfertSize, GrabSizeX, GrabSizeY), optionally behind 133 bytes of
+// envelope, then frames of TransfertSize bytes.  What IRMovie.from_numpy_array writes before it converts to a compressed movie.
+struct PcrHeader {
+    int32_t version, nb_images, x, y, band, bits, interlaced, frequency, images_per_buffer, transfer_size, grab_x, grab_y;
+};
+#define FILE_FORMAT_PCR 1
+#define FILE_FORMAT_ZSTD_COMPRESSED 4 /* video_io.h:17-23 */
+#define FILE_FORMAT_PCR_ENCAPSULATED 3
+
 struct Camera {
     std::string filename;
+    int format = FILE_FORMAT_ZSTD_COMPRESSED;
+    FILE* raw = nullptr;  // PCR files: frames at raw_start + pos * raw_transfer
+    long long raw_start = 0, raw_transfer = 0;
     int zfile = 0;
     int w = 0, h = 0, count = 0;
     std::vector<long long> times;
@@ -217,18 +230,29 @@ struct Camera {
     bool bp_enabled = false, motion_enabled = false;
     int bp_handle = 0;
     std::vector<double> shift_x, shift_y;
+    std::vector<float> inv_emissivity;  // IRVideoLoader::m_invEmissivities: state only, no calibration uses it here
+    std::string temp_file;              // open_camera_from_memory: the bytes live in a temporary file, removed on close
     int last_pos = -1;
     std::mutex mu;
     ~Camera()
     {
         if (zfile) rirb_z_close_file(zfile);
+        if (raw) fclose(raw);
         if (bp_handle) bad_pixels_destroy(bp_handle);
+        if (!temp_file.empty()) remove(temp_file.c_str());
+    }
+    bool read_raw(int pos, unsigned short* pixels)
+    {
+        // bin_read_image's last branch, IRFileLoader.cpp:547-557
+        const size_t bytes = (size_t)w * h * 2;
+        if (fseeko(raw, (off_t)(raw_start + raw_transfer * pos), SEEK_SET) != 0) return false;
+        return fread(pixels, 1, bytes, raw) == bytes;
     }
     // IRFileLoader::readImage, calibration 0 (IRFileLoader.cpp:1168-1247): decode -> += MIN_T -> removeBadPixels -> removeMotion
     bool read(int pos, unsigned short* pixels, bool with_bad_pixels)
     {
         if (pos < 0 || pos >= count) return false;
-        if (rirb_z_read_image(zfile, pos, pixels, nullptr) != 0) return false;
+        if (raw ? !read_raw(pos, pixels) : rirb_z_read_image(zfile, pos, pixels, nullptr) != 0) return false;
         const bool bp = with_bad_pixels && bp_enabled && bp_handle != 0;
         const bool mo = motion_enabled && !shift_x.empty();
         if (min_T == 0 && !bp && !mo) return true;
@@ -237,6 +261,66 @@ struct Camera {
     }
 };
 Table<Camera> g_cameras;
+
+// IRFileLoader::findFileType's PCR tests (IRFileLoader.cpp:124-181) and bin_open_file's raw branch (:404-431): frame count from
+// the file size, timestamps from the last 8 bytes of every frame when they increase strictly (findTimes, :256-283), else
+// i / Frequency.
+static bool open_raw(Camera& c)
+{
+    FILE* f = fopen(c.filename.c_str(), "rb");
+    if (!f) return false;
+    char buf[2000];
+    memset(buf, 0, sizeof(buf));
+    if (fread(buf, 1, sizeof(buf), f) < sizeof(PcrHeader)) {
+        fclose(f);
+        return false;
+    }
+    PcrHeader hd, enc;
+    memcpy(&hd, buf, sizeof(hd));
+    memcpy(&enc, buf + 128 + 5, sizeof(enc));
+    auto plausible = [](const PcrHeader& p, int lim) {
+        return p.bits == 16 && llabs((long long)p.transfer_size - (long long)p.x * p.y * 2) < 2000 && p.x > 0 && p.y > 0 && p.x < lim && p.y < lim;
+    };
+    if (hd.bits == 16 && hd.x == 640 && hd.y == 512 && hd.frequency == 50) {  // "IR lab videos": the transfer size is forced
+        hd.transfer_size = hd.x * hd.y * 2;
+        c.raw_start = 1024;
+    } else if (plausible(hd, 2000)) {
+        c.raw_start = 1024;
+    } else if (plausible(enc, 1000)) {
+        hd = enc;
+        c.raw_start = 1024 + 128 + 5;
+        c.format = FILE_FORMAT_PCR_ENCAPSULATED;
+    } else {
+        fclose(f);
+        return false;
+    }
+    if (c.format != FILE_FORMAT_PCR_ENCAPSULATED) c.format = FILE_FORMAT_PCR;
+    fseeko(f, 0, SEEK_END);
+    const long long size = (long long)ftello(f);
+    c.raw_transfer = hd.transfer_size;
+    c.w = hd.x;
+    c.h = hd.y;
+    c.count = c.raw_transfer > 0 ? (int)((size - c.raw_start) / c.raw_transfer) : 0;
+    if (c.count <= 0 || c.raw_transfer < (long long)c.w * c.h * 2) {
+        fclose(f);
+        return false;
+    }
+    c.times.resize((size_t)c.count);
+    bool has_times = true;
+    for (int i = 0; i < c.count && has_times; ++i) {
+        long long t = 0;
+        has_times = fseeko(f, (off_t)(c.raw_start + c.raw_transfer * (long long)(i + 1) - 8), SEEK_SET) == 0 && fread(&t, 1, 8, f) == 8;
+        c.times[(size_t)i] = t;
+        if (i > 0 && c.times[(size_t)i] <= c.times[(size_t)i - 1]) has_times = false;
+    }
+    if (!has_times) {
+        const double sampling = 1000000000.0 / (double)(hd.frequency > 0 ? hd.frequency : 50);
+        for (int i = 0; i < c.count; ++i) c.times[(size_t)i] = (long long)(i * sampling);
+    }
+    c.raw = f;
+    c.min_T_height = c.h - 3;
+    return true;
+}
 
 std::shared_ptr<Camera> open_camera(const char* filename)
 {
@@ -247,8 +331,12 @@ std::shared_ptr<Camera> open_camera(const char* filename)
         if (ch == '\\') ch = '/';
     c->zfile = rirb_z_open_file_read(filename);
     if (!c->zfile) {
-        fail(std::string("Unable to open camera file ") + filename + ": " + rirb_last_error());
-        return nullptr;
+        const std::string zerr = rirb_last_error();
+        if (!open_raw(*c)) {
+            fail(std::string("Unable to open camera file ") + filename + ": " + zerr);
+            return nullptr;
+        }
+        return c;
     }
     c->count = rirb_z_image_count(c->zfile);
     rirb_z_image_size(c->zfile, &c->w, &c->h);
@@ -546,20 +634,19 @@ int64_t close_video(int writter) { return rirb_z_close_file(writter); }
 // =====================================================================================================================
 // reader
 // =====================================================================================================================
-enum { FILE_FORMAT_ZSTD_COMPRESSED = 4 };  // video_io.h:18-26
 
 int open_camera_file(const char* filename, int* file_format)
 {
     if (file_format) *file_format = 0;
     auto c = open_camera(filename);
     if (!c) return 0;
-    if (file_format) *file_format = FILE_FORMAT_ZSTD_COMPRESSED;
+    if (file_format) *file_format = c->format;
     return g_cameras.add(c);
 }
 int video_file_format(const char* filename)
 {
     auto c = open_camera(filename);
-    return c ? FILE_FORMAT_ZSTD_COMPRESSED : -1;
+    return c ? c->format : -1;
 }
 int close_camera(int cam)
 {
@@ -738,6 +825,106 @@ int motion_correction_enabled(int cam)
     auto c = g_cameras.get(cam);
     return c && c->motion_enabled ? 1 : 0;
 }
+// ---- entries that belong to the camera CALIBRATION objects (video_io.cpp:259-360, 393-438, 464-493, 845-931).  The movies
+//      this library opens carry none, so they answer what the reference answers for such a movie: emissivities are loader
+//      state (IRVideoLoader.h:47-95), everything that needs a calibration says so. ----
+int open_camera_from_memory(void* ptr, int64_t size, int* file_format)
+{
+    // video_io.cpp:110-145 reads the movie out of the caller's buffer; here the bytes go through a temporary file
+    if (file_format) *file_format = 0;
+    if (!ptr || size <= 0) {
+        fail("open_camera_from_memory: empty buffer");
+        return 0;
+    }
+    char name[] = "/tmp/rirb_movie_XXXXXX";
+    const int fd = mkstemp(name);
+    if (fd < 0) {
+        fail("open_camera_from_memory: cannot create a temporary file");
+        return 0;
+    }
+    FILE* f = fdopen(fd, "wb");
+    const bool ok = f && fwrite(ptr, 1, (size_t)size, f) == (size_t)size;
+    if (f) fclose(f);
+    auto c = ok ? open_camera(name) : nullptr;
+    if (!c) {
+        remove(name);
+        return 0;
+    }
+    c->temp_file = name;
+    if (file_format) *file_format = c->format;
+    return g_cameras.add(c);
+}
+int flip_camera_calibration(int camera, int, int) { return g_cameras.get(camera) ? -2 : -1; }  // -2: no calibration attached
+int set_global_emissivity(int cam, float emi)
+{
+    auto c = g_cameras.get(cam);
+    if (emi < 0.f || emi > 1.f || !c) {
+        fail(c ? "set_emissivity: wrong emissivity value" : "set_global_emissivity: NULL camera");
+        return -1;
+    }
+    c->inv_emissivity.assign((size_t)c->w * c->h, 1.f / emi);
+    return 0;
+}
+int set_emissivity(int cam, float* emi, int size)
+{
+    auto c = g_cameras.get(cam);
+    if (!c || !emi || size <= 0) {
+        fail(c ? "set_emissivity: wrong vector size" : "set_emissivity: NULL camera");
+        return -1;
+    }
+    c->inv_emissivity.assign((size_t)c->w * c->h, 1.f);
+    const size_t n = std::min((size_t)size, c->inv_emissivity.size());
+    for (size_t i = 0; i < n; ++i) c->inv_emissivity[i] = 1.f / emi[i];
+    return 0;
+}
+int get_emissivity(int cam, float* emi, int size)
+{
+    auto c = g_cameras.get(cam);
+    if (!c || !emi) {
+        fail("get_emissivity: NULL camera");
+        return -1;
+    }
+    const int s = std::min(size, (int)c->inv_emissivity.size());
+    for (int i = 0; i < s; ++i) emi[i] = 1.f / c->inv_emissivity[(size_t)i];
+    if (s == 0) *emi = 1;
+    return s;
+}
+int support_emissivity(int cam)
+{
+    (void)cam;
+    fail("support_emissivity: NULL camera");  // the reference's message when the loader has no calibration
+    return -1;
+}
+int camera_saturate(int cam) { return g_cameras.get(cam) ? 0 : -1; }
+int calibration_files(int, char*, int*) { return -1; }
+// IRFileLoader::calibrate / calibrateInplace, IRFileLoader.cpp:1060-1097: calibration 0 (digital levels) succeeds and touches
+// nothing; calibration 1 needs the calibration object
+int calibrate_inplace(int cam, unsigned short*, int, int calibration) { return (g_cameras.get(cam) && calibration == 0) ? 0 : -1; }
+int calibrate_image(int cam, unsigned short*, float*, int, int calib) { return (g_cameras.get(cam) && calib == 0) ? 0 : -1; }
+int calibrate_image_inplace(int cam, unsigned short*, int, int calib) { return (g_cameras.get(cam) && calib == 0) ? 0 : -1; }
+int get_table_names(int, char*, int*) { return -1; }
+int get_table(int, const char*, float*, int*) { return -1; }
+// video_io.cpp:911-930: only a file the reader canNOT open is touched; it gets a PCR header for the given geometry
+int correct_PCR_file(const char* filename, int width, int height, int freq)
+{
+    if (!filename || open_camera(filename)) return -1;
+    FILE* f = fopen(filename, "r+b");
+    if (!f) return -1;
+    PcrHeader h;
+    memset(&h, 0, sizeof(h));
+    if (fread(&h, 1, sizeof(h), f) != sizeof(h)) memset(&h, 0, sizeof(h));
+    h.x = h.grab_x = width;
+    h.y = h.grab_y = height;
+    h.bits = 16;
+    h.version = 0;
+    h.transfer_size = width * height * 2;
+    h.frequency = freq;
+    fseeko(f, 0, SEEK_SET);
+    fwrite(&h, 1, sizeof(h), f);
+    fclose(f);
+    return 0;
+}
+
 int get_attribute_count(int cam)
 {
     auto c = g_cameras.get(cam);

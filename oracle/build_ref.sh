@@ -77,4 +77,16 @@ if [ ! -f "$OUT/pkg/librir/__init__.py" ] || [ "$OUT/libs/libvideo_io.so" -nt "$
   mkdir -p "$OUT/pkg/librir/libs"
   for l in tools geometry signal_processing video_io; do cp "$OUT/libs/lib$l.so" "$OUT/pkg/librir/libs/"; done
 fi
+# the reference's own Python tests (tests/python), laid out as the package `tests.python` they import themselves as, so that
+# the GPU box can run them UNMODIFIED on top of the drop-in libraries (tests/test_reference_own_tests.py).  Git-ignored like
+# the rest of oracle/_ref; the 1 MB geometry fixture (circle.py) is left out.
+if [ ! -f "$OUT/reftests/tests/python/conftest.py" ] || [ -n "${FORCE:-}" ]; then
+  echo "build_ref: reference tests -> $OUT/reftests"
+  rm -rf "$OUT/reftests"
+  mkdir -p "$OUT/reftests/tests/python"
+  : > "$OUT/reftests/tests/__init__.py"
+  for f in __init__.py conftest.py test_IRMovie.py test_rir.py test_video_io.py test_registration.py test_FileAttributes.py; do
+    cp "$R/tests/python/$f" "$OUT/reftests/tests/python/"
+  done
+fi
 echo "build_ref: done -> $OUT/libs"

@@ -151,6 +151,9 @@ VIDEO_IO_REFERENCE_EXPORTS = [  # video_io.h:30-314 of the reference, the entrie
     "get_global_attribute_count", "get_global_attribute", "set_ffmpeg_log_enabled", "h264_open_file", "h264_close_file",
     "h264_set_parameter", "h264_set_global_attributes", "h264_add_image_lossless", "h264_add_image_lossy", "h264_add_loss",
     "h264_get_low_errors", "h264_get_high_errors", "open_video_write", "image_write", "close_video",
+    "open_camera_from_memory", "correct_PCR_file", "flip_camera_calibration", "set_global_emissivity", "set_emissivity", "get_emissivity",
+    "support_emissivity", "camera_saturate", "calibration_files", "calibrate_inplace", "calibrate_image", "calibrate_image_inplace",
+    "get_table_names", "get_table",
 ]
 
 
