@@ -959,6 +959,48 @@ def test_entries_are_reentrant_across_threads(best):
     assert not errors, errors[:3]
 
 
+def test_short_lived_threads_give_their_device_memory_back():
+    """Every calling thread owns a stream, staging buffers and (for the one-call host path) three pipeline slots.  They are
+    released when the thread ends -- or on demand with rirb_release_thread_resources() -- so a service that calls from
+    short-lived worker threads does not grow (round-1 review: they were never freed)."""
+    import threading
+
+    from librir_b200 import movie
+
+    lib = _lib.load()
+    mov = ir_movie(40, 256, 320)
+    bp = sp.BadPixels(mov[0])
+    dx = np.zeros(len(mov), np.float32)
+    errors = []
+
+    def work(release_explicitly):
+        try:
+            sp.gaussian_filter(mov[0], 1.0)
+            sp.translate(mov[1], 0.5, 0.25, "nearest")
+            movie.process_movie_host(bp, mov, dx, dx, 1.0, "nearest", 0, gop=10, delta=True, first_frame=0)
+            if release_explicitly:
+                lib.rirb_release_thread_resources()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    def burst(n, release_explicitly):
+        for _ in range(n):
+            t = threading.Thread(target=work, args=(release_explicitly,))
+            t.start()
+            t.join()
+
+    burst(3, False)  # one-time allocations of the process (CUDA context, pools) out of the way
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    burst(12, False)
+    burst(12, True)
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert not errors, errors[:3]
+    per_thread = 3 * 12 * 320 * 256 * 10  # what one thread's host pipeline holds, at the very least
+    assert free0 - free1 < 4 * per_thread, f"device memory shrank by {(free0 - free1) / 1e6:.1f} MB over 24 short-lived threads"
+
+
 @pytest.mark.parametrize("shape", [(5, 64, 128), (3, 200, 264), (4, 70, 136), (2, 5, 8), (3, 130, 640), (2, 33, 20), (2, 64, 127)])
 @pytest.mark.parametrize("sigma", [0.5, 1.0, 1.7, 2.2])
 def test_bad_pixels_correct_gaussian_fused(port, shape, sigma):
