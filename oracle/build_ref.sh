@@ -80,7 +80,7 @@ fi
 # the reference's own Python tests (tests/python), laid out as the package `tests.python` they import themselves as, so that
 # the GPU box can run them UNMODIFIED on top of the drop-in libraries (tests/test_reference_own_tests.py).  Git-ignored like
 # the rest of oracle/_ref; the 1 MB geometry fixture (circle.py) is left out.
-if [ ! -f "$OUT/reftests/tests/python/conftest.py" ] || [ -n "${FORCE:-}" ]; then
+if [ ! -f "$OUT/reftests/tests/python/conftest.py" ] || [ ! -f "$OUT/reftests/examples/ir_saver.py" ] || [ -n "${FORCE:-}" ]; then
   echo "build_ref: reference tests -> $OUT/reftests"
   rm -rf "$OUT/reftests"
   mkdir -p "$OUT/reftests/tests/python"
@@ -88,5 +88,7 @@ if [ ! -f "$OUT/reftests/tests/python/conftest.py" ] || [ -n "${FORCE:-}" ]; the
   for f in __init__.py conftest.py test_IRMovie.py test_rir.py test_video_io.py test_registration.py test_FileAttributes.py; do
     cp "$R/tests/python/$f" "$OUT/reftests/tests/python/"
   done
+  mkdir -p "$OUT/reftests/examples"   # the reference's example scripts of the path (saver / reader, registration)
+  cp "$R/examples/ir_saver.py" "$R/examples/registration.py" "$OUT/reftests/examples/"
 fi
 echo "build_ref: done -> $OUT/libs"

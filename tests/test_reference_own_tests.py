@@ -75,3 +75,21 @@ def test_reference_test_registration(tmp_path):
     res = run_reference_tests(tmp_path, ["test_registration.py"])
     passed, failed = summary(res)
     assert res.returncode == 0 and failed == 0 and passed >= 1, res.stdout[-6000:] + res.stderr[-2000:]
+
+
+@needs_reftests
+@pytest.mark.parametrize("script", ["ir_saver.py", "registration.py"])
+def test_reference_example_scripts(tmp_path, script):
+    """examples/ir_saver.py (lossless and lossy recording, reading back through IRMovie) and examples/registration.py of the
+    reference, unmodified, on the drop-in libraries."""
+    if script == "registration.py":
+        pytest.importorskip("cv2")
+    site = make_site(tmp_path)
+    work = tmp_path / "work"
+    shutil.copytree(os.path.join(REFTESTS, "examples"), work)
+    env = dict(os.environ, PYTHONPATH=str(site), LIBRIR_DISABLE_JOBLIB="1",
+               LIBRIR_B200_FORWARD_LIB=os.path.join(ROOT, "oracle", "_ref", "libs", "libsignal_processing.so"))
+    res = subprocess.run([sys.executable, script], cwd=str(work), env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    if script == "ir_saver.py":
+        assert "Number of images:  100" in res.stdout and "Compression factor is" in res.stdout, res.stdout[-2000:]
