@@ -29,7 +29,7 @@ extern "C" {
 /* ---- saver: replaces video_io.h:222-280 / video_io.cpp:659-843 (H264_Saver, h264.cpp:1668-2617) ----
  * h264_open_file returns a handle > 0 (0 on failure) and removes an existing file; the container is created by the first
  * image.  h264_set_parameter takes the saver's keys (h264.cpp:1709-1781): lowValueError, highValueError, compressionLevel
- * (0..8, mapped onto zstd levels 1..19), codec ("h264" / "h265": accepted, the frames go to the zstd container with the
+ * (0..8, mapped onto zstd levels 1..12), codec ("h264" / "h265": accepted, the frames go to the zstd container with the
  * pre-coder in front; "zstd1" / "zstd2" / "zstd3" pick the container method), GOP, threads (host zstd threads, 0 = all),
  * slices (ignored), stdFactor, inputCamera (must stay 0: the camera calibration is outside this library), removeBadPixels,
  * subtractMin, subtractLocalMin (ignored), runningAverage; -1 for an unknown key.

@@ -151,7 +151,7 @@ struct Saver {
         if (zfile) return true;
         // zstd levels: the saver's compressionLevel 0..8 picks an x264 preset (ultrafast..veryslow, h264.cpp:464-494); the same
         // scale is used for zstd (0 = its fast default, 3; 8 = 19)
-        static const int level_of[9] = {1, 2, 3, 5, 7, 9, 12, 15, 19};
+        static const int level_of[9] = {1, 2, 3, 4, 5, 6, 8, 10, 12};  // beyond 12 zstd costs 5-10x more per frame for a few per cent on byte planes
         const int lv = level_of[clevel < 0 ? 0 : (clevel > 8 ? 8 : clevel)];
         zfile = rirb_z_open_file_write_gop(filename.c_str(), w, h, 50, method, lv, gop);  // 50: the fps h264_* hands H264_Saver::open
         if (!zfile) fail(std::string("cannot create the movie file: ") + rirb_last_error());
