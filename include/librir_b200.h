@@ -279,6 +279,7 @@ RIRB_API int rirb_z_write_images(int handle, const unsigned short* frames, long 
 RIRB_API long long rirb_z_close_file(int handle);
 RIRB_API int rirb_z_open_file_read(const char* filename);
 RIRB_API int rirb_z_image_count(int handle);
+RIRB_API int rirb_z_method(int handle); /* 1: zstd of the raw image (the reference's files), 2 / 3: pre-coded (this repo) */
 RIRB_API int rirb_z_image_size(int handle, int* width, int* height);
 RIRB_API int rirb_z_get_timestamps(int handle, long long* times);
 RIRB_API int rirb_z_read_image(int handle, int pos, unsigned short* img, long long* timestamp);

@@ -109,6 +109,7 @@ SIGNATURES = {
     "rirb_z_close_file": (_ll, [_i]),
     "rirb_z_open_file_read": (_i, [ct.c_char_p]),
     "rirb_z_image_count": (_i, [_i]),
+    "rirb_z_method": (_i, [_i]),
     "rirb_z_image_size": (_i, [_i, _vp, _vp]),
     "rirb_z_get_timestamps": (_i, [_i, _vp]),
     "rirb_z_read_image": (_i, [_i, _i, _vp, _vp]),

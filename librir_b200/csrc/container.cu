@@ -1124,6 +1124,11 @@ int rirb_z_image_count(int handle)
     auto z = g_zfiles.get(handle);
     return z ? (int)z->times.size() : -1;
 }
+int rirb_z_method(int handle)
+{
+    auto z = g_zfiles.get(handle);
+    return z ? z->method : -1;
+}
 int rirb_z_image_size(int handle, int* width, int* height)
 {
     auto z = g_zfiles.get(handle);

@@ -342,6 +342,21 @@ std::shared_ptr<Camera> open_camera(const char* filename)
     rirb_z_image_size(c->zfile, &c->w, &c->h);
     c->times.resize((size_t)(c->count > 0 ? c->count : 0));
     if (c->count > 0) rirb_z_get_timestamps(c->zfile, c->times.data());
+    if (c->count > 0 && rirb_z_method(c->zfile) == 1) {
+        // The reference's own zstd movie files are WEST acquisition files with times in ms: bin_open_file_from_file_reader,
+        // IRFileLoader.cpp:354-372 -- origin-relative ms (first value 28,000-32,000) become ns minus 10 ms, other values that
+        // are not ns already become ns relative to the first image.  (Methods 2 / 3 are written by this library's saver, which
+        // stands in for the mp4 writer: ns, as given.)
+        const long long t0 = c->times[0];
+        if (t0 > 28000 && t0 < 32000) {
+            for (auto& t : c->times) t = t * 1000000LL - 10000000LL;
+        } else if (!(c->times.front() < -1000000000LL || c->times.back() > 1000000000LL)) {
+            for (auto& t : c->times) t = (t - t0) * 1000000LL;
+        }
+    }
+    // "timestamps starting at -2 s for WEST videos" (:458-466, every file type)
+    if (c->count > 0 && c->times.front() > 28000000000LL && c->times.front() < 32000000000LL)
+        for (auto& t : c->times) t -= 32000000000LL;
     // the attribute trailer: global + per-frame attributes
     const int a = rirb_attrs_open_file(filename);
     if (a) {

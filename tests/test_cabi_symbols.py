@@ -195,3 +195,34 @@ def test_video_io_without_gpu_fails_loudly(tmp_path):
     out = np.ones((48, 64), dtype=np.uint16)
     assert lib.load_image(cam, 0, 0, out.ctypes.data_as(ct.c_void_p)) == 0 and not out.any()
     assert lib.close_camera(cam) == 0
+
+
+@pytest.mark.parametrize("times", [[0, 20, 40, 60, 80], [30000, 30020, 30040, 30061], [5, 1_000_000_123, 2_000_000_000], [-3, 7, 1000],
+                                   [29_000_000_000, 29_020_000_000]])
+def test_video_io_reader_applies_the_references_time_conventions(tmp_path, times):
+    """The reference's reader rewrites the timestamps of its zstd movie files (WEST acquisition files, ms): origin-relative ms
+    -> ns - 10 ms, other non-ns values -> ns relative to the first image, and -32 s when the first lands between 28 s and 32 s
+    (IRFileLoader.cpp:354-372, :458-466).  Method-1 files are host code on both sides: no GPU needed."""
+    from oracle import refvio as rv
+
+    if not rv.have_ref_vio():
+        pytest.skip("oracle/_ref/libs/libvideo_io.so not built")
+    lib = ct.CDLL(video_io_lib_path())
+    fn = str(tmp_path / "t.bin").encode()
+    w = lib.open_video_write(fn, 16, 12, 50, 1, 1)
+    assert w > 0
+    img = np.arange(12 * 16, dtype=np.uint16).reshape(12, 16)
+    for t in times:
+        assert lib.image_write(w, img.ctypes.data_as(ct.c_void_p), ct.c_int64(t)) == 0
+    lib.close_video.restype = ct.c_int64
+    assert lib.close_video(w) > 0
+    ref = rv.Camera(fn.decode())
+    fmt = ct.c_int(0)
+    cam = lib.open_camera_file(fn, ct.byref(fmt))
+    assert cam > 0 and fmt.value == 4
+    for i in range(len(times)):
+        t = ct.c_int64(0)
+        assert lib.get_image_time(cam, i, ct.byref(t)) == 0
+        assert t.value == ref.image_time(i), (i, t.value, ref.image_time(i))
+    lib.close_camera(cam)
+    ref.close()
