@@ -82,9 +82,10 @@ RIRB_VIO_API int get_attribute(int camera, int index, char* key, int* key_len, c
 RIRB_VIO_API int get_global_attribute_count(int camera);
 RIRB_VIO_API int get_global_attribute(int camera, int index, char* key, int* key_len, char* value, int* value_len);
 
-/* ---- raw movies and the entries of the calibration objects.  open_camera_file also opens the reference's raw PCR files (a
+/* ---- raw movies and the entries of the calibration objects.  open_camera_file also opens the reference's raw files: PCR (a
  *      1024-byte header, IRFileLoader.h:43-61, then frames; *file_format = 1, or 3 for the encapsulated form) -- what
- *      IRMovie.from_numpy_array writes before it converts; open_camera_from_memory (video_io.cpp:110-145) goes through a
+ *      IRMovie.from_numpy_array writes before it converts -- and uncompressed WEST acquisition files (*file_format = 2), with
+ *      the reference's timestamp search and conversions (IRFileLoader.cpp:256-283, 404-466); open_camera_from_memory (video_io.cpp:110-145) goes through a
  *      temporary file; correct_PCR_file as video_io.cpp:911-930.  The movies this library opens carry no camera calibration:
  *      emissivities are loader state (IRVideoLoader.h:47-95), calibration_files / support_emissivity / calibrate_* /
  *      get_table* answer -1 and flip_camera_calibration -2, the reference's answers for such a movie. ---- */

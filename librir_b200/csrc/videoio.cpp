@@ -213,6 +213,7 @@ struct PcrHeader {
     int32_t version, nb_images, x, y, band, bits, interlaced, frequency, images_per_buffer, transfer_size, grab_x, grab_y;
 };
 #define FILE_FORMAT_PCR 1
+#define FILE_FORMAT_WEST 2
 #define FILE_FORMAT_ZSTD_COMPRESSED 4 /* video_io.h:17-23 */
 #define FILE_FORMAT_PCR_ENCAPSULATED 3
 
@@ -290,11 +291,29 @@ static bool open_raw(Camera& c)
         hd = enc;
         c.raw_start = 1024 + 128 + 5;
         c.format = FILE_FORMAT_PCR_ENCAPSULATED;
+    } else if ((unsigned char)buf[0] < 10 && buf[2] == 0 && buf[1] == 1) {
+        // uncompressed WEST acquisition file (:183-207): BIN_HEADER {version, triggers, compression} in 128 bytes, then one
+        // BIN_TRIGGER of int64 {date, rate, samples, ..., data_size_x, data_size_y} in 128 bytes, then the frames
+        int64_t trig[11];
+        memcpy(trig, buf + 128, sizeof(trig));
+        const int64_t rate = trig[1], sxz = trig[9], syz = trig[10];
+        if (!(sxz > 0 && sxz < 1000 && syz > 0 && syz < 1000 && rate > 0 && rate < 1000)) {
+            fclose(f);
+            return false;
+        }
+        memset(&hd, 0, sizeof(hd));
+        hd.x = (int)sxz;
+        hd.y = (int)syz;
+        hd.transfer_size = hd.x * hd.y * 2;
+        hd.frequency = (int)rate;
+        hd.bits = 16;
+        c.raw_start = 256;
+        c.format = FILE_FORMAT_WEST;
     } else {
         fclose(f);
         return false;
     }
-    if (c.format != FILE_FORMAT_PCR_ENCAPSULATED) c.format = FILE_FORMAT_PCR;
+    if (c.format != FILE_FORMAT_PCR_ENCAPSULATED && c.format != FILE_FORMAT_WEST) c.format = FILE_FORMAT_PCR;
     fseeko(f, 0, SEEK_END);
     const long long size = (long long)ftello(f);
     c.raw_transfer = hd.transfer_size;
@@ -316,7 +335,16 @@ static bool open_raw(Camera& c)
     if (!has_times) {
         const double sampling = 1000000000.0 / (double)(hd.frequency > 0 ? hd.frequency : 50);
         for (int i = 0; i < c.count; ++i) c.times[(size_t)i] = (long long)(i * sampling);
+    } else {  // :433-452: origin-relative ms -> ns; other values that are not ns already -> ns relative to the first image
+        const long long t0 = c.times[0];
+        if (t0 > 28000 && t0 < 32000) {
+            for (auto& t : c.times) t *= 1000000LL;
+        } else if (!(c.times.front() < -1000000000LL || c.times.back() > 1000000000LL)) {
+            for (auto& t : c.times) t = (t - t0) * 1000000LL;
+        }
     }
+    if (c.times.front() > 28000000000LL && c.times.front() < 32000000000LL)  // :458-466
+        for (auto& t : c.times) t -= 32000000000LL;
     c.raw = f;
     c.min_T_height = c.h - 3;
     return true;

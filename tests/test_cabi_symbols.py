@@ -226,3 +226,55 @@ def test_video_io_reader_applies_the_references_time_conventions(tmp_path, times
         assert t.value == ref.image_time(i), (i, t.value, ref.image_time(i))
     lib.close_camera(cam)
     ref.close()
+
+
+def _raw_movie(kind, n, h, w, stamp):
+    """A raw movie file as the reference's reader expects it (IRFileLoader.cpp:124-207): kind 'pcr' (1024-byte header),
+    'pcr_enc' (133 bytes of envelope in front of the header) or 'west' (BIN_HEADER + one BIN_TRIGGER, 128 bytes each)."""
+    rng = np.random.default_rng(n * 1000 + h)
+    mov = rng.integers(0, 16384, (n, h, w), dtype=np.uint16)
+    if stamp is not None:  # findTimes: the last 8 bytes of every image, strictly increasing
+        for i in range(n):
+            mov[i].reshape(-1)[-4:] = np.frombuffer(np.int64(stamp(i)).tobytes(), dtype=np.uint16)
+    pcr = np.zeros(256, np.int32)
+    pcr[[1, 2, 3, 5, 7, 9, 10, 11]] = [n, w, h, 16, 25, w * h * 2, w, h]
+    if kind == "pcr":
+        head = pcr.tobytes()
+    elif kind == "pcr_enc":
+        head = bytes(133) + pcr.tobytes()
+    else:
+        hdr = bytearray(128)
+        hdr[0], hdr[1], hdr[2] = 1, 1, 0
+        trig = np.zeros(16, np.int64)
+        trig[[0, 1, 2, 9, 10]] = [1234, 25, n, w, h]
+        head = bytes(hdr) + trig.tobytes()
+    return head + mov.tobytes(), mov
+
+
+@pytest.mark.parametrize("kind,stamp", [("pcr", None), ("pcr", lambda i: 1000 + 40 * i), ("pcr_enc", None), ("west", lambda i: 30000 + 40 * i),
+                                        ("west", None), ("pcr", lambda i: 5_000_000_000 + 40_000_000 * i)])
+def test_video_io_reader_opens_raw_movies_like_the_reference(tmp_path, kind, stamp):
+    """Raw PCR / encapsulated PCR / uncompressed WEST files (what IRMovie.from_numpy_array writes, and what acquisition
+    systems wrote before compression): format code, frame count, size, every image and every timestamp as the compiled
+    reference's reader gives them.  Host code on both sides: no GPU needed."""
+    from oracle import refvio as rv
+
+    if not rv.have_ref_vio():
+        pytest.skip("oracle/_ref/libs/libvideo_io.so not built")
+    data, mov = _raw_movie(kind, 7, 24, 40, stamp)
+    fn = tmp_path / f"raw.{kind}"
+    fn.write_bytes(data)
+    lib = ct.CDLL(video_io_lib_path())
+    fmt = ct.c_int(0)
+    cam = lib.open_camera_file(str(fn).encode(), ct.byref(fmt))
+    ref = rv.Camera(str(fn))
+    assert cam > 0 and fmt.value == {"pcr": 1, "pcr_enc": 3, "west": 2}[kind]
+    assert lib.get_image_count(cam) == ref.count == len(mov)
+    img = np.empty(mov.shape[1:], np.uint16)
+    for i in range(len(mov)):
+        assert lib.load_image(cam, i, 0, img.ctypes.data_as(ct.c_void_p)) == 0
+        assert np.array_equal(img, ref.load_image(i)) and np.array_equal(img, mov[i]), i
+        t = ct.c_int64(0)
+        assert lib.get_image_time(cam, i, ct.byref(t)) == 0 and t.value == ref.image_time(i), (i, t.value, ref.image_time(i))
+    lib.close_camera(cam)
+    ref.close()
