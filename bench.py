@@ -286,6 +286,9 @@ def measure_configs(dev, rank, world, dist, peak, reps=3):
 
     from librir_b200 import movie, signal_processing as sp, video_io as vio
 
+    INNER = 4  # launches per timed region: the host's work for launch i + 1 (tensor-map encoding, pointer queries, Python) then
+    #            runs under launch i instead of in front of a 0.2 ms kernel; every input is far larger than L2
+
     def timed(fn):
         fn()
         times = []
@@ -293,10 +296,11 @@ def measure_configs(dev, rank, world, dist, peak, reps=3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             e0.record()
-            fn()
+            for _i in range(INNER):
+                fn()
             e1.record()
             torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
+            times.append(e0.elapsed_time(e1) / INNER)
         t = torch.tensor([statistics.median(times)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -380,6 +384,8 @@ def measure_configs(dev, rank, world, dist, peak, reps=3):
         del frames, o16, o32, lo, hi, bp
         torch.cuda.empty_cache()
     out["C5"] = c5
+    out["timing"] = (f"every cell: median of {reps} timed regions of {INNER} back-to-back launches on the launching stream (CUDA events), "
+                     "divided by the launch count; inputs far larger than L2")
     return out
 
 
