@@ -107,14 +107,15 @@ def main():
             for _ in range(3):
                 fn()
             times = []
-            for _ in range(args.reps):
+            for _ in range(args.reps):  # four back-to-back launches per timed region, as bench.py's `configs` cells
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 torch.cuda.synchronize()
                 e0.record()
-                fn()
+                for _i in range(4):
+                    fn()
                 e1.record()
                 torch.cuda.synchronize()
-                times.append(e0.elapsed_time(e1))
+                times.append(e0.elapsed_time(e1) / 4)
             ms = statistics.median(times)
             t = torch.tensor([ms, min(times), max(times)], dtype=torch.float64, device=dev)
             per_rank = None
