@@ -72,6 +72,8 @@ RIRB_API size_t hash_bytes(void* ptr, size_t len);
 /* ---- runtime ---- */
 RIRB_API int rirb_device_count(void);                 /* 0 when no CUDA device is usable */
 RIRB_API int rirb_set_device(int device);             /* cudaSetDevice for the calling thread */
+/* (changing the stream makes the new one wait, on the device, for what this thread enqueued on the old one: the thread's
+ * scratch buffers are shared by its calls) */
 RIRB_API int rirb_set_stream(void* cuda_stream);      /* stream for the calling thread (NULL = default) */
 RIRB_API int rirb_synchronize(void);                  /* wait for the calling thread's stream */
 RIRB_API const char* rirb_last_error(void);           /* calling thread's last error text */

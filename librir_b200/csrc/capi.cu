@@ -33,6 +33,7 @@ struct ThreadState {
     void* dev[SLOTS] = {};
     size_t cap[SLOTS] = {};
     int dev_of[SLOTS] = {};
+    bool enqueued = false;  // something of this thread may still be running on `stream` (device-pointer calls do not synchronise)
     ThreadState()
     {
         for (int i = 0; i < SLOTS; ++i) dev_of[i] = -1;
@@ -136,6 +137,7 @@ static void* scratch(int slot, size_t bytes)
 {
     int dev = 0;
     cudaGetDevice(&dev);
+    tls.enqueued = true;  // whoever asks for scratch is about to enqueue work that uses it (see rirb_set_stream)
     if (tls.cap[slot] < bytes || tls.dev_of[slot] != dev) {
         if (tls.dev[slot]) cudaFree(tls.dev[slot]);  // also when the thread moved to another device: UVA pointers free from anywhere
         tls.dev[slot] = nullptr;
@@ -442,13 +444,26 @@ int rirb_set_device(int device)
 }
 int rirb_set_stream(void* s)
 {
-    tls.stream = (cudaStream_t)s;
+    // The scratch slots belong to the thread, not to the stream, and device-pointer calls return without synchronising: work
+    // enqueued on the old stream may still be using them when the next call arrives on the new one.  The new stream is made
+    // to wait for the old one (an event, no host synchronisation); errors -- the old stream may be gone -- are ignored.
+    const cudaStream_t next = (cudaStream_t)s;
+    if (next != tls.stream && tls.enqueued) {
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+            if (cudaEventRecord(ev, tls.stream) == cudaSuccess) (void)cudaStreamWaitEvent(next, ev, 0);
+            (void)cudaEventDestroy(ev);
+        }
+        (void)cudaGetLastError();
+    }
+    tls.stream = next;
     return 0;
 }
 int rirb_synchronize(void)
 {
     RIRB_REQUIRE_DEVICE();
     RIRB_CUDA_OK(cudaStreamSynchronize(tls.stream));
+    tls.enqueued = false;
     return 0;
 }
 int rirb_set_parameter(const char* key, const char* value)

@@ -959,6 +959,30 @@ def test_entries_are_reentrant_across_threads(best):
     assert not errors, errors[:3]
 
 
+def test_scratch_is_safe_across_a_change_of_stream():
+    """Device-pointer calls return without synchronising and the scratch slots belong to the calling thread: a call on
+    another stream right behind one that is still running must not overwrite its scratch (in-place motion removal keeps a
+    copy of the movie there).  rirb_set_stream makes the new stream wait for the old one."""
+    n, h, w = 300, 256, 320
+    a = ir_movie(n, h, w, seed=1)
+    b = ir_movie(n, h, w, seed=2)
+    sx = np.linspace(-2.5, 2.5, n)
+    sy = np.linspace(1.5, -1.5, n)
+    want_a = to_host(vio.remove_motion(to_dev(a), sx, sy))
+    want_b = to_host(vio.remove_motion(to_dev(b), sy, sx))
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        da, db = to_dev(a), to_dev(b)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s1):
+            vio.remove_motion(da, sx, sy, out=da)  # in place: the input's copy lives in the thread's scratch
+        with torch.cuda.stream(s2):
+            vio.remove_motion(db, sy, sx, out=db)  # same scratch slot, other stream, no synchronisation in between
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(to_host(da), want_a)
+        np.testing.assert_array_equal(to_host(db), want_b)
+
+
 def test_short_lived_threads_give_their_device_memory_back():
     """Every calling thread owns a stream, staging buffers and (for the one-call host path) three pipeline slots.  They are
     released when the thread ends -- or on demand with rirb_release_thread_resources() -- so a service that calls from
